@@ -1,0 +1,749 @@
+// context.cu -- host orchestration and the C ABI (include/gapcu.h).
+//
+// Pipeline of one evaluation (all on ctx->stream, no host sync in between once
+// the neighbour capacity is known):
+//   K1  neigh.cu    bin -> scan -> fill -> per-centre list (reference order)
+//   K2  desc.cu     forward descriptors G[N][D]
+//   K3  gpr.cu      DMMA GPR: e_i and dE/dG
+//   K4  desc.cu     backward: per-slot gradients, centre gradient, strs contraction
+//   K5  gather.cu   force gather (mirror-pair lookup) + per-structure E / stress
+#include <cuda_runtime.h>
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/gapcu.h"
+#include "device_types.cuh"
+#include "launch.cuh"
+#include "potential.hpp"
+
+using namespace gapcu;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+extern "C" const char *gapcu_last_error(void) { return g_err.c_str(); }
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(GAPCU_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
+    } while (0)
+
+namespace {
+
+template <class T>
+struct DBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t want) {
+        if (want <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        size_t grow = want + want / 8 + 64;
+        cudaError_t e = cudaMalloc((void **)&p, grow * sizeof(T));
+        if (e == cudaSuccess) n = grow;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+struct gapcu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // ---- potential
+    bool have_sf = false, have_gpr = false;
+    std::vector<int> z;
+    std::vector<double> w;
+    SfPlan plan;
+    DBuf<int> d_itab;
+    DBuf<double> d_dtab;
+    int M = 0, D = 0, Mp = 0, Dp = 0;
+    std::vector<double> h_theta, h_mm, h_coeff;  // cached GPR data (C order)
+    DBuf<double> d_mm_raw, d_theta_raw, d_coeff_raw, d_Mt, d_mn, d_coeff, d_cmean, d_itheta;
+    // ---- structures
+    int nstruct = 0, ntot = 0, nbins = 0;
+    double rcut = 0.0;
+    std::vector<StructDev> h_structs;
+    std::vector<int> h_natoms;
+    DBuf<StructDev> d_structs;
+    DBuf<int> d_sid, d_arank, d_bin_count, d_bin_start, d_bin_atoms, d_nbr_cnt;
+    DBuf<int4> d_abin;
+    DBuf<double> d_pos, d_wgt, d_G, d_dEdG, d_eatom, d_fpair, d_gself, d_vir, d_force, d_out8, d_mindis;
+    DBuf<uint64_t> d_keys;
+    DBuf<DevFlags> d_flags;
+    DBuf<unsigned char> d_flush;
+    int cap = 0, pcap = 0, last_ntot = -1;
+    bool pcap_known = false;
+    int last_lgrad = 1;
+    bool computed = false;
+    DevFlags h_flags;
+    long launches = 0;
+    // pinned staging
+    void *h_pin = nullptr;
+    size_t h_pin_bytes = 0;
+    // timing instrumentation
+    cudaEvent_t stage_ev[GAPCU_NSTAGE + 1];
+    bool stage_ev_init = false;
+
+    PlanDev plan_dev() const {
+        PlanDev p;
+        p.itab = d_itab.p; p.dtab = d_dtab.p;
+        p.n_itab = (int)plan.itab.size(); p.n_dtab = (int)plan.dtab.size();
+        p.nsf = plan.nsf; p.D = plan.D; p.ncls = plan.ncls; p.n_rad = plan.n_rad; p.n_grp = plan.n_grp; p.n_asf = plan.n_asf;
+        p.o_rad_ii = plan.o_rad_ii; p.o_rad_cls = plan.o_rad_cls; p.o_rad_type = plan.o_rad_type;
+        p.o_cls_grp = plan.o_cls_grp; p.o_grp_sf = plan.o_grp_sf; p.o_asf_ii = plan.o_asf_ii;
+        p.o_rc = plan.o_rc; p.o_t2 = plan.o_t2; p.o_pirc = plan.o_pirc; p.o_rad_p = plan.o_rad_p;
+        p.o_grp_alpha = plan.o_grp_alpha; p.o_asf_lambda = plan.o_asf_lambda;
+        p.ang_prefix_mask = plan.ang_prefix_mask;
+        return p;
+    }
+    int pin(size_t bytes) {
+        if (bytes <= h_pin_bytes) return 0;
+        if (h_pin) cudaFreeHost(h_pin);
+        h_pin = nullptr; h_pin_bytes = 0;
+        size_t grow = bytes + bytes / 4 + 4096;
+        if (cudaMallocHost(&h_pin, grow) != cudaSuccess) return -1;
+        h_pin_bytes = grow;
+        return 0;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// context life cycle
+// ---------------------------------------------------------------------------
+extern "C" int gapcu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" gapcu_ctx *gapcu_ctx_create(int device) {
+    int n = gapcu_device_count();
+    if (n <= 0) { fail(GAPCU_ENODEV, "no CUDA device: gapcu has no CPU fallback"); return nullptr; }
+    if (device < 0 || device >= n) { fail(GAPCU_EARG, "bad device index"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { fail(GAPCU_ECUDA, "cudaSetDevice failed"); return nullptr; }
+    gapcu_ctx *c = new gapcu_ctx();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        fail(GAPCU_ECUDA, "cudaStreamCreate failed");
+        delete c;
+        return nullptr;
+    }
+    memset(&c->h_flags, 0, sizeof c->h_flags);
+    return c;
+}
+
+extern "C" void gapcu_ctx_destroy(gapcu_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->d_itab.release(); c->d_dtab.release(); c->d_mm_raw.release(); c->d_theta_raw.release(); c->d_coeff_raw.release();
+    c->d_Mt.release(); c->d_mn.release(); c->d_coeff.release(); c->d_cmean.release(); c->d_itheta.release();
+    c->d_structs.release(); c->d_sid.release(); c->d_arank.release(); c->d_bin_count.release(); c->d_bin_start.release();
+    c->d_bin_atoms.release(); c->d_nbr_cnt.release(); c->d_abin.release(); c->d_pos.release(); c->d_wgt.release();
+    c->d_G.release(); c->d_dEdG.release(); c->d_eatom.release(); c->d_fpair.release(); c->d_gself.release();
+    c->d_vir.release(); c->d_force.release(); c->d_out8.release(); c->d_mindis.release(); c->d_keys.release();
+    c->d_flags.release(); c->d_flush.release();
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->stage_ev_init) for (auto &e : c->stage_ev) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// ---------------------------------------------------------------------------
+// potential
+// ---------------------------------------------------------------------------
+static int set_sf(gapcu_ctx *c, const std::vector<int> &z, const std::vector<double> &w,
+                  const std::vector<int> &ntype, const std::vector<double> &alpha, const std::vector<double> &cutoff) {
+    cudaSetDevice(c->device);
+    try {
+        c->plan = make_plan(ntype, alpha, cutoff);
+    } catch (const std::exception &e) {
+        return fail(GAPCU_ELIMIT, e.what());
+    }
+    if (c->plan.n_unknown)
+        fprintf(stdout, " Unknown function type in gap_parameters (%d functions left at zero)\n", c->plan.n_unknown);
+    c->z = z; c->w = w;
+    CU(c->d_itab.ensure(c->plan.itab.size() + 1));
+    CU(c->d_dtab.ensure(c->plan.dtab.size() + 1));
+    CU(cudaMemcpyAsync(c->d_itab.p, c->plan.itab.data(), sizeof(int) * c->plan.itab.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_dtab.p, c->plan.dtab.data(), sizeof(double) * c->plan.dtab.size(), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->have_sf = true;
+    c->pcap_known = false;
+    return 0;
+}
+
+static int pick_dp(int D) {
+    int nt = (D + 7) / 8;
+    if (nt <= 16) return 8 * std::max(nt, 1);
+    for (int cand : {20, 24, 28, 32}) if (nt <= cand) return 8 * cand;
+    return -1;
+}
+
+// mm in C order [M][D]
+static int set_gpr(gapcu_ctx *c, int M, int D, const double *theta, const double *mm, const double *coeff) {
+    cudaSetDevice(c->device);
+    if (M < 0 || D <= 0) return fail(GAPCU_EARG, "bad GPR sizes");
+    int Dp = pick_dp(D);
+    if (Dp < 0) return fail(GAPCU_ELIMIT, "des_len > 256 is beyond this build's DMMA tile set");
+    if (c->have_gpr && c->M == M && c->D == D && !memcmp(c->h_theta.data(), theta, sizeof(double) * D) &&
+        !memcmp(c->h_coeff.data(), coeff, sizeof(double) * M) && !memcmp(c->h_mm.data(), mm, sizeof(double) * (size_t)M * D))
+        return 0;  // unchanged: keep the device copy
+    for (int k = 0; k < D; k++)
+        if (!(theta[k] != 0.0)) return fail(GAPCU_EARG, "theta contains a zero");
+    c->h_theta.assign(theta, theta + D);
+    c->h_coeff.assign(coeff, coeff + M);
+    c->h_mm.assign(mm, mm + (size_t)M * D);
+    c->M = M; c->D = D; c->Dp = Dp; c->Mp = round_up(std::max(M, 1), 8);
+    CU(c->d_mm_raw.ensure((size_t)M * D + 1)); CU(c->d_theta_raw.ensure(D)); CU(c->d_coeff_raw.ensure(M + 1));
+    CU(c->d_Mt.ensure((size_t)c->Mp * Dp)); CU(c->d_mn.ensure(c->Mp)); CU(c->d_coeff.ensure(c->Mp));
+    CU(c->d_cmean.ensure(Dp)); CU(c->d_itheta.ensure(Dp));
+    CU(cudaMemcpyAsync(c->d_mm_raw.p, mm, sizeof(double) * (size_t)M * D, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_theta_raw.p, theta, sizeof(double) * D, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_coeff_raw.p, coeff, sizeof(double) * M, cudaMemcpyHostToDevice, c->stream));
+    launch_gpr_prepare(c->stream, M, D, c->d_mm_raw.p, c->d_theta_raw.p, c->d_coeff_raw.p, c->Mp, Dp, c->d_Mt.p,
+                       c->d_mn.p, c->d_coeff.p, c->d_cmean.p, c->d_itheta.p);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    c->have_gpr = true;
+    return 0;
+}
+
+extern "C" int gapcu_ctx_set_potential(gapcu_ctx *c, int nspecies, const int *z, const double *w, int nsf,
+                                       const int *ntype, const double *alpha, const double *cutoff, int nsparse,
+                                       int des_len, const double *theta, const double *mm, const double *coeff) {
+    if (!c) return fail(GAPCU_EARG, "null context");
+    if (des_len != 2 * nsf) return fail(GAPCU_EARG, "des_len must equal 2*nsf (wacsf.f90:59,87)");
+    int rc = set_sf(c, std::vector<int>(z, z + nspecies), std::vector<double>(w, w + nspecies),
+                    std::vector<int>(ntype, ntype + nsf), std::vector<double>(alpha, alpha + nsf),
+                    std::vector<double>(cutoff, cutoff + nsf));
+    if (rc) return rc;
+    return set_gpr(c, nsparse, des_len, theta, mm, coeff);
+}
+
+extern "C" int gapcu_ctx_load_potential(gapcu_ctx *c, const char *path) {
+    if (!c) return fail(GAPCU_EARG, "null context");
+    PotentialFile pf;
+    try {
+        pf = read_gap_parameters(path);
+    } catch (const std::exception &e) {
+        return fail(GAPCU_EFILE, e.what());
+    }
+    return gapcu_ctx_set_potential(c, (int)pf.z.size(), pf.z.data(), pf.w.data(), (int)pf.ntype.size(), pf.ntype.data(),
+                                   pf.alpha.data(), pf.cutoff.data(), pf.nsparse, pf.des_len, pf.theta.data(),
+                                   pf.mm.data(), pf.coeff.data());
+}
+
+// ---------------------------------------------------------------------------
+// structures
+// ---------------------------------------------------------------------------
+// pos_soa: pos is [3][ntot_of_that_structure] per structure (Fortran pos(NA,3)); else C order [ntot][3].
+// need_weights = false for the bond-length path (no potential involved).
+static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, const int *species, const double *lat_c,
+                               const double *pos, bool pos_soa, double rcut, bool need_weights) {
+    cudaSetDevice(c->device);
+    if (nstruct <= 0) return fail(GAPCU_EARG, "nstruct must be positive");
+    if (!(rcut > 0.0)) return fail(GAPCU_EARG, "rcut must be positive");
+    if (need_weights && !c->have_sf) return fail(GAPCU_EARG, "no potential loaded");
+    long ntot = 0;
+    for (int s = 0; s < nstruct; s++) {
+        if (natoms[s] <= 0) return fail(GAPCU_EARG, "structure without atoms");
+        ntot += natoms[s];
+    }
+    if (ntot > (1l << 30)) return fail(GAPCU_ELIMIT, "too many atoms");
+    c->h_structs.resize(nstruct);
+    c->h_natoms.assign(natoms, natoms + nstruct);
+    int boff = 0, aoff = 0;
+    double max_density = 0.0;
+    for (int s = 0; s < nstruct; s++) {
+        CellInfo ci = make_cell(lat_c + 9 * (size_t)s, rcut);
+        if (!(ci.volume > 0.0)) return fail(GAPCU_EARG, "singular lattice");
+        for (int d = 0; d < 3; d++)
+            if (ci.nabc[d] > 500) return fail(GAPCU_ENEIGH, "cell far smaller than rcut: neighbour list would exceed max_neighbor");
+        // keep the bin count proportional to the atom count
+        long cells = (long)ci.nbin[0] * ci.nbin[1] * ci.nbin[2];
+        const long lim = std::max(8l, 2l * natoms[s]);
+        while (cells > lim) {
+            int d = 0;
+            for (int q = 1; q < 3; q++) if (ci.nbin[q] > ci.nbin[d]) d = q;
+            if (ci.nbin[d] <= 1) break;
+            ci.nbin[d]--;
+            cells = (long)ci.nbin[0] * ci.nbin[1] * ci.nbin[2];
+        }
+        StructDev &sd = c->h_structs[s];
+        memcpy(sd.lat, ci.lat, sizeof sd.lat);
+        memcpy(sd.inv, ci.inv, sizeof sd.inv);
+        sd.volume = ci.volume;
+        for (int d = 0; d < 3; d++) {
+            sd.nabc[d] = ci.nabc[d];
+            sd.nbin[d] = ci.nbin[d];
+            sd.mscan[d] = (ci.nbin[d] > 1) ? 1 : ci.nabc[d] + 1;
+        }
+        sd.atom_off = aoff; sd.natoms = natoms[s]; sd.bin_off = boff; sd.nbins = (int)cells;
+        aoff += natoms[s]; boff += (int)cells;
+        max_density = std::max(max_density, natoms[s] / ci.volume);
+    }
+    c->nstruct = nstruct; c->ntot = (int)ntot; c->nbins = boff; c->rcut = rcut;
+    const size_t NT = (size_t)ntot;
+    // ---- pack host staging: structs | sid | pos SoA | wgt
+    size_t b_structs = sizeof(StructDev) * nstruct, b_sid = sizeof(int) * NT, b_pos = sizeof(double) * 3 * NT,
+           b_wgt = sizeof(double) * NT;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t o_structs = 0, o_sid = al(o_structs + b_structs), o_pos = al(o_sid + b_sid), o_wgt = al(o_pos + b_pos),
+           total = al(o_wgt + b_wgt);
+    if (c->pin(total)) return fail(GAPCU_ECUDA, "cudaMallocHost failed");
+    char *hp = (char *)c->h_pin;
+    memcpy(hp + o_structs, c->h_structs.data(), b_structs);
+    int *h_sid = (int *)(hp + o_sid);
+    double *h_pos = (double *)(hp + o_pos), *h_wgt = (double *)(hp + o_wgt);
+    for (int s = 0, a = 0; s < nstruct; s++) {
+        const int n = natoms[s];
+        for (int t = 0; t < n; t++) h_sid[a + t] = s;
+        if (pos_soa) {
+            for (int d = 0; d < 3; d++) memcpy(h_pos + d * NT + a, pos + 3 * (size_t)a + (size_t)d * n, sizeof(double) * n);
+        } else {
+            for (int t = 0; t < n; t++)
+                for (int d = 0; d < 3; d++) h_pos[d * NT + a + t] = pos[3 * (size_t)(a + t) + d];
+        }
+        a += n;
+    }
+    if (need_weights) {
+        // gap_calc.f90:75-83; a species missing from the file is an error here
+        const int ns = (int)c->z.size();
+        for (size_t t = 0; t < NT; t++) {
+            int f = -1;
+            for (int q = 0; q < ns; q++) if (species[t] == c->z[q]) f = q;  // last match wins, as in the reference loop
+            if (f < 0) return fail(GAPCU_ESPECIES, "species " + std::to_string(species[t]) + " is not in gap_parameters");
+            h_wgt[t] = c->w[f];
+        }
+    } else {
+        memset(h_wgt, 0, b_wgt);
+    }
+    // ---- device buffers
+    CU(c->d_structs.ensure(nstruct)); CU(c->d_sid.ensure(NT)); CU(c->d_pos.ensure(3 * NT)); CU(c->d_wgt.ensure(NT));
+    CU(c->d_abin.ensure(NT)); CU(c->d_arank.ensure(NT)); CU(c->d_bin_count.ensure(c->nbins + 1));
+    CU(c->d_bin_start.ensure(c->nbins + 2)); CU(c->d_bin_atoms.ensure(NT)); CU(c->d_nbr_cnt.ensure(NT));
+    CU(c->d_flags.ensure(1)); CU(c->d_out8.ensure(8 * (size_t)nstruct)); CU(c->d_force.ensure(3 * NT));
+    CU(c->d_mindis.ensure(NT));
+    CU(cudaMemcpyAsync(c->d_structs.p, hp + o_structs, b_structs, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_sid.p, h_sid, b_sid, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_pos.p, h_pos, b_pos, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_wgt.p, h_wgt, b_wgt, cudaMemcpyHostToDevice, c->stream));
+    // ---- neighbour capacity estimate (grown on demand)
+    int est = (int)(4.18879 * rcut * rcut * rcut * max_density * 1.25) + 32;
+    est = std::min(1024, std::max(64, round_up(est, 32)));
+    if (c->cap < est) { c->cap = est; c->pcap_known = false; }
+    if (c->last_ntot != c->ntot) { c->pcap_known = false; c->last_ntot = c->ntot; }
+    c->computed = false;
+    return 0;
+}
+
+extern "C" int gapcu_ctx_set_structures(gapcu_ctx *c, int nstruct, const int *natoms, const int *species,
+                                        const double *lat, const double *pos, double rcut) {
+    if (!c) return fail(GAPCU_EARG, "null context");
+    return set_structures_impl(c, nstruct, natoms, species, lat, pos, false, rcut, true);
+}
+
+// ---------------------------------------------------------------------------
+// compute
+// ---------------------------------------------------------------------------
+static int ensure_work_buffers(gapcu_ctx *c) {
+    const size_t NT = (size_t)c->ntot;
+    CU(c->d_keys.ensure(NT * c->cap));
+    CU(c->d_G.ensure(NT * c->D)); CU(c->d_dEdG.ensure(NT * c->D)); CU(c->d_eatom.ensure(NT));
+    CU(c->d_fpair.ensure(NT * c->cap * 3)); CU(c->d_gself.ensure(NT * 3)); CU(c->d_vir.ensure(NT * 6));
+    return 0;
+}
+
+static int run_neighbors(gapcu_ctx *c, bool with_keys, bool with_min) {
+    launch_neighbor_build(c->stream, c->d_structs.p, c->d_sid.p, c->d_pos.p, c->ntot, c->nbins, c->rcut, c->cap,
+                          c->d_abin.p, c->d_arank.p, c->d_bin_count.p, c->d_bin_start.p, c->d_bin_atoms.p,
+                          with_keys ? c->d_keys.p : nullptr, c->d_nbr_cnt.p, with_min ? c->d_mindis.p : nullptr,
+                          c->d_flags.p, &c->launches);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int read_flags(gapcu_ctx *c) {
+    CU(cudaMemcpyAsync(&c->h_flags, c->d_flags.p, sizeof(DevFlags), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// enqueue one full pass; ev (optional) = GAPCU_NSTAGE+1 events recorded at stage boundaries
+static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
+    if (!c->have_sf || !c->have_gpr) return fail(GAPCU_EARG, "no potential loaded");
+    if (c->D != c->plan.D) return fail(GAPCU_EARG, "des_len of the GPR data does not match 2*nsf of the SF table");
+    if (c->ntot <= 0) return fail(GAPCU_EARG, "no structures set");
+    int rc = ensure_work_buffers(c);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(c->d_flags.p, 0, sizeof(DevFlags), c->stream));
+    if (ev) CU(cudaEventRecord(ev[0], c->stream));
+    if ((rc = run_neighbors(c, true, false))) return rc;
+    if (!c->pcap_known) {
+        // first pass for this kind of input: learn the largest neighbour count
+        for (int attempt = 0; attempt < 4; attempt++) {
+            if ((rc = read_flags(c))) return rc;
+            if (c->h_flags.too_many)
+                return fail(GAPCU_ENEIGH, "Atoms neighbor: " + std::to_string(c->h_flags.maxcount) +
+                                              " large than max_neighbor 1000");
+            if (!c->h_flags.overflow) break;
+            c->cap = std::min(1024, round_up(c->h_flags.maxcount + 16, 32));
+            if ((rc = ensure_work_buffers(c))) return rc;
+            CU(cudaMemsetAsync(c->d_flags.p, 0, sizeof(DevFlags), c->stream));
+            if ((rc = run_neighbors(c, true, false))) return rc;
+        }
+        c->pcap = std::min(c->cap, std::max(32, round_up(c->h_flags.maxcount + 8, 32)));
+        c->pcap_known = true;
+    }
+    if (ev) CU(cudaEventRecord(ev[1], c->stream));
+    CentreArgs a;
+    a.plan = c->plan_dev();
+    a.structs = c->d_structs.p; a.sid = c->d_sid.p; a.pos = c->d_pos.p; a.wgt = c->d_wgt.p;
+    a.nbr_keys = c->d_keys.p; a.nbr_cnt = c->d_nbr_cnt.p; a.ntot = c->ntot; a.cap = c->cap; a.pcap = c->pcap;
+    a.G = c->d_G.p; a.dEdG = c->d_dEdG.p; a.fpair = c->d_fpair.p; a.gself = c->d_gself.p; a.vir = c->d_vir.p;
+    a.flags = c->d_flags.p;
+    if (launch_forward(c->stream, a, &c->launches)) return fail(GAPCU_ELIMIT, "descriptor kernel needs more shared memory than an SM has");
+    CU(cudaGetLastError());
+    if (ev) CU(cudaEventRecord(ev[2], c->stream));
+    GprDev g;
+    g.M = c->M; g.Mp = c->Mp; g.D = c->D; g.Dp = c->Dp; g.Mt = c->d_Mt.p; g.mn = c->d_mn.p; g.coeff = c->d_coeff.p;
+    g.cmean = c->d_cmean.p; g.itheta = c->d_itheta.p;
+    if (launch_gpr(c->stream, g, c->d_G.p, c->ntot, c->d_eatom.p, c->d_dEdG.p, &c->launches))
+        return fail(GAPCU_ELIMIT, "unsupported descriptor length for the GPR kernel");
+    CU(cudaGetLastError());
+    if (ev) CU(cudaEventRecord(ev[3], c->stream));
+    if (lgrad) {
+        if (launch_backward(c->stream, a, &c->launches)) return fail(GAPCU_ELIMIT, "descriptor kernel needs more shared memory than an SM has");
+        CU(cudaGetLastError());
+    }
+    if (ev) CU(cudaEventRecord(ev[4], c->stream));
+    launch_gather(c->stream, c->d_structs.p, c->nstruct, c->d_sid.p, c->ntot, c->cap, c->d_keys.p, c->d_nbr_cnt.p,
+                  c->d_fpair.p, c->d_gself.p, c->d_vir.p, c->d_eatom.p, lgrad, c->d_force.p, c->d_out8.p, &c->launches);
+    CU(cudaGetLastError());
+    if (ev) CU(cudaEventRecord(ev[5], c->stream));
+    c->last_lgrad = lgrad;
+    c->computed = true;
+    return 0;
+}
+
+extern "C" int gapcu_ctx_compute(gapcu_ctx *c, int lgrad) {
+    if (!c) return fail(GAPCU_EARG, "null context");
+    cudaSetDevice(c->device);
+    return enqueue_pass(c, lgrad, nullptr);
+}
+
+// wait for the pass; if a list overflowed (neighbour count grew since the
+// capacity was learned) enlarge and run again.
+static int finish_pass(gapcu_ctx *c) {
+    for (int attempt = 0; attempt < 4; attempt++) {
+        int rc = read_flags(c);
+        if (rc) return rc;
+        if (c->h_flags.too_many)
+            return fail(GAPCU_ENEIGH, "Atoms neighbor: " + std::to_string(c->h_flags.maxcount) + " large than max_neighbor 1000");
+        if (!c->h_flags.overflow) return 0;
+        c->cap = std::max(c->cap, std::min(1024, round_up(c->h_flags.maxcount + 16, 32)));
+        c->pcap_known = false;
+        if ((rc = enqueue_pass(c, c->last_lgrad, nullptr))) return rc;
+    }
+    return fail(GAPCU_ECUDA, "neighbour capacity did not converge");
+}
+
+extern "C" int gapcu_ctx_fetch(gapcu_ctx *c, double *ene, double *force, double *stress) {
+    if (!c) return fail(GAPCU_EARG, "null context");
+    if (!c->computed) return fail(GAPCU_EARG, "nothing computed");
+    cudaSetDevice(c->device);
+    int rc = finish_pass(c);
+    if (rc) return rc;
+    if (c->h_flags.close_pairs)
+        fprintf(stdout, " Warning: The distance of two atoms is very small (%d pairs below 0.5)\n", c->h_flags.close_pairs);
+    const size_t NT = (size_t)c->ntot;
+    size_t b_out = sizeof(double) * 8 * c->nstruct, b_f = sizeof(double) * 3 * NT;
+    if (c->pin(b_out + b_f + 512)) return fail(GAPCU_ECUDA, "cudaMallocHost failed");
+    double *h_out = (double *)c->h_pin, *h_f = h_out + 8 * (size_t)c->nstruct;
+    CU(cudaMemcpyAsync(h_out, c->d_out8.p, b_out, cudaMemcpyDeviceToHost, c->stream));
+    if (force) CU(cudaMemcpyAsync(h_f, c->d_force.p, b_f, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < c->nstruct; s++) {
+        if (ene) ene[s] = h_out[8 * s];
+        if (stress) for (int q = 0; q < 6; q++) stress[6 * s + q] = h_out[8 * s + 1 + q];
+    }
+    if (force)
+        for (size_t t = 0; t < NT; t++)
+            for (int d = 0; d < 3; d++) force[3 * t + d] = h_f[d * NT + t];
+    return 0;
+}
+
+extern "C" int gapcu_ctx_fetch_descriptors(gapcu_ctx *c, double *xx, double *dedg, double *eatom) {
+    if (!c || !c->computed) return fail(GAPCU_EARG, "nothing computed");
+    cudaSetDevice(c->device);
+    int rc = finish_pass(c);
+    if (rc) return rc;
+    const size_t n = (size_t)c->ntot * c->D;
+    if (xx) CU(cudaMemcpyAsync(xx, c->d_G.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (dedg) CU(cudaMemcpyAsync(dedg, c->d_dEdG.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (eatom) CU(cudaMemcpyAsync(eatom, c->d_eatom.p, sizeof(double) * c->ntot, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int gapcu_ctx_fetch_neighbors(gapcu_ctx *c, int cap, int *count, int *idx, int *shift, double *dis) {
+    if (!c || !c->computed) return fail(GAPCU_EARG, "nothing computed");
+    cudaSetDevice(c->device);
+    int rc = finish_pass(c);
+    if (rc) return rc;
+    const size_t NT = (size_t)c->ntot;
+    std::vector<int> h_cnt(NT);
+    std::vector<uint64_t> h_keys(NT * c->cap);
+    std::vector<double> h_pos(3 * NT);
+    CU(cudaMemcpy(h_cnt.data(), c->d_nbr_cnt.p, sizeof(int) * NT, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h_keys.data(), c->d_keys.p, sizeof(uint64_t) * NT * c->cap, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h_pos.data(), c->d_pos.p, sizeof(double) * 3 * NT, cudaMemcpyDeviceToHost));
+    int mx = 0, sidx = 0;
+    for (size_t i = 0; i < NT; i++) {
+        while (sidx + 1 < c->nstruct && (int)i >= c->h_structs[sidx + 1].atom_off) sidx++;
+        const StructDev &sd = c->h_structs[sidx];
+        count[i] = h_cnt[i];
+        mx = std::max(mx, h_cnt[i]);
+        if (h_cnt[i] > cap) return fail(GAPCU_EARG, "fetch_neighbors: cap too small");
+        for (int s = 0; s < h_cnt[i]; s++) {
+            int j, n1, n2, n3;
+            nbr_unkey(h_keys[i * c->cap + s], j, n1, n2, n3);
+            const size_t q = i * cap + s;
+            idx[q] = j; shift[3 * q] = n1; shift[3 * q + 1] = n2; shift[3 * q + 2] = n3;
+            if (dis) {  // the reference arithmetic again (host code is built with -ffp-contract=off)
+                const size_t jg = (size_t)sd.atom_off + j;
+                double d2 = 0.0;
+                for (int d = 0; d < 3; d++) {
+                    double x = h_pos[d * NT + jg] + (double)n1 * sd.lat[d];
+                    x = x + (double)n2 * sd.lat[3 + d];
+                    x = x + (double)n3 * sd.lat[6 + d];
+                    const double dr = h_pos[d * NT + i] - x;
+                    d2 = d2 + dr * dr;
+                }
+                dis[q] = std::sqrt(d2);
+            }
+        }
+    }
+    return mx;
+}
+
+extern "C" int gapcu_ctx_work_counters(gapcu_ctx *c, double *out, int n) {
+    if (!c || !c->computed) return fail(GAPCU_EARG, "nothing computed");
+    cudaSetDevice(c->device);
+    int rc = read_flags(c);
+    if (rc) return rc;
+    for (int q = 0; q < n && q < 8; q++) out[q] = (double)c->h_flags.work[q];
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// timing
+// ---------------------------------------------------------------------------
+extern "C" const char *gapcu_stage_name(int s) {
+    static const char *names[GAPCU_NSTAGE] = {"neighbor_build", "descriptor_forward", "gpr_dmma", "descriptor_backward",
+                                              "force_gather_reduce", "", "", ""};
+    return (s >= 0 && s < GAPCU_NSTAGE) ? names[s] : "";
+}
+
+extern "C" int gapcu_ctx_time_compute(gapcu_ctx *c, int lgrad, int steps, long l2_flush_bytes, double *ms_total,
+                                      double *stage_ms, long *launches) {
+    if (!c) return fail(GAPCU_EARG, "null context");
+    cudaSetDevice(c->device);
+    if (!c->stage_ev_init) {
+        for (auto &e : c->stage_ev) CU(cudaEventCreate(&e));
+        c->stage_ev_init = true;
+    }
+    if (l2_flush_bytes > 0) CU(c->d_flush.ensure((size_t)l2_flush_bytes));
+    // make sure capacities are settled before timing
+    int rc = enqueue_pass(c, lgrad, nullptr);
+    if (rc) return rc;
+    if ((rc = finish_pass(c))) return rc;
+    std::vector<cudaEvent_t> ev(2 * (size_t)steps);
+    for (auto &e : ev) CU(cudaEventCreate(&e));
+    const long l0 = c->launches;
+    for (int s = 0; s < steps; s++) {
+        if (l2_flush_bytes > 0) CU(cudaMemsetAsync(c->d_flush.p, s & 0xff, (size_t)l2_flush_bytes, c->stream));
+        CU(cudaEventRecord(ev[2 * s], c->stream));
+        if ((rc = enqueue_pass(c, lgrad, nullptr))) return rc;
+        CU(cudaEventRecord(ev[2 * s + 1], c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    if (launches) *launches = c->launches - l0;
+    double tot = 0.0;
+    for (int s = 0; s < steps; s++) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, ev[2 * s], ev[2 * s + 1]));
+        tot += ms;
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    if (ms_total) *ms_total = tot;
+    if ((rc = finish_pass(c))) return rc;
+    if (stage_ms) {
+        for (int q = 0; q < GAPCU_NSTAGE; q++) stage_ms[q] = 0.0;
+        for (int s = 0; s < steps; s++) {
+            if (l2_flush_bytes > 0) CU(cudaMemsetAsync(c->d_flush.p, s & 0xff, (size_t)l2_flush_bytes, c->stream));
+            if ((rc = enqueue_pass(c, lgrad, c->stage_ev))) return rc;
+            CU(cudaStreamSynchronize(c->stream));
+            for (int q = 0; q < 5; q++) {
+                float ms = 0.f;
+                CU(cudaEventElapsedTime(&ms, c->stage_ev[q], c->stage_ev[q + 1]));
+                stage_ms[q] += ms;
+            }
+        }
+    }
+    return 0;
+}
+
+extern "C" int gapcu_fp64_peaks(gapcu_ctx *c, double *dfma, double *dmma) {
+    if (!c) return fail(GAPCU_EARG, "null context");
+    cudaSetDevice(c->device);
+    launch_fp64_peaks(c->stream, dfma, dmma);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Fortran-layout entry points on a process-wide default context
+// ---------------------------------------------------------------------------
+namespace {
+std::mutex g_mu;
+gapcu_ctx *g_ctx = nullptr;
+struct FileId { dev_t dev = 0; ino_t ino = 0; off_t size = -1; long mt_s = 0, mt_ns = 0; } g_file;
+
+int default_ctx(gapcu_ctx **out) {
+    if (!g_ctx) {
+        int dev = 0;
+        if (const char *e = getenv("GAPCU_DEVICE")) dev = atoi(e);
+        g_ctx = gapcu_ctx_create(dev);
+        if (!g_ctx) return g_err.find("no CUDA device") != std::string::npos ? GAPCU_ENODEV : GAPCU_ECUDA;
+    }
+    *out = g_ctx;
+    return 0;
+}
+
+// (re)load species weights + SF table from ./gap_parameters when the file changed
+int refresh_sf_from_cwd(gapcu_ctx *c) {
+    struct stat st;
+    if (stat("gap_parameters", &st) != 0) return fail(GAPCU_EFILE, "gap_parameters file does not exist!");
+    if (c->have_sf && st.st_dev == g_file.dev && st.st_ino == g_file.ino && st.st_size == g_file.size &&
+        st.st_mtim.tv_sec == g_file.mt_s && st.st_mtim.tv_nsec == g_file.mt_ns)
+        return 0;
+    PotentialFile pf;
+    try {
+        pf = read_gap_parameters("gap_parameters");
+    } catch (const std::exception &e) {
+        return fail(GAPCU_EFILE, e.what());
+    }
+    int rc = set_sf(c, pf.z, pf.w, pf.ntype, pf.alpha, pf.cutoff);
+    if (rc) return rc;
+    g_file.dev = st.st_dev; g_file.ino = st.st_ino; g_file.size = st.st_size;
+    g_file.mt_s = st.st_mtim.tv_sec; g_file.mt_ns = st.st_mtim.tv_nsec;
+    return 0;
+}
+}  // namespace
+
+extern "C" int gapcu_calc(int na, const int *species, const double *lat, const double *pos, int nsparsex, int des_len,
+                          const double *theta, const double *mm, const double *qmm, const double *coeff, double rcut,
+                          int lgrad, double *ene, double *force, double *stress, double *variance) {
+    (void)qmm;
+    std::lock_guard<std::mutex> lk(g_mu);
+    gapcu_ctx *c = nullptr;
+    int rc = default_ctx(&c);
+    if (rc) return rc;
+    if (na <= 0) return fail(GAPCU_EARG, "NA must be positive");
+    if ((rc = refresh_sf_from_cwd(c))) return rc;
+    if (des_len != c->plan.D) return fail(GAPCU_EARG, "des_len does not equal 2*nsf of ./gap_parameters");
+    // mm(nsparseX,des_len) column-major -> C order
+    std::vector<double> mm_c((size_t)nsparsex * des_len);
+    for (int k = 0; k < des_len; k++)
+        for (int s = 0; s < nsparsex; s++) mm_c[(size_t)s * des_len + k] = mm[s + (size_t)nsparsex * k];
+    if ((rc = set_gpr(c, nsparsex, des_len, theta, mm_c.data(), coeff))) return rc;
+    double lat_c[9];
+    for (int r = 0; r < 3; r++) for (int col = 0; col < 3; col++) lat_c[r * 3 + col] = lat[r + 3 * col];
+    if ((rc = set_structures_impl(c, 1, &na, species, lat_c, pos, true, rcut, true))) return rc;
+    if ((rc = enqueue_pass(c, lgrad ? 1 : 0, nullptr))) return rc;
+    if ((rc = finish_pass(c))) return rc;
+    if (c->h_flags.close_pairs)
+        fprintf(stdout, " Warning: The distance of two atoms is very small (%d pairs below 0.5)\n", c->h_flags.close_pairs);
+    // results: out8 | force SoA (= Fortran FORCE(NA,3))
+    size_t b_f = sizeof(double) * 3 * (size_t)na;
+    if (c->pin(64 + b_f)) return fail(GAPCU_ECUDA, "cudaMallocHost failed");
+    double *h_out = (double *)c->h_pin, *h_f = h_out + 8;
+    CU(cudaMemcpyAsync(h_out, c->d_out8.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(h_f, c->d_force.p, b_f, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *ene = h_out[0];
+    for (int q = 0; q < 6; q++) stress[q] = h_out[1 + q];
+    memcpy(force, h_f, b_f);
+    if (variance) *variance = 0.0;  // gap_calc.f90:206
+    return 0;
+}
+
+extern "C" int gapcu_read(const char *path, int *nsparsex, int *des_len, double *theta, int theta_cap, double *mm,
+                          int mm_ld, int mm_cols, double *invcmm, int invcmm_ld, double *coeff, int coeff_cap) {
+    PotentialFile pf;
+    try {
+        pf = read_gap_parameters(path ? path : "gap_parameters");
+    } catch (const std::exception &e) {
+        return fail(GAPCU_EFILE, e.what());
+    }
+    if (pf.nsparse > mm_ld || pf.nsparse > coeff_cap)
+        return fail(GAPCU_ELIMIT, "The siez of sparse set large than nsparseX_max=" + std::to_string(mm_ld));
+    if (pf.des_len > mm_cols || pf.des_len > theta_cap)
+        return fail(GAPCU_ELIMIT, "The length of descriptors large than nsf_max=" + std::to_string(mm_cols));
+    *nsparsex = pf.nsparse;
+    *des_len = pf.des_len;
+    for (int k = 0; k < pf.des_len; k++) theta[k] = pf.theta[k];
+    for (int s = 0; s < pf.nsparse; s++)
+        for (int k = 0; k < pf.des_len; k++) mm[s + (size_t)mm_ld * k] = pf.mm[(size_t)s * pf.des_len + k];
+    if (invcmm) memset(invcmm, 0, sizeof(double) * (size_t)invcmm_ld * invcmm_ld);
+    for (int s = 0; s < pf.nsparse; s++) coeff[s] = pf.coeff[s];
+    return 0;
+}
+
+extern "C" int gapcu_bond(int na, const double *lat, const int *elements, const double *pos, double rcut,
+                          double *min_bond) {
+    (void)elements;
+    std::lock_guard<std::mutex> lk(g_mu);
+    gapcu_ctx *c = nullptr;
+    int rc = default_ctx(&c);
+    if (rc) return rc;
+    if (na <= 0) return fail(GAPCU_EARG, "NA must be positive");
+    double lat_c[9];
+    for (int r = 0; r < 3; r++) for (int col = 0; col < 3; col++) lat_c[r * 3 + col] = lat[r + 3 * col];
+    if ((rc = set_structures_impl(c, 1, &na, nullptr, lat_c, pos, true, rcut, false))) return rc;
+    CU(cudaMemsetAsync(c->d_flags.p, 0, sizeof(DevFlags), c->stream));
+    if ((rc = run_neighbors(c, false, true))) return rc;
+    std::vector<double> h((size_t)na);
+    CU(cudaMemcpyAsync(h.data(), c->d_mindis.p, sizeof(double) * na, cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = read_flags(c))) return rc;
+    double m = 10.0;  // get_bond.f90:32
+    for (int i = 0; i < na; i++) if (h[i] < m) m = h[i];
+    if (c->h_flags.close_pairs)
+        fprintf(stdout, " Warning: The distance of two atoms is very small (%d pairs below 0.5)\n", c->h_flags.close_pairs);
+    *min_bond = m;
+    c->computed = false;
+    return 0;
+}
+
+extern "C" int gapcu_car2acsf_table(int na, int max_neighbor, int nf, const double *pos, const double *neighbor,
+                                    const int *neighbor_count, int lgrad, double *xx, double *dxdy, double *strs) {
+    (void)na; (void)max_neighbor; (void)nf; (void)pos; (void)neighbor; (void)neighbor_count; (void)lgrad;
+    (void)xx; (void)dxdy; (void)strs;
+    return fail(GAPCU_ELIMIT, "car2acsf: dense descriptor export is not implemented yet (SURVEY.md 8(f) N3)");
+}

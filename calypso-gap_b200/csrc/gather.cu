@@ -1,0 +1,124 @@
+// gather.cu -- K5: force assembly and the per-structure reductions.
+//
+// The reference sums  force(i) = - sum_n sum_k dedg(n,k) * dxdy(k,n,i,:)  over ALL
+// centres n through the dense dxdy array (gap_calc.f90:177-185).  Here every
+// centre n left dE_n/dx_slot for each of its neighbour slots (desc.cu); atom i
+// walks its OWN neighbour list and, for each entry (n, shift), finds the mirror
+// entry (i, -shift) in n's sorted list by binary search and reads that gradient:
+// a segmented, atomic-free gather in a fixed order.  The only atomics are one
+// add per atom into the zeroed output and the "orphan" path: a pair kept in one
+// direction only (distance within one ulp of rcut) is pushed by its producer.
+#include <cstdint>
+
+#include "device_types.cuh"
+#include "launch.cuh"
+
+namespace gapcu {
+
+constexpr double GPA2EVPANG = 6.24219e-3;  // gap_calc.f90:9
+
+__global__ void __launch_bounds__(256)
+k_gather(const StructDev *structs, const int *sid, int ntot, int cap, const uint64_t *nbr_keys,
+         const int *nbr_cnt, const double *fpair, const double *gself, double *force) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= ntot) return;
+    const StructDev &sd = structs[sid[i]];
+    const int il = i - sd.atom_off;
+    const int P = min(nbr_cnt[i], cap);
+    double gx = 0.0, gy = 0.0, gz = 0.0;
+    for (int s = lane; s < P; s += 32) {
+        int jl, n1, n2, n3;
+        nbr_unkey(nbr_keys[(size_t)i * cap + s], jl, n1, n2, n3);
+        const int nb = sd.atom_off + jl;
+        const uint64_t want = nbr_key(il, -n1, -n2, -n3);
+        const uint64_t *lst = nbr_keys + (size_t)nb * cap;
+        int lo = 0, hi = min(nbr_cnt[nb], cap);
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (lst[mid] < want) lo = mid + 1; else hi = mid;
+        }
+        if (lo < min(nbr_cnt[nb], cap) && lst[lo] == want) {
+            const double *fp = fpair + ((size_t)nb * cap + lo) * 3;
+            gx += fp[0]; gy += fp[1]; gz += fp[2];
+        } else {
+            // nb does not list me, so nobody will gather what I exert on nb: push it
+            const double *fp = fpair + ((size_t)i * cap + s) * 3;
+            atomicAdd(&force[nb], -fp[0]);
+            atomicAdd(&force[ntot + nb], -fp[1]);
+            atomicAdd(&force[2 * ntot + nb], -fp[2]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        gx += __shfl_xor_sync(0xffffffffu, gx, o);
+        gy += __shfl_xor_sync(0xffffffffu, gy, o);
+        gz += __shfl_xor_sync(0xffffffffu, gz, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&force[i], -(gself[(size_t)i * 3] + gx));
+        atomicAdd(&force[ntot + i], -(gself[(size_t)i * 3 + 1] + gy));
+        atomicAdd(&force[2 * ntot + i], -(gself[(size_t)i * 3 + 2] + gz));
+    }
+}
+
+// One CTA per structure: E = sum e_i (gap_calc.f90:154), stress from the strs
+// contraction (gap_calc.f90:189-203) in the output order of :221-226.
+__global__ void __launch_bounds__(256)
+k_finalize(const StructDev *structs, const double *eatom, const double *vir, int lgrad, double *out8) {
+    __shared__ double red[8][7];
+    const StructDev &sd = structs[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double v[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int t = tid; t < sd.natoms; t += 256) {
+        const int i = sd.atom_off + t;
+        v[0] += eatom[i];
+        if (lgrad)
+#pragma unroll
+            for (int q = 0; q < 6; q++) v[1 + q] += vir[(size_t)i * 6 + q];
+    }
+#pragma unroll
+    for (int q = 0; q < 7; q++) {
+        double x = v[q];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) red[wid][q] = x;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double s[7];
+        for (int q = 0; q < 7; q++) {
+            double x = 0.0;
+            for (int w = 0; w < 8; w++) x += red[w][q];
+            s[q] = x;
+        }
+        double *o = out8 + (size_t)blockIdx.x * 8;
+        o[0] = s[0];
+        const double f = (1.0 / GPA2EVPANG) / sd.volume;
+        // s[1..6] = (xx, xy, xz, yy, yz, zz) of sum delta_a * dE/dx_b ; stress = -that * f
+        o[1] = -s[1] * f;  // xx
+        o[2] = -s[4] * f;  // yy
+        o[3] = -s[6] * f;  // zz
+        o[4] = -s[2] * f;  // xy
+        o[5] = -s[5] * f;  // yz
+        o[6] = -s[3] * f;  // xz
+        o[7] = 0.0;        // variance (gap_calc.f90:206)
+    }
+}
+
+void launch_gather(cudaStream_t st, const StructDev *structs, int nstruct, const int *sid, int ntot, int cap,
+                   const uint64_t *nbr_keys, const int *nbr_cnt, const double *fpair, const double *gself,
+                   const double *vir, const double *eatom, int lgrad, double *force_soa, double *out8,
+                   long *launches) {
+    cudaMemsetAsync(force_soa, 0, sizeof(double) * 3 * (size_t)ntot, st);
+    if (lgrad) {
+        const int wpb = 8;
+        k_gather<<<(ntot + wpb - 1) / wpb, 32 * wpb, 0, st>>>(structs, sid, ntot, cap, nbr_keys, nbr_cnt, fpair,
+                                                               gself, force_soa);
+        if (launches) *launches += 1;
+    }
+    k_finalize<<<nstruct, 256, 0, st>>>(structs, eatom, vir, lgrad, out8);
+    if (launches) *launches += 1;
+}
+
+}  // namespace gapcu

@@ -1,0 +1,48 @@
+// launch.cuh -- host launchers of the kernels (one per .cu file) and shared constants.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "device_types.cuh"
+
+namespace gapcu {
+
+constexpr int MAX_NEIGHBOR_REF_DEV = 1000;  // gap_calc.f90:68
+
+// neigh.cu
+void launch_neighbor_build(cudaStream_t st, const StructDev *structs, const int *sid, const double *pos,
+                           int ntot, int nbins_total, double rcut, int cap, int4 *abin, int *arank,
+                           int *bin_count, int *bin_start, int *bin_atoms, uint64_t *nbr_keys, int *nbr_cnt,
+                           double *min_dis, DevFlags *flags, long *launches);
+
+// desc.cu
+size_t centre_smem_bytes(const PlanDev &plan, int pcap, bool backward);
+int launch_forward(cudaStream_t st, const CentreArgs &a, long *launches);
+int launch_backward(cudaStream_t st, const CentreArgs &a, long *launches);
+
+// gpr.cu
+struct GprDev {
+    int M, Mp, D, Dp;        // Mp: M padded to 8, Dp: D padded to 8
+    const double *Mt;        // [Mp][Dp]  (MM - cmean)/theta, zero padded
+    const double *mn;        // [Mp]      |Mt row|^2
+    const double *coeff;     // [Mp]      zero padded
+    const double *cmean;     // [Dp]
+    const double *itheta;    // [Dp]      1/theta, zero padded
+};
+int launch_gpr(cudaStream_t st, const GprDev &g, const double *G, int ntot, double *eatom, double *dEdG,
+               long *launches);
+void launch_gpr_prepare(cudaStream_t st, int M, int D, const double *mm_c_order, const double *theta,
+                        const double *coeff, int Mp, int Dp, double *Mt, double *mn, double *coeff_p,
+                        double *cmean, double *itheta);
+
+// gather.cu
+void launch_gather(cudaStream_t st, const StructDev *structs, int nstruct, const int *sid, int ntot, int cap,
+                   const uint64_t *nbr_keys, const int *nbr_cnt, const double *fpair, const double *gself,
+                   const double *vir, const double *eatom, int lgrad, double *force_soa, double *out8,
+                   long *launches);
+
+// microbench.cu
+void launch_fp64_peaks(cudaStream_t st, double *dfma_tflops, double *dmma_tflops);
+
+}  // namespace gapcu

@@ -1,0 +1,200 @@
+// neigh.cu -- K1: cell-list neighbour build on the GPU.
+//
+// Replaces the O(N^2 * images) double loop of gap_calc.f90:89-120 (and of
+// get_bond.f90:46-78).  The SET of pairs is the reference's, bit for bit:
+//   * the image position and the distance are formed with the reference's
+//     operation order and without FMA contraction (gap_calc.f90:98-100),
+//   * the test is dis > rcut -> skip (gap_calc.f90:101), only the zero shift of
+//     the atom itself is excluded (:97),
+//   * only shifts inside the reference's +-nabc window are kept (:94-96), so
+//     atoms the caller did not wrap into the cell lose the same neighbours.
+// The cell list only proposes candidates.  Each list is sorted into the
+// reference order (j, n1, n2, n3), which also makes the result deterministic.
+#include <cstdint>
+
+#include "device_types.cuh"
+#include "geom.cuh"
+#include "launch.cuh"
+
+namespace gapcu {
+
+constexpr int NB_THREADS = 128;   // threads per centre in k_neigh
+constexpr int NB_MAXLIST = 1024;  // shared-memory list length (reference stops above 1000)
+
+__device__ __forceinline__ int floordiv_i(int a, int b) {
+    int q = a / b;
+    if ((a % b != 0) && ((a < 0) != (b < 0))) q--;
+    return q;
+}
+
+// fractional coordinates -> wrap offsets and bin; counts atoms per bin.
+__global__ void k_bin(const StructDev *structs, const int *sid, const double *pos, int ntot,
+                      int4 *abin, int *arank, int *bin_count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntot) return;
+    const StructDev &s = structs[sid[i]];
+    double x = pos[i], y = pos[ntot + i], z = pos[2 * ntot + i];
+    int b[3], w[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        double f = x * s.inv[c] + y * s.inv[3 + c] + z * s.inv[6 + c];
+        double fl = floor(f);
+        w[c] = (int)fl;
+        int bc = (int)((f - fl) * s.nbin[c]);
+        bc = min(max(bc, 0), s.nbin[c] - 1);
+        b[c] = bc;
+    }
+    int id = (b[0] * s.nbin[1] + b[1]) * s.nbin[2] + b[2];
+    abin[i] = make_int4(id, w[0], w[1], w[2]);
+    arank[i] = atomicAdd(&bin_count[s.bin_off + id], 1);
+}
+
+// exclusive scan of bin_count -> bin_start[nb+1]; single CTA.
+__global__ void k_scan_bins(const int *bin_count, int *bin_start, int nb) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int base = 0; base < nb; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int v = (i < nb) ? bin_count[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sums[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int s = (lane < nw) ? warp_sums[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += y;
+            }
+            warp_sums[lane] = s;
+        }
+        __syncthreads();
+        int prefix = carry + (wid ? warp_sums[wid - 1] : 0) + x - v;
+        if (i < nb) bin_start[i] = prefix;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = prefix + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) bin_start[nb] = carry;
+}
+
+__global__ void k_fill_bins(const StructDev *structs, const int *sid, const int4 *abin, const int *arank,
+                            const int *bin_start, int ntot, int *bin_atoms) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntot) return;
+    const StructDev &s = structs[sid[i]];
+    bin_atoms[bin_start[s.bin_off + abin[i].x] + arank[i]] = i;
+}
+
+// One CTA per centre atom: gather candidates from the surrounding bins, apply the
+// reference test, sort into reference order, store keys (+ optional min distance).
+__global__ void __launch_bounds__(NB_THREADS)
+k_neigh(const StructDev *structs, const int *sid, const double *pos, const int4 *abin,
+        const int *bin_start, const int *bin_atoms, int ntot, double rcut, int cap,
+        uint64_t *nbr_keys, int *nbr_cnt, double *min_dis, DevFlags *flags) {
+    __shared__ uint64_t keys[NB_MAXLIST];
+    __shared__ int nkeys, nclose;
+    __shared__ double lat[9];
+    __shared__ double wmin[NB_THREADS / 32];
+    const int i = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const StructDev &s = structs[sid[i]];
+    if (tid < 9) lat[tid] = s.lat[tid];
+    if (tid == 0) { nkeys = 0; nclose = 0; }
+    __syncthreads();
+    const double xi = pos[i], yi = pos[ntot + i], zi = pos[2 * ntot + i];
+    const int4 bi = abin[i];
+    const int nb0 = s.nbin[0], nb1 = s.nbin[1], nb2 = s.nbin[2];
+    const int b0 = bi.x / (nb1 * nb2), b1 = (bi.x / nb2) % nb1, b2 = bi.x % nb2;
+    const int m0 = s.mscan[0], m1 = s.mscan[1], m2 = s.mscan[2];
+    const int na0 = s.nabc[0], na1 = s.nabc[1], na2 = s.nabc[2];
+    const int w1 = 2 * m1 + 1, w2 = 2 * m2 + 1;
+    const int nscan = (2 * m0 + 1) * w1 * w2;
+    const int aoff = s.atom_off;
+    double dmin = 1e300;
+    for (int cell = wid; cell < nscan; cell += NB_THREADS / 32) {
+        int d0 = cell / (w1 * w2) - m0, d1 = (cell / w2) % w1 - m1, d2 = cell % w2 - m2;
+        int t0 = b0 + d0, t1 = b1 + d1, t2 = b2 + d2;
+        int s0 = floordiv_i(t0, nb0), s1 = floordiv_i(t1, nb1), s2 = floordiv_i(t2, nb2);
+        int id = ((t0 - s0 * nb0) * nb1 + (t1 - s1 * nb1)) * nb2 + (t2 - s2 * nb2);
+        int start = bin_start[s.bin_off + id], end = bin_start[s.bin_off + id + 1];
+        for (int q = start + lane; q < end; q += 32) {
+            int j = bin_atoms[q];
+            int4 bj = abin[j];
+            // shift between wrapped coordinates -> shift of the caller's coordinates
+            int n1 = s0 - bj.y + bi.y, n2 = s1 - bj.z + bi.z, n3 = s2 - bj.w + bi.w;
+            if (j == i && n1 == 0 && n2 == 0 && n3 == 0) continue;
+            if (abs(n1) > na0 || abs(n2) > na1 || abs(n3) > na2) continue;
+            double ox, oy, oz;
+            double dis = image_distance(pos, ntot, j, lat, n1, n2, n3, xi, yi, zi, ox, oy, oz);
+            if (dis > rcut) continue;
+            if (dis < 0.5) atomicAdd(&nclose, 1);
+            dmin = fmin(dmin, dis);
+            int p = atomicAdd(&nkeys, 1);
+            if (p < NB_MAXLIST) keys[p] = nbr_key(j - aoff, n1, n2, n3);
+        }
+    }
+    if (min_dis) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+        if (lane == 0) wmin[wid] = dmin;
+    }
+    __syncthreads();
+    const int count = nkeys;
+    if (tid == 0) {
+        nbr_cnt[i] = count;
+        atomicMax(&flags->maxcount, count);
+        if (count > MAX_NEIGHBOR_REF_DEV) atomicExch(&flags->too_many, 1);
+        if (count > cap) atomicExch(&flags->overflow, 1);
+        if (nclose) atomicAdd(&flags->close_pairs, nclose);
+        if (min_dis) {
+            double m = wmin[0];
+            for (int w = 1; w < NB_THREADS / 32; w++) m = fmin(m, wmin[w]);
+            min_dis[i] = m;
+        }
+    }
+    if (count > cap || count > NB_MAXLIST || nbr_keys == nullptr) return;
+    // bitonic sort of the keys (padded to a power of two with +inf keys)
+    int n2 = 1;
+    while (n2 < count) n2 <<= 1;
+    for (int p = count + tid; p < n2; p += NB_THREADS) keys[p] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            for (int t = tid; t < n2; t += NB_THREADS) {
+                int p = t ^ jj;
+                if (p > t) {
+                    uint64_t a = keys[t], b = keys[p];
+                    bool up = ((t & k) == 0);
+                    if ((a > b) == up) { keys[t] = b; keys[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int p = tid; p < count; p += NB_THREADS) nbr_keys[(size_t)i * cap + p] = keys[p];
+}
+
+// ---- host launchers ------------------------------------------------------
+void launch_neighbor_build(cudaStream_t st, const StructDev *structs, const int *sid, const double *pos,
+                           int ntot, int nbins_total, double rcut, int cap, int4 *abin, int *arank,
+                           int *bin_count, int *bin_start, int *bin_atoms, uint64_t *nbr_keys, int *nbr_cnt,
+                           double *min_dis, DevFlags *flags, long *launches) {
+    cudaMemsetAsync(bin_count, 0, sizeof(int) * (size_t)nbins_total, st);
+    int tb = 256, gb = (ntot + tb - 1) / tb;
+    k_bin<<<gb, tb, 0, st>>>(structs, sid, pos, ntot, abin, arank, bin_count);
+    k_scan_bins<<<1, 1024, 0, st>>>(bin_count, bin_start, nbins_total);
+    k_fill_bins<<<gb, tb, 0, st>>>(structs, sid, abin, arank, bin_start, ntot, bin_atoms);
+    k_neigh<<<ntot, NB_THREADS, 0, st>>>(structs, sid, pos, abin, bin_start, bin_atoms, ntot, rcut, cap,
+                                          nbr_keys, nbr_cnt, min_dis, flags);
+    if (launches) *launches += 4;
+}
+
+}  // namespace gapcu

@@ -1,0 +1,186 @@
+"""ctypes binding of the additive C ABI in include/gapcu.h (persistent context,
+batches, device-side timing).  The reference-compatible surface is the ``libgap``
+package next to this file; this module is what bench.py and the parity tests use
+to reach the same kernels without the per-call file re-read of the Fortran API.
+
+There is no CPU fallback: ``Context()`` raises if lib/libgapcu.so is missing or
+no CUDA device is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(HERE, "lib", "libgapcu.so")
+NSTAGE = 8
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_vp = C.c_void_p
+_lib = None
+
+# every symbol include/gapcu.h declares (tests check the library exports them all)
+SYMBOLS = [
+    "gapcu_last_error", "gapcu_calc", "gapcu_read", "gapcu_bond", "gapcu_car2acsf_table", "gapcu_print_last_error",
+    "gapcu_device_count", "gapcu_ctx_create", "gapcu_ctx_destroy", "gapcu_ctx_load_potential",
+    "gapcu_ctx_set_potential", "gapcu_ctx_set_structures", "gapcu_ctx_compute", "gapcu_ctx_fetch",
+    "gapcu_ctx_fetch_descriptors", "gapcu_ctx_fetch_neighbors", "gapcu_ctx_time_compute", "gapcu_stage_name",
+    "gapcu_ctx_work_counters", "gapcu_fp64_peaks",
+]
+FORTRAN_SYMBOLS = ["fgap_calc_", "fgap_read_", "fget_bond_", "car2acsf_", "write_array_2dim_"]
+
+
+class GapcuError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "gapcu error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIBPATH):
+            raise ImportError("%s not built: run `python calypso-gap_b200/build.py` (there is no CPU fallback)" % LIBPATH)
+        L = C.CDLL(LIBPATH)
+        L.gapcu_last_error.restype = C.c_char_p
+        L.gapcu_stage_name.restype = C.c_char_p
+        L.gapcu_stage_name.argtypes = [C.c_int]
+        L.gapcu_ctx_create.restype = _vp
+        L.gapcu_ctx_create.argtypes = [C.c_int]
+        L.gapcu_ctx_destroy.argtypes = [_vp]
+        L.gapcu_ctx_load_potential.argtypes = [_vp, C.c_char_p]
+        L.gapcu_ctx_set_potential.argtypes = [_vp, C.c_int, _ip, _dp, C.c_int, _ip, _dp, _dp, C.c_int, C.c_int, _dp, _dp, _dp]
+        L.gapcu_ctx_set_structures.argtypes = [_vp, C.c_int, _ip, _ip, _dp, _dp, C.c_double]
+        L.gapcu_ctx_compute.argtypes = [_vp, C.c_int]
+        L.gapcu_ctx_fetch.argtypes = [_vp, _vp, _vp, _vp]
+        L.gapcu_ctx_fetch_descriptors.argtypes = [_vp, _vp, _vp, _vp]
+        L.gapcu_ctx_fetch_neighbors.argtypes = [_vp, C.c_int, _ip, _ip, _ip, _dp]
+        L.gapcu_ctx_time_compute.argtypes = [_vp, C.c_int, C.c_int, C.c_long, C.POINTER(C.c_double), _vp, C.POINTER(C.c_long)]
+        L.gapcu_ctx_work_counters.argtypes = [_vp, _dp, C.c_int]
+        L.gapcu_fp64_peaks.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.gapcu_calc.argtypes = [C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_double, C.c_int,
+                                 _vp, _vp, _vp, _vp]
+        L.gapcu_bond.argtypes = [C.c_int, _vp, _vp, _vp, C.c_double, C.POINTER(C.c_double)]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc < 0:
+        raise GapcuError(rc, lib().gapcu_last_error().decode(errors="replace"))
+    return rc
+
+
+def device_count():
+    return lib().gapcu_device_count()
+
+
+class Context:
+    """One GPU, one stream, one potential, one resident batch of structures."""
+
+    def __init__(self, device=0):
+        h = lib().gapcu_ctx_create(int(device))
+        if not h:
+            raise GapcuError(-6, lib().gapcu_last_error().decode(errors="replace"))
+        self.h = _vp(h)
+        self.natoms = None
+        self.des_len = None
+
+    def close(self):
+        if self.h:
+            lib().gapcu_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_potential(self, path):
+        _check(lib().gapcu_ctx_load_potential(self.h, os.fsencode(path)))
+
+    def set_potential(self, z, w, ntype, alpha, cutoff, theta, mm, coeff):
+        z = np.ascontiguousarray(z, np.int32); w = np.ascontiguousarray(w, np.float64)
+        ntype = np.ascontiguousarray(ntype, np.int32); alpha = np.ascontiguousarray(alpha, np.float64)
+        cutoff = np.ascontiguousarray(cutoff, np.float64); theta = np.ascontiguousarray(theta, np.float64)
+        mm = np.ascontiguousarray(mm, np.float64); coeff = np.ascontiguousarray(coeff, np.float64)
+        _check(lib().gapcu_ctx_set_potential(self.h, len(z), z, w, len(ntype), ntype, alpha, cutoff, mm.shape[0],
+                                             mm.shape[1], theta, mm, coeff))
+        self.des_len = mm.shape[1]
+
+    def set_structures(self, species_list, lat_list, pos_list, rcut=6.0):
+        """Lists of per-structure arrays (or a single structure's arrays)."""
+        if np.ndim(lat_list) == 2:
+            species_list, lat_list, pos_list = [species_list], [lat_list], [pos_list]
+        natoms = np.array([len(p) for p in pos_list], np.int32)
+        species = np.ascontiguousarray(np.concatenate([np.asarray(s).ravel() for s in species_list]), np.int32)
+        lat = np.ascontiguousarray(np.stack([np.asarray(l, np.float64) for l in lat_list]))
+        pos = np.ascontiguousarray(np.concatenate([np.asarray(p, np.float64).reshape(-1, 3) for p in pos_list]))
+        _check(lib().gapcu_ctx_set_structures(self.h, len(natoms), natoms, species, lat, pos, float(rcut)))
+        self.natoms = natoms
+
+    def compute(self, lgrad=True):
+        _check(lib().gapcu_ctx_compute(self.h, int(bool(lgrad))))
+
+    def fetch(self):
+        ns, nt = len(self.natoms), int(self.natoms.sum())
+        ene = np.zeros(ns); force = np.zeros((nt, 3)); stress = np.zeros((ns, 6))
+        _check(lib().gapcu_ctx_fetch(self.h, ene.ctypes.data, force.ctypes.data, stress.ctypes.data))
+        return ene, force, stress
+
+    def evaluate(self, species, lat, pos, rcut=6.0, lgrad=True):
+        """Single structure convenience: returns dict(energy, forces, stress)."""
+        self.set_structures(species, lat, pos, rcut)
+        self.compute(lgrad)
+        e, f, s = self.fetch()
+        return {"energy": float(e[0]), "forces": f, "stress": s[0]}
+
+    def descriptors(self, des_len):
+        nt = int(self.natoms.sum())
+        xx = np.zeros((nt, des_len)); dedg = np.zeros((nt, des_len)); eat = np.zeros(nt)
+        _check(lib().gapcu_ctx_fetch_descriptors(self.h, xx.ctypes.data, dedg.ctypes.data, eat.ctypes.data))
+        return xx, dedg, eat
+
+    def neighbors(self, cap=1000):
+        nt = int(self.natoms.sum())
+        count = np.zeros(nt, np.int32); idx = np.zeros((nt, cap), np.int32)
+        shift = np.zeros((nt, cap, 3), np.int32); dis = np.zeros((nt, cap))
+        _check(lib().gapcu_ctx_fetch_neighbors(self.h, cap, count, idx, shift, dis))
+        return count, idx, shift, dis
+
+    def time_compute(self, steps, lgrad=True, l2_flush_bytes=0, stages=True):
+        ms = C.c_double(); launches = C.c_long()
+        st = np.zeros(NSTAGE)
+        _check(lib().gapcu_ctx_time_compute(self.h, int(bool(lgrad)), int(steps), int(l2_flush_bytes), C.byref(ms),
+                                            st.ctypes.data if stages else None, C.byref(launches)))
+        names = [lib().gapcu_stage_name(i).decode() for i in range(NSTAGE)]
+        return ms.value, {n: v for n, v in zip(names, st) if n}, launches.value
+
+    def work_counters(self):
+        out = np.zeros(8)
+        _check(lib().gapcu_ctx_work_counters(self.h, out, 8))
+        keys = ["atoms", "pairs", "pair_classes", "candidates", "triplets", "triplet_classes", "triplet_sf", "radial_sf"]
+        return dict(zip(keys, out))
+
+    def fp64_peaks(self):
+        a = C.c_double(); b = C.c_double()
+        _check(lib().gapcu_fp64_peaks(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+def fortran_calc(species, lat, pos, theta, mm, coeff, rcut, lgrad):
+    """gapcu_calc with Fortran-layout buffers built from C-order numpy inputs (the
+    marshalling f2py does); reads ./gap_parameters from the CWD like FGAP_CALC."""
+    species = np.ascontiguousarray(species, np.int32)
+    na = len(species)
+    latf = np.asfortranarray(np.asarray(lat, np.float64)); posf = np.asfortranarray(np.asarray(pos, np.float64))
+    theta = np.ascontiguousarray(theta, np.float64); mmf = np.asfortranarray(np.asarray(mm, np.float64))
+    coeff = np.ascontiguousarray(coeff, np.float64)
+    ene = C.c_double(); var = C.c_double()
+    force = np.zeros((na, 3), order="F"); stress = np.zeros(6)
+    _check(lib().gapcu_calc(na, species.ctypes.data, latf.ctypes.data, posf.ctypes.data, mmf.shape[0], mmf.shape[1],
+                            theta.ctypes.data, mmf.ctypes.data, None, coeff.ctypes.data, float(rcut), int(bool(lgrad)),
+                            C.addressof(ene), force.ctypes.data, stress.ctypes.data, C.addressof(var)))
+    return ene.value, np.ascontiguousarray(force), stress, var.value

@@ -1,0 +1,136 @@
+/*
+ * gapcu.h -- C ABI of the B200-native libgap energy/force/stress path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * Every "fortran-layout" entry point below is what the reference's Fortran
+ * subroutine of the same role would bind through ISO_C_BINDING (see
+ * calypso-gap_b200/fortran/libgap_driver.f90 and INTEGRATION.md):
+ *
+ *   gapcu_calc      <- SUBROUTINE FGAP_CALC   gappy/libgap/gap_calc.f90:1-301
+ *   gapcu_read      <- SUBROUTINE FGAP_READ   gappy/libgap/gap_calc.f90:303-364
+ *   gapcu_bond      <- SUBROUTINE FGET_BOND   gappy/libgap/get_bond.f90:4-116
+ *   gapcu_car2acsf_table <- SUBROUTINE CAR2ACSF gappy/libgap/wacsf.f90:2-796
+ *
+ * Arrays of those four use the Fortran column-major layout of the argument they
+ * replace: pos(NA,3) -> pos[i + NA*c]; lat(3,3) -> lat[r + 3*c] with ROW r the
+ * r-th lattice vector (gap_calc.f90:98); force like pos; mm(nsparseX,des_len)
+ * -> mm[s + nsparseX*k]; stress(6) = xx yy zz xy yz xz in GPa
+ * (gap_calc.f90:221-226).  LOGICAL arguments are int (0/1).
+ *
+ * Like the reference, gapcu_calc / gapcu_car2acsf_table take the species weights and
+ * the symmetry-function table from the file ./gap_parameters in the current
+ * working directory (gap_calc.f90:75-83, wacsf.f90:40-56); the parsed file is
+ * cached and re-read only when its (device, inode, size, mtime) change.
+ *
+ * All functions return 0 on success or a negative GAPCU_E* code; the message is
+ * available from gapcu_last_error() (thread local).  There is NO CPU fallback:
+ * without a CUDA device every compute entry point returns GAPCU_ENODEV.
+ */
+#ifndef GAPCU_H
+#define GAPCU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GAPCU_OK 0
+#define GAPCU_EFILE -1      /* gap_parameters missing or malformed (reference: print + stop) */
+#define GAPCU_ENEIGH -2     /* an atom has > 1000 neighbours (gap_calc.f90:107-111: stop)     */
+#define GAPCU_ESPECIES -3   /* species absent from gap_parameters (reference: uninitialised)   */
+#define GAPCU_ELIMIT -4     /* potential exceeds a compiled limit of this library             */
+#define GAPCU_ECUDA -5      /* CUDA runtime error                                             */
+#define GAPCU_ENODEV -6     /* no CUDA device                                                 */
+#define GAPCU_EARG -7       /* invalid argument                                               */
+
+const char *gapcu_last_error(void);
+
+/* ---- Fortran-layout entry points (the reference's f2py surface) ---------- */
+
+/* FGAP_CALC.  qmm is accepted and ignored (the reference never reads it:
+ * gap_calc.f90:205-210), variance is set to 0 (gap_calc.f90:206). */
+int gapcu_calc(int na, const int *species, const double *lat, const double *pos,
+               int nsparsex, int des_len, const double *theta, const double *mm,
+               const double *qmm, const double *coeff, double rcut, int lgrad,
+               double *ene, double *force, double *stress, double *variance);
+
+/* FGAP_READ with explicit capacities.  theta[theta_cap], mm[mm_ld x mm_cols]
+ * column-major, coeff[coeff_cap]; entries beyond the file's sizes are left
+ * untouched.  invcmm (may be NULL) is zero-filled as invcmm_ld x invcmm_ld
+ * (gap_calc.f90:361).  Host only, no GPU needed. */
+int gapcu_read(const char *path, int *nsparsex, int *des_len, double *theta, int theta_cap,
+               double *mm, int mm_ld, int mm_cols, double *invcmm, int invcmm_ld, double *coeff,
+               int coeff_cap);
+
+/* FGET_BOND: smallest image distance <= rcut (10.0 if none, get_bond.f90:32). */
+int gapcu_bond(int na, const double *lat, const int *elements, const double *pos, double rcut,
+               double *min_bond);
+
+/* CAR2ACSF with the reference's own arguments: neighbor(NA,max_neighbor,6) holds
+ * per neighbour the absolute image position (1:3), the distance (4), the species
+ * weight (5) and real(j) (6) as built by gap_calc.f90:112-115; outputs
+ * xx(nf,na), dxdy(nf,na,na,3), strs(3,3,nf,na), all column-major.  The SF table
+ * comes from ./gap_parameters (wacsf.f90:40-56) and nf must equal 2*nsf. */
+int gapcu_car2acsf_table(int na, int max_neighbor, int nf, const double *pos, const double *neighbor,
+                         const int *neighbor_count, int lgrad, double *xx, double *dxdy, double *strs);
+
+/* prints gapcu_last_error() on stdout the way the reference prints before STOP */
+void gapcu_print_last_error(void);
+
+/* ---- additive API: persistent context, batches, device-side timing ------- */
+
+typedef struct gapcu_ctx gapcu_ctx;
+
+int gapcu_device_count(void);
+gapcu_ctx *gapcu_ctx_create(int device);          /* NULL on failure */
+void gapcu_ctx_destroy(gapcu_ctx *ctx);
+
+/* potential = SF table + species weights + GPR data, from a file ...          */
+int gapcu_ctx_load_potential(gapcu_ctx *ctx, const char *path);
+/* ... or from arrays (C order: mm[nsparse][des_len]).                          */
+int gapcu_ctx_set_potential(gapcu_ctx *ctx, int nspecies, const int *z, const double *w, int nsf,
+                            const int *ntype, const double *alpha, const double *cutoff,
+                            int nsparse, int des_len, const double *theta, const double *mm,
+                            const double *coeff);
+
+/* A batch of nstruct independent periodic structures (C order this time:
+ * natoms[nstruct]; species[sum natoms]; lat[nstruct][3][3] rows = lattice
+ * vectors; pos[sum natoms][3]).  Copies host -> device. */
+int gapcu_ctx_set_structures(gapcu_ctx *ctx, int nstruct, const int *natoms, const int *species,
+                             const double *lat, const double *pos, double rcut);
+/* Enqueue the whole E/F/stress pipeline on the context's stream (asynchronous). */
+int gapcu_ctx_compute(gapcu_ctx *ctx, int lgrad);
+/* Wait and copy device -> host.  ene[nstruct], force[sum natoms][3] (C order),
+ * stress[nstruct][6]; any may be NULL. */
+int gapcu_ctx_fetch(gapcu_ctx *ctx, double *ene, double *force, double *stress);
+/* Descriptors / dE/dG / atomic energies of the last compute ([sum natoms][des_len], C order). */
+int gapcu_ctx_fetch_descriptors(gapcu_ctx *ctx, double *xx, double *dedg, double *eatom);
+/* Neighbour lists of the last compute in reference order (j, n1, n2, n3):
+ * count[ntot], idx[ntot][cap] (index within the structure), shift[ntot][cap][3],
+ * dis[ntot][cap].  Returns the largest count, or a negative code. */
+int gapcu_ctx_fetch_neighbors(gapcu_ctx *ctx, int cap, int *count, int *idx, int *shift, double *dis);
+
+/* Device-side timing of `steps` back-to-back gapcu_ctx_compute passes with CUDA
+ * events on the context's stream (inputs resident).  If l2_flush_bytes > 0 a
+ * buffer of that size is overwritten between passes, outside the timed events.
+ * ms_total = sum of per-pass event times.  stage_ms (may be NULL) receives the
+ * summed time of each pipeline stage, GAPCU_NSTAGE entries, measured in a
+ * separate instrumented run of the same passes (see gapcu_stage_name). */
+#define GAPCU_NSTAGE 8
+int gapcu_ctx_time_compute(gapcu_ctx *ctx, int lgrad, int steps, long l2_flush_bytes,
+                           double *ms_total, double *stage_ms, long *launches);
+const char *gapcu_stage_name(int stage);
+
+/* Work counters of the last compute, for the roofline:
+ * out[0]=atoms, [1]=sum P (pairs), [2]=sum_c P_c, [3]=candidate pairs tested,
+ * [4]=kept triplets, [5]=sum_c T_c (triplet-class evaluations),
+ * [6]=sum_c n_ang(c) T_c, [7]=sum_c n_rad(c) P_c. */
+int gapcu_ctx_work_counters(gapcu_ctx *ctx, double *out, int n);
+
+/* FP64 peak micro-benchmarks on the context's device: DFMA-chain (CUDA cores)
+ * and mma.sync m8n8k4 f64 (DMMA).  TFLOP/s each. */
+int gapcu_fp64_peaks(gapcu_ctx *ctx, double *dfma_tflops, double *dmma_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAPCU_H */

@@ -1,0 +1,156 @@
+"""Parity of the CUDA path (through the C ABI in lib/libgapcu.so) against the CPU
+oracle and the reference's golden trajectory.  Gates (BASELINE.json north_star):
+|dE|/|E| <= 1e-10, max |dF| <= 1e-8 eV/A; stress stated here as <= 1e-7 GPa.
+Neighbour sets: bit-exact after canonical sorting (they come out sorted)."""
+import os
+
+import numpy as np
+import pytest
+
+from structures import cubic_supercell, random_candidate, sheared
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+E_TOL, F_TOL, S_TOL = 1e-10, 1e-8, 1e-7
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import gapcu
+    c = gapcu.Context(0)
+    c.load_potential(os.path.join(GOLDEN, "gap_parameters"))
+    yield c
+    c.close()
+
+
+def _cmp(got, want):
+    assert abs(got["energy"] - want["energy"]) <= E_TOL * abs(want["energy"])
+    assert np.abs(got["forces"] - want["forces"]).max() <= F_TOL
+    assert np.abs(got["stress"] - want["stress"]).max() <= S_TOL
+
+
+@pytest.mark.parametrize("frame", range(11))
+def test_golden_trajectory(ctx, golden_frames, frame):
+    """The reference's own output (ase.traj), all 11 frames."""
+    g = golden_frames
+    r = ctx.evaluate(g["numbers"], g["cell"][frame], g["positions"][frame], 6.0, True)
+    _cmp(r, {"energy": g["energy"][frame], "forces": g["forces"][frame], "stress": g["stress"][frame]})
+
+
+def test_descriptors_and_gpr_vs_oracle(ctx, shipped_pot, bc_structure):
+    cell, pos = sheared(bc_structure["cell"], bc_structure["positions"])
+    z = bc_structure["numbers"].astype(np.int32)
+    want = shipped_pot.calc_sparse(z, cell, pos, 6.0, True, desc=True)
+    got = ctx.evaluate(z, cell, pos, 6.0, True)
+    xx, dedg, eat = ctx.descriptors(shipped_pot.des_len)
+    scale = np.abs(want["xx"]).max(0) + 1e-300
+    assert (np.abs(xx - want["xx"]) / scale).max() < 1e-13
+    assert np.abs(eat - want["eatom"]).max() < 1e-9          # sum|coeff| ~ 3.6e5 amplifies 1e-16
+    assert np.abs(dedg - want["dedg"]).max() <= 1e-9 * np.abs(want["dedg"]).max()
+    _cmp(got, want)
+    assert len(set(np.round(got["stress"], 3))) == 6           # all six components distinct
+
+
+def test_neighbor_sets_bit_exact(ctx, oracle, bc_structure):
+    cell, pos = sheared(bc_structure["cell"], bc_structure["positions"])
+    z = bc_structure["numbers"].astype(np.int32)
+    ctx.evaluate(z, cell, pos, 6.0, False)
+    cnt, idx, sh, dis = ctx.neighbors(1000)
+    ocnt, oidx, osh, odis = oracle.neighbors(cell, pos, 6.0)
+    assert np.array_equal(cnt, ocnt) and np.array_equal(idx, oidx) and np.array_equal(sh, osh)
+    assert np.array_equal(dis, odis)                            # same arithmetic -> same bits
+
+
+def test_neighbor_sets_unwrapped_atoms_and_ties(ctx, oracle, bc_structure):
+    cell, pos = sheared(bc_structure["cell"], bc_structure["positions"])
+    pos = pos.copy(); pos[3] += 2 * cell[0] - cell[2]; pos[17] -= cell[1]
+    z = bc_structure["numbers"].astype(np.int32)
+    ctx.evaluate(z, cell, pos, 6.0, False)
+    got, want = ctx.neighbors(1000), oracle.neighbors(cell, pos, 6.0)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    # perfect simple-cubic lattice: shells exactly at the cutoff are inside
+    cell = np.eye(3) * 4.0
+    pos = np.array([[0, 0, 0], [2, 0, 0], [0, 2, 0], [2, 2, 0], [0, 0, 2], [2, 0, 2], [0, 2, 2], [2, 2, 2.0]])
+    ctx.evaluate(np.full(8, 6, np.int32), cell, pos, 6.0, False)
+    got, want = ctx.neighbors(1000), oracle.neighbors(cell, pos, 6.0)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+
+
+def test_lgrad_false(ctx, golden_frames):
+    g = golden_frames
+    r = ctx.evaluate(g["numbers"], g["cell"][0], g["positions"][0], 6.0, False)
+    assert abs(r["energy"] - g["energy"][0]) <= E_TOL * abs(g["energy"][0])
+    assert not r["forces"].any() and not r["stress"].any()
+
+
+@pytest.mark.parametrize("seed", [3000, 3001, 3002, 3003])
+def test_small_triclinic_cells_with_self_images(ctx, shipped_pot, seed):
+    cell, pos, z = random_candidate(seed, 32, 64, species=(5, 6))
+    want = shipped_pot.calc_sparse(z, cell, pos, 6.0, True)
+    _cmp(ctx.evaluate(z, cell, pos, 6.0, True), want)
+
+
+def test_batch_equals_singles(ctx, shipped_pot):
+    structs = [random_candidate(3100 + i, 32, 96, species=(5, 6)) for i in range(6)]
+    ctx.set_structures([s[2] for s in structs], [s[0] for s in structs], [s[1] for s in structs], 6.0)
+    ctx.compute(True)
+    e, f, s = ctx.fetch()
+    off = 0
+    for i, (cell, pos, z) in enumerate(structs):
+        want = shipped_pot.calc_sparse(z, cell, pos, 6.0, True)
+        _cmp({"energy": e[i], "forces": f[off:off + len(pos)], "stress": s[i]}, want)
+        off += len(pos)
+
+
+def test_supercell_1000_atoms_three_species(oracle, tmp_path):
+    """BASELINE config 2 shape: 1000 atoms, 3 species, synthetic potential."""
+    import gapcu
+    from potentials import synthetic_potential
+    pot = synthetic_potential(oracle, os.path.join(GOLDEN, "gap_parameters"), str(tmp_path / "gap_parameters"))
+    cell, pos, z = cubic_supercell(10, 10, 10)
+    want = pot.calc_sparse(z, cell, pos, 6.0, True)
+    c = gapcu.Context(0)
+    c.load_potential(str(tmp_path / "gap_parameters"))
+    got = c.evaluate(z, cell, pos, 6.0, True)
+    _cmp(got, want)
+    # size-independent properties: zero net force, symmetric response to a rigid shift
+    assert np.abs(got["forces"].sum(0)).max() < 1e-7
+    shifted = c.evaluate(z, cell, pos + np.array([0.37, -1.2, 2.9]), 6.0, True)
+    assert abs(shifted["energy"] - got["energy"]) <= 1e-10 * abs(got["energy"])
+    c.close()
+
+
+def test_fortran_abi_entry_point(shipped_pot, golden_frames, monkeypatch):
+    """gapcu_calc with Fortran-layout buffers and the ./gap_parameters side channel."""
+    import gapcu
+    monkeypatch.chdir(GOLDEN)
+    g = golden_frames
+    p = shipped_pot
+    e, f, s, v = gapcu.fortran_calc(g["numbers"], g["cell"][3], g["positions"][3], p.theta, p.mm, p.coeff, 6.0, True)
+    _cmp({"energy": e, "forces": f, "stress": s},
+         {"energy": g["energy"][3], "forces": g["forces"][3], "stress": g["stress"][3]})
+    assert v == 0.0
+
+
+def test_f2py_module_and_python_classes(golden_frames, bc_structure, oracle, monkeypatch):
+    """libgap.GAP.Calculator / libgap.BOND.Bond exactly as example/BC/test.py uses them."""
+    monkeypatch.chdir(GOLDEN)
+    from libgap.BOND import Bond
+    from libgap.GAP import Calculator
+    g = golden_frames
+    gap = Calculator(rcut=6.0)
+    gap.gap_read()
+    assert (gap.nsparseX, gap.des_len) == (129, 66) and gap.mm.shape == (4000, 100) and gap.invcmm.shape == (4000, 4000)
+    for species in (g["numbers"], ["C"] * 64):                  # numbers or symbols (GAP.py:49-52)
+        ene, force, stress, var = gap.gap_calc(species, g["cell"][7], g["positions"][7], True)
+        _cmp({"energy": ene, "forces": force, "stress": stress},
+             {"energy": g["energy"][7], "forces": g["forces"][7], "stress": g["stress"][7]})
+    # sliced / Fortran-ordered inputs
+    posf = np.asfortranarray(g["positions"][7])
+    ene2 = gap.gap_calc(g["numbers"], g["cell"][7].T.copy().T, posf, True)[0]
+    assert ene2 == ene
+    cell, pos = bc_structure["cell"], bc_structure["positions"]
+    assert Bond(rcut=6.0).get_min_bond(cell, bc_structure["numbers"], pos) == oracle.get_bond(cell, pos, 6.0)
