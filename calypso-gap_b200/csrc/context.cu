@@ -547,7 +547,7 @@ extern "C" int gapcu_ctx_work_counters(gapcu_ctx *c, double *out, int n) {
     cudaSetDevice(c->device);
     int rc = read_flags(c);
     if (rc) return rc;
-    for (int q = 0; q < n && q < 8; q++) out[q] = (double)c->h_flags.work[q];
+    for (int q = 0; q < n && q < 10; q++) out[q] = (double)c->h_flags.work[q];
     return 0;
 }
 

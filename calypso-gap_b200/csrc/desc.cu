@@ -195,6 +195,12 @@ __global__ void __launch_bounds__(CT, 2) k_centre(CentreArgs a) {
     }
     __syncthreads();
 
+    if (!BWD && tid < ncls && cls_grp[tid + 1] > cls_grp[tid]) {
+        // sum_c Q_c of SURVEY.md 8(d): candidate pairs of every angular cutoff class
+        unsigned long long pc = 0;
+        for (int s = 0; s < P; s++) pc += (s_nc[s] > tid);
+        atomicAdd(&a.flags->work[8], pc * (pc - 1) / 2);
+    }
     // ---- 3: angular functions ---------------------------------------------
     unsigned long long wk_cand = 0, wk_trip = 0, wk_tc = 0, wk_tsf = 0;
     const uint32_t angmask = pl.ang_prefix_mask;

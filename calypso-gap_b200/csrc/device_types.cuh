@@ -34,7 +34,7 @@ struct DevFlags {
     int maxcount;        // largest neighbour count seen
     int too_many;        // some atom exceeds the reference's 1000-neighbour limit
     int close_pairs;     // pairs closer than 0.5 A (reference prints a warning)
-    unsigned long long work[8];  // see gapcu_ctx_work_counters
+    unsigned long long work[10];  // see gapcu_ctx_work_counters
 };
 
 // Symmetry-function tables on the device (flat int / double tables + offsets).

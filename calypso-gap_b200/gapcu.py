@@ -159,9 +159,9 @@ class Context:
         return ms.value, {n: v for n, v in zip(names, st) if n}, launches.value
 
     def work_counters(self):
-        out = np.zeros(8)
-        _check(lib().gapcu_ctx_work_counters(self.h, out, 8))
-        keys = ["atoms", "pairs", "pair_classes", "candidates", "triplets", "triplet_classes", "triplet_sf", "radial_sf"]
+        out = np.zeros(10)
+        _check(lib().gapcu_ctx_work_counters(self.h, out, 10))
+        keys = ["atoms", "pairs", "pair_classes", "candidates", "triplets", "triplet_classes", "triplet_sf", "radial_sf", "class_candidates"]
         return dict(zip(keys, out))
 
     def fp64_peaks(self):

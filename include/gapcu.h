@@ -123,7 +123,8 @@ const char *gapcu_stage_name(int stage);
 /* Work counters of the last compute, for the roofline:
  * out[0]=atoms, [1]=sum P (pairs), [2]=sum_c P_c, [3]=candidate pairs tested,
  * [4]=kept triplets, [5]=sum_c T_c (triplet-class evaluations),
- * [6]=sum_c n_ang(c) T_c, [7]=sum_c n_rad(c) P_c. */
+ * [6]=sum_c n_ang(c) T_c, [7]=sum_c n_rad(c) P_c, [8]=sum_c Q_c (candidate pairs
+ * per angular cutoff class, P_c(P_c-1)/2). */
 int gapcu_ctx_work_counters(gapcu_ctx *ctx, double *out, int n);
 
 /* FP64 peak micro-benchmarks on the context's device: DFMA-chain (CUDA cores)

@@ -151,6 +151,6 @@ def test_f2py_module_and_python_classes(golden_frames, bc_structure, oracle, mon
     # sliced / Fortran-ordered inputs
     posf = np.asfortranarray(g["positions"][7])
     ene2 = gap.gap_calc(g["numbers"], g["cell"][7].T.copy().T, posf, True)[0]
-    assert ene2 == ene
+    assert abs(ene2 - ene) <= 1e-11 * abs(ene)      # shared-memory atomics: summation order varies run to run
     cell, pos = bc_structure["cell"], bc_structure["positions"]
     assert Bond(rcut=6.0).get_min_bond(cell, bc_structure["numbers"], pos) == oracle.get_bond(cell, pos, 6.0)
