@@ -19,10 +19,10 @@ OBJ = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
-CU_SOURCES = ["neigh.cu", "desc.cu", "gpr.cu", "gather.cu", "microbench.cu", "context.cu"]
+CU_SOURCES = ["neigh.cu", "centre.cu", "gpr.cu", "gather.cu", "microbench.cu", "context.cu"]
 CPP_SOURCES = ["potential.cpp"]
 C_SOURCES = ["fortran_shim.c"]
-HEADERS = ["device_types.cuh", "geom.cuh", "launch.cuh", "potential.hpp", os.path.join("..", "..", "include", "gapcu.h")]
+HEADERS = ["device_types.cuh", "fastmath.cuh", "geom.cuh", "launch.cuh", "potential.hpp", os.path.join("..", "..", "include", "gapcu.h")]
 
 
 def _newer(target, deps):

@@ -1,0 +1,637 @@
+// centre.cu -- the per-centre wACSF kernel (K2 forward, K4 backward, or both fused
+// with an in-CTA GPR): one CTA per centre atom.
+//
+// What is computed (reference loops wacsf.f90:65-795):
+//   radial  type 1  G = sum_j exp(-a r^2) fc(r)            wacsf.f90:69-162
+//           type 3  G = sum_j exp(-4 (r-rs)^2) fc(r)       wacsf.f90:436-527
+//   angular type 2/4  G = sum_{j<k} (1 +- cos) exp(-a (rij^2+rik^2+rjk^2)) fc fc fc
+//                                                          wacsf.f90:169-432, 534-791
+//   each in an unweighted channel ii and a species-weighted channel ii+nsf, then
+//   (fused mode) e_i and dE/dG from the sparse GPR (gap_calc.f90:143-166), then the
+//   chain rule dE/dG * dG/dr (gap_calc.f90:177-203) WITHOUT the reference's dense
+//   dxdy(D,N,N,3): the geometry is recomputed and contracted on the fly, leaving
+//   per neighbour slot dE_i/dx_slot, plus dE_i/dx_i and the centre's strs sums.
+//
+// Structure per centre (all orders fixed -> results are bit-reproducible):
+//   1. stage neighbours in shared memory: absolute image coordinates (reference
+//      arithmetic, geom.cuh), r, 1/r, weight, and fc/fc' for each cutoff class
+//      the neighbour belongs to (classes = distinct cutoffs, descending, so the
+//      classes of a distance are a prefix);
+//   2. radial functions: one thread per neighbour, warp-shuffle sums;
+//   3. triplet list: all pairs q=(a<b) of the flat triangular index are tested ONCE
+//      with the exact reference arithmetic (squared-distance thresholds equivalent
+//      to the reference's sqrt(..) > cutoff); survivors carry their "bucket" = number
+//      of classes they belong to; a deterministic counting sort orders them by bucket
+//      (descending), so the items of class c are the prefix S[0 .. npre[c]);
+//   4. forward: class-outer loop over that prefix, per-thread register accumulators
+//      per (class, alpha) group [sum pe, sum pe*cos, and the two weighted sums; the
+//      lambda=+-1 functions are (sum pe +- sum pe*cos)], one warp reduction per class;
+//   5. (fused) GPR for this atom in the CTA: difference form, no cancellation;
+//   6. backward: warps take batches of 32 triplets of the SAME bucket; per class one
+//      sincos and per (class, alpha) one exp: the sum over symmetry functions is
+//      folded into four per-centre constants per group (sum du, sum dw, sum lam*du,
+//      sum lam*dw), so there is no inner loop over functions; the three leg scalars
+//      go to per-warp private accumulators (dE/dx_j = A_j d_j - V_j) with in-warp
+//      conflict serialisation: no atomics anywhere.
+#include <cstdint>
+#include <cstring>
+
+#include "device_types.cuh"
+#include "fastmath.cuh"
+#include "geom.cuh"
+#include "launch.cuh"
+
+namespace gapcu {
+
+constexpr int CT = 256;  // threads per centre CTA
+constexpr int NW = CT / 32;
+constexpr int MAXG = 4;  // alpha groups of one class handled per forward pass (register accumulators)
+
+enum { MODE_FWD = 0, MODE_BWD = 1, MODE_FUSED = 2 };
+
+// shared-memory layout (byte offsets)
+struct SmemLayout {
+    int t32, galpha, gd, x, r, ir, w, fc, dfc, gw, sG, sdu, xs, sW, acc, red, S, scratch, ctl, rad, nc, total;
+};
+
+__host__ __device__ inline SmemLayout make_layout(const CentreArgs &a, int mode) {
+    SmemLayout L;
+    int o = 0;
+    auto take = [&](long bytes) { int r = o; o += (int)((bytes + 15) & ~15l); return r; };
+    const int pcap = a.pcap, D = a.plan.D;
+    const bool bwd = mode != MODE_FWD, fwd = mode != MODE_BWD, fused = mode == MODE_FUSED;
+    L.t32 = take(8 * 32);
+    L.galpha = take(8 * (a.plan.n_grp + 1));
+    L.gd = bwd ? take(8 * 4 * (a.plan.n_grp + 1)) : 0;
+    L.x = take(8 * 3 * pcap);
+    L.r = take(8 * pcap);
+    L.ir = take(8 * pcap);
+    L.w = take(8 * pcap);
+    L.fc = take(8 * a.plan.ncls * pcap);
+    L.dfc = bwd ? take(8 * a.plan.ncls * pcap) : 0;
+    L.gw = fwd ? take(8 * NW * D) : 0;
+    L.sG = fused ? take(8 * D) : 0;
+    L.sdu = bwd ? take(8 * D) : 0;
+    L.xs = fused ? take(8 * D) : 0;
+    L.sW = fused ? take(8 * a.gpr_Mp) : 0;
+    L.acc = bwd ? take(8 * 4 * pcap) : 0;
+    L.red = take(8 * NW * 16);
+    L.S = take(4 * (a.lcap + 32));
+    const long scr_u = 4l * (a.lcap + NW * 32 + 32), scr_pa = (bwd && a.npa > 1) ? 8l * a.npa * 4 * pcap : 0;
+    L.scratch = take(scr_u > scr_pa ? scr_u : scr_pa);
+    L.ctl = take(4 * 512);
+    L.rad = take(16 * (a.plan.n_rad + 1));
+    L.nc = take(pcap);
+    L.total = o;
+    return L;
+}
+
+size_t centre_smem_bytes(const CentreArgs &a, int mode) { return (size_t)make_layout(a, mode).total; }
+
+// control block in shared memory
+struct Ctl {
+    int cntw[NW];               // kept items per warp segment
+    int hw[NW][MAXC_DEV + 1];   // kept items per (warp, bucket)
+    int basew[NW][MAXC_DEV + 1];// running output position per (warp, bucket)
+    int tot[MAXC_DEV + 1];      // items per bucket
+    int npre[MAXC_DEV + 1];     // items with bucket > c  (prefix length of class c)
+    int obase[MAXC_DEV + 1];    // start of order slot o (bucket ncls-o) in S
+    int ocnt[MAXC_DEV + 1];
+    int obq[MAXC_DEV + 1];      // batches of order slot o
+    int obp[MAXC_DEV + 2];      // first batch of order slot o
+    int TB, nkept;
+};
+static_assert(sizeof(Ctl) <= 4 * 512, "Ctl does not fit");
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// pair index q -> (a < b), q = b(b-1)/2 + a
+__device__ __forceinline__ void tri_decode(int q, int &a, int &b) {
+    int bb = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)q)) * 0.5f);
+    if (bb * (bb - 1) / 2 > q) bb--;
+    if ((bb + 1) * bb / 2 <= q) bb++;
+    b = bb;
+    a = q - bb * (bb - 1) / 2;
+}
+
+// add four values to a [4][pcap] accumulator at index idx.  Private (per warp) set:
+// lanes that hit the same idx take turns in lane order (deterministic, no atomics).
+// Shared set (very long neighbour lists only): shared-memory atomics.
+__device__ __forceinline__ void scatter4(double *pa, int pcap, int idx, double v0, double v1, double v2, double v3,
+                                         unsigned amask, unsigned ltmask, bool priv) {
+    if (priv) {
+        const unsigned peers = __match_any_sync(amask, idx);
+        const int rank = __popc(peers & ltmask);
+        const int maxr = __reduce_max_sync(amask, rank);
+        for (int r = 0; r <= maxr; r++) {
+            if (rank == r) {
+                pa[idx] += v0;
+                pa[pcap + idx] += v1;
+                pa[2 * pcap + idx] += v2;
+                pa[3 * pcap + idx] += v3;
+            }
+            __syncwarp(amask);
+        }
+    } else {
+        atomicAdd(&pa[idx], v0);
+        atomicAdd(&pa[pcap + idx], v1);
+        atomicAdd(&pa[2 * pcap + idx], v2);
+        atomicAdd(&pa[3 * pcap + idx], v3);
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr bool FWD = MODE != MODE_BWD, BWD = MODE != MODE_FWD, FUSED = MODE == MODE_FUSED;
+    const PlanDev &pl = a.plan;
+    const int ncls = pl.ncls, D = pl.D, nsf = pl.nsf, pcap = a.pcap, lcap = a.lcap;
+    const SmemLayout L = make_layout(a, MODE);
+    double *s_t32 = (double *)(smem + L.t32);
+    double *s_galpha = (double *)(smem + L.galpha);
+    double *s_gd = (double *)(smem + L.gd);      // [n_grp][4]: DU, DW, DUL, DWL (backward)
+    double *s_x = (double *)(smem + L.x);        // [3][pcap]
+    double *s_r = (double *)(smem + L.r);
+    double *s_ir = (double *)(smem + L.ir);
+    double *s_w = (double *)(smem + L.w);
+    double *s_fc = (double *)(smem + L.fc);      // [ncls][pcap]
+    double *s_dfc = (double *)(smem + L.dfc);
+    double *s_gw = (double *)(smem + L.gw);      // [NW][D] per-warp partial descriptors
+    double *s_G = (double *)(smem + L.sG);
+    double *s_du = (double *)(smem + L.sdu);     // dE/dG of this centre
+    double *s_xs = (double *)(smem + L.xs);
+    double *s_W = (double *)(smem + L.sW);
+    double *s_acc = (double *)(smem + L.acc);    // [4][pcap]: A, Vx, Vy, Vz
+    double *s_red = (double *)(smem + L.red);
+    uint32_t *s_S = (uint32_t *)(smem + L.S);
+    uint32_t *s_U = (uint32_t *)(smem + L.scratch);
+    double *s_pa = (double *)(smem + L.scratch);  // [NW][4][pcap] (aliases U; live only in backward phase B)
+    Ctl *ctl = (Ctl *)(smem + L.ctl);
+    int2 *s_radi = (int2 *)(smem + L.rad);        // per radial function: (ii, cls | type<<16)
+    double *s_radp = (double *)(smem + L.rad + 8 * (pl.n_rad + 1));
+    unsigned char *s_nc = smem + L.nc;
+
+    const int i = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned ltmask = (1u << lane) - 1u;
+    const int P = a.nbr_cnt[i];
+    if (P > pcap || P > a.cap) {  // host re-runs with a larger capacity
+        if (tid == 0) atomicExch(&a.flags->overflow, 1);
+        return;
+    }
+    const StructDev &sd = a.structs[a.sid[i]];
+    const int ntot = a.ntot;
+    const int *g_iplus = pl.itab + pl.o_grp_iplus, *g_iminus = pl.itab + pl.o_grp_iminus;
+
+    // ---- 0: tables ------------------------------------------------------------
+    if (tid < 32) s_t32[tid] = a.exp2_table[tid];
+    for (int t = tid; t < pl.n_grp; t += CT) s_galpha[t] = pl.dtab[pl.o_grp_alpha + t];
+    for (int t = tid; t < pl.n_rad; t += CT) {
+        s_radi[t] = make_int2(pl.itab[pl.o_rad_ii + t], pl.itab[pl.o_rad_cls + t] | (pl.itab[pl.o_rad_type + t] << 16));
+        s_radp[t] = pl.dtab[pl.o_rad_p + t];
+    }
+    if (FWD) for (int t = tid; t < NW * D; t += CT) s_gw[t] = 0.0;
+    if (MODE == MODE_BWD) for (int t = tid; t < D; t += CT) s_du[t] = a.dEdG[(size_t)i * D + t];
+    __shared__ double s_lat[9];
+    if (tid < 9) s_lat[tid] = sd.lat[tid];
+    __syncthreads();
+
+    const double xi = a.pos[i], yi = a.pos[ntot + i], zi = a.pos[2 * ntot + i];
+    unsigned long long wk_pc = 0, wk_rad = 0;
+
+    // ---- 1: stage neighbours; 2: radial forward ------------------------------------
+    for (int s0 = 0; s0 < P; s0 += CT) {
+        const int s = s0 + tid;
+        double dis = 0.0, wj = 0.0;
+        int nc = 0;
+        if (s < P) {
+            int jl, n1, n2, n3;
+            nbr_unkey(a.nbr_keys[(size_t)i * a.cap + s], jl, n1, n2, n3);
+            const int j = sd.atom_off + jl;
+            double ox, oy, oz;
+            dis = image_distance(a.pos, ntot, j, s_lat, n1, n2, n3, xi, yi, zi, ox, oy, oz);
+            wj = a.wgt[j];
+            s_x[s] = ox; s_x[pcap + s] = oy; s_x[2 * pcap + s] = oz;
+            s_r[s] = dis;
+            s_ir[s] = 1.0 / dis;
+            s_w[s] = wj;
+            while (nc < ncls && !(dis > a.cls.rc[nc])) nc++;  // reference: "if (rij.gt.cutoff) cycle"
+            s_nc[s] = (unsigned char)nc;
+            for (int c = 0; c < nc; c++) {
+                double sn, cs;
+                sincos_0pi(dis * a.cls.pirc[c], &sn, &cs);
+                s_fc[c * pcap + s] = 0.5 * (cs + 1.0);
+                if (BWD) s_dfc[c * pcap + s] = -0.5 * a.cls.pirc[c] * sn;
+            }
+            wk_pc += nc;
+        }
+        if (FWD) {
+            // whole warps without neighbours skip; the others reduce each function's value
+            if (s0 + (wid << 5) < P) {
+                for (int q = 0; q < pl.n_rad; q++) {
+                    const int2 ri = s_radi[q];
+                    const int c = ri.y & 0xffff;
+                    double g = 0.0;
+                    if (s < P && c < nc) {
+                        const double fc = s_fc[c * pcap + s];
+                        double arg;
+                        if ((ri.y >> 16) == 1) arg = -s_radp[q] * dis * dis;
+                        else { const double d = dis - s_radp[q]; arg = -4.0 * d * d; }
+                        g = exp_neg(arg, s_t32) * fc;
+                        wk_rad++;
+                    }
+                    const double gu = warp_sum(g), gwt = warp_sum(g * wj);
+                    if (lane == 0) { s_gw[wid * D + ri.x] += gu; s_gw[wid * D + ri.x + nsf] += gwt; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (FWD && tid < ncls && a.cls.grp_begin[tid + 1] > a.cls.grp_begin[tid]) {
+        // sum_c Q_c of SURVEY.md 8(d): candidate pairs of every angular cutoff class
+        unsigned long long pc = 0;
+        for (int s = 0; s < P; s++) pc += (s_nc[s] > tid);
+        atomicAdd(&a.flags->work[8], pc * (pc - 1) / 2);
+    }
+
+    // ---- 3: triplet list builder (phase A + deterministic counting sort) ----------
+    const uint32_t angmask = a.cls.angmask;
+    const int Q = P * (P - 1) / 2;
+    const int nchunk = (angmask && Q > 0) ? (Q + lcap - 1) / lcap : 0;
+    const int qchunk = nchunk ? ((Q + nchunk - 1) / nchunk + 31) & ~31 : 0;
+    unsigned long long wk_trip = 0, wk_tc = 0, wk_tsf = 0;
+
+    auto build_list = [&](int q0, int q1, bool count_work) {
+        const int n = q1 - q0;
+        const int R = (((n + NW - 1) / NW) + 31) & ~31;  // per-warp contiguous sub-range
+        const int wq0 = q0 + wid * R, wq1 = min(q1, wq0 + R);
+        uint32_t *seg = s_U + wid * R;
+        int cnt = 0;
+        unsigned long long hp0 = 0, hp1 = 0;  // per-lane bucket histogram, 8-bit fields
+        for (int qb = wq0; qb < wq1; qb += 32) {
+            const int q = qb + lane;
+            int bk = 0, ra = 0, rb = 0;
+            if (q < wq1) {
+                tri_decode(q, ra, rb);
+                const int lim = min((int)s_nc[ra], (int)s_nc[rb]);
+                if (lim) {
+                    const double rjk2 = pair_dist2(s_x[ra], s_x[pcap + ra], s_x[2 * pcap + ra], s_x[rb], s_x[pcap + rb],
+                                                   s_x[2 * pcap + rb]);
+#pragma unroll
+                    for (int c = 0; c < MAXC_DEV; c++) {
+                        if (c >= ncls) break;
+                        bk += (c < lim && rjk2 <= a.cls.t2[c]);   // t2 descending: the hits are a prefix
+                    }
+                    if (!((angmask >> bk) & 1u)) bk = 0;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, bk > 0);
+            if (bk > 0) {
+                seg[cnt + __popc(m & ltmask)] = (uint32_t)ra | ((uint32_t)rb << 10) | ((uint32_t)bk << 20);
+                if (bk < 8) hp0 += 1ull << (8 * bk); else hp1 += 1ull << (8 * (bk - 8));
+            }
+            cnt += __popc(m);
+        }
+        for (int v = 1; v <= ncls; v++) {
+            const unsigned c = (unsigned)(((v < 8) ? (hp0 >> (8 * v)) : (hp1 >> (8 * (v - 8)))) & 255ull);
+            const unsigned tsum = __reduce_add_sync(0xffffffffu, c);
+            if (lane == 0) ctl->hw[wid][v] = (int)tsum;
+        }
+        if (lane == 0) ctl->cntw[wid] = cnt;
+        __syncthreads();
+        if (tid == 0) {
+            int off = 0, bp = 0, kept = 0;
+            for (int o = 0; o < ncls; o++) {
+                const int v = ncls - o;
+                int t = 0;
+                for (int w = 0; w < NW; w++) { ctl->basew[w][v] = off + t; t += ctl->hw[w][v]; }
+                ctl->tot[v] = t;
+                ctl->obase[o] = off; ctl->ocnt[o] = t; ctl->obq[o] = (t + 31) >> 5; ctl->obp[o] = bp;
+                off += t; bp += (t + 31) >> 5; kept += t;
+            }
+            ctl->obp[ncls] = bp; ctl->TB = bp; ctl->nkept = kept;
+            int pre = 0;
+            for (int c = ncls - 1; c >= 0; c--) { pre += ctl->tot[c + 1]; ctl->npre[c] = pre; }
+            if (count_work) {
+                wk_trip += kept;
+                for (int c = 0; c < ncls; c++) {
+                    const int g0 = a.cls.grp_begin[c], g1 = a.cls.grp_begin[c + 1];
+                    if (g1 > g0) {
+                        int nf = 0;
+                        for (int g = g0; g < g1; g++) nf += (g_iplus[g] >= 0) + (g_iminus[g] >= 0);
+                        wk_tc += ctl->npre[c];
+                        wk_tsf += (unsigned long long)ctl->npre[c] * nf;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int t0 = 0; t0 < cnt; t0 += 32) {
+            const int t = t0 + lane;
+            const bool act = t < cnt;
+            const unsigned am = __ballot_sync(0xffffffffu, act);
+            if (act) {
+                const uint32_t it = seg[t];
+                const int v = it >> 20;
+                const unsigned peers = __match_any_sync(am, v);
+                const int rank = __popc(peers & ltmask);
+                const int base = ctl->basew[wid][v];
+                s_S[base + rank] = it;
+                __syncwarp(am);
+                if (rank == 0) ctl->basew[wid][v] = base + __popc(peers);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+    };
+
+    // ---- 4: forward over the sorted list ----------------------------------------------
+    auto forward_list = [&]() {
+        for (int c = 0; c < ncls; c++) {
+            const int g0 = a.cls.grp_begin[c], g1 = a.cls.grp_begin[c + 1];
+            const int n_c = ctl->npre[c];
+            if (g0 == g1 || n_c == 0) continue;
+            const double pirc = a.cls.pirc[c];
+            const double *fcc = s_fc + c * pcap;
+            for (int gb = g0; gb < g1; gb += MAXG) {
+                const int ng = min(MAXG, g1 - gb);
+                double acc[MAXG][4];
+#pragma unroll
+                for (int g = 0; g < MAXG; g++) acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.0;
+                for (int t = tid; t < n_c; t += CT) {
+                    const uint32_t it = s_S[t];
+                    const int ra = it & 1023, rb = (it >> 10) & 1023;
+                    const double rjk2 = pair_dist2(s_x[ra], s_x[pcap + ra], s_x[2 * pcap + ra], s_x[rb], s_x[pcap + rb],
+                                                   s_x[2 * pcap + rb]);
+                    const double rja = s_r[ra], rkb = s_r[rb];
+                    const double ra2 = rja * rja, rb2 = rkb * rkb;
+                    const double cosv = (ra2 + rb2 - rjk2) * 0.5 * s_ir[ra] * s_ir[rb];
+                    const double ssum = ra2 + rb2 + rjk2;
+                    const double ww = s_w[ra] * s_w[rb];
+                    const double rjk = rjk2 > 0.0 ? rjk2 * rsqrt(rjk2) : 0.0;
+                    double sn, cs;
+                    sincos_0pi(rjk * pirc, &sn, &cs);
+                    const double phi = fcc[ra] * fcc[rb] * (0.5 * (cs + 1.0));
+#pragma unroll
+                    for (int g = 0; g < MAXG; g++) {
+                        if (g < ng) {
+                            const double pe = phi * exp_neg(-s_galpha[gb + g] * ssum, s_t32);
+                            const double pw = pe * ww;
+                            acc[g][0] += pe;
+                            acc[g][1] = fma(pe, cosv, acc[g][1]);
+                            acc[g][2] += pw;
+                            acc[g][3] = fma(pw, cosv, acc[g][3]);
+                        }
+                    }
+                }
+                if ((wid << 5) < n_c) {
+#pragma unroll
+                    for (int g = 0; g < MAXG; g++) {
+                        if (g < ng) {
+                            const double a0 = warp_sum(acc[g][0]), a1 = warp_sum(acc[g][1]);
+                            const double b0 = warp_sum(acc[g][2]), b1 = warp_sum(acc[g][3]);
+                            if (lane == 0) {
+                                const int ip = g_iplus[gb + g], im = g_iminus[gb + g];
+                                double *gw = s_gw + wid * D;
+                                if (ip >= 0) { gw[ip] += a0 + a1; gw[ip + nsf] += b0 + b1; }
+                                if (im >= 0) { gw[im] += a0 - a1; gw[im + nsf] += b0 - b1; }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    };
+
+    // ---- 6: backward over the sorted list -----------------------------------------------
+    auto backward_list = [&]() {
+        const bool priv = a.npa > 1;
+        double *pa = priv ? s_pa + (size_t)wid * 4 * pcap : s_acc;
+        if (priv) {
+            for (int t = lane; t < 4 * pcap; t += 32) pa[t] = 0.0;
+            __syncwarp();
+        }
+        const int TB = ctl->TB;
+        for (int g = wid; g < TB; g += NW) {
+            int o = 0;
+            while (o + 1 < ncls && g >= ctl->obp[o + 1]) o++;
+            const int v = ncls - o, q = g - ctl->obp[o], Qb = ctl->obq[o], n = ctl->ocnt[o];
+            const int idx = lane * Qb + q;  // lanes far apart in the list -> mostly distinct rows
+            const bool act = idx < n;
+            const unsigned am = __ballot_sync(0xffffffffu, act);
+            if (!act) continue;
+            const uint32_t it = s_S[ctl->obase[o] + idx];
+            const int ra = it & 1023, rb = (it >> 10) & 1023;
+            const double xa = s_x[ra], ya = s_x[pcap + ra], za = s_x[2 * pcap + ra];
+            const double xb = s_x[rb], yb = s_x[pcap + rb], zb = s_x[2 * pcap + rb];
+            const double rja = s_r[ra], rkb = s_r[rb], ira = s_ir[ra], irb = s_ir[rb];
+            const double rjk2 = pair_dist2(xa, ya, za, xb, yb, zb);
+            const double irjk = rsqrt(rjk2);
+            const double rjk = rjk2 * irjk;
+            const double ra2 = rja * rja, rb2 = rkb * rkb;
+            const double cosv = (ra2 + rb2 - rjk2) * 0.5 * ira * irb;
+            const double ssum = ra2 + rb2 + rjk2;
+            const double ww = s_w[ra] * s_w[rb];
+            const double u1 = irb - cosv * ira, u2 = ira - cosv * irb, u3 = -rjk * ira * irb;
+            double cij = 0.0, cik = 0.0, cjk = 0.0;
+            for (int c = 0; c < v; c++) {
+                const int g0 = a.cls.grp_begin[c], g1 = a.cls.grp_begin[c + 1];
+                if (g0 == g1) continue;
+                const double pirc = a.cls.pirc[c];
+                double sn, cs;
+                sincos_0pi(rjk * pirc, &sn, &cs);
+                const double fjk = 0.5 * (cs + 1.0), dfjk = -0.5 * pirc * sn;
+                const double fa = s_fc[c * pcap + ra], fb = s_fc[c * pcap + rb];
+                const double dfa = s_dfc[c * pcap + ra], dfb = s_dfc[c * pcap + rb];
+                const double fab = fa * fb, phi = fab * fjk;
+                // S1 = sum gamma e lam, T0 = sum gamma e, S3 = sum alpha gamma e (1 + lam cos)
+                double S1 = 0.0, T0 = 0.0, S3 = 0.0;
+                for (int gg = g0; gg < g1; gg++) {
+                    const double al = s_galpha[gg];
+                    const double e = exp_neg(-al * ssum, s_t32);
+                    const double4 gd = *(const double4 *)(s_gd + 4 * gg);   // DU, DW, DUL, DWL
+                    const double t0 = e * fma(ww, gd.y, gd.x), t1 = e * fma(ww, gd.w, gd.z);
+                    T0 += t0;
+                    S1 += t1;
+                    S3 = fma(al, fma(cosv, t1, t0), S3);
+                }
+                const double S2 = fma(cosv, S1, T0);  // sum gamma e (1 + lam cos)
+                const double pS1 = phi * S1, pS3 = 2.0 * phi * S3;
+                cij += pS1 * u1 - pS3 * rja + S2 * (dfa * fb * fjk);
+                cik += pS1 * u2 - pS3 * rkb + S2 * (fa * dfb * fjk);
+                cjk += pS1 * u3 - pS3 * rjk + S2 * (fab * dfjk);
+            }
+            // dE/dx_j = (gij+gjk) d_j - gjk d_k ; dE/dx_k = (gik+gjk) d_k - gjk d_j
+            const double gij = cij * ira, gik = cik * irb, gjk = cjk * irjk;
+            scatter4(pa, pcap, ra, gij + gjk, gjk * (xb - xi), gjk * (yb - yi), gjk * (zb - zi), am, ltmask, priv);
+            scatter4(pa, pcap, rb, gik + gjk, gjk * (xa - xi), gjk * (ya - yi), gjk * (za - zi), am, ltmask, priv);
+        }
+        __syncthreads();
+        if (priv) {
+            for (int t = tid; t < 4 * pcap; t += CT) {
+                double v = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; w++) v += s_pa[(size_t)w * 4 * pcap + t];
+                s_acc[t] += v;
+            }
+            __syncthreads();
+        }
+    };
+
+    // ---- drive the phases ---------------------------------------------------------------
+    bool list_ready = false;
+    if (FWD) {
+        for (int ch = 0; ch < nchunk; ch++) {
+            build_list(ch * qchunk, min(Q, (ch + 1) * qchunk), true);
+            forward_list();
+            __syncthreads();
+        }
+        list_ready = (nchunk == 1);
+        __syncthreads();
+        // per-warp partial sums -> descriptors (fixed order)
+        for (int k = tid; k < D; k += CT) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) v += s_gw[w * D + k];
+            if (FUSED) s_G[k] = v;
+            if (a.G) a.G[(size_t)i * D + k] = v;
+        }
+        // work counters
+        unsigned long long v0 = wk_pc, v1 = wk_rad;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); }
+        if (lane == 0) { atomicAdd(&a.flags->work[2], v0); atomicAdd(&a.flags->work[7], v1); }
+        if (tid == 0) {
+            atomicAdd(&a.flags->work[0], 1ull);
+            atomicAdd(&a.flags->work[1], (unsigned long long)P);
+            atomicAdd(&a.flags->work[3], (unsigned long long)Q);
+            atomicAdd(&a.flags->work[4], wk_trip);
+            atomicAdd(&a.flags->work[5], wk_tc);
+            atomicAdd(&a.flags->work[6], wk_tsf);
+        }
+    }
+    if (FUSED) {
+        // ---- 5: sparse GPR of this atom (gap_calc.f90:143-166), difference form ----------
+        __syncthreads();
+        const int M = a.gpr_M, Mp = a.gpr_Mp, Dp = a.gpr_Dp;
+        for (int k = tid; k < D; k += CT) s_xs[k] = (s_G[k] - a.gpr_cmean[k]) * a.gpr_itheta[k];
+        __syncthreads();
+        double esum = 0.0;
+        for (int j = tid; j < Mp; j += CT) {
+            double sacc = 0.0;
+            for (int k = 0; k < D; k++) {
+                const double d = s_xs[k] - a.gpr_MtT[(size_t)k * Mp + j];
+                sacc = fma(d, d, sacc);
+            }
+            const double wv = (j < M) ? exp_neg(-0.5 * sacc, s_t32) * a.gpr_coeff[j] : 0.0;
+            s_W[j] = wv;
+            esum += wv;
+        }
+        esum = warp_sum(esum);
+        if (lane == 0) s_red[wid] = esum;
+        __syncthreads();
+        if (tid == 0) {
+            double e = 0.0;
+            for (int w = 0; w < NW; w++) e += s_red[w];
+            a.eatom[i] = e;
+        }
+        for (int k = tid; k < D; k += CT) {
+            double acc = 0.0;
+            const double xk = s_xs[k];
+            for (int j = 0; j < M; j++) acc = fma(s_W[j], xk - a.gpr_Mt[(size_t)j * Dp + k], acc);
+            const double v = -a.gpr_itheta[k] * acc;
+            s_du[k] = v;
+            if (a.dEdG_out) a.dEdG_out[(size_t)i * D + k] = v;
+        }
+        __syncthreads();
+    }
+    if (BWD) {
+        if (!a.lgrad) return;
+        // per (class, alpha) group: sums of dE/dG over its functions
+        for (int g = tid; g < pl.n_grp; g += CT) {
+            const int ip = g_iplus[g], im = g_iminus[g];
+            const double dup = ip >= 0 ? s_du[ip] : 0.0, dwp = ip >= 0 ? s_du[ip + nsf] : 0.0;
+            const double dum = im >= 0 ? s_du[im] : 0.0, dwm = im >= 0 ? s_du[im + nsf] : 0.0;
+            s_gd[4 * g] = dup + dum; s_gd[4 * g + 1] = dwp + dwm; s_gd[4 * g + 2] = dup - dum; s_gd[4 * g + 3] = dwp - dwm;
+        }
+        // radial backward: one thread per neighbour
+        for (int s = tid; s < pcap; s += CT) {
+            double cacc = 0.0;
+            if (s < P) {
+                const double dis = s_r[s], wj = s_w[s];
+                const int nc = s_nc[s];
+                for (int q = 0; q < pl.n_rad; q++) {
+                    const int2 ri = s_radi[q];
+                    const int c = ri.y & 0xffff;
+                    if (c >= nc) continue;
+                    double arg, dgf;
+                    if ((ri.y >> 16) == 1) { const double al = s_radp[q]; arg = -al * dis * dis; dgf = -2.0 * al * dis; }
+                    else { const double d = dis - s_radp[q]; arg = -4.0 * d * d; dgf = -8.0 * d; }
+                    const double dg = exp_neg(arg, s_t32) * fma(dgf, s_fc[c * pcap + s], s_dfc[c * pcap + s]);
+                    cacc = fma(s_du[ri.x] + wj * s_du[ri.x + nsf], dg, cacc);
+                }
+                cacc *= s_ir[s];
+            }
+            s_acc[s] = cacc;
+            s_acc[pcap + s] = 0.0; s_acc[2 * pcap + s] = 0.0; s_acc[3 * pcap + s] = 0.0;
+        }
+        __syncthreads();
+        for (int ch = 0; ch < nchunk; ch++) {
+            if (!list_ready) build_list(ch * qchunk, min(Q, (ch + 1) * qchunk), false);
+            backward_list();
+        }
+        // ---- epilogue: per neighbour gradient, centre gradient, strs contraction ----------
+        double acc9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // gself xyz, vir xx xy xz yy yz zz
+        for (int s = tid; s < P; s += CT) {
+            const double dx = s_x[s] - xi, dy = s_x[pcap + s] - yi, dz = s_x[2 * pcap + s] - zi;
+            const double A = s_acc[s];
+            const double gx = A * dx - s_acc[pcap + s], gy = A * dy - s_acc[2 * pcap + s], gz = A * dz - s_acc[3 * pcap + s];
+            double *fp = a.fpair + ((size_t)i * a.cap + s) * 3;
+            fp[0] = gx; fp[1] = gy; fp[2] = gz;
+            acc9[0] -= gx; acc9[1] -= gy; acc9[2] -= gz;
+            acc9[3] += dx * gx; acc9[4] += dx * gy; acc9[5] += dx * gz;
+            acc9[6] += dy * gy; acc9[7] += dy * gz; acc9[8] += dz * gz;
+        }
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+            const double v = warp_sum(acc9[q]);
+            if (lane == 0) s_red[wid * 16 + q] = v;
+        }
+        __syncthreads();
+        if (tid < 9) {
+            double v = 0.0;
+            for (int w = 0; w < NW; w++) v += s_red[w * 16 + tid];
+            if (tid < 3) a.gself[(size_t)i * 3 + tid] = v;
+            else a.vir[(size_t)i * 6 + (tid - 3)] = v;
+        }
+    }
+}
+
+template <int MODE>
+static int launch_mode(cudaStream_t st, const CentreArgs &a) {
+    const size_t sm = centre_smem_bytes(a, MODE);
+    if (sm > 227 * 1024) return -1;
+    if (cudaFuncSetAttribute((const void *)k_centre<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
+        return -2;
+    k_centre<MODE><<<a.ntot, CT, sm, st>>>(a);
+    return 0;
+}
+
+int launch_forward(cudaStream_t st, const CentreArgs &a, long *launches) {
+    if (launches) *launches += 1;
+    return launch_mode<MODE_FWD>(st, a);
+}
+int launch_backward(cudaStream_t st, const CentreArgs &a, long *launches) {
+    if (launches) *launches += 1;
+    return launch_mode<MODE_BWD>(st, a);
+}
+int launch_fused(cudaStream_t st, const CentreArgs &a, long *launches) {
+    if (launches) *launches += 1;
+    return launch_mode<MODE_FUSED>(st, a);
+}
+
+}  // namespace gapcu

@@ -23,6 +23,7 @@
 #include "../../include/gapcu.h"
 #include "device_types.cuh"
 #include "launch.cuh"
+#include "fastmath.cuh"
 #include "potential.hpp"
 
 using namespace gapcu;
@@ -72,7 +73,8 @@ struct gapcu_ctx {
     DBuf<double> d_dtab;
     int M = 0, D = 0, Mp = 0, Dp = 0;
     std::vector<double> h_theta, h_mm, h_coeff;  // cached GPR data (C order)
-    DBuf<double> d_mm_raw, d_theta_raw, d_coeff_raw, d_Mt, d_mn, d_coeff, d_cmean, d_itheta;
+    DBuf<double> d_mm_raw, d_theta_raw, d_coeff_raw, d_Mt, d_MtT, d_mn, d_coeff, d_cmean, d_itheta, d_exp2;
+    int pipeline = 0;  // 0 auto, 1 split (K2 -> DMMA K3 -> K4), 2 fused single centre kernel
     // ---- structures
     int nstruct = 0, ntot = 0, nbins = 0;
     double rcut = 0.0;
@@ -102,13 +104,19 @@ struct gapcu_ctx {
         PlanDev p;
         p.itab = d_itab.p; p.dtab = d_dtab.p;
         p.n_itab = (int)plan.itab.size(); p.n_dtab = (int)plan.dtab.size();
-        p.nsf = plan.nsf; p.D = plan.D; p.ncls = plan.ncls; p.n_rad = plan.n_rad; p.n_grp = plan.n_grp; p.n_asf = plan.n_asf;
+        p.nsf = plan.nsf; p.D = plan.D; p.ncls = plan.ncls; p.n_rad = plan.n_rad; p.n_grp = plan.n_grp;
         p.o_rad_ii = plan.o_rad_ii; p.o_rad_cls = plan.o_rad_cls; p.o_rad_type = plan.o_rad_type;
-        p.o_cls_grp = plan.o_cls_grp; p.o_grp_sf = plan.o_grp_sf; p.o_asf_ii = plan.o_asf_ii;
-        p.o_rc = plan.o_rc; p.o_t2 = plan.o_t2; p.o_pirc = plan.o_pirc; p.o_rad_p = plan.o_rad_p;
-        p.o_grp_alpha = plan.o_grp_alpha; p.o_asf_lambda = plan.o_asf_lambda;
-        p.ang_prefix_mask = plan.ang_prefix_mask;
+        p.o_grp_iplus = plan.o_grp_iplus; p.o_grp_iminus = plan.o_grp_iminus;
+        p.o_rad_p = plan.o_rad_p; p.o_grp_alpha = plan.o_grp_alpha;
         return p;
+    }
+    ClassTab class_tab() const {
+        ClassTab t;
+        memset(&t, 0, sizeof t);
+        for (int c = 0; c < plan.ncls; c++) { t.rc[c] = plan.rc[c]; t.t2[c] = plan.t2[c]; t.pirc[c] = plan.pirc[c]; }
+        for (int c = 0; c <= MAXC_DEV; c++) t.grp_begin[c] = plan.grp_begin[c];
+        t.angmask = plan.ang_prefix_mask;
+        return t;
     }
     int pin(size_t bytes) {
         if (bytes <= h_pin_bytes) return 0;
@@ -143,6 +151,15 @@ extern "C" gapcu_ctx *gapcu_ctx_create(int device) {
         return nullptr;
     }
     memset(&c->h_flags, 0, sizeof c->h_flags);
+    double t32[32];
+    fill_exp2_table(t32);
+    if (c->d_exp2.ensure(32) != cudaSuccess ||
+        cudaMemcpy(c->d_exp2.p, t32, sizeof t32, cudaMemcpyHostToDevice) != cudaSuccess) {
+        fail(GAPCU_ECUDA, "cudaMalloc failed");
+        delete c;
+        return nullptr;
+    }
+    if (const char *e = getenv("GAPCU_PIPELINE")) c->pipeline = !strcmp(e, "split") ? 1 : !strcmp(e, "fused") ? 2 : 0;
     return c;
 }
 
@@ -151,7 +168,7 @@ extern "C" void gapcu_ctx_destroy(gapcu_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->d_itab.release(); c->d_dtab.release(); c->d_mm_raw.release(); c->d_theta_raw.release(); c->d_coeff_raw.release();
-    c->d_Mt.release(); c->d_mn.release(); c->d_coeff.release(); c->d_cmean.release(); c->d_itheta.release();
+    c->d_Mt.release(); c->d_MtT.release(); c->d_exp2.release(); c->d_mn.release(); c->d_coeff.release(); c->d_cmean.release(); c->d_itheta.release();
     c->d_structs.release(); c->d_sid.release(); c->d_arank.release(); c->d_bin_count.release(); c->d_bin_start.release();
     c->d_bin_atoms.release(); c->d_nbr_cnt.release(); c->d_abin.release(); c->d_pos.release(); c->d_wgt.release();
     c->d_G.release(); c->d_dEdG.release(); c->d_eatom.release(); c->d_fpair.release(); c->d_gself.release();
@@ -210,13 +227,13 @@ static int set_gpr(gapcu_ctx *c, int M, int D, const double *theta, const double
     c->h_mm.assign(mm, mm + (size_t)M * D);
     c->M = M; c->D = D; c->Dp = Dp; c->Mp = round_up(std::max(M, 1), 8);
     CU(c->d_mm_raw.ensure((size_t)M * D + 1)); CU(c->d_theta_raw.ensure(D)); CU(c->d_coeff_raw.ensure(M + 1));
-    CU(c->d_Mt.ensure((size_t)c->Mp * Dp)); CU(c->d_mn.ensure(c->Mp)); CU(c->d_coeff.ensure(c->Mp));
+    CU(c->d_Mt.ensure((size_t)c->Mp * Dp)); CU(c->d_MtT.ensure((size_t)c->Mp * Dp)); CU(c->d_mn.ensure(c->Mp)); CU(c->d_coeff.ensure(c->Mp));
     CU(c->d_cmean.ensure(Dp)); CU(c->d_itheta.ensure(Dp));
     CU(cudaMemcpyAsync(c->d_mm_raw.p, mm, sizeof(double) * (size_t)M * D, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_theta_raw.p, theta, sizeof(double) * D, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_coeff_raw.p, coeff, sizeof(double) * M, cudaMemcpyHostToDevice, c->stream));
     launch_gpr_prepare(c->stream, M, D, c->d_mm_raw.p, c->d_theta_raw.p, c->d_coeff_raw.p, c->Mp, Dp, c->d_Mt.p,
-                       c->d_mn.p, c->d_coeff.p, c->d_cmean.p, c->d_itheta.p);
+                       c->d_MtT.p, c->d_mn.p, c->d_coeff.p, c->d_cmean.p, c->d_itheta.p);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
     c->have_gpr = true;
@@ -246,6 +263,12 @@ extern "C" int gapcu_ctx_load_potential(gapcu_ctx *c, const char *path) {
     return gapcu_ctx_set_potential(c, (int)pf.z.size(), pf.z.data(), pf.w.data(), (int)pf.ntype.size(), pf.ntype.data(),
                                    pf.alpha.data(), pf.cutoff.data(), pf.nsparse, pf.des_len, pf.theta.data(),
                                    pf.mm.data(), pf.coeff.data());
+}
+
+extern "C" int gapcu_ctx_set_pipeline(gapcu_ctx *c, int mode) {
+    if (!c || mode < 0 || mode > 2) return fail(GAPCU_EARG, "bad pipeline mode");
+    c->pipeline = mode;
+    return 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -412,26 +435,52 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
     }
     if (ev) CU(cudaEventRecord(ev[1], c->stream));
     CentreArgs a;
+    memset(&a, 0, sizeof a);
     a.plan = c->plan_dev();
+    a.cls = c->class_tab();
     a.structs = c->d_structs.p; a.sid = c->d_sid.p; a.pos = c->d_pos.p; a.wgt = c->d_wgt.p;
-    a.nbr_keys = c->d_keys.p; a.nbr_cnt = c->d_nbr_cnt.p; a.ntot = c->ntot; a.cap = c->cap; a.pcap = c->pcap;
-    a.G = c->d_G.p; a.dEdG = c->d_dEdG.p; a.fpair = c->d_fpair.p; a.gself = c->d_gself.p; a.vir = c->d_vir.p;
+    a.nbr_keys = c->d_keys.p; a.nbr_cnt = c->d_nbr_cnt.p; a.exp2_table = c->d_exp2.p;
+    a.ntot = c->ntot; a.cap = c->cap; a.pcap = c->pcap; a.lgrad = lgrad;
+    a.G = c->d_G.p; a.dEdG = c->d_dEdG.p; a.dEdG_out = c->d_dEdG.p; a.eatom = c->d_eatom.p;
+    a.fpair = c->d_fpair.p; a.gself = c->d_gself.p; a.vir = c->d_vir.p;
+    a.gpr_M = c->M; a.gpr_Mp = c->Mp; a.gpr_Dp = c->Dp; a.gpr_Mt = c->d_Mt.p; a.gpr_MtT = c->d_MtT.p;
+    a.gpr_coeff = c->d_coeff.p; a.gpr_cmean = c->d_cmean.p; a.gpr_itheta = c->d_itheta.p;
     a.flags = c->d_flags.p;
-    if (launch_forward(c->stream, a, &c->launches)) return fail(GAPCU_ELIMIT, "descriptor kernel needs more shared memory than an SM has");
-    CU(cudaGetLastError());
-    if (ev) CU(cudaEventRecord(ev[2], c->stream));
-    GprDev g;
-    g.M = c->M; g.Mp = c->Mp; g.D = c->D; g.Dp = c->Dp; g.Mt = c->d_Mt.p; g.mn = c->d_mn.p; g.coeff = c->d_coeff.p;
-    g.cmean = c->d_cmean.p; g.itheta = c->d_itheta.p;
-    if (launch_gpr(c->stream, g, c->d_G.p, c->ntot, c->d_eatom.p, c->d_dEdG.p, &c->launches))
-        return fail(GAPCU_ELIMIT, "unsupported descriptor length for the GPR kernel");
-    CU(cudaGetLastError());
-    if (ev) CU(cudaEventRecord(ev[3], c->stream));
-    if (lgrad) {
-        if (launch_backward(c->stream, a, &c->launches)) return fail(GAPCU_ELIMIT, "descriptor kernel needs more shared memory than an SM has");
-        CU(cudaGetLastError());
+    // The in-CTA GPR re-reads the sparse set once per atom: worth it while that set is
+    // small (it stays in L1/L2 and a separate GEMM launch would be latency bound);
+    // large sets go through the tiled DMMA kernel.
+    const bool fused = c->pipeline == 2 || (c->pipeline == 0 && (size_t)c->Mp * c->Dp <= 64 * 1024);
+    // shared-memory budget: triplet-list capacity and private accumulator sets
+    {
+        const int q = c->pcap * (c->pcap - 1) / 2;
+        a.lcap = std::min(8192, std::max(2048, round_up(q, 32)));
+        a.npa = 8;
+        const size_t limit = 200 * 1024;
+        const int mode = fused ? 2 : 1;
+        if (centre_smem_bytes(a, mode) > limit) a.npa = 1;
+        while (centre_smem_bytes(a, mode) > limit && a.lcap > 1024) a.lcap -= 1024;
     }
-    if (ev) CU(cudaEventRecord(ev[4], c->stream));
+    if (fused) {
+        if (launch_fused(c->stream, a, &c->launches)) return fail(GAPCU_ELIMIT, "centre kernel needs more shared memory than an SM has");
+        CU(cudaGetLastError());
+        if (ev) { CU(cudaEventRecord(ev[2], c->stream)); CU(cudaEventRecord(ev[3], c->stream)); CU(cudaEventRecord(ev[4], c->stream)); }
+    } else {
+        if (launch_forward(c->stream, a, &c->launches)) return fail(GAPCU_ELIMIT, "centre kernel needs more shared memory than an SM has");
+        CU(cudaGetLastError());
+        if (ev) CU(cudaEventRecord(ev[2], c->stream));
+        GprDev g;
+        g.M = c->M; g.Mp = c->Mp; g.D = c->D; g.Dp = c->Dp; g.Mt = c->d_Mt.p; g.MtT = c->d_MtT.p; g.mn = c->d_mn.p;
+        g.coeff = c->d_coeff.p; g.cmean = c->d_cmean.p; g.itheta = c->d_itheta.p;
+        if (launch_gpr(c->stream, g, c->d_G.p, c->ntot, c->d_eatom.p, c->d_dEdG.p, &c->launches))
+            return fail(GAPCU_ELIMIT, "unsupported descriptor length for the GPR kernel");
+        CU(cudaGetLastError());
+        if (ev) CU(cudaEventRecord(ev[3], c->stream));
+        if (lgrad) {
+            if (launch_backward(c->stream, a, &c->launches)) return fail(GAPCU_ELIMIT, "centre kernel needs more shared memory than an SM has");
+            CU(cudaGetLastError());
+        }
+        if (ev) CU(cudaEventRecord(ev[4], c->stream));
+    }
     launch_gather(c->stream, c->d_structs.p, c->nstruct, c->d_sid.p, c->ntot, c->cap, c->d_keys.p, c->d_nbr_cnt.p,
                   c->d_fpair.p, c->d_gself.p, c->d_vir.p, c->d_eatom.p, lgrad, c->d_force.p, c->d_out8.p, &c->launches);
     CU(cudaGetLastError());

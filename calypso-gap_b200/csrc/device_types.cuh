@@ -37,32 +37,58 @@ struct DevFlags {
     unsigned long long work[10];  // see gapcu_ctx_work_counters
 };
 
+constexpr int MAXC_DEV = 16;  // distinct cutoffs (classes) supported
+
 // Symmetry-function tables on the device (flat int / double tables + offsets).
+// Angular functions are grouped: class (cutoff) -> groups of equal alpha; a group
+// holds at most one lambda=+1 (type 2) and one lambda=-1 (type 4) function.
 struct PlanDev {
     const int *itab;
     const double *dtab;
     int n_itab, n_dtab;
-    int nsf, D, ncls, n_rad, n_grp, n_asf;
-    int o_rad_ii, o_rad_cls, o_rad_type, o_cls_grp, o_grp_sf, o_asf_ii;
-    int o_rc, o_t2, o_pirc, o_rad_p, o_grp_alpha, o_asf_lambda;
-    uint32_t ang_prefix_mask;
+    int nsf, D, ncls, n_rad, n_grp;
+    int o_rad_ii, o_rad_cls, o_rad_type, o_grp_iplus, o_grp_iminus;  // offsets into itab
+    int o_rad_p, o_grp_alpha;                                         // offsets into dtab
 };
 
-// Everything the per-centre kernels need.
+// Cutoff-class tables, passed by value in the kernel parameters (constant bank).
+struct ClassTab {
+    double rc[MAXC_DEV];    // class cutoff, descending
+    double t2[MAXC_DEV];    // largest x with sqrt_rn(x) <= rc
+    double pirc[MAXC_DEV];  // PI_REF / rc
+    int grp_begin[MAXC_DEV + 1];
+    uint32_t angmask;       // bit b: some class c < b holds angular functions
+};
+
+// Everything the per-centre kernel needs.
 struct CentreArgs {
     PlanDev plan;
+    ClassTab cls;
     const StructDev *structs;
     const int *sid;             // [NT] structure of each atom
     const double *pos;          // [3][NT] SoA
     const double *wgt;          // [NT] species weight
     const uint64_t *nbr_keys;   // [NT][cap]
     const int *nbr_cnt;         // [NT]
-    int ntot, cap, pcap;        // pcap: shared-memory capacity (>= max count)
-    double *G;                  // [NT][D]   forward out
-    const double *dEdG;         // [NT][D]   backward in
-    double *fpair;              // [NT][cap][3] dE_i/dx_(slot)  backward out
+    const double *exp2_table;   // [32] 2^(j/32)
+    int ntot, cap, pcap;        // pcap: shared-memory neighbour capacity (>= max count)
+    int lcap;                   // triplet-list capacity per chunk
+    int npa;                    // private accumulator sets in backward: NW, or 1 (= shared + atomics)
+    int lgrad;
+    double *G;                  // [NT][D]   descriptors out (forward / fused; may be null in fused)
+    const double *dEdG;         // [NT][D]   backward in (MODE_BWD)
+    double *dEdG_out;           // [NT][D]   fused: dE/dG out (may be null)
+    double *eatom;              // [NT]      fused: atomic energies
+    double *fpair;              // [NT][cap][3] dE_i/dx_(slot)
     double *gself;              // [NT][3]      dE_i/dx_i
     double *vir;                // [NT][6]      sum_slots delta_a * grad_b, (xx,xy,xz,yy,yz,zz)
+    // fused GPR (scaled, centred sparse set; see gpr.cu)
+    int gpr_M, gpr_Mp, gpr_Dp;
+    const double *gpr_Mt;       // [Mp][Dp]
+    const double *gpr_MtT;      // [Dp][Mp]
+    const double *gpr_coeff;    // [Mp]
+    const double *gpr_cmean;    // [Dp]
+    const double *gpr_itheta;   // [Dp]
     DevFlags *flags;
 };
 

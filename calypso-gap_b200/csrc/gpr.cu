@@ -103,7 +103,7 @@ k_gpr(GprDev p, const double *__restrict__ G, int ntot, double *__restrict__ eat
 
 // Scaled/centred sparse set (once per potential).  One thread per (row, column).
 __global__ void k_gpr_prepare(int M, int D, const double *mm, const double *theta, const double *coeff, int Mp,
-                              int Dp, double *Mt, double *mn, double *coeff_p, double *cmean, double *itheta) {
+                              int Dp, double *Mt, double *MtT, double *mn, double *coeff_p, double *cmean, double *itheta) {
     // phase 1 (block 0 does the column means; tiny problem, run as <<<1, 256>>>)
     for (int k = threadIdx.x; k < Dp; k += blockDim.x) {
         double s = 0.0;
@@ -117,6 +117,7 @@ __global__ void k_gpr_prepare(int M, int D, const double *mm, const double *thet
         for (int k = 0; k < Dp; k++) {
             double v = (j < M && k < D) ? (mm[(size_t)j * D + k] - cmean[k]) * itheta[k] : 0.0;
             Mt[(size_t)j * Dp + k] = v;
+            MtT[(size_t)k * Mp + j] = v;
             nn += v * v;
         }
         mn[j] = nn;
@@ -125,9 +126,9 @@ __global__ void k_gpr_prepare(int M, int D, const double *mm, const double *thet
 }
 
 void launch_gpr_prepare(cudaStream_t st, int M, int D, const double *mm_c_order, const double *theta,
-                        const double *coeff, int Mp, int Dp, double *Mt, double *mn, double *coeff_p,
-                        double *cmean, double *itheta) {
-    k_gpr_prepare<<<1, 256, 0, st>>>(M, D, mm_c_order, theta, coeff, Mp, Dp, Mt, mn, coeff_p, cmean, itheta);
+                        const double *coeff, int Mp, int Dp, double *Mt, double *MtT, double *mn,
+                        double *coeff_p, double *cmean, double *itheta) {
+    k_gpr_prepare<<<1, 256, 0, st>>>(M, D, mm_c_order, theta, coeff, Mp, Dp, Mt, MtT, mn, coeff_p, cmean, itheta);
 }
 
 template <int NT>

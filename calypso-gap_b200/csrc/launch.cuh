@@ -16,15 +16,17 @@ void launch_neighbor_build(cudaStream_t st, const StructDev *structs, const int 
                            int *bin_count, int *bin_start, int *bin_atoms, uint64_t *nbr_keys, int *nbr_cnt,
                            double *min_dis, DevFlags *flags, long *launches);
 
-// desc.cu
-size_t centre_smem_bytes(const PlanDev &plan, int pcap, bool backward);
+// centre.cu  (mode: 0 forward, 1 backward, 2 fused forward + GPR + backward)
+size_t centre_smem_bytes(const CentreArgs &a, int mode);
 int launch_forward(cudaStream_t st, const CentreArgs &a, long *launches);
 int launch_backward(cudaStream_t st, const CentreArgs &a, long *launches);
+int launch_fused(cudaStream_t st, const CentreArgs &a, long *launches);
 
 // gpr.cu
 struct GprDev {
     int M, Mp, D, Dp;        // Mp: M padded to 8, Dp: D padded to 8
     const double *Mt;        // [Mp][Dp]  (MM - cmean)/theta, zero padded
+    const double *MtT;       // [Dp][Mp]  its transpose (in-CTA GPR of the fused kernel)
     const double *mn;        // [Mp]      |Mt row|^2
     const double *coeff;     // [Mp]      zero padded
     const double *cmean;     // [Dp]
@@ -33,8 +35,8 @@ struct GprDev {
 int launch_gpr(cudaStream_t st, const GprDev &g, const double *G, int ntot, double *eatom, double *dEdG,
                long *launches);
 void launch_gpr_prepare(cudaStream_t st, int M, int D, const double *mm_c_order, const double *theta,
-                        const double *coeff, int Mp, int Dp, double *Mt, double *mn, double *coeff_p,
-                        double *cmean, double *itheta);
+                        const double *coeff, int Mp, int Dp, double *Mt, double *MtT, double *mn,
+                        double *coeff_p, double *cmean, double *itheta);
 
 // gather.cu
 void launch_gather(cudaStream_t st, const StructDev *structs, int nstruct, const int *sid, int ntot, int cap,

@@ -128,29 +128,27 @@ SfPlan make_plan(const std::vector<int> &ntype, const std::vector<double> &alpha
         pl.pirc[c] = PI_REF / rcs[c];
     }
     auto cls_of = [&](double rc) { return (int)(std::find(rcs.begin(), rcs.end(), rc) - rcs.begin()); };
-    pl.cls_grp_begin.assign(pl.ncls + 1, 0);
     for (int c = 0; c < pl.ncls; c++) {
-        pl.cls_grp_begin[c] = (int)pl.grp_alpha.size();
-        // distinct alphas of the angular functions of this class, in file order
-        std::vector<double> als;
-        for (int i = 0; i < pl.nsf; i++)
-            if ((ntype[i] == 2 || ntype[i] == 4) && cutoff[i] == rcs[c] &&
-                std::find(als.begin(), als.end(), alpha[i]) == als.end())
-                als.push_back(alpha[i]);
-        for (double al : als) {
-            pl.grp_alpha.push_back(al);
-            pl.grp_sf_begin.push_back((int)pl.asf_ii.size());
-            for (int i = 0; i < pl.nsf; i++)
-                if ((ntype[i] == 2 || ntype[i] == 4) && cutoff[i] == rcs[c] && alpha[i] == al) {
-                    pl.asf_ii.push_back(i);
-                    pl.asf_lambda.push_back(ntype[i] == 2 ? 1.0 : -1.0);
-                }
+        pl.grp_begin[c] = (int)pl.grp_alpha.size();
+        const size_t first = pl.grp_alpha.size();
+        for (int i = 0; i < pl.nsf; i++) {
+            if (!(ntype[i] == 2 || ntype[i] == 4) || cutoff[i] != rcs[c]) continue;
+            const bool plus = ntype[i] == 2;
+            size_t g = first;
+            for (; g < pl.grp_alpha.size(); g++)
+                if (pl.grp_alpha[g] == alpha[i] && (plus ? pl.grp_iplus[g] : pl.grp_iminus[g]) < 0) break;
+            if (g == pl.grp_alpha.size()) {
+                pl.grp_alpha.push_back(alpha[i]);
+                pl.grp_iplus.push_back(-1);
+                pl.grp_iminus.push_back(-1);
+            }
+            (plus ? pl.grp_iplus[g] : pl.grp_iminus[g]) = i;
+            pl.n_asf++;
         }
-        if (!als.empty())
+        if (pl.grp_alpha.size() > first)
             for (int b = c + 1; b <= pl.ncls; b++) pl.ang_prefix_mask |= (1u << b);
     }
-    pl.cls_grp_begin[pl.ncls] = (int)pl.grp_alpha.size();
-    pl.grp_sf_begin.push_back((int)pl.asf_ii.size());
+    for (int c = pl.ncls; c <= MAXC; c++) pl.grp_begin[c] = (int)pl.grp_alpha.size();
     for (int i = 0; i < pl.nsf; i++) {
         if (ntype[i] == 1 || ntype[i] == 3) {
             pl.rad_ii.push_back(i);
@@ -163,21 +161,15 @@ SfPlan make_plan(const std::vector<int> &ntype, const std::vector<double> &alpha
     }
     pl.n_rad = (int)pl.rad_ii.size();
     pl.n_grp = (int)pl.grp_alpha.size();
-    pl.n_asf = (int)pl.asf_ii.size();
     auto puti = [&](const std::vector<int> &v) { int o = (int)pl.itab.size(); pl.itab.insert(pl.itab.end(), v.begin(), v.end()); return o; };
-    auto putd = [&](const double *v, size_t n) { int o = (int)pl.dtab.size(); pl.dtab.insert(pl.dtab.end(), v, v + n); return o; };
+    auto putd = [&](const std::vector<double> &v) { int o = (int)pl.dtab.size(); pl.dtab.insert(pl.dtab.end(), v.begin(), v.end()); return o; };
     pl.o_rad_ii = puti(pl.rad_ii);
     pl.o_rad_cls = puti(pl.rad_cls);
     pl.o_rad_type = puti(pl.rad_type);
-    pl.o_cls_grp = puti(pl.cls_grp_begin);
-    pl.o_grp_sf = puti(pl.grp_sf_begin);
-    pl.o_asf_ii = puti(pl.asf_ii);
-    pl.o_rc = putd(pl.rc, pl.ncls);
-    pl.o_t2 = putd(pl.t2, pl.ncls);
-    pl.o_pirc = putd(pl.pirc, pl.ncls);
-    pl.o_rad_p = putd(pl.rad_p.data(), pl.rad_p.size());
-    pl.o_grp_alpha = putd(pl.grp_alpha.data(), pl.grp_alpha.size());
-    pl.o_asf_lambda = putd(pl.asf_lambda.data(), pl.asf_lambda.size());
+    pl.o_grp_iplus = puti(pl.grp_iplus);
+    pl.o_grp_iminus = puti(pl.grp_iminus);
+    pl.o_rad_p = putd(pl.rad_p);
+    pl.o_grp_alpha = putd(pl.grp_alpha);
     return pl;
 }
 

@@ -29,28 +29,28 @@ PotentialFile read_gap_parameters(const std::string &path);
 
 // Symmetry functions regrouped for the kernels.  Cutoff classes are the distinct
 // cutoffs in DESCENDING order, so the classes a distance belongs to are always a
-// prefix 0..nc-1 of the list.
+// prefix 0..nc-1 of the list.  Angular functions of a class are grouped by alpha;
+// a group holds at most one lambda=+1 (type 2) and one lambda=-1 (type 4) function
+// (a repeated (cutoff, alpha, lambda) opens a further group of the same alpha).
 struct SfPlan {
     int nsf = 0, D = 0, ncls = 0;
     double rc[MAXC];        // class cutoff
     double t2[MAXC];        // largest x with sqrt_rn(x) <= rc  (exact squared test)
     double pirc[MAXC];      // PI_REF / rc
+    int grp_begin[MAXC + 1];
     // radial functions (types 1 and 3)
     std::vector<int> rad_ii, rad_cls, rad_type;
     std::vector<double> rad_p;      // alpha (type 1) or r_shift (type 3)
-    // angular functions (types 2 and 4): class -> alpha groups -> functions
-    std::vector<int> cls_grp_begin; // [ncls+1]
+    // angular groups
     std::vector<double> grp_alpha;  // [ngrp]
-    std::vector<int> grp_sf_begin;  // [ngrp+1]
-    std::vector<int> asf_ii;        // [nasf]
-    std::vector<double> asf_lambda; // [nasf]  +1 (type 2) / -1 (type 4)
+    std::vector<int> grp_iplus, grp_iminus;  // descriptor index of the type-2 / type-4 function, -1 if absent
     uint32_t ang_prefix_mask = 0;   // bit b: some class c < b holds angular functions
     int n_unknown = 0;              // functions of unknown type (reference: print and continue)
     // flat tables uploaded to the device: ints then doubles
     std::vector<int> itab;
     std::vector<double> dtab;
-    int o_rad_ii, o_rad_cls, o_rad_type, o_cls_grp, o_grp_sf, o_asf_ii;  // offsets into itab
-    int o_rc, o_t2, o_pirc, o_rad_p, o_grp_alpha, o_asf_lambda;          // offsets into dtab
+    int o_rad_ii, o_rad_cls, o_rad_type, o_grp_iplus, o_grp_iminus;  // offsets into itab
+    int o_rad_p, o_grp_alpha;                                        // offsets into dtab
     int n_rad = 0, n_grp = 0, n_asf = 0;
 };
 

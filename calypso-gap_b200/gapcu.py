@@ -24,7 +24,7 @@ _lib = None
 SYMBOLS = [
     "gapcu_last_error", "gapcu_calc", "gapcu_read", "gapcu_bond", "gapcu_car2acsf_table", "gapcu_print_last_error",
     "gapcu_device_count", "gapcu_ctx_create", "gapcu_ctx_destroy", "gapcu_ctx_load_potential",
-    "gapcu_ctx_set_potential", "gapcu_ctx_set_structures", "gapcu_ctx_compute", "gapcu_ctx_fetch",
+    "gapcu_ctx_set_potential", "gapcu_ctx_set_pipeline", "gapcu_ctx_set_structures", "gapcu_ctx_compute", "gapcu_ctx_fetch",
     "gapcu_ctx_fetch_descriptors", "gapcu_ctx_fetch_neighbors", "gapcu_ctx_time_compute", "gapcu_stage_name",
     "gapcu_ctx_work_counters", "gapcu_fp64_peaks",
 ]
@@ -53,6 +53,7 @@ def lib():
         L.gapcu_ctx_set_potential.argtypes = [_vp, C.c_int, _ip, _dp, C.c_int, _ip, _dp, _dp, C.c_int, C.c_int, _dp, _dp, _dp]
         L.gapcu_ctx_set_structures.argtypes = [_vp, C.c_int, _ip, _ip, _dp, _dp, C.c_double]
         L.gapcu_ctx_compute.argtypes = [_vp, C.c_int]
+        L.gapcu_ctx_set_pipeline.argtypes = [_vp, C.c_int]
         L.gapcu_ctx_fetch.argtypes = [_vp, _vp, _vp, _vp]
         L.gapcu_ctx_fetch_descriptors.argtypes = [_vp, _vp, _vp, _vp]
         L.gapcu_ctx_fetch_neighbors.argtypes = [_vp, C.c_int, _ip, _ip, _ip, _dp]
@@ -120,6 +121,10 @@ class Context:
         pos = np.ascontiguousarray(np.concatenate([np.asarray(p, np.float64).reshape(-1, 3) for p in pos_list]))
         _check(lib().gapcu_ctx_set_structures(self.h, len(natoms), natoms, species, lat, pos, float(rcut)))
         self.natoms = natoms
+
+    def set_pipeline(self, mode):
+        """'auto' | 'split' (K2 -> DMMA GPR -> K4) | 'fused' (one centre kernel)."""
+        _check(lib().gapcu_ctx_set_pipeline(self.h, {"auto": 0, "split": 1, "fused": 2}[mode]))
 
     def compute(self, lgrad=True):
         _check(lib().gapcu_ctx_compute(self.h, int(bool(lgrad))))

@@ -92,6 +92,12 @@ int gapcu_ctx_set_potential(gapcu_ctx *ctx, int nspecies, const int *z, const do
                             int nsparse, int des_len, const double *theta, const double *mm,
                             const double *coeff);
 
+/* Pipeline choice: 0 = automatic (default), 1 = split: forward kernel -> tiled DMMA GPR
+ * kernel -> backward kernel, 2 = fused: one centre kernel with the GPR of each atom
+ * done inside its CTA (chosen automatically while the sparse set is small).  Also
+ * settable with the environment variable GAPCU_PIPELINE=split|fused. */
+int gapcu_ctx_set_pipeline(gapcu_ctx *ctx, int mode);
+
 /* A batch of nstruct independent periodic structures (C order this time:
  * natoms[nstruct]; species[sum natoms]; lat[nstruct][3][3] rows = lattice
  * vectors; pos[sum natoms][3]).  Copies host -> device. */

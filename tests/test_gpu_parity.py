@@ -15,10 +15,13 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 E_TOL, F_TOL, S_TOL = 1e-10, 1e-8, 1e-7
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=["fused", "split"])
+def ctx(request):
+    """Both pipelines: 'fused' (one centre kernel, GPR inside the CTA) and 'split'
+    (forward kernel -> DMMA GPR kernel -> backward kernel)."""
     import gapcu
     c = gapcu.Context(0)
+    c.set_pipeline(request.param)
     c.load_potential(os.path.join(GOLDEN, "gap_parameters"))
     yield c
     c.close()
@@ -118,6 +121,11 @@ def test_supercell_1000_atoms_three_species(oracle, tmp_path):
     _cmp(got, want)
     # size-independent properties: zero net force, symmetric response to a rigid shift
     assert np.abs(got["forces"].sum(0)).max() < 1e-7
+    again = c.evaluate(z, cell, pos, 6.0, True)                 # fixed summation orders: bit-reproducible
+    assert again["energy"] == got["energy"] and np.array_equal(again["forces"], got["forces"])
+    c.set_pipeline("split")
+    _cmp(c.evaluate(z, cell, pos, 6.0, True), want)
+    c.set_pipeline("auto")
     shifted = c.evaluate(z, cell, pos + np.array([0.37, -1.2, 2.9]), 6.0, True)
     assert abs(shifted["energy"] - got["energy"]) <= 1e-10 * abs(got["energy"])
     c.close()
