@@ -43,24 +43,20 @@
 
 namespace gapcu {
 
-constexpr int CT = 256;  // threads per centre CTA
+constexpr int CT = 256;  // threads per centre CTA (measured: 384 threads x 2 CTAs/SM is no faster, barrier stalls grow)
 constexpr int NW = CT / 32;
 constexpr int MAXG = 4;  // alpha groups of one class handled per forward pass (register accumulators)
 
 enum { MODE_FWD = 0, MODE_BWD = 1, MODE_FUSED = 2 };
 
-// shared-memory layout (byte offsets)
-struct SmemLayout {
-    int t32, galpha, gd, x, r, ir, w, fc, dfc, gw, sG, sdu, xs, sW, acc, red, S, scratch, ctl, rad, nc, total;
-};
-
-__host__ __device__ inline SmemLayout make_layout(const CentreArgs &a, int mode) {
+static SmemLayout make_layout(const CentreArgs &a, int mode) {
     SmemLayout L;
     int o = 0;
     auto take = [&](long bytes) { int r = o; o += (int)((bytes + 15) & ~15l); return r; };
     const int pcap = a.pcap, D = a.plan.D;
     const bool bwd = mode != MODE_FWD, fwd = mode != MODE_BWD, fused = mode == MODE_FUSED;
     L.t32 = take(8 * 32);
+    L.t2 = take(8 * MAXC_DEV);
     L.galpha = take(8 * (a.plan.n_grp + 1));
     L.gd = bwd ? take(8 * 4 * (a.plan.n_grp + 1)) : 0;
     L.x = take(8 * 3 * pcap);
@@ -69,17 +65,24 @@ __host__ __device__ inline SmemLayout make_layout(const CentreArgs &a, int mode)
     L.w = take(8 * pcap);
     L.fc = take(8 * a.plan.ncls * pcap);
     L.dfc = bwd ? take(8 * a.plan.ncls * pcap) : 0;
-    L.gw = fwd ? take(8 * NW * D) : 0;
     L.sG = fused ? take(8 * D) : 0;
     L.sdu = bwd ? take(8 * D) : 0;
-    L.xs = fused ? take(8 * D) : 0;
-    L.sW = fused ? take(8 * a.gpr_Mp) : 0;
     L.acc = bwd ? take(8 * 4 * pcap) : 0;
     L.red = take(8 * NW * 16);
     L.S = take(4 * (a.lcap + 32));
-    const long scr_u = 4l * (a.lcap + NW * 32 + 32), scr_pa = (bwd && a.npa > 1) ? 8l * a.npa * 4 * pcap : 0;
-    L.scratch = take(scr_u > scr_pa ? scr_u : scr_pa);
-    L.ctl = take(4 * 512);
+    // scratch region, three lives: [U | gw] while lists are built and the forward runs,
+    // [part | xs | W] during the in-CTA GPR, [private accumulators] during the backward
+    const long scr_u = ((4l * (a.lcap + NW * 32 + 32) + 15) & ~15l);
+    const long scr_fwd = scr_u + (fwd ? 8l * NW * D : 0);
+    const long scr_gpr = fused ? 8l * (CT + D + a.gpr_Mp + 8) : 0;
+    const long scr_pa = (bwd && a.npa > 1) ? 8l * a.npa * 4 * pcap : 8l * CT;
+    long scr = scr_fwd > scr_pa ? scr_fwd : scr_pa;
+    if (scr_gpr > scr) scr = scr_gpr;
+    L.scratch = take(scr);
+    L.gw = L.scratch + (int)scr_u;
+    L.xs = L.scratch + 8 * CT;
+    L.sW = L.xs + 8 * ((D + 1) & ~1);
+    L.ctl = take(4 * 1024);
     L.rad = take(16 * (a.plan.n_rad + 1));
     L.nc = take(pcap);
     L.total = o;
@@ -87,6 +90,7 @@ __host__ __device__ inline SmemLayout make_layout(const CentreArgs &a, int mode)
 }
 
 size_t centre_smem_bytes(const CentreArgs &a, int mode) { return (size_t)make_layout(a, mode).total; }
+int centre_warps() { return NW; }
 
 // control block in shared memory
 struct Ctl {
@@ -101,12 +105,36 @@ struct Ctl {
     int obp[MAXC_DEV + 2];      // first batch of order slot o
     int TB, nkept;
 };
-static_assert(sizeof(Ctl) <= 4 * 512, "Ctl does not fit");
+static_assert(sizeof(Ctl) <= 4 * 1024, "Ctl does not fit");
+
+// exp(x), x <= 0; clamp only when the potential can produce arguments below -700
+__device__ __forceinline__ double exp_arg(double x, const double *T32, int clamp) {
+    if (clamp) x = fmax(x, -700.0);
+    return exp_neg(x, T32);
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Sum four per-lane values over the warp with 6 instead of 20 value shuffles: after the
+// call the lanes with (lane>>3) == k hold the total of v_k.
+__device__ __forceinline__ double warp_sum4(double v0, double v1, double v2, double v3, int lane) {
+    const bool hi16 = lane & 16, hi8 = lane & 8;
+    // lanes with bit4 = 0 keep (v0, v1), the others (v2, v3); each gets the partner's copy
+    double k0 = hi16 ? v2 : v0, k1 = hi16 ? v3 : v1;
+    const double s0 = hi16 ? v0 : v2, s1 = hi16 ? v1 : v3;
+    k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+    k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    double k = hi8 ? k1 : k0;
+    const double s = hi8 ? k0 : k1;
+    k += __shfl_xor_sync(0xffffffffu, s, 8);
+    k += __shfl_xor_sync(0xffffffffu, k, 4);
+    k += __shfl_xor_sync(0xffffffffu, k, 2);
+    k += __shfl_xor_sync(0xffffffffu, k, 1);
+    return k;
 }
 
 // pair index q -> (a < b), q = b(b-1)/2 + a
@@ -150,8 +178,9 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
     constexpr bool FWD = MODE != MODE_BWD, BWD = MODE != MODE_FWD, FUSED = MODE == MODE_FUSED;
     const PlanDev &pl = a.plan;
     const int ncls = pl.ncls, D = pl.D, nsf = pl.nsf, pcap = a.pcap, lcap = a.lcap;
-    const SmemLayout L = make_layout(a, MODE);
+    const SmemLayout &L = a.lay;
     double *s_t32 = (double *)(smem + L.t32);
+    double *s_t2 = (double *)(smem + L.t2);       // class thresholds padded with -1 (never passes)
     double *s_galpha = (double *)(smem + L.galpha);
     double *s_gd = (double *)(smem + L.gd);      // [n_grp][4]: DU, DW, DUL, DWL (backward)
     double *s_x = (double *)(smem + L.x);        // [3][pcap]
@@ -189,6 +218,7 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
 
     // ---- 0: tables ------------------------------------------------------------
     if (tid < 32) s_t32[tid] = a.exp2_table[tid];
+    if (tid < MAXC_DEV) s_t2[tid] = tid < ncls ? a.cls.t2[tid] : -1.0;
     for (int t = tid; t < pl.n_grp; t += CT) s_galpha[t] = pl.dtab[pl.o_grp_alpha + t];
     for (int t = tid; t < pl.n_rad; t += CT) {
         s_radi[t] = make_int2(pl.itab[pl.o_rad_ii + t], pl.itab[pl.o_rad_cls + t] | (pl.itab[pl.o_rad_type + t] << 16));
@@ -203,51 +233,54 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
     const double xi = a.pos[i], yi = a.pos[ntot + i], zi = a.pos[2 * ntot + i];
     unsigned long long wk_pc = 0, wk_rad = 0;
 
-    // ---- 1: stage neighbours; 2: radial forward ------------------------------------
-    for (int s0 = 0; s0 < P; s0 += CT) {
-        const int s = s0 + tid;
-        double dis = 0.0, wj = 0.0;
+    // ---- 1: stage neighbours (a: geometry per neighbour, b: fc/fc' per (neighbour, class)) ----
+    for (int s = tid; s < P; s += CT) {
+        int jl, n1, n2, n3;
+        nbr_unkey(a.nbr_keys[(size_t)i * a.cap + s], jl, n1, n2, n3);
+        const int j = sd.atom_off + jl;
+        double ox, oy, oz;
+        const double dis = image_distance(a.pos, ntot, j, s_lat, n1, n2, n3, xi, yi, zi, ox, oy, oz);
+        s_x[s] = ox; s_x[pcap + s] = oy; s_x[2 * pcap + s] = oz;
+        s_r[s] = dis;
+        s_ir[s] = 1.0 / dis;
+        s_w[s] = a.wgt[j];
         int nc = 0;
-        if (s < P) {
-            int jl, n1, n2, n3;
-            nbr_unkey(a.nbr_keys[(size_t)i * a.cap + s], jl, n1, n2, n3);
-            const int j = sd.atom_off + jl;
-            double ox, oy, oz;
-            dis = image_distance(a.pos, ntot, j, s_lat, n1, n2, n3, xi, yi, zi, ox, oy, oz);
-            wj = a.wgt[j];
-            s_x[s] = ox; s_x[pcap + s] = oy; s_x[2 * pcap + s] = oz;
-            s_r[s] = dis;
-            s_ir[s] = 1.0 / dis;
-            s_w[s] = wj;
-            while (nc < ncls && !(dis > a.cls.rc[nc])) nc++;  // reference: "if (rij.gt.cutoff) cycle"
-            s_nc[s] = (unsigned char)nc;
-            for (int c = 0; c < nc; c++) {
-                double sn, cs;
-                sincos_0pi(dis * a.cls.pirc[c], &sn, &cs);
-                s_fc[c * pcap + s] = 0.5 * (cs + 1.0);
-                if (BWD) s_dfc[c * pcap + s] = -0.5 * a.cls.pirc[c] * sn;
-            }
-            wk_pc += nc;
+        while (nc < ncls && !(dis > a.cls.rc[nc])) nc++;  // reference: "if (rij.gt.cutoff) cycle"
+        s_nc[s] = (unsigned char)nc;
+        wk_pc += nc;
+    }
+    __syncthreads();
+    const int P32 = (P + 31) & ~31;
+    for (int t = tid; t < ncls * P32; t += CT) {
+        const int c = t / P32, s = t - c * P32;
+        if (s < P && c < s_nc[s]) {
+            double sn, cs;
+            sincos_0pi(s_r[s] * a.cls.pirc[c], &sn, &cs);
+            s_fc[c * pcap + s] = 0.5 * (cs + 1.0);
+            if (BWD) s_dfc[c * pcap + s] = -0.5 * a.cls.pirc[c] * sn;
         }
-        if (FWD) {
-            // whole warps without neighbours skip; the others reduce each function's value
-            if (s0 + (wid << 5) < P) {
-                for (int q = 0; q < pl.n_rad; q++) {
-                    const int2 ri = s_radi[q];
-                    const int c = ri.y & 0xffff;
-                    double g = 0.0;
-                    if (s < P && c < nc) {
-                        const double fc = s_fc[c * pcap + s];
-                        double arg;
-                        if ((ri.y >> 16) == 1) arg = -s_radp[q] * dis * dis;
-                        else { const double d = dis - s_radp[q]; arg = -4.0 * d * d; }
-                        g = exp_neg(arg, s_t32) * fc;
-                        wk_rad++;
-                    }
-                    const double gu = warp_sum(g), gwt = warp_sum(g * wj);
-                    if (lane == 0) { s_gw[wid * D + ri.x] += gu; s_gw[wid * D + ri.x + nsf] += gwt; }
+    }
+    __syncthreads();
+    // ---- 2: radial forward: one warp task per function, lanes over neighbours ----------
+    if (FWD) {
+        for (int q = wid; q < pl.n_rad; q += NW) {
+            const int2 ri = s_radi[q];
+            const int c = ri.y & 0xffff;
+            const double prm = s_radp[q];
+            const bool t1 = (ri.y >> 16) == 1;
+            double gu = 0.0, gwt = 0.0;
+            for (int s = lane; s < P; s += 32) {
+                if (c < s_nc[s]) {
+                    const double dis = s_r[s];
+                    const double d = t1 ? dis : dis - prm;
+                    const double g = exp_arg((t1 ? -prm : -4.0) * d * d, s_t32, a.exp_clamp) * s_fc[c * pcap + s];
+                    gu += g;
+                    gwt = fma(g, s_w[s], gwt);
+                    wk_rad++;
                 }
             }
+            gu = warp_sum(gu); gwt = warp_sum(gwt);
+            if (lane == 0) { s_gw[wid * D + ri.x] += gu; s_gw[wid * D + ri.x + nsf] += gwt; }
         }
     }
     __syncthreads();
@@ -271,35 +304,38 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
         const int wq0 = q0 + wid * R, wq1 = min(q1, wq0 + R);
         uint32_t *seg = s_U + wid * R;
         int cnt = 0;
-        unsigned long long hp0 = 0, hp1 = 0;  // per-lane bucket histogram, 8-bit fields
+        if (lane <= ncls) ctl->hw[wid][lane] = 0;
+        __syncwarp();
+        int ra = 0, rb = 1;
+        if (wq0 + lane < wq1) tri_decode(wq0 + lane, ra, rb);
         for (int qb = wq0; qb < wq1; qb += 32) {
-            const int q = qb + lane;
-            int bk = 0, ra = 0, rb = 0;
-            if (q < wq1) {
-                tri_decode(q, ra, rb);
+            int bk = 0;
+            if (qb + lane < wq1) {
                 const int lim = min((int)s_nc[ra], (int)s_nc[rb]);
                 if (lim) {
                     const double rjk2 = pair_dist2(s_x[ra], s_x[pcap + ra], s_x[2 * pcap + ra], s_x[rb], s_x[pcap + rb],
                                                    s_x[2 * pcap + rb]);
+                    // thresholds descend: the classes with rjk2 <= t2[c] are a prefix; count it by bisection
+                    int lo = 0;
 #pragma unroll
-                    for (int c = 0; c < MAXC_DEV; c++) {
-                        if (c >= ncls) break;
-                        bk += (c < lim && rjk2 <= a.cls.t2[c]);   // t2 descending: the hits are a prefix
-                    }
+                    for (int step = MAXC_DEV / 2; step; step >>= 1)
+                        if (rjk2 <= s_t2[lo + step - 1]) lo += step;
+                    if (lo == MAXC_DEV - 1 && rjk2 <= s_t2[MAXC_DEV - 1]) lo = MAXC_DEV;
+                    bk = min(lo, lim);
                     if (!((angmask >> bk) & 1u)) bk = 0;
                 }
             }
             const unsigned m = __ballot_sync(0xffffffffu, bk > 0);
             if (bk > 0) {
                 seg[cnt + __popc(m & ltmask)] = (uint32_t)ra | ((uint32_t)rb << 10) | ((uint32_t)bk << 20);
-                if (bk < 8) hp0 += 1ull << (8 * bk); else hp1 += 1ull << (8 * (bk - 8));
+                const unsigned peers = __match_any_sync(m, bk);
+                if ((peers & ltmask) == 0) ctl->hw[wid][bk] += __popc(peers);  // one lane per bucket present
             }
+            __syncwarp();
             cnt += __popc(m);
-        }
-        for (int v = 1; v <= ncls; v++) {
-            const unsigned c = (unsigned)(((v < 8) ? (hp0 >> (8 * v)) : (hp1 >> (8 * (v - 8)))) & 255ull);
-            const unsigned tsum = __reduce_add_sync(0xffffffffu, c);
-            if (lane == 0) ctl->hw[wid][v] = (int)tsum;
+            // next pair of this lane: q += 32
+            ra += 32;
+            while (ra >= rb) { ra -= rb; rb++; }
         }
         if (lane == 0) ctl->cntw[wid] = cnt;
         __syncthreads();
@@ -379,7 +415,7 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
 #pragma unroll
                     for (int g = 0; g < MAXG; g++) {
                         if (g < ng) {
-                            const double pe = phi * exp_neg(-s_galpha[gb + g] * ssum, s_t32);
+                            const double pe = phi * exp_arg(-s_galpha[gb + g] * ssum, s_t32, a.exp_clamp);
                             const double pw = pe * ww;
                             acc[g][0] += pe;
                             acc[g][1] = fma(pe, cosv, acc[g][1]);
@@ -392,13 +428,15 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
 #pragma unroll
                     for (int g = 0; g < MAXG; g++) {
                         if (g < ng) {
-                            const double a0 = warp_sum(acc[g][0]), a1 = warp_sum(acc[g][1]);
-                            const double b0 = warp_sum(acc[g][2]), b1 = warp_sum(acc[g][3]);
-                            if (lane == 0) {
+                            // lanes 0,8,16,24 end up with sum pe, sum pe*cos, sum w*pe, sum w*pe*cos
+                            const double tot = warp_sum4(acc[g][0], acc[g][1], acc[g][2], acc[g][3], lane);
+                            const double oth = __shfl_xor_sync(0xffffffffu, tot, 8);  // the cos partner / the plain partner
+                            if ((lane & 7) == 0) {
                                 const int ip = g_iplus[gb + g], im = g_iminus[gb + g];
-                                double *gw = s_gw + wid * D;
-                                if (ip >= 0) { gw[ip] += a0 + a1; gw[ip + nsf] += b0 + b1; }
-                                if (im >= 0) { gw[im] += a0 - a1; gw[im + nsf] += b0 - b1; }
+                                double *gw = s_gw + wid * D + ((lane & 16) ? nsf : 0);
+                                // lane&8 == 0: tot = plain sum, oth = cos sum -> lambda=+1 ; else the lambda=-1 one
+                                if (!(lane & 8)) { if (ip >= 0) gw[ip] += tot + oth; }
+                                else { if (im >= 0) gw[im] += oth - tot; }
                             }
                         }
                     }
@@ -416,8 +454,8 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
             __syncwarp();
         }
         const int TB = ctl->TB;
+        int o = 0;
         for (int g = wid; g < TB; g += NW) {
-            int o = 0;
             while (o + 1 < ncls && g >= ctl->obp[o + 1]) o++;
             const int v = ncls - o, q = g - ctl->obp[o], Qb = ctl->obq[o], n = ctl->ocnt[o];
             const int idx = lane * Qb + q;  // lanes far apart in the list -> mostly distinct rows
@@ -452,7 +490,7 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
                 double S1 = 0.0, T0 = 0.0, S3 = 0.0;
                 for (int gg = g0; gg < g1; gg++) {
                     const double al = s_galpha[gg];
-                    const double e = exp_neg(-al * ssum, s_t32);
+                    const double e = exp_arg(-al * ssum, s_t32, a.exp_clamp);
                     const double4 gd = *(const double4 *)(s_gd + 4 * gg);   // DU, DW, DUL, DWL
                     const double t0 = e * fma(ww, gd.y, gd.x), t1 = e * fma(ww, gd.w, gd.z);
                     T0 += t0;
@@ -522,12 +560,16 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
         __syncthreads();
         double esum = 0.0;
         for (int j = tid; j < Mp; j += CT) {
-            double sacc = 0.0;
-            for (int k = 0; k < D; k++) {
-                const double d = s_xs[k] - a.gpr_MtT[(size_t)k * Mp + j];
-                sacc = fma(d, d, sacc);
+            double s0 = 0.0, s1 = 0.0;
+            const double *col = a.gpr_MtT + j;
+            int k = 0;
+            for (; k + 1 < D; k += 2) {
+                const double d0 = s_xs[k] - col[(size_t)k * Mp], d1 = s_xs[k + 1] - col[(size_t)(k + 1) * Mp];
+                s0 = fma(d0, d0, s0);
+                s1 = fma(d1, d1, s1);
             }
-            const double wv = (j < M) ? exp_neg(-0.5 * sacc, s_t32) * a.gpr_coeff[j] : 0.0;
+            if (k < D) { const double d0 = s_xs[k] - col[(size_t)k * Mp]; s0 = fma(d0, d0, s0); }
+            const double wv = (j < M) ? exp_arg(-0.5 * (s0 + s1), s_t32, 1) * a.gpr_coeff[j] : 0.0;
             s_W[j] = wv;
             esum += wv;
         }
@@ -539,13 +581,34 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
             for (int w = 0; w < NW; w++) e += s_red[w];
             a.eatom[i] = e;
         }
-        for (int k = tid; k < D; k += CT) {
-            double acc = 0.0;
-            const double xk = s_xs[k];
-            for (int j = 0; j < M; j++) acc = fma(s_W[j], xk - a.gpr_Mt[(size_t)j * Dp + k], acc);
-            const double v = -a.gpr_itheta[k] * acc;
-            s_du[k] = v;
-            if (a.dEdG_out) a.dEdG_out[(size_t)i * D + k] = v;
+        // dE/dG_k = -(1/theta_k) sum_j W_j (x'_k - m'_jk): thread (k, part), parts split the sparse points
+        {
+            const int D32 = (D + 31) & ~31;
+            const int nparts = max(1, min(CT / D32, 8));
+            double *part = (double *)(smem + L.scratch);  // [nparts][D32]
+            const int p = tid / D32, k = tid - p * D32;
+            if (p < nparts && k < D) {
+                const int chunk = (M + nparts - 1) / nparts;
+                const int j0 = p * chunk, j1 = min(M, j0 + chunk);
+                const double xk = s_xs[k];
+                const double *row = a.gpr_Mt + k;
+                double a0 = 0.0, a1 = 0.0;
+                int j = j0;
+                for (; j + 1 < j1; j += 2) {
+                    a0 = fma(s_W[j], xk - row[(size_t)j * Dp], a0);
+                    a1 = fma(s_W[j + 1], xk - row[(size_t)(j + 1) * Dp], a1);
+                }
+                if (j < j1) a0 = fma(s_W[j], xk - row[(size_t)j * Dp], a0);
+                part[p * D32 + k] = a0 + a1;
+            }
+            __syncthreads();
+            for (int k2 = tid; k2 < D; k2 += CT) {
+                double acc = 0.0;
+                for (int pp = 0; pp < nparts; pp++) acc += part[pp * D32 + k2];
+                const double v = -a.gpr_itheta[k2] * acc;
+                s_du[k2] = v;
+                if (a.dEdG_out) a.dEdG_out[(size_t)i * D + k2] = v;
+            }
         }
         __syncthreads();
     }
@@ -558,26 +621,43 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
             const double dum = im >= 0 ? s_du[im] : 0.0, dwm = im >= 0 ? s_du[im + nsf] : 0.0;
             s_gd[4 * g] = dup + dum; s_gd[4 * g + 1] = dwp + dwm; s_gd[4 * g + 2] = dup - dum; s_gd[4 * g + 3] = dwp - dwm;
         }
-        // radial backward: one thread per neighbour
-        for (int s = tid; s < pcap; s += CT) {
-            double cacc = 0.0;
-            if (s < P) {
-                const double dis = s_r[s], wj = s_w[s];
-                const int nc = s_nc[s];
-                for (int q = 0; q < pl.n_rad; q++) {
-                    const int2 ri = s_radi[q];
-                    const int c = ri.y & 0xffff;
-                    if (c >= nc) continue;
-                    double arg, dgf;
-                    if ((ri.y >> 16) == 1) { const double al = s_radp[q]; arg = -al * dis * dis; dgf = -2.0 * al * dis; }
-                    else { const double d = dis - s_radp[q]; arg = -4.0 * d * d; dgf = -8.0 * d; }
-                    const double dg = exp_neg(arg, s_t32) * fma(dgf, s_fc[c * pcap + s], s_dfc[c * pcap + s]);
-                    cacc = fma(s_du[ri.x] + wj * s_du[ri.x + nsf], dg, cacc);
+        // radial backward: thread (neighbour, part); part p takes the functions q = p, p+nparts, ...
+        {
+            const int nparts = P32 <= CT ? min(CT / P32, 8) : 1;
+            const int stride = P32 <= CT ? P32 : CT;       // neighbours covered per sweep
+            double *part = s_pa;  // [nparts][stride] scratch, <= CT doubles (free until backward_list)
+            const int p = tid / stride, s0 = tid - p * stride;
+            for (int sb = 0; sb < P32; sb += stride) {
+                const int s = sb + s0;
+                double cacc = 0.0;
+                if (p < nparts && s < P) {
+                    const double dis = s_r[s], wj = s_w[s];
+                    const int nc = s_nc[s];
+                    for (int q = p; q < pl.n_rad; q += nparts) {
+                        const int2 ri = s_radi[q];
+                        const int c = ri.y & 0xffff;
+                        if (c >= nc) continue;
+                        double arg, dgf;
+                        if ((ri.y >> 16) == 1) { const double al = s_radp[q]; arg = -al * dis * dis; dgf = -2.0 * al * dis; }
+                        else { const double d = dis - s_radp[q]; arg = -4.0 * d * d; dgf = -8.0 * d; }
+                        const double dg = exp_arg(arg, s_t32, a.exp_clamp) * fma(dgf, s_fc[c * pcap + s], s_dfc[c * pcap + s]);
+                        cacc = fma(s_du[ri.x] + wj * s_du[ri.x + nsf], dg, cacc);
+                    }
                 }
-                cacc *= s_ir[s];
+                if (p < nparts) part[p * stride + s0] = cacc;
+                __syncthreads();
+                if (tid < stride && sb + tid < pcap) {
+                    double v = 0.0;
+                    for (int pp = 0; pp < nparts; pp++) v += part[pp * stride + tid];
+                    const int s2 = sb + tid;
+                    s_acc[s2] = s2 < P ? v * s_ir[s2] : 0.0;
+                    s_acc[pcap + s2] = 0.0; s_acc[2 * pcap + s2] = 0.0; s_acc[3 * pcap + s2] = 0.0;
+                }
+                __syncthreads();
             }
-            s_acc[s] = cacc;
-            s_acc[pcap + s] = 0.0; s_acc[2 * pcap + s] = 0.0; s_acc[3 * pcap + s] = 0.0;
+            for (int s2 = P32 + tid; s2 < pcap; s2 += CT) {
+                s_acc[s2] = 0.0; s_acc[pcap + s2] = 0.0; s_acc[2 * pcap + s2] = 0.0; s_acc[3 * pcap + s2] = 0.0;
+            }
         }
         __syncthreads();
         for (int ch = 0; ch < nchunk; ch++) {
@@ -612,8 +692,10 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
 }
 
 template <int MODE>
-static int launch_mode(cudaStream_t st, const CentreArgs &a) {
-    const size_t sm = centre_smem_bytes(a, MODE);
+static int launch_mode(cudaStream_t st, const CentreArgs &a_in) {
+    CentreArgs a = a_in;
+    a.lay = make_layout(a, MODE);
+    const size_t sm = (size_t)a.lay.total;
     if (sm > 227 * 1024) return -1;
     if (cudaFuncSetAttribute((const void *)k_centre<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
         return -2;

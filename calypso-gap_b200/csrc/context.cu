@@ -74,6 +74,7 @@ struct gapcu_ctx {
     int M = 0, D = 0, Mp = 0, Dp = 0;
     std::vector<double> h_theta, h_mm, h_coeff;  // cached GPR data (C order)
     DBuf<double> d_mm_raw, d_theta_raw, d_coeff_raw, d_Mt, d_MtT, d_mn, d_coeff, d_cmean, d_itheta, d_exp2;
+    int exp_clamp = 0;
     int pipeline = 0;  // 0 auto, 1 split (K2 -> DMMA K3 -> K4), 2 fused single centre kernel
     // ---- structures
     int nstruct = 0, ntot = 0, nbins = 0;
@@ -194,6 +195,17 @@ static int set_sf(gapcu_ctx *c, const std::vector<int> &z, const std::vector<dou
     if (c->plan.n_unknown)
         fprintf(stdout, " Unknown function type in gap_parameters (%d functions left at zero)\n", c->plan.n_unknown);
     c->z = z; c->w = w;
+    {   // can any exponent argument -alpha*(rij^2+rik^2+rjk^2) / -alpha*r^2 / -4 (r-rs)^2 drop below -700?
+        double worst = 0.0;
+        for (size_t i = 0; i < ntype.size(); i++) {
+            const double rc2 = cutoff[i] * cutoff[i];
+            if (ntype[i] == 1) worst = std::max(worst, std::fabs(alpha[i]) * rc2);
+            if (ntype[i] == 2 || ntype[i] == 4) worst = std::max(worst, std::fabs(alpha[i]) * 3.0 * rc2);
+            if (ntype[i] == 3) worst = std::max(worst, 4.0 * std::max(rc2, alpha[i] * alpha[i]));
+            if ((ntype[i] == 1 || ntype[i] == 2 || ntype[i] == 4) && alpha[i] < 0.0) return fail(GAPCU_ELIMIT, "negative symmetry-function alpha is not supported");
+        }
+        c->exp_clamp = worst > 690.0;
+    }
     CU(c->d_itab.ensure(c->plan.itab.size() + 1));
     CU(c->d_dtab.ensure(c->plan.dtab.size() + 1));
     CU(cudaMemcpyAsync(c->d_itab.p, c->plan.itab.data(), sizeof(int) * c->plan.itab.size(), cudaMemcpyHostToDevice, c->stream));
@@ -441,6 +453,7 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
     a.structs = c->d_structs.p; a.sid = c->d_sid.p; a.pos = c->d_pos.p; a.wgt = c->d_wgt.p;
     a.nbr_keys = c->d_keys.p; a.nbr_cnt = c->d_nbr_cnt.p; a.exp2_table = c->d_exp2.p;
     a.ntot = c->ntot; a.cap = c->cap; a.pcap = c->pcap; a.lgrad = lgrad;
+    a.exp_clamp = c->exp_clamp;
     a.G = c->d_G.p; a.dEdG = c->d_dEdG.p; a.dEdG_out = c->d_dEdG.p; a.eatom = c->d_eatom.p;
     a.fpair = c->d_fpair.p; a.gself = c->d_gself.p; a.vir = c->d_vir.p;
     a.gpr_M = c->M; a.gpr_Mp = c->Mp; a.gpr_Dp = c->Dp; a.gpr_Mt = c->d_Mt.p; a.gpr_MtT = c->d_MtT.p;
@@ -450,15 +463,22 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
     // small (it stays in L1/L2 and a separate GEMM launch would be latency bound);
     // large sets go through the tiled DMMA kernel.
     const bool fused = c->pipeline == 2 || (c->pipeline == 0 && (size_t)c->Mp * c->Dp <= 64 * 1024);
-    // shared-memory budget: triplet-list capacity and private accumulator sets
+    // shared-memory budget: triplet-list capacity and private accumulator sets.  Prefer a
+    // footprint that lets 3 CTAs share an SM (the kernel is latency bound: more resident
+    // warps matter more than building the triplet list in one chunk), then 2, then 1.
     {
         const int q = c->pcap * (c->pcap - 1) / 2;
-        a.lcap = std::min(8192, std::max(2048, round_up(q, 32)));
-        a.npa = 8;
-        const size_t limit = 200 * 1024;
+        const int want = std::min(8192, std::max(2048, round_up(q, 32)));
         const int mode = fused ? 2 : 1;
-        if (centre_smem_bytes(a, mode) > limit) a.npa = 1;
-        while (centre_smem_bytes(a, mode) > limit && a.lcap > 1024) a.lcap -= 1024;
+        const size_t targets[2] = {112 * 1024, 220 * 1024};   // 2 CTAs per SM, else 1
+        bool ok = false;
+        for (int t = 0; t < 2 && !ok; t++)
+            for (int pass = 0; pass < 2 && !ok; pass++) {
+                a.npa = pass == 0 ? centre_warps() : 1;
+                for (a.lcap = want; a.lcap >= (t == 0 ? 3072 : 1024); a.lcap -= 512)
+                    if (centre_smem_bytes(a, mode) <= targets[t]) { ok = true; break; }
+            }
+        if (!ok) return fail(GAPCU_ELIMIT, "centre kernel needs more shared memory than an SM has");
     }
     if (fused) {
         if (launch_fused(c->stream, a, &c->launches)) return fail(GAPCU_ELIMIT, "centre kernel needs more shared memory than an SM has");

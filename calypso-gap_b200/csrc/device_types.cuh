@@ -60,10 +60,16 @@ struct ClassTab {
     uint32_t angmask;       // bit b: some class c < b holds angular functions
 };
 
+// shared-memory layout of the centre kernel (byte offsets), computed on the host
+struct SmemLayout {
+    int t32, t2, galpha, gd, x, r, ir, w, fc, dfc, gw, sG, sdu, xs, sW, acc, red, S, scratch, ctl, rad, nc, total;
+};
+
 // Everything the per-centre kernel needs.
 struct CentreArgs {
     PlanDev plan;
     ClassTab cls;
+    SmemLayout lay;
     const StructDev *structs;
     const int *sid;             // [NT] structure of each atom
     const double *pos;          // [3][NT] SoA
@@ -75,6 +81,7 @@ struct CentreArgs {
     int lcap;                   // triplet-list capacity per chunk
     int npa;                    // private accumulator sets in backward: NW, or 1 (= shared + atomics)
     int lgrad;
+    int exp_clamp;              // 1: exponent arguments may fall below -700 and are clamped
     double *G;                  // [NT][D]   descriptors out (forward / fused; may be null in fused)
     const double *dEdG;         // [NT][D]   backward in (MODE_BWD)
     double *dEdG_out;           // [NT][D]   fused: dE/dG out (may be null)

@@ -18,6 +18,7 @@ void launch_neighbor_build(cudaStream_t st, const StructDev *structs, const int 
 
 // centre.cu  (mode: 0 forward, 1 backward, 2 fused forward + GPR + backward)
 size_t centre_smem_bytes(const CentreArgs &a, int mode);
+int centre_warps();
 int launch_forward(cudaStream_t st, const CentreArgs &a, long *launches);
 int launch_backward(cudaStream_t st, const CentreArgs &a, long *launches);
 int launch_fused(cudaStream_t st, const CentreArgs &a, long *launches);
