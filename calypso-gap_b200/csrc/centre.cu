@@ -67,22 +67,23 @@ static SmemLayout make_layout(const CentreArgs &a, int mode) {
     L.dfc = bwd ? take(8 * a.plan.ncls * pcap) : 0;
     L.sG = fused ? take(8 * D) : 0;
     L.sdu = bwd ? take(8 * D) : 0;
-    L.acc = bwd ? take(8 * 4 * pcap) : 0;
+    L.acc = bwd ? take(8 * 3 * pcap) : 0;
     L.red = take(8 * NW * 16);
     L.S = take(4 * (a.lcap + 32));
     // scratch region, three lives: [U | gw] while lists are built and the forward runs,
     // [part | xs | W] during the in-CTA GPR, [private accumulators] during the backward
     const long scr_u = ((4l * (a.lcap + NW * 32 + 32) + 15) & ~15l);
     const long scr_fwd = scr_u + (fwd ? 8l * NW * D : 0);
-    const long scr_gpr = fused ? 8l * (CT + D + a.gpr_Mp + 8) : 0;
-    const long scr_pa = (bwd && a.npa > 1) ? 8l * a.npa * 4 * pcap : 8l * CT;
+    const long gpr_part = 8l * NW * (a.gpr_Mp > D ? a.gpr_Mp : D);
+    const long scr_gpr = fused ? gpr_part + 8l * (D + a.gpr_Mp + 8) : 0;
+    const long scr_pa = (bwd && a.npa > 1) ? 8l * a.npa * 3 * pcap : 8l * CT;
     long scr = scr_fwd > scr_pa ? scr_fwd : scr_pa;
     if (scr_gpr > scr) scr = scr_gpr;
     L.scratch = take(scr);
     L.gw = L.scratch + (int)scr_u;
-    L.xs = L.scratch + 8 * CT;
+    L.xs = L.scratch + (int)gpr_part;
     L.sW = L.xs + 8 * ((D + 1) & ~1);
-    L.ctl = take(4 * 1024);
+    L.ctl = take(4 * 512);
     L.rad = take(16 * (a.plan.n_rad + 1));
     L.nc = take(pcap);
     L.total = o;
@@ -105,7 +106,7 @@ struct Ctl {
     int obp[MAXC_DEV + 2];      // first batch of order slot o
     int TB, nkept;
 };
-static_assert(sizeof(Ctl) <= 4 * 1024, "Ctl does not fit");
+static_assert(sizeof(Ctl) <= 4 * 512, "Ctl does not fit");
 
 // exp(x), x <= 0; clamp only when the potential can produce arguments below -700
 __device__ __forceinline__ double exp_arg(double x, const double *T32, int clamp) {
@@ -146,10 +147,10 @@ __device__ __forceinline__ void tri_decode(int q, int &a, int &b) {
     a = q - bb * (bb - 1) / 2;
 }
 
-// add four values to a [4][pcap] accumulator at index idx.  Private (per warp) set:
-// lanes that hit the same idx take turns in lane order (deterministic, no atomics).
-// Shared set (very long neighbour lists only): shared-memory atomics.
-__device__ __forceinline__ void scatter4(double *pa, int pcap, int idx, double v0, double v1, double v2, double v3,
+// add a 3-vector to a [3][pcap] accumulator at index idx.  Private (per warp) set: lanes
+// that hit the same idx take turns in lane order (deterministic, no atomics).  Shared set
+// (very long neighbour lists only): shared-memory atomics.
+__device__ __forceinline__ void scatter3(double *pa, int pcap, int idx, double v0, double v1, double v2,
                                          unsigned amask, unsigned ltmask, bool priv) {
     if (priv) {
         const unsigned peers = __match_any_sync(amask, idx);
@@ -160,7 +161,6 @@ __device__ __forceinline__ void scatter4(double *pa, int pcap, int idx, double v
                 pa[idx] += v0;
                 pa[pcap + idx] += v1;
                 pa[2 * pcap + idx] += v2;
-                pa[3 * pcap + idx] += v3;
             }
             __syncwarp(amask);
         }
@@ -168,13 +168,11 @@ __device__ __forceinline__ void scatter4(double *pa, int pcap, int idx, double v
         atomicAdd(&pa[idx], v0);
         atomicAdd(&pa[pcap + idx], v1);
         atomicAdd(&pa[2 * pcap + idx], v2);
-        atomicAdd(&pa[3 * pcap + idx], v3);
     }
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
+__device__ __forceinline__ void process_centre(const CentreArgs &a, const int i, unsigned char *smem) {
     constexpr bool FWD = MODE != MODE_BWD, BWD = MODE != MODE_FWD, FUSED = MODE == MODE_FUSED;
     const PlanDev &pl = a.plan;
     const int ncls = pl.ncls, D = pl.D, nsf = pl.nsf, pcap = a.pcap, lcap = a.lcap;
@@ -194,17 +192,16 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
     double *s_du = (double *)(smem + L.sdu);     // dE/dG of this centre
     double *s_xs = (double *)(smem + L.xs);
     double *s_W = (double *)(smem + L.sW);
-    double *s_acc = (double *)(smem + L.acc);    // [4][pcap]: A, Vx, Vy, Vz
+    double *s_acc = (double *)(smem + L.acc);    // [3][pcap]: dE_i/dx of every neighbour slot
     double *s_red = (double *)(smem + L.red);
     uint32_t *s_S = (uint32_t *)(smem + L.S);
     uint32_t *s_U = (uint32_t *)(smem + L.scratch);
-    double *s_pa = (double *)(smem + L.scratch);  // [NW][4][pcap] (aliases U; live only in backward phase B)
+    double *s_pa = (double *)(smem + L.scratch);  // [NW][3][pcap] (aliases U; live only in backward phase B)
     Ctl *ctl = (Ctl *)(smem + L.ctl);
     int2 *s_radi = (int2 *)(smem + L.rad);        // per radial function: (ii, cls | type<<16)
     double *s_radp = (double *)(smem + L.rad + 8 * (pl.n_rad + 1));
     unsigned char *s_nc = smem + L.nc;
 
-    const int i = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned ltmask = (1u << lane) - 1u;
     const int P = a.nbr_cnt[i];
@@ -339,21 +336,31 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
         }
         if (lane == 0) ctl->cntw[wid] = cnt;
         __syncthreads();
-        if (tid == 0) {
-            int off = 0, bp = 0, kept = 0;
-            for (int o = 0; o < ncls; o++) {
-                const int v = ncls - o;
-                int t = 0;
-                for (int w = 0; w < NW; w++) { ctl->basew[w][v] = off + t; t += ctl->hw[w][v]; }
-                ctl->tot[v] = t;
-                ctl->obase[o] = off; ctl->ocnt[o] = t; ctl->obq[o] = (t + 31) >> 5; ctl->obp[o] = bp;
-                off += t; bp += (t + 31) >> 5; kept += t;
+        if (wid == 0) {
+            // lane o <-> bucket v = ncls - o (heavy buckets first); totals over warps, then an
+            // exclusive scan over the lanes gives every bucket its place in S
+            const int o = lane, v = ncls - lane;
+            int t = 0;
+            if (o < ncls)
+                for (int w = 0; w < NW; w++) { const int h = ctl->hw[w][v]; ctl->basew[w][v] = t; t += h; }
+            const int nb = (t + 31) >> 5;
+            int off = t, bp = nb;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int yo = __shfl_up_sync(0xffffffffu, off, d), yb = __shfl_up_sync(0xffffffffu, bp, d);
+                if (lane >= d) { off += yo; bp += yb; }
             }
-            ctl->obp[ncls] = bp; ctl->TB = bp; ctl->nkept = kept;
-            int pre = 0;
-            for (int c = ncls - 1; c >= 0; c--) { pre += ctl->tot[c + 1]; ctl->npre[c] = pre; }
-            if (count_work) {
-                wk_trip += kept;
+            // off/bp are inclusive sums over order slots 0..o
+            if (o < ncls) {
+                ctl->tot[v] = t;
+                ctl->obase[o] = off - t; ctl->ocnt[o] = t; ctl->obq[o] = nb; ctl->obp[o] = bp - nb;
+                for (int w = 0; w < NW; w++) ctl->basew[w][v] += off - t;
+                ctl->npre[v - 1] = off;   // items with bucket > v-1, i.e. bucket >= v: slots 0..o
+            }
+            if (o == ncls - 1 || (ncls == 0 && o == 0)) { ctl->obp[ncls] = bp; ctl->TB = bp; ctl->nkept = off; }
+            __syncwarp();
+            if (count_work && lane == 0) {
+                wk_trip += ctl->nkept;
                 for (int c = 0; c < ncls; c++) {
                     const int g0 = a.cls.grp_begin[c], g1 = a.cls.grp_begin[c + 1];
                     if (g1 > g0) {
@@ -387,10 +394,13 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
 
     // ---- 4: forward over the sorted list ----------------------------------------------
     auto forward_list = [&]() {
+        int rot = 0;  // items dealt so far: the next class continues the round robin where this one stopped
         for (int c = 0; c < ncls; c++) {
             const int g0 = a.cls.grp_begin[c], g1 = a.cls.grp_begin[c + 1];
             const int n_c = ctl->npre[c];
             if (g0 == g1 || n_c == 0) continue;
+            const int myrank = (tid - rot + CT) % CT;   // this thread's position in the deal for class c
+            rot = (rot + n_c) % CT;
             const double pirc = a.cls.pirc[c];
             const double *fcc = s_fc + c * pcap;
             for (int gb = g0; gb < g1; gb += MAXG) {
@@ -398,7 +408,7 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
                 double acc[MAXG][4];
 #pragma unroll
                 for (int g = 0; g < MAXG; g++) acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.0;
-                for (int t = tid; t < n_c; t += CT) {
+                for (int t = myrank; t < n_c; t += CT) {
                     const uint32_t it = s_S[t];
                     const int ra = it & 1023, rb = (it >> 10) & 1023;
                     const double rjk2 = pair_dist2(s_x[ra], s_x[pcap + ra], s_x[2 * pcap + ra], s_x[rb], s_x[pcap + rb],
@@ -424,7 +434,7 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
                         }
                     }
                 }
-                if ((wid << 5) < n_c) {
+                if (__any_sync(0xffffffffu, myrank < n_c)) {
 #pragma unroll
                     for (int g = 0; g < MAXG; g++) {
                         if (g < ng) {
@@ -448,14 +458,18 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
     // ---- 6: backward over the sorted list -----------------------------------------------
     auto backward_list = [&]() {
         const bool priv = a.npa > 1;
-        double *pa = priv ? s_pa + (size_t)wid * 4 * pcap : s_acc;
+        double *pa = priv ? s_pa + (size_t)wid * 3 * pcap : s_acc;
         if (priv) {
-            for (int t = lane; t < 4 * pcap; t += 32) pa[t] = 0.0;
+            for (int t = lane; t < 3 * pcap; t += 32) pa[t] = 0.0;
             __syncwarp();
         }
         const int TB = ctl->TB;
         int o = 0;
-        for (int g = wid; g < TB; g += NW) {
+        // batches are ordered heavy bucket first; deal them 0..NW-1, NW-1..0, 0..NW-1, ... so that
+        // every warp gets a similar mix (fixed assignment: keeps the summation order reproducible)
+        for (int round = 0; round * NW < TB; round++) {
+            const int g = round * NW + ((round & 1) ? NW - 1 - wid : wid);
+            if (g >= TB) continue;
             while (o + 1 < ncls && g >= ctl->obp[o + 1]) o++;
             const int v = ncls - o, q = g - ctl->obp[o], Qb = ctl->obq[o], n = ctl->ocnt[o];
             const int idx = lane * Qb + q;  // lanes far apart in the list -> mostly distinct rows
@@ -505,15 +519,17 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
             }
             // dE/dx_j = (gij+gjk) d_j - gjk d_k ; dE/dx_k = (gik+gjk) d_k - gjk d_j
             const double gij = cij * ira, gik = cik * irb, gjk = cjk * irjk;
-            scatter4(pa, pcap, ra, gij + gjk, gjk * (xb - xi), gjk * (yb - yi), gjk * (zb - zi), am, ltmask, priv);
-            scatter4(pa, pcap, rb, gik + gjk, gjk * (xa - xi), gjk * (ya - yi), gjk * (za - zi), am, ltmask, priv);
+            const double dxa = xa - xi, dya = ya - yi, dza = za - zi, dxb = xb - xi, dyb = yb - yi, dzb = zb - zi;
+            const double ga = gij + gjk, gb = gik + gjk;
+            scatter3(pa, pcap, ra, fma(ga, dxa, -gjk * dxb), fma(ga, dya, -gjk * dyb), fma(ga, dza, -gjk * dzb), am, ltmask, priv);
+            scatter3(pa, pcap, rb, fma(gb, dxb, -gjk * dxa), fma(gb, dyb, -gjk * dya), fma(gb, dzb, -gjk * dza), am, ltmask, priv);
         }
         __syncthreads();
         if (priv) {
-            for (int t = tid; t < 4 * pcap; t += CT) {
+            for (int t = tid; t < 3 * pcap; t += CT) {
                 double v = 0.0;
 #pragma unroll
-                for (int w = 0; w < NW; w++) v += s_pa[(size_t)w * 4 * pcap + t];
+                for (int w = 0; w < NW; w++) v += s_pa[(size_t)w * 3 * pcap + t];
                 s_acc[t] += v;
             }
             __syncthreads();
@@ -558,18 +574,24 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
         const int M = a.gpr_M, Mp = a.gpr_Mp, Dp = a.gpr_Dp;
         for (int k = tid; k < D; k += CT) s_xs[k] = (s_G[k] - a.gpr_cmean[k]) * a.gpr_itheta[k];
         __syncthreads();
+        // squared distances: warp w sums its slab of descriptor components for every sparse point
+        double *part = (double *)(smem + L.scratch);          // [NW][Mp] partial sums (gw/U are dead by now)
+        {
+            const int kslab = (D + NW - 1) / NW, k0 = wid * kslab, k1 = min(D, k0 + kslab);
+            for (int j = lane; j < Mp; j += 32) {
+                double s0 = 0.0;
+                const double *col = a.gpr_MtT + j;
+                for (int k = k0; k < k1; k++) { const double d0 = s_xs[k] - col[(size_t)k * Mp]; s0 = fma(d0, d0, s0); }
+                part[wid * Mp + j] = s0;
+            }
+        }
+        __syncthreads();
         double esum = 0.0;
         for (int j = tid; j < Mp; j += CT) {
-            double s0 = 0.0, s1 = 0.0;
-            const double *col = a.gpr_MtT + j;
-            int k = 0;
-            for (; k + 1 < D; k += 2) {
-                const double d0 = s_xs[k] - col[(size_t)k * Mp], d1 = s_xs[k + 1] - col[(size_t)(k + 1) * Mp];
-                s0 = fma(d0, d0, s0);
-                s1 = fma(d1, d1, s1);
-            }
-            if (k < D) { const double d0 = s_xs[k] - col[(size_t)k * Mp]; s0 = fma(d0, d0, s0); }
-            const double wv = (j < M) ? exp_arg(-0.5 * (s0 + s1), s_t32, 1) * a.gpr_coeff[j] : 0.0;
+            double sacc = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) sacc += part[w * Mp + j];
+            const double wv = (j < M) ? exp_arg(-0.5 * sacc, s_t32, 1) * a.gpr_coeff[j] : 0.0;
             s_W[j] = wv;
             esum += wv;
         }
@@ -581,34 +603,25 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
             for (int w = 0; w < NW; w++) e += s_red[w];
             a.eatom[i] = e;
         }
-        // dE/dG_k = -(1/theta_k) sum_j W_j (x'_k - m'_jk): thread (k, part), parts split the sparse points
+        // dE/dG_k = -(1/theta_k) sum_j W_j (x'_k - m'_jk): warp w takes a slab of sparse points, lanes over k
         {
-            const int D32 = (D + 31) & ~31;
-            const int nparts = max(1, min(CT / D32, 8));
-            double *part = (double *)(smem + L.scratch);  // [nparts][D32]
-            const int p = tid / D32, k = tid - p * D32;
-            if (p < nparts && k < D) {
-                const int chunk = (M + nparts - 1) / nparts;
-                const int j0 = p * chunk, j1 = min(M, j0 + chunk);
+            const int jslab = (M + NW - 1) / NW, j0 = wid * jslab, j1 = min(M, j0 + jslab);
+            for (int k = lane; k < D; k += 32) {
                 const double xk = s_xs[k];
                 const double *row = a.gpr_Mt + k;
-                double a0 = 0.0, a1 = 0.0;
-                int j = j0;
-                for (; j + 1 < j1; j += 2) {
-                    a0 = fma(s_W[j], xk - row[(size_t)j * Dp], a0);
-                    a1 = fma(s_W[j + 1], xk - row[(size_t)(j + 1) * Dp], a1);
-                }
-                if (j < j1) a0 = fma(s_W[j], xk - row[(size_t)j * Dp], a0);
-                part[p * D32 + k] = a0 + a1;
+                double a0 = 0.0;
+                for (int j = j0; j < j1; j++) a0 = fma(s_W[j], xk - row[(size_t)j * Dp], a0);
+                part[wid * D + k] = a0;       // W was consumed into registers/s_W; part is reused with stride D
             }
-            __syncthreads();
-            for (int k2 = tid; k2 < D; k2 += CT) {
-                double acc = 0.0;
-                for (int pp = 0; pp < nparts; pp++) acc += part[pp * D32 + k2];
-                const double v = -a.gpr_itheta[k2] * acc;
-                s_du[k2] = v;
-                if (a.dEdG_out) a.dEdG_out[(size_t)i * D + k2] = v;
-            }
+        }
+        __syncthreads();
+        for (int k2 = tid; k2 < D; k2 += CT) {
+            double acc = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) acc += part[w * D + k2];
+            const double v = -a.gpr_itheta[k2] * acc;
+            s_du[k2] = v;
+            if (a.dEdG_out) a.dEdG_out[(size_t)i * D + k2] = v;
         }
         __syncthreads();
     }
@@ -650,13 +663,16 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
                     double v = 0.0;
                     for (int pp = 0; pp < nparts; pp++) v += part[pp * stride + tid];
                     const int s2 = sb + tid;
-                    s_acc[s2] = s2 < P ? v * s_ir[s2] : 0.0;
-                    s_acc[pcap + s2] = 0.0; s_acc[2 * pcap + s2] = 0.0; s_acc[3 * pcap + s2] = 0.0;
+                    const bool in = s2 < P;
+                    const double g = in ? v * s_ir[s2] : 0.0;     // (dE/dr) / r
+                    s_acc[s2] = in ? g * (s_x[s2] - xi) : 0.0;
+                    s_acc[pcap + s2] = in ? g * (s_x[pcap + s2] - yi) : 0.0;
+                    s_acc[2 * pcap + s2] = in ? g * (s_x[2 * pcap + s2] - zi) : 0.0;
                 }
                 __syncthreads();
             }
             for (int s2 = P32 + tid; s2 < pcap; s2 += CT) {
-                s_acc[s2] = 0.0; s_acc[pcap + s2] = 0.0; s_acc[2 * pcap + s2] = 0.0; s_acc[3 * pcap + s2] = 0.0;
+                s_acc[s2] = 0.0; s_acc[pcap + s2] = 0.0; s_acc[2 * pcap + s2] = 0.0;
             }
         }
         __syncthreads();
@@ -668,8 +684,7 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
         double acc9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // gself xyz, vir xx xy xz yy yz zz
         for (int s = tid; s < P; s += CT) {
             const double dx = s_x[s] - xi, dy = s_x[pcap + s] - yi, dz = s_x[2 * pcap + s] - zi;
-            const double A = s_acc[s];
-            const double gx = A * dx - s_acc[pcap + s], gy = A * dy - s_acc[2 * pcap + s], gz = A * dz - s_acc[3 * pcap + s];
+            const double gx = s_acc[s], gy = s_acc[pcap + s], gz = s_acc[2 * pcap + s];
             double *fp = a.fpair + ((size_t)i * a.cap + s) * 3;
             fp[0] = gx; fp[1] = gy; fp[2] = gz;
             acc9[0] -= gx; acc9[1] -= gy; acc9[2] -= gz;
@@ -691,6 +706,23 @@ __global__ void __launch_bounds__(CT, 2) k_centre(const CentreArgs a) {
     }
 }
 
+// Persistent CTAs: as many as fit the device, each pulling centre atoms from a queue
+// ordered by descending neighbour count (longest first), so that 1000 centres on 296
+// resident CTAs do not cost four full waves and the heavy centres do not form the tail.
+template <int MODE>
+__global__ void __launch_bounds__(CT, 3) k_centre(const CentreArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_next;
+    for (;;) {
+        __syncthreads();  // everybody is done with the previous centre's shared memory
+        if (threadIdx.x == 0) s_next = atomicAdd(&a.flags->queue[MODE], 1);
+        __syncthreads();
+        const int n = s_next;
+        if (n >= a.ntot) break;
+        process_centre<MODE>(a, a.order ? a.order[n] : n, smem);
+    }
+}
+
 template <int MODE>
 static int launch_mode(cudaStream_t st, const CentreArgs &a_in) {
     CentreArgs a = a_in;
@@ -699,7 +731,12 @@ static int launch_mode(cudaStream_t st, const CentreArgs &a_in) {
     if (sm > 227 * 1024) return -1;
     if (cudaFuncSetAttribute((const void *)k_centre<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
         return -2;
-    k_centre<MODE><<<a.ntot, CT, sm, st>>>(a);
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_centre<MODE>, CT, sm) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int grid = a.ntot < sms * per_sm ? a.ntot : sms * per_sm;
+    k_centre<MODE><<<grid, CT, sm, st>>>(a);
     return 0;
 }
 

@@ -82,7 +82,7 @@ struct gapcu_ctx {
     std::vector<StructDev> h_structs;
     std::vector<int> h_natoms;
     DBuf<StructDev> d_structs;
-    DBuf<int> d_sid, d_arank, d_bin_count, d_bin_start, d_bin_atoms, d_nbr_cnt;
+    DBuf<int> d_sid, d_arank, d_bin_count, d_bin_start, d_bin_atoms, d_nbr_cnt, d_order;
     DBuf<int4> d_abin;
     DBuf<double> d_pos, d_wgt, d_G, d_dEdG, d_eatom, d_fpair, d_gself, d_vir, d_force, d_out8, d_mindis;
     DBuf<uint64_t> d_keys;
@@ -171,7 +171,7 @@ extern "C" void gapcu_ctx_destroy(gapcu_ctx *c) {
     c->d_itab.release(); c->d_dtab.release(); c->d_mm_raw.release(); c->d_theta_raw.release(); c->d_coeff_raw.release();
     c->d_Mt.release(); c->d_MtT.release(); c->d_exp2.release(); c->d_mn.release(); c->d_coeff.release(); c->d_cmean.release(); c->d_itheta.release();
     c->d_structs.release(); c->d_sid.release(); c->d_arank.release(); c->d_bin_count.release(); c->d_bin_start.release();
-    c->d_bin_atoms.release(); c->d_nbr_cnt.release(); c->d_abin.release(); c->d_pos.release(); c->d_wgt.release();
+    c->d_bin_atoms.release(); c->d_nbr_cnt.release(); c->d_order.release(); c->d_abin.release(); c->d_pos.release(); c->d_wgt.release();
     c->d_G.release(); c->d_dEdG.release(); c->d_eatom.release(); c->d_fpair.release(); c->d_gself.release();
     c->d_vir.release(); c->d_force.release(); c->d_out8.release(); c->d_mindis.release(); c->d_keys.release();
     c->d_flags.release(); c->d_flush.release();
@@ -371,7 +371,7 @@ static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, con
     // ---- device buffers
     CU(c->d_structs.ensure(nstruct)); CU(c->d_sid.ensure(NT)); CU(c->d_pos.ensure(3 * NT)); CU(c->d_wgt.ensure(NT));
     CU(c->d_abin.ensure(NT)); CU(c->d_arank.ensure(NT)); CU(c->d_bin_count.ensure(c->nbins + 1));
-    CU(c->d_bin_start.ensure(c->nbins + 2)); CU(c->d_bin_atoms.ensure(NT)); CU(c->d_nbr_cnt.ensure(NT));
+    CU(c->d_bin_start.ensure(c->nbins + 2)); CU(c->d_bin_atoms.ensure(NT)); CU(c->d_nbr_cnt.ensure(NT)); CU(c->d_order.ensure(NT));
     CU(c->d_flags.ensure(1)); CU(c->d_out8.ensure(8 * (size_t)nstruct)); CU(c->d_force.ensure(3 * NT));
     CU(c->d_mindis.ensure(NT));
     CU(cudaMemcpyAsync(c->d_structs.p, hp + o_structs, b_structs, cudaMemcpyHostToDevice, c->stream));
@@ -445,13 +445,15 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
         c->pcap = std::min(c->cap, std::max(32, round_up(c->h_flags.maxcount + 8, 32)));
         c->pcap_known = true;
     }
+    launch_order(c->stream, c->d_nbr_cnt.p, c->ntot, c->d_order.p, &c->launches);
+    CU(cudaGetLastError());
     if (ev) CU(cudaEventRecord(ev[1], c->stream));
     CentreArgs a;
     memset(&a, 0, sizeof a);
     a.plan = c->plan_dev();
     a.cls = c->class_tab();
     a.structs = c->d_structs.p; a.sid = c->d_sid.p; a.pos = c->d_pos.p; a.wgt = c->d_wgt.p;
-    a.nbr_keys = c->d_keys.p; a.nbr_cnt = c->d_nbr_cnt.p; a.exp2_table = c->d_exp2.p;
+    a.nbr_keys = c->d_keys.p; a.nbr_cnt = c->d_nbr_cnt.p; a.order = c->d_order.p; a.exp2_table = c->d_exp2.p;
     a.ntot = c->ntot; a.cap = c->cap; a.pcap = c->pcap; a.lgrad = lgrad;
     a.exp_clamp = c->exp_clamp;
     a.G = c->d_G.p; a.dEdG = c->d_dEdG.p; a.dEdG_out = c->d_dEdG.p; a.eatom = c->d_eatom.p;
@@ -470,12 +472,14 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
         const int q = c->pcap * (c->pcap - 1) / 2;
         const int want = std::min(8192, std::max(2048, round_up(q, 32)));
         const int mode = fused ? 2 : 1;
-        const size_t targets[2] = {112 * 1024, 220 * 1024};   // 2 CTAs per SM, else 1
+        const size_t targets[3] = {74 * 1024, 112 * 1024, 220 * 1024};   // 3, 2, 1 CTAs per SM
+        const int lmin[3] = {3584, 3072, 1024};
         bool ok = false;
-        for (int t = 0; t < 2 && !ok; t++)
+        for (int t = 0; t < 3 && !ok; t++)
             for (int pass = 0; pass < 2 && !ok; pass++) {
+                if (pass == 1 && t < 2) continue;          // the atomics fallback only as a last resort
                 a.npa = pass == 0 ? centre_warps() : 1;
-                for (a.lcap = want; a.lcap >= (t == 0 ? 3072 : 1024); a.lcap -= 512)
+                for (a.lcap = want; a.lcap >= std::min(want, lmin[t]); a.lcap -= 512)
                     if (centre_smem_bytes(a, mode) <= targets[t]) { ok = true; break; }
             }
         if (!ok) return fail(GAPCU_ELIMIT, "centre kernel needs more shared memory than an SM has");

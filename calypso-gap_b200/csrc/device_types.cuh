@@ -34,6 +34,7 @@ struct DevFlags {
     int maxcount;        // largest neighbour count seen
     int too_many;        // some atom exceeds the reference's 1000-neighbour limit
     int close_pairs;     // pairs closer than 0.5 A (reference prints a warning)
+    int queue[4];        // work-queue heads of the persistent centre kernels (one per mode)
     unsigned long long work[10];  // see gapcu_ctx_work_counters
 };
 
@@ -76,6 +77,7 @@ struct CentreArgs {
     const double *wgt;          // [NT] species weight
     const uint64_t *nbr_keys;   // [NT][cap]
     const int *nbr_cnt;         // [NT]
+    const int *order;           // [NT] centres by descending neighbour count (null: natural order)
     const double *exp2_table;   // [32] 2^(j/32)
     int ntot, cap, pcap;        // pcap: shared-memory neighbour capacity (>= max count)
     int lcap;                   // triplet-list capacity per chunk

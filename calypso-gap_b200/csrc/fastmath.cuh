@@ -86,23 +86,16 @@ GAPCU_HD void sincos_0pi(double y, double *sn, double *cs) {
     const double q = rint(y * KC(7));
     double t = fma(q, KC(8), y);                         // q*hi exact
     t = fma(q, KC(9), t);
-    const double z = t * t;
-    double s = fma(z, KC(10), KC(11));
-    s = fma(s, z, KC(12));
-    s = fma(s, z, KC(13));
-    s = fma(s, z, KC(14));
-    s = fma(s, z, KC(15));
-    s = fma(s, z, KC(16));
-    s = fma(s, z, KC(17));
+    const double z = t * t, z2 = z * z, z4 = z2 * z2;
+    // Estrin evaluation: four independent pairs per polynomial instead of one 8-long chain
+    const double s01 = fma(z, KC(16), KC(17)), s23 = fma(z, KC(14), KC(15));
+    const double s45 = fma(z, KC(12), KC(13)), s67 = fma(z, KC(10), KC(11));
+    double s = fma(z4, fma(z2, s67, s45), fma(z2, s23, s01));
     s = fma(s * z, t, t);                                // sin(t)
-    double c = fma(z, KC(18), KC(19));
-    c = fma(c, z, KC(20));
-    c = fma(c, z, KC(21));
-    c = fma(c, z, KC(22));
-    c = fma(c, z, KC(23));
-    c = fma(c, z, KC(24));
-    c = fma(c, z, -0.5);
-    c = fma(c, z, 1.0);                                  // cos(t)
+    const double c01 = fma(z, -0.5, 1.0), c23 = fma(z, KC(23), KC(24));
+    const double c45 = fma(z, KC(21), KC(22)), c67 = fma(z, KC(19), KC(20));
+    const double c03 = fma(z2, c23, c01), c47 = fma(z2, c67, c45);
+    double c = fma(z4, fma(z4, KC(18), c47), c03);       // cos(t): degree 8 in z
     // q = 0: (s, c); q = 1: (c, -s); q = 2: (-s, -c)
     const bool odd = (q == 1.0);
     const bool two = (q == 2.0);

@@ -16,6 +16,8 @@ void launch_neighbor_build(cudaStream_t st, const StructDev *structs, const int 
                            int *bin_count, int *bin_start, int *bin_atoms, uint64_t *nbr_keys, int *nbr_cnt,
                            double *min_dis, DevFlags *flags, long *launches);
 
+void launch_order(cudaStream_t st, const int *nbr_cnt, int ntot, int *order, long *launches);
+
 // centre.cu  (mode: 0 forward, 1 backward, 2 fused forward + GPR + backward)
 size_t centre_smem_bytes(const CentreArgs &a, int mode);
 int centre_warps();

@@ -182,6 +182,44 @@ k_neigh(const StructDev *structs, const int *sid, const double *pos, const int4 
     for (int p = tid; p < count; p += NB_THREADS) nbr_keys[(size_t)i * cap + p] = keys[p];
 }
 
+// Centres ordered by descending neighbour count (counting sort; single CTA).  The order
+// only schedules the persistent centre kernel; results do not depend on it.
+__global__ void __launch_bounds__(1024) k_order_by_count(const int *nbr_cnt, int ntot, int *order) {
+    __shared__ int hist[NB_MAXLIST + 2];
+    __shared__ int wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int t = tid; t < NB_MAXLIST + 2; t += 1024) hist[t] = 0;
+    __syncthreads();
+    for (int i = tid; i < ntot; i += 1024) atomicAdd(&hist[NB_MAXLIST - min(max(nbr_cnt[i], 0), NB_MAXLIST)], 1);
+    __syncthreads();
+    // exclusive scan of hist (1026 entries, one per thread + tail), key 0 = largest count
+    int v = (tid < NB_MAXLIST + 1) ? hist[tid] : 0, x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wsum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int s = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+        wsum[lane] = s;
+    }
+    __syncthreads();
+    const int excl = (wid ? wsum[wid - 1] : 0) + x - v;
+    __syncthreads();
+    if (tid < NB_MAXLIST + 1) hist[tid] = excl;
+    __syncthreads();
+    for (int i = tid; i < ntot; i += 1024) {
+        const int key = NB_MAXLIST - min(max(nbr_cnt[i], 0), NB_MAXLIST);
+        order[atomicAdd(&hist[key], 1)] = i;
+    }
+}
+
+void launch_order(cudaStream_t st, const int *nbr_cnt, int ntot, int *order, long *launches) {
+    k_order_by_count<<<1, 1024, 0, st>>>(nbr_cnt, ntot, order);
+    if (launches) *launches += 1;
+}
+
 // ---- host launchers ------------------------------------------------------
 void launch_neighbor_build(cudaStream_t st, const StructDev *structs, const int *sid, const double *pos,
                            int ntot, int nbins_total, double rcut, int cap, int4 *abin, int *arank,
