@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(CT, 3) k_centre(const CentreArgs a) {
         if (threadIdx.x == 0) s_next = atomicAdd(&a.flags->queue[MODE], 1);
         __syncthreads();
         const int n = s_next;
-        if (n >= a.ntot) break;
+        if (n >= (a.n_centres ? *a.n_centres : a.ntot)) break;
         process_centre<MODE>(a, a.order ? a.order[n] : n, smem);
     }
 }

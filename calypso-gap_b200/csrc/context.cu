@@ -8,6 +8,7 @@
 //   K4  desc.cu     backward: per-slot gradients, centre gradient, strs contraction
 //   K5  gather.cu   force gather (mirror-pair lookup) + per-structure E / stress
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <sys/stat.h>
 
 #include <algorithm>
@@ -88,6 +89,12 @@ struct gapcu_ctx {
     DBuf<uint64_t> d_keys;
     DBuf<DevFlags> d_flags;
     DBuf<unsigned char> d_flush;
+    // ---- spatial decomposition over ranks + NCCL (loaded lazily with dlopen)
+    DomainDev dom = {0, {1, 1, 1}, {0, 0, 0}, {0.0, 0.0, 0.0}};
+    DBuf<unsigned char> d_role;
+    DBuf<int> d_active;
+    void *nccl_comm = nullptr;
+    int nccl_ranks = 1;
     int cap = 0, pcap = 0, last_ntot = -1;
     bool pcap_known = false;
     int last_lgrad = 1;
@@ -174,7 +181,7 @@ extern "C" void gapcu_ctx_destroy(gapcu_ctx *c) {
     c->d_bin_atoms.release(); c->d_nbr_cnt.release(); c->d_order.release(); c->d_abin.release(); c->d_pos.release(); c->d_wgt.release();
     c->d_G.release(); c->d_dEdG.release(); c->d_eatom.release(); c->d_fpair.release(); c->d_gself.release();
     c->d_vir.release(); c->d_force.release(); c->d_out8.release(); c->d_mindis.release(); c->d_keys.release();
-    c->d_flags.release(); c->d_flush.release();
+    c->d_flags.release(); c->d_flush.release(); c->d_role.release(); c->d_active.release();
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->stage_ev_init) for (auto &e : c->stage_ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -373,7 +380,7 @@ static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, con
     CU(c->d_abin.ensure(NT)); CU(c->d_arank.ensure(NT)); CU(c->d_bin_count.ensure(c->nbins + 1));
     CU(c->d_bin_start.ensure(c->nbins + 2)); CU(c->d_bin_atoms.ensure(NT)); CU(c->d_nbr_cnt.ensure(NT)); CU(c->d_order.ensure(NT));
     CU(c->d_flags.ensure(1)); CU(c->d_out8.ensure(8 * (size_t)nstruct)); CU(c->d_force.ensure(3 * NT));
-    CU(c->d_mindis.ensure(NT));
+    CU(c->d_mindis.ensure(NT)); CU(c->d_role.ensure(NT)); CU(c->d_active.ensure(NT));
     CU(cudaMemcpyAsync(c->d_structs.p, hp + o_structs, b_structs, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_sid.p, h_sid, b_sid, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_pos.p, h_pos, b_pos, cudaMemcpyHostToDevice, c->stream));
@@ -394,6 +401,79 @@ extern "C" int gapcu_ctx_set_structures(gapcu_ctx *c, int nstruct, const int *na
 }
 
 // ---------------------------------------------------------------------------
+// NCCL, resolved at run time (the library has no link-time dependency on it)
+// ---------------------------------------------------------------------------
+namespace {
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    int (*GetUniqueId)(NcclId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+} g_nccl;
+
+int load_nccl() {
+    if (g_nccl.ok) return 0;
+    void *h = nullptr;
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) if ((h = dlopen(name, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!h) return fail(GAPCU_ECUDA, std::string("cannot load NCCL: ") + dlerror());
+    g_nccl.GetUniqueId = (int (*)(NcclId *))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void **, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) return fail(GAPCU_ECUDA, "NCCL symbols missing");
+    g_nccl.ok = true;
+    return 0;
+}
+}  // namespace
+
+static int nccl_allreduce_sum(gapcu_ctx *c, double *buf, size_t count) {
+    const int r = g_nccl.AllReduce(buf, buf, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl_comm, c->stream);
+    if (r) return fail(GAPCU_ECUDA, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+    return 0;
+}
+
+extern "C" int gapcu_nccl_unique_id(char *out128) {
+    int rc = load_nccl();
+    if (rc) return rc;
+    NcclId id;
+    const int r = g_nccl.GetUniqueId(&id);
+    if (r) return fail(GAPCU_ECUDA, "ncclGetUniqueId failed");
+    memcpy(out128, id.internal, 128);
+    return 0;
+}
+
+extern "C" int gapcu_ctx_nccl_init(gapcu_ctx *c, int nranks, int rank, const char *id128) {
+    if (!c || nranks < 1 || rank < 0 || rank >= nranks) return fail(GAPCU_EARG, "bad NCCL rank/size");
+    int rc = load_nccl();
+    if (rc) return rc;
+    cudaSetDevice(c->device);
+    NcclId id;
+    memcpy(id.internal, id128, 128);
+    void *comm = nullptr;
+    const int r = g_nccl.CommInitRank(&comm, nranks, id, rank);
+    if (r) return fail(GAPCU_ECUDA, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+    c->nccl_comm = comm;
+    c->nccl_ranks = nranks;
+    return 0;
+}
+
+extern "C" int gapcu_ctx_set_domain(gapcu_ctx *c, int g0, int g1, int g2, int m0, int m1, int m2) {
+    if (!c) return fail(GAPCU_EARG, "null context");
+    if (g0 < 1 || g1 < 1 || g2 < 1) return fail(GAPCU_EARG, "bad domain grid");
+    if (g0 * g1 * g2 == 1) { c->dom.enabled = 0; return 0; }
+    if (m0 < 0 || m0 >= g0 || m1 < 0 || m1 >= g1 || m2 < 0 || m2 >= g2) return fail(GAPCU_EARG, "brick outside the grid");
+    c->dom.enabled = 1;
+    c->dom.grid[0] = g0; c->dom.grid[1] = g1; c->dom.grid[2] = g2;
+    c->dom.mine[0] = m0; c->dom.mine[1] = m1; c->dom.mine[2] = m2;
+    c->pcap_known = false;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
 // compute
 // ---------------------------------------------------------------------------
 static int ensure_work_buffers(gapcu_ctx *c) {
@@ -408,7 +488,7 @@ static int run_neighbors(gapcu_ctx *c, bool with_keys, bool with_min) {
     launch_neighbor_build(c->stream, c->d_structs.p, c->d_sid.p, c->d_pos.p, c->ntot, c->nbins, c->rcut, c->cap,
                           c->d_abin.p, c->d_arank.p, c->d_bin_count.p, c->d_bin_start.p, c->d_bin_atoms.p,
                           with_keys ? c->d_keys.p : nullptr, c->d_nbr_cnt.p, with_min ? c->d_mindis.p : nullptr,
-                          c->d_flags.p, &c->launches);
+                          c->d_flags.p, c->dom, c->d_role.p, c->d_active.p, &c->launches);
     CU(cudaGetLastError());
     return 0;
 }
@@ -426,6 +506,14 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
     if (c->ntot <= 0) return fail(GAPCU_EARG, "no structures set");
     int rc = ensure_work_buffers(c);
     if (rc) return rc;
+    if (c->dom.enabled) {
+        if (c->nstruct != 1) return fail(GAPCU_EARG, "spatial decomposition works on a single structure");
+        const StructDev &sd = c->h_structs[0];
+        for (int d = 0; d < 3; d++) {
+            const double len = std::sqrt(sd.inv[d] * sd.inv[d] + sd.inv[3 + d] * sd.inv[3 + d] + sd.inv[6 + d] * sd.inv[6 + d]);
+            c->dom.margin[d] = c->rcut * len;   // rcut / interplanar spacing
+        }
+    }
     CU(cudaMemsetAsync(c->d_flags.p, 0, sizeof(DevFlags), c->stream));
     if (ev) CU(cudaEventRecord(ev[0], c->stream));
     if ((rc = run_neighbors(c, true, false))) return rc;
@@ -445,7 +533,7 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
         c->pcap = std::min(c->cap, std::max(32, round_up(c->h_flags.maxcount + 8, 32)));
         c->pcap_known = true;
     }
-    launch_order(c->stream, c->d_nbr_cnt.p, c->ntot, c->d_order.p, &c->launches);
+    launch_order(c->stream, c->d_nbr_cnt.p, c->ntot, c->d_order.p, c->d_role.p, c->d_flags.p, &c->launches);
     CU(cudaGetLastError());
     if (ev) CU(cudaEventRecord(ev[1], c->stream));
     CentreArgs a;
@@ -453,7 +541,7 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
     a.plan = c->plan_dev();
     a.cls = c->class_tab();
     a.structs = c->d_structs.p; a.sid = c->d_sid.p; a.pos = c->d_pos.p; a.wgt = c->d_wgt.p;
-    a.nbr_keys = c->d_keys.p; a.nbr_cnt = c->d_nbr_cnt.p; a.order = c->d_order.p; a.exp2_table = c->d_exp2.p;
+    a.nbr_keys = c->d_keys.p; a.nbr_cnt = c->d_nbr_cnt.p; a.order = c->d_order.p; a.n_centres = &c->d_flags.p->n_centres; a.exp2_table = c->d_exp2.p;
     a.ntot = c->ntot; a.cap = c->cap; a.pcap = c->pcap; a.lgrad = lgrad;
     a.exp_clamp = c->exp_clamp;
     a.G = c->d_G.p; a.dEdG = c->d_dEdG.p; a.dEdG_out = c->d_dEdG.p; a.eatom = c->d_eatom.p;
@@ -506,8 +594,15 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
         if (ev) CU(cudaEventRecord(ev[4], c->stream));
     }
     launch_gather(c->stream, c->d_structs.p, c->nstruct, c->d_sid.p, c->ntot, c->cap, c->d_keys.p, c->d_nbr_cnt.p,
-                  c->d_fpair.p, c->d_gself.p, c->d_vir.p, c->d_eatom.p, lgrad, c->d_force.p, c->d_out8.p, &c->launches);
+                  c->d_fpair.p, c->d_gself.p, c->d_vir.p, c->d_eatom.p, lgrad, c->d_force.p, c->d_out8.p, c->d_role.p,
+                  c->dom.enabled ? c->d_active.p : nullptr, c->d_flags.p, &c->launches);
     CU(cudaGetLastError());
+    if (c->dom.enabled && c->nccl_comm) {
+        // ghost-force return and the (E, stress) partial sums: one sum over ranks each
+        int rc2 = nccl_allreduce_sum(c, c->d_force.p, 3 * (size_t)c->ntot);
+        if (!rc2) rc2 = nccl_allreduce_sum(c, c->d_out8.p, 8 * (size_t)c->nstruct);
+        if (rc2) return rc2;
+    }
     if (ev) CU(cudaEventRecord(ev[5], c->stream));
     c->last_lgrad = lgrad;
     c->computed = true;

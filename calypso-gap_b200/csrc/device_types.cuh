@@ -15,6 +15,18 @@ struct StructDev {
     int atom_off, natoms, bin_off, nbins;
 };
 
+// Spatial decomposition of ONE large structure over ranks: the cell is cut
+// into grid[0] x grid[1] x grid[2] bricks in fractional coordinates; a rank OWNS the atoms of
+// its brick (it evaluates them as centres) and additionally lists the GHOST atoms within rcut
+// of the brick (it needs their neighbour lists to hand back the forces its centres exert on
+// them).  role: 0 = not involved, 1 = ghost, 2 = owned.  Disabled: every atom is owned.
+struct DomainDev {
+    int enabled;
+    int grid[3];
+    int mine[3];
+    double margin[3];   // rcut / interplanar spacing: ghost shell thickness in fractional units
+};
+
 // Neighbour key: canonical (reference) order (j, n1, n2, n3) is plain integer order.
 //   bits 63..32 atom index j (global within the batch), 29..20 n1+512, 19..10 n2+512, 9..0 n3+512
 __host__ __device__ inline uint64_t nbr_key(int j, int n1, int n2, int n3) {
@@ -34,6 +46,8 @@ struct DevFlags {
     int maxcount;        // largest neighbour count seen
     int too_many;        // some atom exceeds the reference's 1000-neighbour limit
     int close_pairs;     // pairs closer than 0.5 A (reference prints a warning)
+    int n_active;        // atoms with role >= 1 (decomposed runs)
+    int n_centres;       // atoms with role == 2
     int queue[4];        // work-queue heads of the persistent centre kernels (one per mode)
     unsigned long long work[10];  // see gapcu_ctx_work_counters
 };
@@ -78,6 +92,7 @@ struct CentreArgs {
     const uint64_t *nbr_keys;   // [NT][cap]
     const int *nbr_cnt;         // [NT]
     const int *order;           // [NT] centres by descending neighbour count (null: natural order)
+    const int *n_centres;       // device count of entries in `order` (null: ntot)
     const double *exp2_table;   // [32] 2^(j/32)
     int ntot, cap, pcap;        // pcap: shared-memory neighbour capacity (>= max count)
     int lcap;                   // triplet-list capacity per chunk

@@ -19,10 +19,13 @@ constexpr double GPA2EVPANG = 6.24219e-3;  // gap_calc.f90:9
 
 __global__ void __launch_bounds__(256)
 k_gather(const StructDev *structs, const int *sid, int ntot, int cap, const uint64_t *nbr_keys,
-         const int *nbr_cnt, const double *fpair, const double *gself, double *force) {
-    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+         const int *nbr_cnt, const double *fpair, const double *gself, double *force,
+         const unsigned char *role, const int *active, const DevFlags *flags) {
+    const int slot_i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (i >= ntot) return;
+    if (slot_i >= (active ? flags->n_active : ntot)) return;
+    const int i = active ? active[slot_i] : slot_i;
+    const bool i_owned = !role || role[i] == 2;
     const StructDev &sd = structs[sid[i]];
     const int il = i - sd.atom_off;
     const int P = min(nbr_cnt[i], cap);
@@ -31,6 +34,8 @@ k_gather(const StructDev *structs, const int *sid, int ntot, int cap, const uint
         int jl, n1, n2, n3;
         nbr_unkey(nbr_keys[(size_t)i * cap + s], jl, n1, n2, n3);
         const int nb = sd.atom_off + jl;
+        const bool nb_owned = !role || role[nb] == 2;      // only this rank's centres have gradients here
+        if (!nb_owned && !i_owned) continue;
         const uint64_t want = nbr_key(il, -n1, -n2, -n3);
         const uint64_t *lst = nbr_keys + (size_t)nb * cap;
         int lo = 0, hi = min(nbr_cnt[nb], cap);
@@ -39,9 +44,11 @@ k_gather(const StructDev *structs, const int *sid, int ntot, int cap, const uint
             if (lst[mid] < want) lo = mid + 1; else hi = mid;
         }
         if (lo < min(nbr_cnt[nb], cap) && lst[lo] == want) {
-            const double *fp = fpair + ((size_t)nb * cap + lo) * 3;
-            gx += fp[0]; gy += fp[1]; gz += fp[2];
-        } else {
+            if (nb_owned) {
+                const double *fp = fpair + ((size_t)nb * cap + lo) * 3;
+                gx += fp[0]; gy += fp[1]; gz += fp[2];
+            }
+        } else if (i_owned) {
             // nb does not list me, so nobody will gather what I exert on nb: push it
             const double *fp = fpair + ((size_t)i * cap + s) * 3;
             atomicAdd(&force[nb], -fp[0]);
@@ -56,22 +63,26 @@ k_gather(const StructDev *structs, const int *sid, int ntot, int cap, const uint
         gz += __shfl_xor_sync(0xffffffffu, gz, o);
     }
     if (lane == 0) {
-        atomicAdd(&force[i], -(gself[(size_t)i * 3] + gx));
-        atomicAdd(&force[ntot + i], -(gself[(size_t)i * 3 + 1] + gy));
-        atomicAdd(&force[2 * ntot + i], -(gself[(size_t)i * 3 + 2] + gz));
+        const double sx = i_owned ? gself[(size_t)i * 3] : 0.0, sy = i_owned ? gself[(size_t)i * 3 + 1] : 0.0;
+        const double sz = i_owned ? gself[(size_t)i * 3 + 2] : 0.0;
+        atomicAdd(&force[i], -(sx + gx));
+        atomicAdd(&force[ntot + i], -(sy + gy));
+        atomicAdd(&force[2 * ntot + i], -(sz + gz));
     }
 }
 
 // One CTA per structure: E = sum e_i (gap_calc.f90:154), stress from the strs
 // contraction (gap_calc.f90:189-203) in the output order of :221-226.
 __global__ void __launch_bounds__(256)
-k_finalize(const StructDev *structs, const double *eatom, const double *vir, int lgrad, double *out8) {
+k_finalize(const StructDev *structs, const double *eatom, const double *vir, int lgrad, double *out8,
+           const unsigned char *role) {
     __shared__ double red[8][7];
     const StructDev &sd = structs[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double v[7] = {0, 0, 0, 0, 0, 0, 0};
     for (int t = tid; t < sd.natoms; t += 256) {
         const int i = sd.atom_off + t;
+        if (role && role[i] != 2) continue;   // decomposed run: partial sums over this rank's centres
         v[0] += eatom[i];
         if (lgrad)
 #pragma unroll
@@ -109,15 +120,15 @@ k_finalize(const StructDev *structs, const double *eatom, const double *vir, int
 void launch_gather(cudaStream_t st, const StructDev *structs, int nstruct, const int *sid, int ntot, int cap,
                    const uint64_t *nbr_keys, const int *nbr_cnt, const double *fpair, const double *gself,
                    const double *vir, const double *eatom, int lgrad, double *force_soa, double *out8,
-                   long *launches) {
+                   const unsigned char *role, const int *active, const DevFlags *flags, long *launches) {
     cudaMemsetAsync(force_soa, 0, sizeof(double) * 3 * (size_t)ntot, st);
     if (lgrad) {
         const int wpb = 8;
         k_gather<<<(ntot + wpb - 1) / wpb, 32 * wpb, 0, st>>>(structs, sid, ntot, cap, nbr_keys, nbr_cnt, fpair,
-                                                               gself, force_soa);
+                                                               gself, force_soa, role, active, flags);
         if (launches) *launches += 1;
     }
-    k_finalize<<<nstruct, 256, 0, st>>>(structs, eatom, vir, lgrad, out8);
+    k_finalize<<<nstruct, 256, 0, st>>>(structs, eatom, vir, lgrad, out8, role);
     if (launches) *launches += 1;
 }
 

@@ -14,9 +14,11 @@ constexpr int MAX_NEIGHBOR_REF_DEV = 1000;  // gap_calc.f90:68
 void launch_neighbor_build(cudaStream_t st, const StructDev *structs, const int *sid, const double *pos,
                            int ntot, int nbins_total, double rcut, int cap, int4 *abin, int *arank,
                            int *bin_count, int *bin_start, int *bin_atoms, uint64_t *nbr_keys, int *nbr_cnt,
-                           double *min_dis, DevFlags *flags, long *launches);
+                           double *min_dis, DevFlags *flags, const DomainDev &dom, unsigned char *role, int *active,
+                           long *launches);
 
-void launch_order(cudaStream_t st, const int *nbr_cnt, int ntot, int *order, long *launches);
+void launch_order(cudaStream_t st, const int *nbr_cnt, int ntot, int *order, const unsigned char *role,
+                  DevFlags *flags, long *launches);
 
 // centre.cu  (mode: 0 forward, 1 backward, 2 fused forward + GPR + backward)
 size_t centre_smem_bytes(const CentreArgs &a, int mode);
@@ -45,7 +47,7 @@ void launch_gpr_prepare(cudaStream_t st, int M, int D, const double *mm_c_order,
 void launch_gather(cudaStream_t st, const StructDev *structs, int nstruct, const int *sid, int ntot, int cap,
                    const uint64_t *nbr_keys, const int *nbr_cnt, const double *fpair, const double *gself,
                    const double *vir, const double *eatom, int lgrad, double *force_soa, double *out8,
-                   long *launches);
+                   const unsigned char *role, const int *active, const DevFlags *flags, long *launches);
 
 // microbench.cu
 void launch_fp64_peaks(cudaStream_t st, double *dfma_tflops, double *dmma_tflops);

@@ -29,21 +29,38 @@ __device__ __forceinline__ int floordiv_i(int a, int b) {
 
 // fractional coordinates -> wrap offsets and bin; counts atoms per bin.
 __global__ void k_bin(const StructDev *structs, const int *sid, const double *pos, int ntot,
-                      int4 *abin, int *arank, int *bin_count) {
+                      int4 *abin, int *arank, int *bin_count, DomainDev dom, unsigned char *role, int *active,
+                      DevFlags *flags) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ntot) return;
     const StructDev &s = structs[sid[i]];
     double x = pos[i], y = pos[ntot + i], z = pos[2 * ntot + i];
     int b[3], w[3];
+    int rl = 2;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         double f = x * s.inv[c] + y * s.inv[3 + c] + z * s.inv[6 + c];
         double fl = floor(f);
         w[c] = (int)fl;
-        int bc = (int)((f - fl) * s.nbin[c]);
+        const double fw = f - fl;
+        int bc = (int)(fw * s.nbin[c]);
         bc = min(max(bc, 0), s.nbin[c] - 1);
         b[c] = bc;
+        if (dom.enabled && dom.grid[c] > 1) {
+            const int g = dom.grid[c];
+            const int mybrick = min(max((int)(fw * g), 0), g - 1);
+            if (mybrick != dom.mine[c]) {
+                // periodic distance (fractional) from fw to the brick [lo, hi]
+                const double lo = (double)dom.mine[c] / g, hi = (double)(dom.mine[c] + 1) / g;
+                double dlo = lo - fw, dhi = fw - hi;
+                dlo -= floor(dlo); dhi -= floor(dhi);          // into [0,1)
+                const double dist = fmin(dlo, dhi);
+                rl = min(rl, dist <= dom.margin[c] * (1.0 + 1e-9) + 1e-12 ? 1 : 0);
+            }
+        }
     }
+    if (role) role[i] = (unsigned char)rl;
+    if (active && rl >= 1) active[atomicAdd(&flags->n_active, 1)] = i;
     int id = (b[0] * s.nbin[1] + b[1]) * s.nbin[2] + b[2];
     abin[i] = make_int4(id, w[0], w[1], w[2]);
     arank[i] = atomicAdd(&bin_count[s.bin_off + id], 1);
@@ -99,12 +116,13 @@ __global__ void k_fill_bins(const StructDev *structs, const int *sid, const int4
 __global__ void __launch_bounds__(NB_THREADS)
 k_neigh(const StructDev *structs, const int *sid, const double *pos, const int4 *abin,
         const int *bin_start, const int *bin_atoms, int ntot, double rcut, int cap,
-        uint64_t *nbr_keys, int *nbr_cnt, double *min_dis, DevFlags *flags) {
+        uint64_t *nbr_keys, int *nbr_cnt, double *min_dis, DevFlags *flags, const int *active) {
     __shared__ uint64_t keys[NB_MAXLIST];
     __shared__ int nkeys, nclose;
     __shared__ double lat[9];
     __shared__ double wmin[NB_THREADS / 32];
-    const int i = blockIdx.x;
+    if (active && (int)blockIdx.x >= flags->n_active) return;
+    const int i = active ? active[blockIdx.x] : blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const StructDev &s = structs[sid[i]];
     if (tid < 9) lat[tid] = s.lat[tid];
@@ -184,16 +202,18 @@ k_neigh(const StructDev *structs, const int *sid, const double *pos, const int4 
 
 // Centres ordered by descending neighbour count (counting sort; single CTA).  The order
 // only schedules the persistent centre kernel; results do not depend on it.
-__global__ void __launch_bounds__(1024) k_order_by_count(const int *nbr_cnt, int ntot, int *order) {
+__global__ void __launch_bounds__(1024) k_order_by_count(const int *nbr_cnt, int ntot, int *order,
+                                                        const unsigned char *role, DevFlags *flags) {
     __shared__ int hist[NB_MAXLIST + 2];
     __shared__ int wsum[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int t = tid; t < NB_MAXLIST + 2; t += 1024) hist[t] = 0;
     __syncthreads();
-    for (int i = tid; i < ntot; i += 1024) atomicAdd(&hist[NB_MAXLIST - min(max(nbr_cnt[i], 0), NB_MAXLIST)], 1);
+    for (int i = tid; i < ntot; i += 1024)
+        if (!role || role[i] == 2) atomicAdd(&hist[NB_MAXLIST - min(max(nbr_cnt[i], 1), NB_MAXLIST)], 1);
     __syncthreads();
-    // exclusive scan of hist (1026 entries, one per thread + tail), key 0 = largest count
-    int v = (tid < NB_MAXLIST + 1) ? hist[tid] : 0, x = v;
+    // exclusive scan of the 1024 keys (one per thread), key 0 = largest count
+    int v = hist[tid], x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
     if (lane == 31) wsum[wid] = x;
@@ -207,16 +227,19 @@ __global__ void __launch_bounds__(1024) k_order_by_count(const int *nbr_cnt, int
     __syncthreads();
     const int excl = (wid ? wsum[wid - 1] : 0) + x - v;
     __syncthreads();
-    if (tid < NB_MAXLIST + 1) hist[tid] = excl;
+    hist[tid] = excl;
     __syncthreads();
+    if (tid == NB_MAXLIST - 1) flags->n_centres = excl + v;   // total number of owned atoms
     for (int i = tid; i < ntot; i += 1024) {
-        const int key = NB_MAXLIST - min(max(nbr_cnt[i], 0), NB_MAXLIST);
+        if (role && role[i] != 2) continue;
+        const int key = NB_MAXLIST - min(max(nbr_cnt[i], 1), NB_MAXLIST);   // 0..1023 (0 and 1 neighbours share a key)
         order[atomicAdd(&hist[key], 1)] = i;
     }
 }
 
-void launch_order(cudaStream_t st, const int *nbr_cnt, int ntot, int *order, long *launches) {
-    k_order_by_count<<<1, 1024, 0, st>>>(nbr_cnt, ntot, order);
+void launch_order(cudaStream_t st, const int *nbr_cnt, int ntot, int *order, const unsigned char *role,
+                  DevFlags *flags, long *launches) {
+    k_order_by_count<<<1, 1024, 0, st>>>(nbr_cnt, ntot, order, role, flags);
     if (launches) *launches += 1;
 }
 
@@ -224,14 +247,15 @@ void launch_order(cudaStream_t st, const int *nbr_cnt, int ntot, int *order, lon
 void launch_neighbor_build(cudaStream_t st, const StructDev *structs, const int *sid, const double *pos,
                            int ntot, int nbins_total, double rcut, int cap, int4 *abin, int *arank,
                            int *bin_count, int *bin_start, int *bin_atoms, uint64_t *nbr_keys, int *nbr_cnt,
-                           double *min_dis, DevFlags *flags, long *launches) {
+                           double *min_dis, DevFlags *flags, const DomainDev &dom, unsigned char *role, int *active,
+                           long *launches) {
     cudaMemsetAsync(bin_count, 0, sizeof(int) * (size_t)nbins_total, st);
     int tb = 256, gb = (ntot + tb - 1) / tb;
-    k_bin<<<gb, tb, 0, st>>>(structs, sid, pos, ntot, abin, arank, bin_count);
+    k_bin<<<gb, tb, 0, st>>>(structs, sid, pos, ntot, abin, arank, bin_count, dom, role, dom.enabled ? active : nullptr, flags);
     k_scan_bins<<<1, 1024, 0, st>>>(bin_count, bin_start, nbins_total);
     k_fill_bins<<<gb, tb, 0, st>>>(structs, sid, abin, arank, bin_start, ntot, bin_atoms);
     k_neigh<<<ntot, NB_THREADS, 0, st>>>(structs, sid, pos, abin, bin_start, bin_atoms, ntot, rcut, cap,
-                                          nbr_keys, nbr_cnt, min_dis, flags);
+                                          nbr_keys, nbr_cnt, min_dis, flags, dom.enabled ? active : nullptr);
     if (launches) *launches += 4;
 }
 

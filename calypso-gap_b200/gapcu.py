@@ -24,7 +24,8 @@ _lib = None
 SYMBOLS = [
     "gapcu_last_error", "gapcu_calc", "gapcu_read", "gapcu_bond", "gapcu_car2acsf_table", "gapcu_print_last_error",
     "gapcu_device_count", "gapcu_ctx_create", "gapcu_ctx_destroy", "gapcu_ctx_load_potential",
-    "gapcu_ctx_set_potential", "gapcu_ctx_set_pipeline", "gapcu_ctx_set_structures", "gapcu_ctx_compute", "gapcu_ctx_fetch",
+    "gapcu_ctx_set_potential", "gapcu_ctx_set_pipeline", "gapcu_nccl_unique_id", "gapcu_ctx_nccl_init",
+    "gapcu_ctx_set_domain", "gapcu_ctx_set_structures", "gapcu_ctx_compute", "gapcu_ctx_fetch",
     "gapcu_ctx_fetch_descriptors", "gapcu_ctx_fetch_neighbors", "gapcu_ctx_time_compute", "gapcu_stage_name",
     "gapcu_ctx_work_counters", "gapcu_fp64_peaks",
 ]
@@ -54,6 +55,9 @@ def lib():
         L.gapcu_ctx_set_structures.argtypes = [_vp, C.c_int, _ip, _ip, _dp, _dp, C.c_double]
         L.gapcu_ctx_compute.argtypes = [_vp, C.c_int]
         L.gapcu_ctx_set_pipeline.argtypes = [_vp, C.c_int]
+        L.gapcu_nccl_unique_id.argtypes = [C.c_char_p]
+        L.gapcu_ctx_nccl_init.argtypes = [_vp, C.c_int, C.c_int, C.c_char_p]
+        L.gapcu_ctx_set_domain.argtypes = [_vp] + [C.c_int] * 6
         L.gapcu_ctx_fetch.argtypes = [_vp, _vp, _vp, _vp]
         L.gapcu_ctx_fetch_descriptors.argtypes = [_vp, _vp, _vp, _vp]
         L.gapcu_ctx_fetch_neighbors.argtypes = [_vp, C.c_int, _ip, _ip, _ip, _dp]
@@ -126,6 +130,13 @@ class Context:
         """'auto' | 'split' (K2 -> DMMA GPR -> K4) | 'fused' (one centre kernel)."""
         _check(lib().gapcu_ctx_set_pipeline(self.h, {"auto": 0, "split": 1, "fused": 2}[mode]))
 
+    def nccl_init(self, world, rank, unique_id):
+        _check(lib().gapcu_ctx_nccl_init(self.h, int(world), int(rank), unique_id))
+
+    def set_domain(self, grid, mine):
+        """Spatial decomposition: this rank owns brick `mine` of `grid` (see domain_grid)."""
+        _check(lib().gapcu_ctx_set_domain(self.h, *[int(v) for v in grid], *[int(v) for v in mine]))
+
     def compute(self, lgrad=True):
         _check(lib().gapcu_ctx_compute(self.h, int(bool(lgrad))))
 
@@ -173,6 +184,38 @@ class Context:
         a = C.c_double(); b = C.c_double()
         _check(lib().gapcu_fp64_peaks(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    _check(lib().gapcu_nccl_unique_id(buf))
+    return buf.raw
+
+
+def domain_grid(world, cell, rcut=6.0):
+    """Brick grid g0 x g1 x g2 = world with the smallest ghost shell for this cell
+    (1-D slabs along the longest direction for 2, then 2x2x1, 2x2x2, ...)."""
+    cell = np.asarray(cell, float)
+    inv = np.linalg.inv(cell)
+    spacing = 1.0 / np.linalg.norm(inv, axis=0)          # interplanar spacings
+    best = None
+    for g0 in range(1, world + 1):
+        if world % g0:
+            continue
+        for g1 in range(1, world // g0 + 1):
+            if (world // g0) % g1:
+                continue
+            g = (g0, g1, world // g0 // g1)
+            w = [spacing[c] / g[c] for c in range(3)]    # brick widths
+            shell = np.prod([min(w[c] + 2 * rcut, spacing[c]) if g[c] > 1 else w[c] for c in range(3)]) - np.prod(w)
+            key = (round(float(shell), 9), g)
+            if best is None or key < best:
+                best = key
+    return best[1]
+
+
+def brick_of(rank, grid):
+    return (rank // (grid[1] * grid[2]), (rank // grid[2]) % grid[1], rank % grid[2])
 
 
 def fortran_calc(species, lat, pos, theta, mm, coeff, rcut, lgrad):

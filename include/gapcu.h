@@ -98,6 +98,18 @@ int gapcu_ctx_set_potential(gapcu_ctx *ctx, int nspecies, const int *z, const do
  * settable with the environment variable GAPCU_PIPELINE=split|fused. */
 int gapcu_ctx_set_pipeline(gapcu_ctx *ctx, int mode);
 
+/* Spatial decomposition of ONE large structure over the ranks of a node (SURVEY.md 8(e),
+ * BASELINE config 4).  Every rank holds all positions; the cell is cut into g0 x g1 x g2
+ * bricks in fractional coordinates; this rank evaluates the centres of brick (m0,m1,m2),
+ * lists the ghost atoms within rcut of it, and the forces its centres exert on ghosts are
+ * returned by one NCCL sum over ranks (as are E and the stress partial sums).  After
+ * gapcu_ctx_fetch every rank holds the full result.  g0*g1*g2 == 1 switches it off.
+ * NCCL is loaded with dlopen at the first call; the unique id made by rank 0 with
+ * gapcu_nccl_unique_id (128 bytes) must be sent to the other ranks by the caller. */
+int gapcu_nccl_unique_id(char *out128);
+int gapcu_ctx_nccl_init(gapcu_ctx *ctx, int nranks, int rank, const char *id128);
+int gapcu_ctx_set_domain(gapcu_ctx *ctx, int g0, int g1, int g2, int m0, int m1, int m2);
+
 /* A batch of nstruct independent periodic structures (C order this time:
  * natoms[nstruct]; species[sum natoms]; lat[nstruct][3][3] rows = lattice
  * vectors; pos[sum natoms][3]).  Copies host -> device. */

@@ -162,3 +162,54 @@ def test_f2py_module_and_python_classes(golden_frames, bc_structure, oracle, mon
     assert abs(ene2 - ene) <= 1e-11 * abs(ene)      # shared-memory atomics: summation order varies run to run
     cell, pos = bc_structure["cell"], bc_structure["positions"]
     assert Bond(rcut=6.0).get_min_bond(cell, bc_structure["numbers"], pos) == oracle.get_bond(cell, pos, 6.0)
+
+
+def _decomp_worker(rank, world, port, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in ("oracle", "tests", "calypso-gap_b200"):
+        sys.path.insert(0, os.path.join(root, p))
+    import torch
+    import torch.distributed as dist
+    import gapcu
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    cell, pos, z = cubic_supercell(12, 10, 8, seed=4000)
+    c = gapcu.Context(rank)
+    c.load_potential(os.path.join(root, "bench_data", "gap_parameters_c2"))
+    obj = [gapcu.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    c.nccl_init(world, rank, obj[0])
+    grid = gapcu.domain_grid(world, cell)
+    c.set_domain(grid, gapcu.brick_of(rank, grid))
+    r = c.evaluate(z, cell, pos, 6.0, True)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, r["energy"], r["forces"], r["stress"]))
+
+
+def test_spatial_decomposition_two_gpus_equals_one(oracle):
+    """BASELINE config 4 shape (small): 2 ranks, bricks + ghost-force return over NCCL; every
+    rank ends with the full result, equal to the single-GPU one to <= 1e-12 relative."""
+    import gapcu
+    if gapcu.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = 29600 + os.getpid() % 2000
+    procs = [ctxm.Process(target=_decomp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(60)
+    cell, pos, z = cubic_supercell(12, 10, 8, seed=4000)
+    one = gapcu.Context(0)
+    one.load_potential(os.path.join(os.path.dirname(GOLDEN), "..", "bench_data", "gap_parameters_c2"))
+    want = one.evaluate(z, cell, pos, 6.0, True)
+    for _, e, f, s in got:
+        assert abs(e - want["energy"]) <= 1e-12 * abs(want["energy"])
+        assert np.abs(f - want["forces"]).max() <= 1e-9
+        assert np.abs(s - want["stress"]).max() <= 1e-8
