@@ -232,15 +232,23 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
 
     // ---- 1: stage neighbours (a: geometry per neighbour, b: fc/fc' per (neighbour, class)) ----
     for (int s = tid; s < P; s += CT) {
-        int jl, n1, n2, n3;
-        nbr_unkey(a.nbr_keys[(size_t)i * a.cap + s], jl, n1, n2, n3);
-        const int j = sd.atom_off + jl;
-        double ox, oy, oz;
-        const double dis = image_distance(a.pos, ntot, j, s_lat, n1, n2, n3, xi, yi, zi, ox, oy, oz);
+        double ox, oy, oz, dis, wj;
+        if (a.nbr_table) {
+            // CAR2ACSF: image position, distance and weight as the caller tabulated them (wacsf.f90:80-84)
+            const size_t NA = (size_t)ntot, ld = (size_t)a.table_ld;
+            const double *T = a.nbr_table + i + NA * s;
+            ox = T[0]; oy = T[NA * ld]; oz = T[2 * NA * ld]; dis = T[3 * NA * ld]; wj = T[4 * NA * ld];
+        } else {
+            int jl, n1, n2, n3;
+            nbr_unkey(a.nbr_keys[(size_t)i * a.cap + s], jl, n1, n2, n3);
+            const int j = sd.atom_off + jl;
+            dis = image_distance(a.pos, ntot, j, s_lat, n1, n2, n3, xi, yi, zi, ox, oy, oz);
+            wj = a.wgt[j];
+        }
         s_x[s] = ox; s_x[pcap + s] = oy; s_x[2 * pcap + s] = oz;
         s_r[s] = dis;
         s_ir[s] = 1.0 / dis;
-        s_w[s] = a.wgt[j];
+        s_w[s] = wj;
         int nc = 0;
         while (nc < ncls && !(dis > a.cls.rc[nc])) nc++;  // reference: "if (rij.gt.cutoff) cycle"
         s_nc[s] = (unsigned char)nc;

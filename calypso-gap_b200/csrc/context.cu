@@ -499,6 +499,50 @@ static int read_flags(gapcu_ctx *c) {
     return 0;
 }
 
+// kernel arguments of the centre kernel for the context's current state; picks the pipeline
+// and the shared-memory budget (triplet-list capacity, private accumulator sets)
+static int make_centre_args(gapcu_ctx *c, int lgrad, CentreArgs *out, bool *fused_out) {
+    CentreArgs a;
+    memset(&a, 0, sizeof a);
+    a.plan = c->plan_dev();
+    a.cls = c->class_tab();
+    a.structs = c->d_structs.p; a.sid = c->d_sid.p; a.pos = c->d_pos.p; a.wgt = c->d_wgt.p;
+    a.nbr_keys = c->d_keys.p; a.nbr_cnt = c->d_nbr_cnt.p; a.order = c->d_order.p; a.n_centres = &c->d_flags.p->n_centres; a.exp2_table = c->d_exp2.p;
+    a.ntot = c->ntot; a.cap = c->cap; a.pcap = c->pcap; a.lgrad = lgrad;
+    a.exp_clamp = c->exp_clamp;
+    a.G = c->d_G.p; a.dEdG = c->d_dEdG.p; a.dEdG_out = c->d_dEdG.p; a.eatom = c->d_eatom.p;
+    a.fpair = c->d_fpair.p; a.gself = c->d_gself.p; a.vir = c->d_vir.p;
+    a.gpr_M = c->M; a.gpr_Mp = c->Mp; a.gpr_Dp = c->Dp; a.gpr_Mt = c->d_Mt.p; a.gpr_MtT = c->d_MtT.p;
+    a.gpr_coeff = c->d_coeff.p; a.gpr_cmean = c->d_cmean.p; a.gpr_itheta = c->d_itheta.p;
+    a.flags = c->d_flags.p;
+    // The in-CTA GPR re-reads the sparse set once per atom: worth it while that set is
+    // small (it stays in L1/L2 and a separate GEMM launch would be latency bound);
+    // large sets go through the tiled DMMA kernel.
+    const bool fused = c->pipeline == 2 || (c->pipeline == 0 && (size_t)c->Mp * c->Dp <= 64 * 1024);
+    // shared-memory budget: triplet-list capacity and private accumulator sets.  Prefer a
+    // footprint that lets 3 CTAs share an SM (the kernel is latency bound: more resident
+    // warps matter more than building the triplet list in one chunk), then 2, then 1.
+    {
+        const int q = c->pcap * (c->pcap - 1) / 2;
+        const int want = std::min(8192, std::max(2048, round_up(q, 32)));
+        const int mode = fused ? 2 : 1;
+        const size_t targets[3] = {74 * 1024, 112 * 1024, 220 * 1024};   // 3, 2, 1 CTAs per SM
+        const int lmin[3] = {3584, 3072, 1024};
+        bool ok = false;
+        for (int t = 0; t < 3 && !ok; t++)
+            for (int pass = 0; pass < 2 && !ok; pass++) {
+                if (pass == 1 && t < 2) continue;          // the atomics fallback only as a last resort
+                a.npa = pass == 0 ? centre_warps() : 1;
+                for (a.lcap = want; a.lcap >= std::min(want, lmin[t]); a.lcap -= 512)
+                    if (centre_smem_bytes(a, mode) <= targets[t]) { ok = true; break; }
+            }
+        if (!ok) return fail(GAPCU_ELIMIT, "centre kernel needs more shared memory than an SM has");
+    }
+    *out = a;
+    *fused_out = fused;
+    return 0;
+}
+
 // enqueue one full pass; ev (optional) = GAPCU_NSTAGE+1 events recorded at stage boundaries
 static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
     if (!c->have_sf || !c->have_gpr) return fail(GAPCU_EARG, "no potential loaded");
@@ -537,41 +581,8 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
     CU(cudaGetLastError());
     if (ev) CU(cudaEventRecord(ev[1], c->stream));
     CentreArgs a;
-    memset(&a, 0, sizeof a);
-    a.plan = c->plan_dev();
-    a.cls = c->class_tab();
-    a.structs = c->d_structs.p; a.sid = c->d_sid.p; a.pos = c->d_pos.p; a.wgt = c->d_wgt.p;
-    a.nbr_keys = c->d_keys.p; a.nbr_cnt = c->d_nbr_cnt.p; a.order = c->d_order.p; a.n_centres = &c->d_flags.p->n_centres; a.exp2_table = c->d_exp2.p;
-    a.ntot = c->ntot; a.cap = c->cap; a.pcap = c->pcap; a.lgrad = lgrad;
-    a.exp_clamp = c->exp_clamp;
-    a.G = c->d_G.p; a.dEdG = c->d_dEdG.p; a.dEdG_out = c->d_dEdG.p; a.eatom = c->d_eatom.p;
-    a.fpair = c->d_fpair.p; a.gself = c->d_gself.p; a.vir = c->d_vir.p;
-    a.gpr_M = c->M; a.gpr_Mp = c->Mp; a.gpr_Dp = c->Dp; a.gpr_Mt = c->d_Mt.p; a.gpr_MtT = c->d_MtT.p;
-    a.gpr_coeff = c->d_coeff.p; a.gpr_cmean = c->d_cmean.p; a.gpr_itheta = c->d_itheta.p;
-    a.flags = c->d_flags.p;
-    // The in-CTA GPR re-reads the sparse set once per atom: worth it while that set is
-    // small (it stays in L1/L2 and a separate GEMM launch would be latency bound);
-    // large sets go through the tiled DMMA kernel.
-    const bool fused = c->pipeline == 2 || (c->pipeline == 0 && (size_t)c->Mp * c->Dp <= 64 * 1024);
-    // shared-memory budget: triplet-list capacity and private accumulator sets.  Prefer a
-    // footprint that lets 3 CTAs share an SM (the kernel is latency bound: more resident
-    // warps matter more than building the triplet list in one chunk), then 2, then 1.
-    {
-        const int q = c->pcap * (c->pcap - 1) / 2;
-        const int want = std::min(8192, std::max(2048, round_up(q, 32)));
-        const int mode = fused ? 2 : 1;
-        const size_t targets[3] = {74 * 1024, 112 * 1024, 220 * 1024};   // 3, 2, 1 CTAs per SM
-        const int lmin[3] = {3584, 3072, 1024};
-        bool ok = false;
-        for (int t = 0; t < 3 && !ok; t++)
-            for (int pass = 0; pass < 2 && !ok; pass++) {
-                if (pass == 1 && t < 2) continue;          // the atomics fallback only as a last resort
-                a.npa = pass == 0 ? centre_warps() : 1;
-                for (a.lcap = want; a.lcap >= std::min(want, lmin[t]); a.lcap -= 512)
-                    if (centre_smem_bytes(a, mode) <= targets[t]) { ok = true; break; }
-            }
-        if (!ok) return fail(GAPCU_ELIMIT, "centre kernel needs more shared memory than an SM has");
-    }
+    bool fused = false;
+    if ((rc = make_centre_args(c, lgrad, &a, &fused))) return rc;
     if (fused) {
         if (launch_fused(c->stream, a, &c->launches)) return fail(GAPCU_ELIMIT, "centre kernel needs more shared memory than an SM has");
         CU(cudaGetLastError());
@@ -911,7 +922,95 @@ extern "C" int gapcu_bond(int na, const double *lat, const int *elements, const 
 
 extern "C" int gapcu_car2acsf_table(int na, int max_neighbor, int nf, const double *pos, const double *neighbor,
                                     const int *neighbor_count, int lgrad, double *xx, double *dxdy, double *strs) {
-    (void)na; (void)max_neighbor; (void)nf; (void)pos; (void)neighbor; (void)neighbor_count; (void)lgrad;
-    (void)xx; (void)dxdy; (void)strs;
-    return fail(GAPCU_ELIMIT, "car2acsf: dense descriptor export is not implemented yet (SURVEY.md 8(f) N3)");
+    std::lock_guard<std::mutex> lk(g_mu);
+    gapcu_ctx *c = nullptr;
+    int rc = default_ctx(&c);
+    if (rc) return rc;
+    if (na <= 0 || max_neighbor <= 0) return fail(GAPCU_EARG, "NA and max_neighbor must be positive");
+    if ((rc = refresh_sf_from_cwd(c))) return rc;
+    if (nf != c->plan.D) return fail(GAPCU_EARG, "nf does not equal 2*nsf of ./gap_parameters");
+    const int D = nf;
+    int maxcnt = 0;
+    for (int i = 0; i < na; i++) {
+        if (neighbor_count[i] < 0 || neighbor_count[i] > max_neighbor) return fail(GAPCU_EARG, "neighbor_count out of range");
+        maxcnt = std::max(maxcnt, neighbor_count[i]);
+    }
+    if (maxcnt > 1023) return fail(GAPCU_ENEIGH, "more than 1023 neighbours");
+    cudaSetDevice(c->device);
+    // a single pseudo structure: the kernels only need the centre positions and the table
+    const size_t NA = (size_t)na;
+    c->h_structs.assign(1, StructDev());
+    StructDev &sd = c->h_structs[0];
+    memset(&sd, 0, sizeof sd);
+    sd.lat[0] = sd.lat[4] = sd.lat[8] = 1.0; sd.inv[0] = sd.inv[4] = sd.inv[8] = 1.0; sd.volume = 1.0;
+    sd.natoms = na; sd.nbins = 1; sd.nbin[0] = sd.nbin[1] = sd.nbin[2] = 1;
+    c->h_natoms.assign(1, na);
+    c->nstruct = 1; c->ntot = na; c->nbins = 1; c->computed = false; c->pcap_known = false; c->last_ntot = -1;
+    c->cap = std::max(32, round_up(maxcnt, 32)); c->pcap = c->cap;
+    if (!c->have_gpr || c->D != D) {  // the GPR part is irrelevant here; give the kernels a consistent dummy
+        std::vector<double> th(D, 1.0), m1(D, 0.0), c1(1, 0.0);
+        if ((rc = set_gpr(c, 1, D, th.data(), m1.data(), c1.data()))) return rc;
+    }
+    DBuf<double> d_table;
+    std::vector<int> h_sid(NA, 0);
+    std::vector<unsigned char> h_role(NA, 2);
+    CU(c->d_structs.ensure(1)); CU(c->d_sid.ensure(NA)); CU(c->d_pos.ensure(3 * NA)); CU(c->d_wgt.ensure(NA));
+    CU(c->d_nbr_cnt.ensure(NA)); CU(c->d_flags.ensure(1)); CU(c->d_role.ensure(NA)); CU(c->d_order.ensure(NA));
+    CU(d_table.ensure(NA * max_neighbor * 6));
+    if ((rc = ensure_work_buffers(c))) { d_table.release(); return rc; }
+    auto bail = [&](int code) { d_table.release(); return code; };
+    if (cudaMemcpy(c->d_structs.p, &sd, sizeof sd, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(c->d_sid.p, h_sid.data(), sizeof(int) * NA, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(c->d_pos.p, pos, sizeof(double) * 3 * NA, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(c->d_nbr_cnt.p, neighbor_count, sizeof(int) * NA, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(c->d_role.p, h_role.data(), NA, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(d_table.p, neighbor, sizeof(double) * NA * max_neighbor * 6, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemset(c->d_wgt.p, 0, sizeof(double) * NA) != cudaSuccess)
+        return bail(fail(GAPCU_ECUDA, "upload failed"));
+    CentreArgs a;
+    bool fused = false;
+    if ((rc = make_centre_args(c, 1, &a, &fused))) return bail(rc);
+    a.nbr_table = d_table.p; a.table_ld = max_neighbor; a.order = nullptr; a.n_centres = nullptr; a.lgrad = 1;
+    auto run = [&](bool backward) -> int {
+        if (cudaMemsetAsync(c->d_flags.p, 0, sizeof(DevFlags), c->stream) != cudaSuccess) return fail(GAPCU_ECUDA, "memset failed");
+        int r = backward ? launch_backward(c->stream, a, &c->launches) : launch_forward(c->stream, a, &c->launches);
+        if (r) return fail(GAPCU_ELIMIT, "centre kernel needs more shared memory than an SM has");
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) return fail(GAPCU_ECUDA, "centre kernel failed");
+        return 0;
+    };
+    // descriptors: xx(nf,na) column-major == G[na][D] row-major
+    if ((rc = run(false))) return bail(rc);
+    if (cudaMemcpy(xx, c->d_G.p, sizeof(double) * NA * D, cudaMemcpyDeviceToHost) != cudaSuccess) return bail(fail(GAPCU_ECUDA, "download failed"));
+    memset(dxdy, 0, sizeof(double) * (size_t)D * NA * NA * 3);
+    memset(strs, 0, sizeof(double) * 9 * (size_t)D * NA);
+    if (lgrad) {
+        // one backward pass per descriptor with dE/dG = e_k: the per-slot gradients ARE dG_k/dr
+        std::vector<double> h_fp(NA * c->cap * 3), h_gs(NA * 3), h_vir(NA * 6);
+        for (int k = 0; k < D; k++) {
+            launch_onehot(c->stream, c->d_dEdG.p, na, D, k);
+            if ((rc = run(true))) return bail(rc);
+            if (cudaMemcpy(h_fp.data(), c->d_fpair.p, sizeof(double) * h_fp.size(), cudaMemcpyDeviceToHost) != cudaSuccess ||
+                cudaMemcpy(h_gs.data(), c->d_gself.p, sizeof(double) * h_gs.size(), cudaMemcpyDeviceToHost) != cudaSuccess ||
+                cudaMemcpy(h_vir.data(), c->d_vir.p, sizeof(double) * h_vir.size(), cudaMemcpyDeviceToHost) != cudaSuccess)
+                return bail(fail(GAPCU_ECUDA, "download failed"));
+            for (size_t n = 0; n < NA; n++) {
+                for (int d = 0; d < 3; d++) dxdy[k + (size_t)D * (n + NA * (n + NA * d))] += h_gs[n * 3 + d];
+                for (int s = 0; s < neighbor_count[n]; s++) {
+                    const long j = (long)neighbor[n + NA * (s + (size_t)max_neighbor * 5)] - 1;  // real(j), 1-based (gap_calc.f90:115)
+                    if (j < 0 || j >= na) return bail(fail(GAPCU_EARG, "neighbor index out of range"));
+                    for (int d = 0; d < 3; d++)
+                        dxdy[k + (size_t)D * (n + NA * ((size_t)j + NA * d))] += h_fp[(n * c->cap + s) * 3 + d];
+                }
+                // strs(a,b,k,n) = sum delta_a * dG/dx_b ; the kernel keeps the upper triangle (xx,xy,xz,yy,yz,zz)
+                double *S = strs + 9 * ((size_t)k + (size_t)D * n);
+                const double *v = &h_vir[n * 6];
+                S[0] = v[0]; S[4] = v[3]; S[8] = v[5];
+                S[3] = S[1] = v[1]; S[6] = S[2] = v[2]; S[7] = S[5] = v[4];
+            }
+        }
+    }
+    d_table.release();
+    c->have_gpr = false;      // the dummy GPR set must not survive into the next fgap_calc
+    c->pcap_known = false;
+    return 0;
 }

@@ -91,6 +91,8 @@ struct CentreArgs {
     const double *wgt;          // [NT] species weight
     const uint64_t *nbr_keys;   // [NT][cap]
     const int *nbr_cnt;         // [NT]
+    const double *nbr_table;    // CAR2ACSF entry: the caller's neighbor(NA,ld,6) table (column-major) instead of keys
+    int table_ld;
     const int *order;           // [NT] centres by descending neighbour count (null: natural order)
     const int *n_centres;       // device count of entries in `order` (null: ntot)
     const double *exp2_table;   // [32] 2^(j/32)

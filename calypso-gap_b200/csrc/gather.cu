@@ -117,6 +117,16 @@ k_finalize(const StructDev *structs, const double *eatom, const double *vir, int
     }
 }
 
+// dE/dG := unit vector e_k for every atom (CAR2ACSF export: one backward pass per descriptor)
+__global__ void k_onehot(double *dEdG, int ntot, int D, int k) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (size_t)ntot * D) dEdG[t] = ((int)(t % D) == k) ? 1.0 : 0.0;
+}
+void launch_onehot(cudaStream_t st, double *dEdG, int ntot, int D, int k) {
+    const size_t n = (size_t)ntot * D;
+    k_onehot<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dEdG, ntot, D, k);
+}
+
 void launch_gather(cudaStream_t st, const StructDev *structs, int nstruct, const int *sid, int ntot, int cap,
                    const uint64_t *nbr_keys, const int *nbr_cnt, const double *fpair, const double *gself,
                    const double *vir, const double *eatom, int lgrad, double *force_soa, double *out8,

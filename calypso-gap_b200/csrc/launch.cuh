@@ -49,6 +49,8 @@ void launch_gather(cudaStream_t st, const StructDev *structs, int nstruct, const
                    const double *vir, const double *eatom, int lgrad, double *force_soa, double *out8,
                    const unsigned char *role, const int *active, const DevFlags *flags, long *launches);
 
+void launch_onehot(cudaStream_t st, double *dEdG, int ntot, int D, int k);
+
 // microbench.cu
 void launch_fp64_peaks(cudaStream_t st, double *dfma_tflops, double *dmma_tflops);
 

@@ -213,3 +213,35 @@ def test_spatial_decomposition_two_gpus_equals_one(oracle):
         assert abs(e - want["energy"]) <= 1e-12 * abs(want["energy"])
         assert np.abs(f - want["forces"]).max() <= 1e-9
         assert np.abs(s - want["stress"]).max() <= 1e-8
+
+
+def test_car2acsf_dense_export(oracle, shipped_pot, bc_structure, monkeypatch):
+    """The reference's public car2acsf (wacsf.f90:2-12) through the f2py module: dense
+    xx(nf,na), dxdy(nf,na,na,3), strs(3,3,nf,na) from a caller-built neighbour table."""
+    import libgap.libgap as m
+    monkeypatch.chdir(GOLDEN)
+    cell, pos = sheared(bc_structure["cell"], bc_structure["positions"])
+    z = bc_structure["numbers"].astype(np.int32)
+    na, nf, mx = len(pos), shipped_pot.des_len, 300
+    cnt, idx, sh, dis = oracle.neighbors(cell, pos, 6.0, cap=mx)
+    wz = {int(a): b for a, b in zip(shipped_pot.z, shipped_pot.w)}
+    nb = np.zeros((na, mx, 6))
+    for i in range(na):
+        n = cnt[i]
+        nb[i, :n, 0:3] = pos[idx[i, :n]] + sh[i, :n] @ cell       # gap_calc.f90:112
+        nb[i, :n, 3] = dis[i, :n]
+        nb[i, :n, 4] = [wz[int(z[j])] for j in idx[i, :n]]
+        nb[i, :n, 5] = idx[i, :n] + 1                             # real(j), 1-based
+    xx, dxdy, strs = m.car2acsf(nf, pos, nb, cnt, True)
+    oxx, odx, ostr = shipped_pot.car2acsf_dense(z, cell, pos, 6.0, True)   # [na][D], [n][i][c][k], [n][k][a][b]
+    assert xx.shape == (nf, na) and dxdy.shape == (nf, na, na, 3) and strs.shape == (3, 3, nf, na)
+    scale = np.abs(oxx).max(0)[:, None] + 1e-300
+    assert (np.abs(xx - oxx.T) / scale).max() < 1e-13
+    want_dx = np.transpose(odx, (3, 0, 1, 2))                     # -> [k][n][i][c]
+    assert np.abs(dxdy - want_dx).max() <= 1e-12 * np.abs(want_dx).max()
+    want_st = np.transpose(ostr, (2, 3, 1, 0))                    # -> [a][b][k][n]
+    assert np.abs(strs - want_st).max() <= 1e-11 * np.abs(want_st).max()
+    # and E/F/stress still work afterwards through the same default context
+    from libgap.GAP import Calculator
+    ene = Calculator(rcut=6.0).gap_calc(z, cell, pos, True)[0]
+    assert abs(ene - shipped_pot.calc_sparse(z, cell, pos, 6.0, False)["energy"]) <= 1e-10 * abs(ene)
