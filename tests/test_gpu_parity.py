@@ -245,3 +245,26 @@ def test_car2acsf_dense_export(oracle, shipped_pot, bc_structure, monkeypatch):
     from libgap.GAP import Calculator
     ene = Calculator(rcut=6.0).gap_calc(z, cell, pos, True)[0]
     assert abs(ene - shipped_pot.calc_sparse(z, cell, pos, 6.0, False)["energy"]) <= 1e-10 * abs(ene)
+
+
+def test_ase_calculators_with_stub_ase(golden_frames, monkeypatch):
+    """gappy/ASE/gap_calc.py's GAP calculator (and the persistent variant) on the golden
+    MD frames, driven through a stub `ase` package (ase is not installed in this image)."""
+    import sys
+    stub = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stub_ase")
+    monkeypatch.syspath_prepend(stub)
+    monkeypatch.syspath_prepend(os.path.join(os.path.dirname(GOLDEN), "..", "calypso-gap_b200", "ase_calculators"))
+    for mod in [m for m in sys.modules if m == "ase" or m.startswith("ase.")]:
+        monkeypatch.delitem(sys.modules, mod)
+    monkeypatch.chdir(GOLDEN)
+    import ase
+    import gap_calc
+    g = golden_frames
+    for calc in (gap_calc.GAP(rcut=6.0), gap_calc.GAPPersistent(rcut=6.0)):
+        assert calc.implemented_properties == ['energy', 'forces', 'stress']
+        for frame in (0, 6):
+            at = ase.Atoms(g["numbers"], g["positions"][frame], g["cell"][frame])
+            at.set_calculator(calc)
+            _cmp({"energy": at.get_potential_energy(), "forces": at.get_forces(), "stress": at.get_stress()},
+                 {"energy": g["energy"][frame], "forces": g["forces"][frame], "stress": g["stress"][frame]})
+            assert calc.results["free_energy"] == calc.results["energy"] and calc.results["variance"] == 0.0
