@@ -85,7 +85,7 @@ struct gapcu_ctx {
     DBuf<StructDev> d_structs;
     DBuf<int> d_sid, d_arank, d_bin_count, d_bin_start, d_bin_atoms, d_nbr_cnt, d_order;
     DBuf<int4> d_abin;
-    DBuf<double> d_pos, d_wgt, d_G, d_dEdG, d_eatom, d_fpair, d_gself, d_vir, d_force, d_out8, d_mindis;
+    DBuf<double> d_pos, d_wgt, d_G, d_dEdG, d_eatom, d_fpair, d_gself, d_vir, d_force, d_out8, d_mindis, d_epart, d_accpart;
     DBuf<uint64_t> d_keys;
     DBuf<DevFlags> d_flags;
     DBuf<unsigned char> d_flush;
@@ -181,7 +181,7 @@ extern "C" void gapcu_ctx_destroy(gapcu_ctx *c) {
     c->d_bin_atoms.release(); c->d_nbr_cnt.release(); c->d_order.release(); c->d_abin.release(); c->d_pos.release(); c->d_wgt.release();
     c->d_G.release(); c->d_dEdG.release(); c->d_eatom.release(); c->d_fpair.release(); c->d_gself.release();
     c->d_vir.release(); c->d_force.release(); c->d_out8.release(); c->d_mindis.release(); c->d_keys.release();
-    c->d_flags.release(); c->d_flush.release(); c->d_role.release(); c->d_active.release();
+    c->d_epart.release(); c->d_accpart.release(); c->d_flags.release(); c->d_flush.release(); c->d_role.release(); c->d_active.release();
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->stage_ev_init) for (auto &e : c->stage_ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -224,9 +224,8 @@ static int set_sf(gapcu_ctx *c, const std::vector<int> &z, const std::vector<dou
 }
 
 static int pick_dp(int D) {
-    int nt = (D + 7) / 8;
-    if (nt <= 16) return 8 * std::max(nt, 1);
-    for (int cand : {20, 24, 28, 32}) if (nt <= cand) return 8 * cand;
+    const int nt = (D + 7) / 8;
+    for (int cand : {2, 4, 6, 8, 9, 10, 12, 14, 16, 20, 24, 28, 32}) if (nt <= cand) return 8 * cand;  // k_gpr<NT> instances
     return -1;
 }
 
@@ -244,7 +243,7 @@ static int set_gpr(gapcu_ctx *c, int M, int D, const double *theta, const double
     c->h_theta.assign(theta, theta + D);
     c->h_coeff.assign(coeff, coeff + M);
     c->h_mm.assign(mm, mm + (size_t)M * D);
-    c->M = M; c->D = D; c->Dp = Dp; c->Mp = round_up(std::max(M, 1), 8);
+    c->M = M; c->D = D; c->Dp = Dp; c->Mp = round_up(std::max(M, 1), 16);
     CU(c->d_mm_raw.ensure((size_t)M * D + 1)); CU(c->d_theta_raw.ensure(D)); CU(c->d_coeff_raw.ensure(M + 1));
     CU(c->d_Mt.ensure((size_t)c->Mp * Dp)); CU(c->d_MtT.ensure((size_t)c->Mp * Dp)); CU(c->d_mn.ensure(c->Mp)); CU(c->d_coeff.ensure(c->Mp));
     CU(c->d_cmean.ensure(Dp)); CU(c->d_itheta.ensure(Dp));
@@ -594,7 +593,12 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
         GprDev g;
         g.M = c->M; g.Mp = c->Mp; g.D = c->D; g.Dp = c->Dp; g.Mt = c->d_Mt.p; g.MtT = c->d_MtT.p; g.mn = c->d_mn.p;
         g.coeff = c->d_coeff.p; g.cmean = c->d_cmean.p; g.itheta = c->d_itheta.p;
-        if (launch_gpr(c->stream, g, c->d_G.p, c->ntot, c->d_eatom.p, c->d_dEdG.p, &c->launches))
+        int nslice = 1, mslice = c->Mp;
+        gpr_slicing(c->ntot, c->Mp, &nslice, &mslice);
+        CU(c->d_epart.ensure((size_t)nslice * c->ntot));
+        CU(c->d_accpart.ensure((size_t)nslice * c->ntot * c->Dp));
+        if (launch_gpr(c->stream, g, c->d_G.p, c->ntot, c->d_eatom.p, c->d_dEdG.p, c->d_epart.p, c->d_accpart.p, nslice,
+                       mslice, &c->launches))
             return fail(GAPCU_ELIMIT, "unsupported descriptor length for the GPR kernel");
         CU(cudaGetLastError());
         if (ev) CU(cudaEventRecord(ev[3], c->stream));

@@ -23,7 +23,8 @@
 
 namespace gapcu {
 
-constexpr int GPR_WARPS = 4;
+constexpr int GPR_WARPS = 4;   // 32 atoms per CTA share one staged tile of the sparse set
+constexpr int GPR_TS = 16;     // sparse points per staged tile
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -31,18 +32,27 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-// NT = number of 8-wide descriptor tiles (Dp = 8*NT)
+// row stride (doubles) of the staged tile: == 4 (mod 16) makes the GEMM 1 fragment loads
+// (8 rows x 4 consecutive doubles per half warp pair) hit 16 distinct bank pairs
+__host__ __device__ constexpr int gpr_ldt(int Dp) { return Dp + ((20 - Dp % 16) % 16); }
+
+// NT = number of 8-wide descriptor tiles (Dp = 8*NT).  grid = (ceil(N/32), M slices).
+// Every CTA handles 32 atoms x one slice of the sparse set and writes PARTIAL sums
+// (E over the slice, W*m' over the slice); k_gpr_combine adds the slices in fixed order.
 template <int NT>
 __global__ void __launch_bounds__(32 * GPR_WARPS)
-k_gpr(GprDev p, const double *__restrict__ G, int ntot, double *__restrict__ eatom, double *__restrict__ dEdG) {
-    extern __shared__ __align__(16) double xs_all[];  // [GPR_WARPS][8][Dp+1]
+k_gpr(GprDev p, const double *__restrict__ G, int ntot, int mslice, double *__restrict__ epart,
+      double *__restrict__ accpart) {
+    extern __shared__ __align__(16) double sm[];
     constexpr int Dp = 8 * NT;
     constexpr int LDX = Dp + 1;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int LDT = gpr_ldt(Dp);
+    double *xs_all = sm;                               // [GPR_WARPS][8][LDX]
+    double *tile = sm + GPR_WARPS * 8 * LDX;           // [GPR_TS][LDT]; 32*LDX doubles is a multiple of 16 bytes
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     double *xs = xs_all + (size_t)wid * 8 * LDX;
     const int row0 = (blockIdx.x * GPR_WARPS + wid) * 8;
-    if (row0 >= ntot) return;
     // scaled, centred descriptors of this warp's 8 atoms
     for (int k = lane; k < Dp; k += 32) {
         const double it = p.itheta[k], cm = p.cmean[k];
@@ -53,7 +63,6 @@ k_gpr(GprDev p, const double *__restrict__ G, int ntot, double *__restrict__ eat
         }
     }
     __syncwarp();
-    // |x'|^2 of row g (the 4 lanes of a quad split k, then combine)
     double xn = 0.0;
     for (int k = t; k < Dp; k += 4) { const double v = xs[g * LDX + k]; xn += v * v; }
     xn += __shfl_xor_sync(0xffffffffu, xn, 1);
@@ -63,41 +72,75 @@ k_gpr(GprDev p, const double *__restrict__ G, int ntot, double *__restrict__ eat
 #pragma unroll
     for (int n = 0; n < NT; n++) acc[n][0] = acc[n][1] = 0.0;
     double esum = 0.0;
-    const double *__restrict__ Mt = p.Mt;
-    for (int sp0 = 0; sp0 < p.Mp; sp0 += 8) {
-        // GEMM 1: S(8 atoms x 8 sparse) over k = descriptor index
-        double c0 = 0.0, c1 = 0.0;
-        const double *mrow = Mt + (size_t)(sp0 + g) * Dp + t;  // B(k=t, n=g) = Mt[sp0+g][4ks+t]
-        const double *xrow = xs + g * LDX + t;                 // A(row=g, k=t)
+    const int sp_begin = blockIdx.y * mslice, sp_end = min(p.Mp, sp_begin + mslice);
+    for (int sp0 = sp_begin; sp0 < sp_end; sp0 += GPR_TS) {
+        __syncthreads();  // the previous tile has been consumed by every warp
+        {   // stage GPR_TS rows of the scaled sparse set, 16 bytes per thread and step
+            const double2 *src = (const double2 *)(p.Mt + (size_t)sp0 * Dp);
+            for (int idx = tid; idx < GPR_TS * (Dp / 2); idx += 32 * GPR_WARPS) {
+                const int r = idx / (Dp / 2), c2 = idx - r * (Dp / 2);
+                *(double2 *)(tile + r * LDT + 2 * c2) = src[idx];
+            }
+        }
+        __syncthreads();
+        // GEMM 1: S(8 atoms x 16 sparse) over the descriptor index; one A fragment feeds both 8-wide halves
+        double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+        const double *xrow = xs + g * LDX + t;              // A(row=g, k=t)
+        const double *m0 = tile + g * LDT + t;              // B(k=t, n=g) = tile[g][4ks+t]
+        const double *m1 = m0 + 8 * LDT;
 #pragma unroll 4
-        for (int ks = 0; ks < 2 * NT; ks++) dmma884(c0, c1, xrow[4 * ks], __ldg(mrow + 4 * ks));
+        for (int ks = 0; ks < 2 * NT; ks++) {
+            const double av = xrow[4 * ks];
+            dmma884(c00, c01, av, m0[4 * ks]);
+            dmma884(c10, c11, av, m1[4 * ks]);
+        }
         const int col = sp0 + 2 * t;
-        const double w0 = exp(-0.5 * (xn + __ldg(p.mn + col) - 2.0 * c0)) * __ldg(p.coeff + col);
-        const double w1 = exp(-0.5 * (xn + __ldg(p.mn + col + 1) - 2.0 * c1)) * __ldg(p.coeff + col + 1);
-        esum += w0 + w1;
-        // GEMM 2: acc(8 atoms x Dp) += W(8 x 8 sparse) * Mt(8 sparse x Dp);
-        // k-step 0 enumerates sparse points 2t, k-step 1 the points 2t+1.
-        const double *b0 = Mt + (size_t)(sp0 + 2 * t) * Dp + g;  // B(k=t, n=g) = Mt[sp0+2t][8n+g]
-        const double *b1 = b0 + Dp;
+        const double w00 = exp(-0.5 * (xn + __ldg(p.mn + col) - 2.0 * c00)) * __ldg(p.coeff + col);
+        const double w01 = exp(-0.5 * (xn + __ldg(p.mn + col + 1) - 2.0 * c01)) * __ldg(p.coeff + col + 1);
+        const double w10 = exp(-0.5 * (xn + __ldg(p.mn + col + 8) - 2.0 * c10)) * __ldg(p.coeff + col + 8);
+        const double w11 = exp(-0.5 * (xn + __ldg(p.mn + col + 9) - 2.0 * c11)) * __ldg(p.coeff + col + 9);
+        esum += (w00 + w01) + (w10 + w11);
+        // GEMM 2: acc(8 atoms x Dp) += W(8 x 16 sparse) * tile(16 sparse x Dp).  The C fragment of
+        // GEMM 1 (row g, columns 2t, 2t+1) is used as the A operand as is: k-step j enumerates
+        // the sparse points (2t) resp. (2t+1), so B(k=t, n=g) = tile[2t(+1)][8n+g].
+        const double *b0 = tile + (2 * t) * LDT + g;
+        const double *b1 = b0 + LDT, *b2 = b0 + 8 * LDT, *b3 = b2 + LDT;
 #pragma unroll
         for (int n = 0; n < NT; n++) {
-            dmma884(acc[n][0], acc[n][1], w0, __ldg(b0 + 8 * n));
-            dmma884(acc[n][0], acc[n][1], w1, __ldg(b1 + 8 * n));
+            dmma884(acc[n][0], acc[n][1], w00, b0[8 * n]);
+            dmma884(acc[n][0], acc[n][1], w01, b1[8 * n]);
+            dmma884(acc[n][0], acc[n][1], w10, b2[8 * n]);
+            dmma884(acc[n][0], acc[n][1], w11, b3[8 * n]);
         }
     }
     esum += __shfl_xor_sync(0xffffffffu, esum, 1);
     esum += __shfl_xor_sync(0xffffffffu, esum, 2);
     const int row = row0 + g;
     if (row < ntot) {
-        if (t == 0) eatom[row] = esum;
+        const size_t o = (size_t)blockIdx.y * ntot + row;
+        if (t == 0) epart[o] = esum;
 #pragma unroll
         for (int n = 0; n < NT; n++) {
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int k = 8 * n + 2 * t + e;
-                if (k < p.D) dEdG[(size_t)row * p.D + k] = -p.itheta[k] * (xs[g * LDX + k] * esum - acc[n][e]);
-            }
+            const int k = 8 * n + 2 * t;
+            *(double2 *)(accpart + o * Dp + k) = make_double2(acc[n][0], acc[n][1]);
         }
+    }
+}
+
+// e_i = sum over slices; dE/dG_ik = -(x'_ik e_i - sum_slices acc_ik) / theta_k     (fixed order)
+__global__ void k_gpr_combine(GprDev p, const double *__restrict__ G, int ntot, int nslice,
+                              const double *__restrict__ epart, const double *__restrict__ accpart,
+                              double *__restrict__ eatom, double *__restrict__ dEdG) {
+    const int row = blockIdx.x;
+    double e = 0.0;
+    for (int s = 0; s < nslice; s++) e += epart[(size_t)s * ntot + row];
+    if (threadIdx.x == 0) eatom[row] = e;
+    for (int k = threadIdx.x; k < p.D; k += blockDim.x) {
+        double a = 0.0;
+        for (int s = 0; s < nslice; s++) a += accpart[((size_t)s * ntot + row) * p.Dp + k];
+        const double it = p.itheta[k];
+        const double xk = (G[(size_t)row * p.D + k] - p.cmean[k]) * it;
+        dEdG[(size_t)row * p.D + k] = -it * (xk * e - a);
     }
 }
 
@@ -132,27 +175,43 @@ void launch_gpr_prepare(cudaStream_t st, int M, int D, const double *mm_c_order,
 }
 
 template <int NT>
-static int launch_gpr_nt(cudaStream_t st, const GprDev &g, const double *G, int ntot, double *eatom, double *dEdG) {
-    const size_t sm = sizeof(double) * GPR_WARPS * 8 * (8 * NT + 1);
-    if (sm > 48 * 1024)
-        if (cudaFuncSetAttribute((const void *)k_gpr<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
-            return -1;
-    const int blocks = (ntot + 8 * GPR_WARPS - 1) / (8 * GPR_WARPS);
-    k_gpr<NT><<<blocks, 32 * GPR_WARPS, sm, st>>>(g, G, ntot, eatom, dEdG);
+static int launch_gpr_nt(cudaStream_t st, const GprDev &g, const double *G, int ntot, int nslice, int mslice,
+                         double *epart, double *accpart) {
+    constexpr int Dp = 8 * NT;
+    const size_t sm = sizeof(double) * (GPR_WARPS * 8 * (Dp + 1) + GPR_TS * gpr_ldt(Dp));
+    if (cudaFuncSetAttribute((const void *)k_gpr<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
+        return -1;
+    dim3 grid((ntot + 8 * GPR_WARPS - 1) / (8 * GPR_WARPS), nslice);
+    k_gpr<NT><<<grid, 32 * GPR_WARPS, sm, st>>>(g, G, ntot, mslice, epart, accpart);
     return 0;
 }
 
+// how the sparse set is sliced over blockIdx.y: enough CTAs to fill the device at small N
+void gpr_slicing(int ntot, int Mp, int *nslice, int *mslice) {
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int row_ctas = (ntot + 8 * GPR_WARPS - 1) / (8 * GPR_WARPS);
+    int want = (2 * sms + row_ctas - 1) / row_ctas;          // about two CTAs per SM
+    const int tiles = (Mp + GPR_TS - 1) / GPR_TS;
+    want = want < 1 ? 1 : (want > tiles ? tiles : want);
+    const int tps = (tiles + want - 1) / want;               // tiles per slice
+    *mslice = tps * GPR_TS;
+    *nslice = (tiles + tps - 1) / tps;
+}
+
 int launch_gpr(cudaStream_t st, const GprDev &g, const double *G, int ntot, double *eatom, double *dEdG,
-               long *launches) {
-    if (launches) *launches += 1;
+               double *epart, double *accpart, int nslice, int mslice, long *launches) {
+    if (launches) *launches += 2;
+    int rc = -1;
     switch (g.Dp / 8) {
-#define CASE(n) case n: return launch_gpr_nt<n>(st, g, G, ntot, eatom, dEdG);
-        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12)
-        CASE(13) CASE(14) CASE(15) CASE(16) CASE(20) CASE(24) CASE(28) CASE(32)
+#define CASE(n) case n: rc = launch_gpr_nt<n>(st, g, G, ntot, nslice, mslice, epart, accpart); break;
+        CASE(2) CASE(4) CASE(6) CASE(8) CASE(9) CASE(10) CASE(12) CASE(14) CASE(16) CASE(20) CASE(24) CASE(28) CASE(32)
 #undef CASE
         default: return -1;
     }
+    if (rc) return rc;
+    k_gpr_combine<<<ntot, 128, 0, st>>>(g, G, ntot, nslice, epart, accpart, eatom, dEdG);
+    return 0;
 }
 
-// Dp choices the dispatcher above supports (host picks the smallest >= ceil(D/8)*8)
 }  // namespace gapcu

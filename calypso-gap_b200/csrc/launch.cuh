@@ -29,7 +29,7 @@ int launch_fused(cudaStream_t st, const CentreArgs &a, long *launches);
 
 // gpr.cu
 struct GprDev {
-    int M, Mp, D, Dp;        // Mp: M padded to 8, Dp: D padded to 8
+    int M, Mp, D, Dp;        // Mp: M padded to 16, Dp: D padded to a supported multiple of 8
     const double *Mt;        // [Mp][Dp]  (MM - cmean)/theta, zero padded
     const double *MtT;       // [Dp][Mp]  its transpose (in-CTA GPR of the fused kernel)
     const double *mn;        // [Mp]      |Mt row|^2
@@ -37,8 +37,9 @@ struct GprDev {
     const double *cmean;     // [Dp]
     const double *itheta;    // [Dp]      1/theta, zero padded
 };
+void gpr_slicing(int ntot, int Mp, int *nslice, int *mslice);
 int launch_gpr(cudaStream_t st, const GprDev &g, const double *G, int ntot, double *eatom, double *dEdG,
-               long *launches);
+               double *epart, double *accpart, int nslice, int mslice, long *launches);
 void launch_gpr_prepare(cudaStream_t st, int M, int D, const double *mm_c_order, const double *theta,
                         const double *coeff, int Mp, int Dp, double *Mt, double *MtT, double *mn,
                         double *coeff_p, double *cmean, double *itheta);

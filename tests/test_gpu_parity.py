@@ -268,3 +268,42 @@ def test_ase_calculators_with_stub_ase(golden_frames, monkeypatch):
             _cmp({"energy": at.get_potential_energy(), "forces": at.get_forces(), "stress": at.get_stress()},
                  {"energy": g["energy"][frame], "forces": g["forces"][frame], "stress": g["stress"][frame]})
             assert calc.results["free_energy"] == calc.results["energy"] and calc.results["variance"] == 0.0
+
+
+def test_wide_descriptor_large_sparse_set(oracle, bc_structure):
+    """BASELINE config 5 shape, scaled down: nsf = 128 (D = 256), M = 600 sparse points ->
+    the split pipeline with the DMMA GPR kernel (NT = 32, sliced sparse set), end to end
+    against the oracle."""
+    import gapcu
+    ntype, alpha, cut = [], [], []
+    for a in np.geomspace(1e-3, 2.0, 32): ntype.append(1); alpha.append(a); cut.append(6.0)
+    for rs in np.linspace(0.5, 5.5, 32): ntype.append(3); alpha.append(rs); cut.append(6.0)
+    for rc in (3.0, 4.0, 5.0, 6.0):
+        for a in np.geomspace(2e-3, 0.3, 12): ntype.append(2); alpha.append(a); cut.append(rc)
+        for a in np.geomspace(2e-3, 0.3, 12)[::3]: ntype.append(4); alpha.append(a); cut.append(rc)
+    ntype = np.array(ntype, np.int32); alpha = np.round(np.array(alpha), 5); cut = np.array(cut)
+    D = 2 * len(ntype)
+    z3 = np.array([5, 6], np.int32); w3 = np.array([-1.0, 4.0])
+    cell, pos = sheared(bc_structure["cell"], bc_structure["positions"])
+    z = bc_structure["numbers"].astype(np.int32)
+    c = gapcu.Context(0)
+    c.set_potential(z3, w3, ntype, alpha, cut, np.ones(D), np.zeros((16, D)), np.zeros(16))
+    rows = []
+    rng = np.random.default_rng(11)
+    for k in range(10):                                   # sparse points: descriptors of jittered copies
+        c.evaluate(z, cell, pos + rng.normal(0, 0.08, pos.shape), 6.0, False)
+        rows.append(c.descriptors(D)[0])
+    mm = np.vstack(rows)[:600]
+    theta = np.maximum(mm.std(0), 1e-3) * np.sqrt(D)
+    coeff = rng.normal(size=len(mm)) * 20.0
+    c.set_potential(z3, w3, ntype, alpha, cut, theta, mm, coeff)
+    pot = oracle.make(z3, w3, ntype, alpha, cut, theta, mm, coeff)
+    want = pot.calc_sparse(z, cell, pos, 6.0, True, desc=True)
+    for mode in ("split", "fused"):
+        c.set_pipeline(mode)
+        got = c.evaluate(z, cell, pos, 6.0, True)
+        xx, dedg, eat = c.descriptors(D)
+        assert (np.abs(xx - want["xx"]) / (np.abs(want["xx"]).max(0) + 1e-300)).max() < 1e-12
+        assert np.abs(dedg - want["dedg"]).max() <= 1e-10 * np.abs(want["dedg"]).max()
+        _cmp(got, want)
+    c.close()
