@@ -851,25 +851,50 @@ extern "C" int gapcu_calc(int na, const int *species, const double *lat, const d
     if (na <= 0) return fail(GAPCU_EARG, "NA must be positive");
     if ((rc = refresh_sf_from_cwd(c))) return rc;
     if (des_len != c->plan.D) return fail(GAPCU_EARG, "des_len does not equal 2*nsf of ./gap_parameters");
-    // mm(nsparseX,des_len) column-major -> C order
-    std::vector<double> mm_c((size_t)nsparsex * des_len);
-    for (int k = 0; k < des_len; k++)
-        for (int s = 0; s < nsparsex; s++) mm_c[(size_t)s * des_len + k] = mm[s + (size_t)nsparsex * k];
-    if ((rc = set_gpr(c, nsparsex, des_len, theta, mm_c.data(), coeff))) return rc;
+    // GPR data: compare the caller's (Fortran-layout) arrays with the last call's; only a
+    // changed set is transposed (mm(nsparseX,des_len) column-major -> C order) and uploaded
+    {
+        const size_t nmm = (size_t)nsparsex * des_len;
+        static std::vector<double> last_mm, last_theta, last_coeff;
+        const bool same = c->have_gpr && c->M == nsparsex && c->D == des_len && last_mm.size() == nmm &&
+                          !memcmp(last_mm.data(), mm, sizeof(double) * nmm) &&
+                          !memcmp(last_theta.data(), theta, sizeof(double) * des_len) &&
+                          !memcmp(last_coeff.data(), coeff, sizeof(double) * nsparsex);
+        if (!same) {
+            std::vector<double> mm_c(nmm);
+            for (int k = 0; k < des_len; k++)
+                for (int s = 0; s < nsparsex; s++) mm_c[(size_t)s * des_len + k] = mm[s + (size_t)nsparsex * k];
+            c->have_gpr = false;
+            if ((rc = set_gpr(c, nsparsex, des_len, theta, mm_c.data(), coeff))) return rc;
+            last_mm.assign(mm, mm + nmm); last_theta.assign(theta, theta + des_len); last_coeff.assign(coeff, coeff + nsparsex);
+        }
+    }
     double lat_c[9];
     for (int r = 0; r < 3; r++) for (int col = 0; col < 3; col++) lat_c[r * 3 + col] = lat[r + 3 * col];
     if ((rc = set_structures_impl(c, 1, &na, species, lat_c, pos, true, rcut, true))) return rc;
     if ((rc = enqueue_pass(c, lgrad ? 1 : 0, nullptr))) return rc;
-    if ((rc = finish_pass(c))) return rc;
+    // results: flags | out8 | force SoA (= Fortran FORCE(NA,3)) in one batch, one synchronisation
+    size_t b_f = sizeof(double) * 3 * (size_t)na;
+    if (c->pin(sizeof(DevFlags) + 64 + b_f + 64)) return fail(GAPCU_ECUDA, "cudaMallocHost failed");
+    DevFlags *h_fl = (DevFlags *)c->h_pin;
+    double *h_out = (double *)((char *)c->h_pin + ((sizeof(DevFlags) + 63) & ~(size_t)63)), *h_f = h_out + 8;
+    for (int attempt = 0;; attempt++) {
+        CU(cudaMemcpyAsync(h_fl, c->d_flags.p, sizeof(DevFlags), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(h_out, c->d_out8.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(h_f, c->d_force.p, b_f, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->h_flags = *h_fl;
+        if (c->h_flags.too_many)
+            return fail(GAPCU_ENEIGH, "Atoms neighbor: " + std::to_string(c->h_flags.maxcount) + " large than max_neighbor 1000");
+        if (!c->h_flags.overflow) break;
+        if (attempt >= 3) return fail(GAPCU_ECUDA, "neighbour capacity did not converge");
+        // the neighbour count outgrew the learned capacity: enlarge and run again
+        c->cap = std::max(c->cap, std::min(1024, round_up(c->h_flags.maxcount + 16, 32)));
+        c->pcap_known = false;
+        if ((rc = enqueue_pass(c, lgrad ? 1 : 0, nullptr))) return rc;
+    }
     if (c->h_flags.close_pairs)
         fprintf(stdout, " Warning: The distance of two atoms is very small (%d pairs below 0.5)\n", c->h_flags.close_pairs);
-    // results: out8 | force SoA (= Fortran FORCE(NA,3))
-    size_t b_f = sizeof(double) * 3 * (size_t)na;
-    if (c->pin(64 + b_f)) return fail(GAPCU_ECUDA, "cudaMallocHost failed");
-    double *h_out = (double *)c->h_pin, *h_f = h_out + 8;
-    CU(cudaMemcpyAsync(h_out, c->d_out8.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(h_f, c->d_force.p, b_f, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
     *ene = h_out[0];
     for (int q = 0; q < 6; q++) stress[q] = h_out[1 + q];
     memcpy(force, h_f, b_f);
