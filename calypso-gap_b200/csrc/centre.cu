@@ -92,6 +92,7 @@ static SmemLayout make_layout(const CentreArgs &a, int mode) {
 
 size_t centre_smem_bytes(const CentreArgs &a, int mode) { return (size_t)make_layout(a, mode).total; }
 int centre_warps() { return NW; }
+size_t centre_stash_words(const CentreArgs &a, int chunks, int ctas) { return (size_t)ctas * chunks * (size_t)(a.lcap + 32 + 512); }
 
 // control block in shared memory
 struct Ctl {
@@ -107,6 +108,7 @@ struct Ctl {
     int TB, nkept;
 };
 static_assert(sizeof(Ctl) <= 4 * 512, "Ctl does not fit");
+static_assert(sizeof(Ctl) <= 4 * 512, "Ctl does not fit its stash slot");
 
 // exp(x), x <= 0; clamp only when the potential can produce arguments below -700
 __device__ __forceinline__ double exp_arg(double x, const double *T32, int clamp) {
@@ -172,7 +174,7 @@ __device__ __forceinline__ void scatter3(double *pa, int pcap, int idx, double v
 }
 
 template <int MODE>
-__device__ __forceinline__ void process_centre(const CentreArgs &a, const int i, unsigned char *smem) {
+__device__ __forceinline__ void process_centre(const CentreArgs &a, const int i, unsigned char *smem, const bool first) {
     constexpr bool FWD = MODE != MODE_BWD, BWD = MODE != MODE_FWD, FUSED = MODE == MODE_FUSED;
     const PlanDev &pl = a.plan;
     const int ncls = pl.ncls, D = pl.D, nsf = pl.nsf, pcap = a.pcap, lcap = a.lcap;
@@ -213,13 +215,15 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
     const int ntot = a.ntot;
     const int *g_iplus = pl.itab + pl.o_grp_iplus, *g_iminus = pl.itab + pl.o_grp_iminus;
 
-    // ---- 0: tables ------------------------------------------------------------
-    if (tid < 32) s_t32[tid] = a.exp2_table[tid];
-    if (tid < MAXC_DEV) s_t2[tid] = tid < ncls ? a.cls.t2[tid] : -1.0;
-    for (int t = tid; t < pl.n_grp; t += CT) s_galpha[t] = pl.dtab[pl.o_grp_alpha + t];
-    for (int t = tid; t < pl.n_rad; t += CT) {
-        s_radi[t] = make_int2(pl.itab[pl.o_rad_ii + t], pl.itab[pl.o_rad_cls + t] | (pl.itab[pl.o_rad_type + t] << 16));
-        s_radp[t] = pl.dtab[pl.o_rad_p + t];
+    // ---- 0: tables (centre independent: loaded once per persistent CTA) ----------------
+    if (first) {
+        if (tid < 32) s_t32[tid] = a.exp2_table[tid];
+        if (tid < MAXC_DEV) s_t2[tid] = tid < ncls ? a.cls.t2[tid] : -1.0;
+        for (int t = tid; t < pl.n_grp; t += CT) s_galpha[t] = pl.dtab[pl.o_grp_alpha + t];
+        for (int t = tid; t < pl.n_rad; t += CT) {
+            s_radi[t] = make_int2(pl.itab[pl.o_rad_ii + t], pl.itab[pl.o_rad_cls + t] | (pl.itab[pl.o_rad_type + t] << 16));
+            s_radp[t] = pl.dtab[pl.o_rad_p + t];
+        }
     }
     if (FWD) for (int t = tid; t < NW * D; t += CT) s_gw[t] = 0.0;
     if (MODE == MODE_BWD) for (int t = tid; t < D; t += CT) s_du[t] = a.dEdG[(size_t)i * D + t];
@@ -545,14 +549,24 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
     };
 
     // ---- drive the phases ---------------------------------------------------------------
-    bool list_ready = false;
+    bool list_ready = false, list_stashed = false;
     if (FWD) {
+        const bool stash = FUSED && nchunk > 1 && a.list_scratch && nchunk <= a.list_scratch_chunks;
         for (int ch = 0; ch < nchunk; ch++) {
             build_list(ch * qchunk, min(Q, (ch + 1) * qchunk), true);
+            if (stash) {
+                // keep the sorted list of this chunk (L2 resident) for the backward pass
+                uint32_t *dst = a.list_scratch + ((size_t)blockIdx.x * a.list_scratch_chunks + ch) * (size_t)(lcap + 32 + 512);
+                const int n = ctl->nkept;
+                for (int t = tid; t < n; t += CT) dst[t] = s_S[t];
+                const int *cs = (const int *)ctl;
+                for (int t = tid; t < (int)(sizeof(Ctl) / 4); t += CT) dst[lcap + 32 + t] = (uint32_t)cs[t];
+            }
             forward_list();
             __syncthreads();
         }
         list_ready = (nchunk == 1);
+        list_stashed = stash;
         __syncthreads();
         // per-warp partial sums -> descriptors (fixed order)
         for (int k = tid; k < D; k += CT) {
@@ -685,7 +699,17 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         }
         __syncthreads();
         for (int ch = 0; ch < nchunk; ch++) {
-            if (!list_ready) build_list(ch * qchunk, min(Q, (ch + 1) * qchunk), false);
+            if (list_stashed) {
+                const uint32_t *src = a.list_scratch + ((size_t)blockIdx.x * a.list_scratch_chunks + ch) * (size_t)(lcap + 32 + 512);
+                int *cs = (int *)ctl;
+                for (int t = tid; t < (int)(sizeof(Ctl) / 4); t += CT) cs[t] = (int)src[lcap + 32 + t];
+                __syncthreads();
+                const int n = ctl->nkept;
+                for (int t = tid; t < n; t += CT) s_S[t] = src[t];
+                __syncthreads();
+            } else if (!list_ready) {
+                build_list(ch * qchunk, min(Q, (ch + 1) * qchunk), false);
+            }
             backward_list();
         }
         // ---- epilogue: per neighbour gradient, centre gradient, strs contraction ----------
@@ -721,13 +745,26 @@ template <int MODE>
 __global__ void __launch_bounds__(CT, 3) k_centre(const CentreArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_next;
+    bool first = true;
+    unsigned long long t0 = 0;
+    if (threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
     for (;;) {
         __syncthreads();  // everybody is done with the previous centre's shared memory
         if (threadIdx.x == 0) s_next = atomicAdd(&a.flags->queue[MODE], 1);
         __syncthreads();
         const int n = s_next;
         if (n >= (a.n_centres ? *a.n_centres : a.ntot)) break;
-        process_centre<MODE>(a, a.order ? a.order[n] : n, smem);
+        process_centre<MODE>(a, a.order ? a.order[n] : n, smem, first);
+        first = false;
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+        atomicMax(&a.flags->t_start_min, ~t0);   // flags start zeroed: minima are kept as maxima of the complement
+        atomicMax(&a.flags->t_exit_min, ~t1);
+        atomicMax(&a.flags->t_exit_max, t1);
+        atomicAdd(&a.flags->t_busy_sum, t1 - t0);
+        atomicAdd(&a.flags->n_ctas, 1ull);
     }
 }
 

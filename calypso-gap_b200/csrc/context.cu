@@ -87,6 +87,8 @@ struct gapcu_ctx {
     DBuf<int4> d_abin;
     DBuf<double> d_pos, d_wgt, d_G, d_dEdG, d_eatom, d_fpair, d_gself, d_vir, d_force, d_out8, d_mindis, d_epart, d_accpart;
     DBuf<uint64_t> d_keys;
+    DBuf<uint32_t> d_stash;
+    int sm_count = 0;
     DBuf<DevFlags> d_flags;
     DBuf<unsigned char> d_flush;
     // ---- spatial decomposition over ranks + NCCL (loaded lazily with dlopen)
@@ -181,7 +183,7 @@ extern "C" void gapcu_ctx_destroy(gapcu_ctx *c) {
     c->d_bin_atoms.release(); c->d_nbr_cnt.release(); c->d_order.release(); c->d_abin.release(); c->d_pos.release(); c->d_wgt.release();
     c->d_G.release(); c->d_dEdG.release(); c->d_eatom.release(); c->d_fpair.release(); c->d_gself.release();
     c->d_vir.release(); c->d_force.release(); c->d_out8.release(); c->d_mindis.release(); c->d_keys.release();
-    c->d_epart.release(); c->d_accpart.release(); c->d_flags.release(); c->d_flush.release(); c->d_role.release(); c->d_active.release();
+    c->d_stash.release(); c->d_epart.release(); c->d_accpart.release(); c->d_flags.release(); c->d_flush.release(); c->d_role.release(); c->d_active.release();
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->stage_ev_init) for (auto &e : c->stage_ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -536,6 +538,14 @@ static int make_centre_args(gapcu_ctx *c, int lgrad, CentreArgs *out, bool *fuse
                     if (centre_smem_bytes(a, mode) <= targets[t]) { ok = true; break; }
             }
         if (!ok) return fail(GAPCU_ELIMIT, "centre kernel needs more shared memory than an SM has");
+        // several chunks per centre: the forward pass parks its sorted lists for the backward pass
+        const int chunks = (q + a.lcap - 1) / a.lcap;
+        if (fused && chunks > 1 && chunks <= 16) {
+            if (!c->sm_count) cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
+            const int ctas = c->sm_count * 4;   // upper bound of the persistent grid
+            CU(c->d_stash.ensure(centre_stash_words(a, chunks, ctas)));
+            a.list_scratch = c->d_stash.p; a.list_scratch_chunks = chunks;
+        }
     }
     *out = a;
     *fused_out = fused;
@@ -723,6 +733,20 @@ extern "C" int gapcu_ctx_fetch_neighbors(gapcu_ctx *c, int cap, int *count, int 
         }
     }
     return mx;
+}
+
+extern "C" int gapcu_ctx_balance(gapcu_ctx *c, double *out4) {
+    if (!c || !c->computed) return fail(GAPCU_EARG, "nothing computed");
+    cudaSetDevice(c->device);
+    int rc = read_flags(c);
+    if (rc) return rc;
+    const DevFlags &f = c->h_flags;
+    out4[0] = (double)f.n_ctas;
+    const unsigned long long tstart = ~f.t_start_min, tfirst = ~f.t_exit_min;     // stored as complements
+    out4[1] = (double)(f.t_exit_max - tstart) * 1e-3;                              // kernel span, us
+    out4[2] = (double)(tfirst - tstart) * 1e-3;                                    // first CTA done, us
+    out4[3] = f.n_ctas ? (double)f.t_busy_sum / ((double)f.n_ctas * (double)(f.t_exit_max - tstart)) : 0.0;
+    return 0;
 }
 
 extern "C" int gapcu_ctx_work_counters(gapcu_ctx *c, double *out, int n) {

@@ -50,6 +50,9 @@ struct DevFlags {
     int n_centres;       // atoms with role == 2
     int queue[4];        // work-queue heads of the persistent centre kernels (one per mode)
     unsigned long long work[10];  // see gapcu_ctx_work_counters
+    // persistent centre kernel, nanoseconds of %globaltimer: earliest start, earliest / latest
+    // exit and the sum of the CTAs' busy times (load-balance diagnostics)
+    unsigned long long t_start_min, t_exit_min, t_exit_max, t_busy_sum, n_ctas;
 };
 
 constexpr int MAXC_DEV = 16;  // distinct cutoffs (classes) supported
@@ -98,6 +101,8 @@ struct CentreArgs {
     const double *exp2_table;   // [32] 2^(j/32)
     int ntot, cap, pcap;        // pcap: shared-memory neighbour capacity (>= max count)
     int lcap;                   // triplet-list capacity per chunk
+    uint32_t *list_scratch;     // [ctas][list_scratch_chunks][lcap+32+512] sorted lists kept from forward to backward
+    int list_scratch_chunks;
     int npa;                    // private accumulator sets in backward: NW, or 1 (= shared + atomics)
     int lgrad;
     int exp_clamp;              // 1: exponent arguments may fall below -700 and are clamped

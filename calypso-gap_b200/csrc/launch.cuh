@@ -23,6 +23,7 @@ void launch_order(cudaStream_t st, const int *nbr_cnt, int ntot, int *order, con
 // centre.cu  (mode: 0 forward, 1 backward, 2 fused forward + GPR + backward)
 size_t centre_smem_bytes(const CentreArgs &a, int mode);
 int centre_warps();
+size_t centre_stash_words(const CentreArgs &a, int chunks, int ctas);
 int launch_forward(cudaStream_t st, const CentreArgs &a, long *launches);
 int launch_backward(cudaStream_t st, const CentreArgs &a, long *launches);
 int launch_fused(cudaStream_t st, const CentreArgs &a, long *launches);

@@ -27,7 +27,7 @@ SYMBOLS = [
     "gapcu_ctx_set_potential", "gapcu_ctx_set_pipeline", "gapcu_nccl_unique_id", "gapcu_ctx_nccl_init",
     "gapcu_ctx_set_domain", "gapcu_ctx_set_structures", "gapcu_ctx_compute", "gapcu_ctx_fetch",
     "gapcu_ctx_fetch_descriptors", "gapcu_ctx_fetch_neighbors", "gapcu_ctx_time_compute", "gapcu_stage_name",
-    "gapcu_ctx_work_counters", "gapcu_fp64_peaks",
+    "gapcu_ctx_work_counters", "gapcu_ctx_balance", "gapcu_fp64_peaks",
 ]
 FORTRAN_SYMBOLS = ["fgap_calc_", "fgap_read_", "fget_bond_", "car2acsf_", "write_array_2dim_"]
 
@@ -179,6 +179,12 @@ class Context:
         _check(lib().gapcu_ctx_work_counters(self.h, out, 10))
         keys = ["atoms", "pairs", "pair_classes", "candidates", "triplets", "triplet_classes", "triplet_sf", "radial_sf", "class_candidates"]
         return dict(zip(keys, out))
+
+    def balance(self):
+        out = np.zeros(4)
+        lib().gapcu_ctx_balance.argtypes = [_vp, _dp]
+        _check(lib().gapcu_ctx_balance(self.h, out))
+        return {"ctas": int(out[0]), "span_us": out[1], "first_idle_us": out[2], "busy_frac": out[3]}
 
     def fp64_peaks(self):
         a = C.c_double(); b = C.c_double()

@@ -145,6 +145,10 @@ const char *gapcu_stage_name(int stage);
  * per angular cutoff class, P_c(P_c-1)/2). */
 int gapcu_ctx_work_counters(gapcu_ctx *ctx, double *out, int n);
 
+/* Load balance of the persistent centre kernel in the last compute: out4 = {CTAs, span of
+ * the kernel in us, time until the first CTA ran out of work in us, mean busy fraction}. */
+int gapcu_ctx_balance(gapcu_ctx *ctx, double *out4);
+
 /* FP64 peak micro-benchmarks on the context's device: DFMA-chain (CUDA cores)
  * and mma.sync m8n8k4 f64 (DMMA).  TFLOP/s each. */
 int gapcu_fp64_peaks(gapcu_ctx *ctx, double *dfma_tflops, double *dmma_tflops);

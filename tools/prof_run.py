@@ -17,3 +17,4 @@ for _ in range(steps):
     c.compute(True)
 e, f, s = c.fetch()
 print("E", e[0])
+print("balance", c.balance())
