@@ -114,6 +114,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    os.environ["GAPCU_DEVICE"] = str(local)   # device of the Fortran-style entry points (gapcu_calc) on this rank
     cell, pos, z = workload(rank)
     natoms = len(pos)
     ctx = gapcu.Context(local)
@@ -137,7 +138,7 @@ def run_ours(args):
     while rank == 0 and time.time() < t_end:
         ctx.time_compute(50, True, 0, stages=False)
     clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms], dtype=torch.float64, device=torch.device("cuda", local))
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
@@ -192,7 +193,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     os.chdir(cwd)
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dt], dtype=torch.float64, device=torch.device("cuda", local))
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = natoms * args.steps * world / float(t.item())

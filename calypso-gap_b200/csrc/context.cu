@@ -60,6 +60,18 @@ struct DBuf {
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+// Every public entry point runs on its context's device and gives the caller's current
+// device back on return (a host application such as PyTorch keeps its own per-thread device).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 }  // namespace
 
 struct gapcu_ctx {
@@ -152,7 +164,11 @@ extern "C" gapcu_ctx *gapcu_ctx_create(int device) {
     int n = gapcu_device_count();
     if (n <= 0) { fail(GAPCU_ENODEV, "no CUDA device: gapcu has no CPU fallback"); return nullptr; }
     if (device < 0 || device >= n) { fail(GAPCU_EARG, "bad device index"); return nullptr; }
-    if (cudaSetDevice(device) != cudaSuccess) { fail(GAPCU_ECUDA, "cudaSetDevice failed"); return nullptr; }
+    DeviceGuard dg_(device);
+    {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cur != device) { fail(GAPCU_ECUDA, "cudaSetDevice failed"); return nullptr; }
+    }
     gapcu_ctx *c = new gapcu_ctx();
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -175,7 +191,7 @@ extern "C" gapcu_ctx *gapcu_ctx_create(int device) {
 
 extern "C" void gapcu_ctx_destroy(gapcu_ctx *c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard dg_(c->device);
     cudaStreamSynchronize(c->stream);
     c->d_itab.release(); c->d_dtab.release(); c->d_mm_raw.release(); c->d_theta_raw.release(); c->d_coeff_raw.release();
     c->d_Mt.release(); c->d_MtT.release(); c->d_exp2.release(); c->d_mn.release(); c->d_coeff.release(); c->d_cmean.release(); c->d_itheta.release();
@@ -195,7 +211,7 @@ extern "C" void gapcu_ctx_destroy(gapcu_ctx *c) {
 // ---------------------------------------------------------------------------
 static int set_sf(gapcu_ctx *c, const std::vector<int> &z, const std::vector<double> &w,
                   const std::vector<int> &ntype, const std::vector<double> &alpha, const std::vector<double> &cutoff) {
-    cudaSetDevice(c->device);
+    DeviceGuard dg_(c->device);
     try {
         c->plan = make_plan(ntype, alpha, cutoff);
     } catch (const std::exception &e) {
@@ -233,7 +249,7 @@ static int pick_dp(int D) {
 
 // mm in C order [M][D]
 static int set_gpr(gapcu_ctx *c, int M, int D, const double *theta, const double *mm, const double *coeff) {
-    cudaSetDevice(c->device);
+    DeviceGuard dg_(c->device);
     if (M < 0 || D <= 0) return fail(GAPCU_EARG, "bad GPR sizes");
     int Dp = pick_dp(D);
     if (Dp < 0) return fail(GAPCU_ELIMIT, "des_len > 256 is beyond this build's DMMA tile set");
@@ -298,7 +314,7 @@ extern "C" int gapcu_ctx_set_pipeline(gapcu_ctx *c, int mode) {
 // need_weights = false for the bond-length path (no potential involved).
 static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, const int *species, const double *lat_c,
                                const double *pos, bool pos_soa, double rcut, bool need_weights) {
-    cudaSetDevice(c->device);
+    DeviceGuard dg_(c->device);
     if (nstruct <= 0) return fail(GAPCU_EARG, "nstruct must be positive");
     if (!(rcut > 0.0)) return fail(GAPCU_EARG, "rcut must be positive");
     if (need_weights && !c->have_sf) return fail(GAPCU_EARG, "no potential loaded");
@@ -451,7 +467,7 @@ extern "C" int gapcu_ctx_nccl_init(gapcu_ctx *c, int nranks, int rank, const cha
     if (!c || nranks < 1 || rank < 0 || rank >= nranks) return fail(GAPCU_EARG, "bad NCCL rank/size");
     int rc = load_nccl();
     if (rc) return rc;
-    cudaSetDevice(c->device);
+    DeviceGuard dg_(c->device);
     NcclId id;
     memcpy(id.internal, id128, 128);
     void *comm = nullptr;
@@ -636,7 +652,7 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
 
 extern "C" int gapcu_ctx_compute(gapcu_ctx *c, int lgrad) {
     if (!c) return fail(GAPCU_EARG, "null context");
-    cudaSetDevice(c->device);
+    DeviceGuard dg_(c->device);
     return enqueue_pass(c, lgrad, nullptr);
 }
 
@@ -659,7 +675,7 @@ static int finish_pass(gapcu_ctx *c) {
 extern "C" int gapcu_ctx_fetch(gapcu_ctx *c, double *ene, double *force, double *stress) {
     if (!c) return fail(GAPCU_EARG, "null context");
     if (!c->computed) return fail(GAPCU_EARG, "nothing computed");
-    cudaSetDevice(c->device);
+    DeviceGuard dg_(c->device);
     int rc = finish_pass(c);
     if (rc) return rc;
     if (c->h_flags.close_pairs)
@@ -683,7 +699,7 @@ extern "C" int gapcu_ctx_fetch(gapcu_ctx *c, double *ene, double *force, double 
 
 extern "C" int gapcu_ctx_fetch_descriptors(gapcu_ctx *c, double *xx, double *dedg, double *eatom) {
     if (!c || !c->computed) return fail(GAPCU_EARG, "nothing computed");
-    cudaSetDevice(c->device);
+    DeviceGuard dg_(c->device);
     int rc = finish_pass(c);
     if (rc) return rc;
     const size_t n = (size_t)c->ntot * c->D;
@@ -696,7 +712,7 @@ extern "C" int gapcu_ctx_fetch_descriptors(gapcu_ctx *c, double *xx, double *ded
 
 extern "C" int gapcu_ctx_fetch_neighbors(gapcu_ctx *c, int cap, int *count, int *idx, int *shift, double *dis) {
     if (!c || !c->computed) return fail(GAPCU_EARG, "nothing computed");
-    cudaSetDevice(c->device);
+    DeviceGuard dg_(c->device);
     int rc = finish_pass(c);
     if (rc) return rc;
     const size_t NT = (size_t)c->ntot;
@@ -737,7 +753,7 @@ extern "C" int gapcu_ctx_fetch_neighbors(gapcu_ctx *c, int cap, int *count, int 
 
 extern "C" int gapcu_ctx_balance(gapcu_ctx *c, double *out4) {
     if (!c || !c->computed) return fail(GAPCU_EARG, "nothing computed");
-    cudaSetDevice(c->device);
+    DeviceGuard dg_(c->device);
     int rc = read_flags(c);
     if (rc) return rc;
     const DevFlags &f = c->h_flags;
@@ -751,7 +767,7 @@ extern "C" int gapcu_ctx_balance(gapcu_ctx *c, double *out4) {
 
 extern "C" int gapcu_ctx_work_counters(gapcu_ctx *c, double *out, int n) {
     if (!c || !c->computed) return fail(GAPCU_EARG, "nothing computed");
-    cudaSetDevice(c->device);
+    DeviceGuard dg_(c->device);
     int rc = read_flags(c);
     if (rc) return rc;
     for (int q = 0; q < n && q < 10; q++) out[q] = (double)c->h_flags.work[q];
@@ -770,7 +786,7 @@ extern "C" const char *gapcu_stage_name(int s) {
 extern "C" int gapcu_ctx_time_compute(gapcu_ctx *c, int lgrad, int steps, long l2_flush_bytes, double *ms_total,
                                       double *stage_ms, long *launches) {
     if (!c) return fail(GAPCU_EARG, "null context");
-    cudaSetDevice(c->device);
+    DeviceGuard dg_(c->device);
     if (!c->stage_ev_init) {
         for (auto &e : c->stage_ev) CU(cudaEventCreate(&e));
         c->stage_ev_init = true;
@@ -818,7 +834,7 @@ extern "C" int gapcu_ctx_time_compute(gapcu_ctx *c, int lgrad, int steps, long l
 
 extern "C" int gapcu_fp64_peaks(gapcu_ctx *c, double *dfma, double *dmma) {
     if (!c) return fail(GAPCU_EARG, "null context");
-    cudaSetDevice(c->device);
+    DeviceGuard dg_(c->device);
     launch_fp64_peaks(c->stream, dfma, dmma);
     CU(cudaGetLastError());
     return 0;
@@ -873,6 +889,7 @@ extern "C" int gapcu_calc(int na, const int *species, const double *lat, const d
     int rc = default_ctx(&c);
     if (rc) return rc;
     if (na <= 0) return fail(GAPCU_EARG, "NA must be positive");
+    DeviceGuard dg_(c->device);
     if ((rc = refresh_sf_from_cwd(c))) return rc;
     if (des_len != c->plan.D) return fail(GAPCU_EARG, "des_len does not equal 2*nsf of ./gap_parameters");
     // GPR data: compare the caller's (Fortran-layout) arrays with the last call's; only a
@@ -956,6 +973,7 @@ extern "C" int gapcu_bond(int na, const double *lat, const int *elements, const 
     int rc = default_ctx(&c);
     if (rc) return rc;
     if (na <= 0) return fail(GAPCU_EARG, "NA must be positive");
+    DeviceGuard dg_(c->device);
     double lat_c[9];
     for (int r = 0; r < 3; r++) for (int col = 0; col < 3; col++) lat_c[r * 3 + col] = lat[r + 3 * col];
     if ((rc = set_structures_impl(c, 1, &na, nullptr, lat_c, pos, true, rcut, false))) return rc;
@@ -989,7 +1007,7 @@ extern "C" int gapcu_car2acsf_table(int na, int max_neighbor, int nf, const doub
         maxcnt = std::max(maxcnt, neighbor_count[i]);
     }
     if (maxcnt > 1023) return fail(GAPCU_ENEIGH, "more than 1023 neighbours");
-    cudaSetDevice(c->device);
+    DeviceGuard dg_(c->device);
     // a single pseudo structure: the kernels only need the centre positions and the table
     const size_t NA = (size_t)na;
     c->h_structs.assign(1, StructDev());

@@ -310,3 +310,21 @@ def test_wide_descriptor_large_sparse_set(oracle, bc_structure):
         assert np.abs(dedg - want["dedg"]).max() <= 1e-10 * np.abs(want["dedg"]).max()
         _cmp(got, want)
     c.close()
+
+
+def test_entry_points_restore_the_callers_device(golden_frames):
+    """A context on GPU 1 must not leave GPU 1 as the calling thread's current device
+    (bench.py ranks, PyTorch hosts)."""
+    import gapcu
+    if gapcu.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import torch
+    torch.cuda.set_device(0)
+    c = gapcu.Context(1)
+    c.load_potential(os.path.join(GOLDEN, "gap_parameters"))
+    g = golden_frames
+    r = c.evaluate(g["numbers"], g["cell"][0], g["positions"][0], 6.0, True)
+    assert abs(r["energy"] - g["energy"][0]) <= E_TOL * abs(g["energy"][0])
+    assert torch.cuda.current_device() == 0
+    assert torch.zeros(1, device="cuda").device.index == 0
+    c.close()
