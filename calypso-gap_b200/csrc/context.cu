@@ -347,6 +347,8 @@ static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, con
         memcpy(sd.lat, ci.lat, sizeof sd.lat);
         memcpy(sd.inv, ci.inv, sizeof sd.inv);
         sd.volume = ci.volume;
+        for (int d = 0; d < 3; d++)
+            sd.spacing[d] = 1.0 / std::sqrt(ci.inv[d] * ci.inv[d] + ci.inv[3 + d] * ci.inv[3 + d] + ci.inv[6 + d] * ci.inv[6 + d]);
         for (int d = 0; d < 3; d++) {
             sd.nabc[d] = ci.nabc[d];
             sd.nbin[d] = ci.nbin[d];

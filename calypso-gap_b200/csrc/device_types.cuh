@@ -9,6 +9,7 @@ struct StructDev {
     double lat[9];   // rows = lattice vectors
     double inv[9];   // frac = pos * inv
     double volume;
+    double spacing[3];   // interplanar spacing of each lattice direction
     int nabc[3];
     int nbin[3];
     int mscan[3];

@@ -17,12 +17,15 @@ namespace gapcu {
 
 constexpr double GPA2EVPANG = 6.24219e-3;  // gap_calc.f90:9
 
-__global__ void __launch_bounds__(256)
+constexpr int GT = 128;  // threads per atom in k_gather: one mirror lookup per thread for P <= 128
+
+__global__ void __launch_bounds__(GT)
 k_gather(const StructDev *structs, const int *sid, int ntot, int cap, const uint64_t *nbr_keys,
          const int *nbr_cnt, const double *fpair, const double *gself, double *force,
          const unsigned char *role, const int *active, const DevFlags *flags) {
-    const int slot_i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    __shared__ double red[GT / 32][3];
+    const int slot_i = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (slot_i >= (active ? flags->n_active : ntot)) return;
     const int i = active ? active[slot_i] : slot_i;
     const bool i_owned = !role || role[i] == 2;
@@ -30,7 +33,7 @@ k_gather(const StructDev *structs, const int *sid, int ntot, int cap, const uint
     const int il = i - sd.atom_off;
     const int P = min(nbr_cnt[i], cap);
     double gx = 0.0, gy = 0.0, gz = 0.0;
-    for (int s = lane; s < P; s += 32) {
+    for (int s = tid; s < P; s += GT) {
         int jl, n1, n2, n3;
         nbr_unkey(nbr_keys[(size_t)i * cap + s], jl, n1, n2, n3);
         const int nb = sd.atom_off + jl;
@@ -38,12 +41,13 @@ k_gather(const StructDev *structs, const int *sid, int ntot, int cap, const uint
         if (!nb_owned && !i_owned) continue;
         const uint64_t want = nbr_key(il, -n1, -n2, -n3);
         const uint64_t *lst = nbr_keys + (size_t)nb * cap;
-        int lo = 0, hi = min(nbr_cnt[nb], cap);
+        const int cnt_nb = min(nbr_cnt[nb], cap);
+        int lo = 0, hi = cnt_nb;
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
             if (lst[mid] < want) lo = mid + 1; else hi = mid;
         }
-        if (lo < min(nbr_cnt[nb], cap) && lst[lo] == want) {
+        if (lo < cnt_nb && lst[lo] == want) {
             if (nb_owned) {
                 const double *fp = fpair + ((size_t)nb * cap + lo) * 3;
                 gx += fp[0]; gy += fp[1]; gz += fp[2];
@@ -62,12 +66,14 @@ k_gather(const StructDev *structs, const int *sid, int ntot, int cap, const uint
         gy += __shfl_xor_sync(0xffffffffu, gy, o);
         gz += __shfl_xor_sync(0xffffffffu, gz, o);
     }
-    if (lane == 0) {
-        const double sx = i_owned ? gself[(size_t)i * 3] : 0.0, sy = i_owned ? gself[(size_t)i * 3 + 1] : 0.0;
-        const double sz = i_owned ? gself[(size_t)i * 3 + 2] : 0.0;
-        atomicAdd(&force[i], -(sx + gx));
-        atomicAdd(&force[ntot + i], -(sy + gy));
-        atomicAdd(&force[2 * ntot + i], -(sz + gz));
+    if (lane == 0) { red[wid][0] = gx; red[wid][1] = gy; red[wid][2] = gz; }
+    __syncthreads();
+    if (tid < 3) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < GT / 32; w++) v += red[w][tid];
+        const double self = i_owned ? gself[(size_t)i * 3 + tid] : 0.0;
+        atomicAdd(&force[(size_t)tid * ntot + i], -(self + v));
     }
 }
 
@@ -133,9 +139,8 @@ void launch_gather(cudaStream_t st, const StructDev *structs, int nstruct, const
                    const unsigned char *role, const int *active, const DevFlags *flags, long *launches) {
     cudaMemsetAsync(force_soa, 0, sizeof(double) * 3 * (size_t)ntot, st);
     if (lgrad) {
-        const int wpb = 8;
-        k_gather<<<(ntot + wpb - 1) / wpb, 32 * wpb, 0, st>>>(structs, sid, ntot, cap, nbr_keys, nbr_cnt, fpair,
-                                                               gself, force_soa, role, active, flags);
+        k_gather<<<ntot, GT, 0, st>>>(structs, sid, ntot, cap, nbr_keys, nbr_cnt, fpair, gself, force_soa, role, active,
+                                       flags);
         if (launches) *launches += 1;
     }
     k_finalize<<<nstruct, 256, 0, st>>>(structs, eatom, vir, lgrad, out8, role);

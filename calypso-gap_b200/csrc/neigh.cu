@@ -20,6 +20,7 @@ namespace gapcu {
 
 constexpr int NB_THREADS = 128;   // threads per centre in k_neigh
 constexpr int NB_MAXLIST = 1024;  // shared-memory list length (reference stops above 1000)
+constexpr int NB_CELLS = 128;     // cells whose candidates are enumerated together
 
 __device__ __forceinline__ int floordiv_i(int a, int b) {
     int q = a / b;
@@ -111,6 +112,75 @@ __global__ void k_fill_bins(const StructDev *structs, const int *sid, const int4
     bin_atoms[bin_start[s.bin_off + abin[i].x] + arank[i]] = i;
 }
 
+// Small batches: bin, scan and fill in ONE single-CTA kernel (shared-memory counters) instead
+// of a memset and three launches; same outputs as k_bin / k_scan_bins / k_fill_bins.
+constexpr int SMALL_NBINS = 4096;
+__global__ void __launch_bounds__(1024)
+k_bin_small(const StructDev *structs, const int *sid, const double *pos, int ntot, int nbins_total, int4 *abin,
+            int *bin_start, int *bin_atoms, DomainDev dom, unsigned char *role, int *active, DevFlags *flags) {
+    __shared__ int cnt[SMALL_NBINS + 1];
+    __shared__ int wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int t = tid; t <= nbins_total; t += 1024) cnt[t] = 0;
+    __syncthreads();
+    for (int i = tid; i < ntot; i += 1024) {
+        const StructDev &s = structs[sid[i]];
+        const double x = pos[i], y = pos[ntot + i], z = pos[2 * ntot + i];
+        int b[3], w[3], rl = 2;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double f = x * s.inv[c] + y * s.inv[3 + c] + z * s.inv[6 + c];
+            const double fl = floor(f);
+            w[c] = (int)fl;
+            const double fw = f - fl;
+            b[c] = min(max((int)(fw * s.nbin[c]), 0), s.nbin[c] - 1);
+            if (dom.enabled && dom.grid[c] > 1) {
+                const int g = dom.grid[c];
+                if (min(max((int)(fw * g), 0), g - 1) != dom.mine[c]) {
+                    const double lo = (double)dom.mine[c] / g, hi = (double)(dom.mine[c] + 1) / g;
+                    double dlo = lo - fw, dhi = fw - hi;
+                    dlo -= floor(dlo); dhi -= floor(dhi);
+                    rl = min(rl, fmin(dlo, dhi) <= dom.margin[c] * (1.0 + 1e-9) + 1e-12 ? 1 : 0);
+                }
+            }
+        }
+        const int id = (b[0] * s.nbin[1] + b[1]) * s.nbin[2] + b[2];
+        abin[i] = make_int4(id, w[0], w[1], w[2]);
+        if (role) role[i] = (unsigned char)rl;
+        if (active && rl >= 1) active[atomicAdd(&flags->n_active, 1)] = i;
+        atomicAdd(&cnt[s.bin_off + id], 1);
+    }
+    __syncthreads();
+    // exclusive scan of cnt[0..nbins_total) in chunks of 1024
+    int carry = 0;
+    for (int base = 0; base < nbins_total; base += 1024) {
+        const int idx = base + tid;
+        const int v = idx < nbins_total ? cnt[idx] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) wsum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int sv = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, sv, o); if (lane >= o) sv += y; }
+            wsum[lane] = sv;
+        }
+        __syncthreads();
+        const int excl = carry + (wid ? wsum[wid - 1] : 0) + x - v;
+        if (idx < nbins_total) { cnt[idx] = excl; bin_start[idx] = excl; }
+        carry += wsum[31];
+        __syncthreads();
+    }
+    if (tid == 0) bin_start[nbins_total] = carry;
+    __syncthreads();
+    for (int i = tid; i < ntot; i += 1024) {
+        const StructDev &s = structs[sid[i]];
+        bin_atoms[atomicAdd(&cnt[s.bin_off + abin[i].x], 1)] = i;
+    }
+}
+
 // One CTA per centre atom: gather candidates from the surrounding bins, apply the
 // reference test, sort into reference order, store keys (+ optional min distance).
 __global__ void __launch_bounds__(NB_THREADS)
@@ -121,6 +191,8 @@ k_neigh(const StructDev *structs, const int *sid, const double *pos, const int4 
     __shared__ int nkeys, nclose;
     __shared__ double lat[9];
     __shared__ double wmin[NB_THREADS / 32];
+    __shared__ int c_start[NB_CELLS], c_off[NB_CELLS + 1];
+    __shared__ int4 c_shift[NB_CELLS];
     if (active && (int)blockIdx.x >= flags->n_active) return;
     const int i = active ? active[blockIdx.x] : blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -137,26 +209,80 @@ k_neigh(const StructDev *structs, const int *sid, const double *pos, const int4 
     const int w1 = 2 * m1 + 1, w2 = 2 * m2 + 1;
     const int nscan = (2 * m0 + 1) * w1 * w2;
     const int aoff = s.atom_off;
+    // wrapped fractional coordinates of the centre: a whole cell is skipped when the slab gap to it
+    // along any lattice direction already exceeds rcut (prunes corner bins and far images)
+    double fw[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double f = xi * s.inv[c] + yi * s.inv[3 + c] + zi * s.inv[6 + c];
+        fw[c] = f - floor(f);
+    }
+    // bin width in length units along each direction
+    const double bw0 = s.spacing[0] / nb0, bw1 = s.spacing[1] / nb1, bw2 = s.spacing[2] / nb2;
+    const double fb0 = fw[0] * nb0, fb1 = fw[1] * nb1, fb2 = fw[2] * nb2;   // centre in bin units
+    const double rprune = rcut * (1.0 + 1e-9) + 1e-9;
+    const bool prune = nscan > 27;
     double dmin = 1e300;
-    for (int cell = wid; cell < nscan; cell += NB_THREADS / 32) {
-        int d0 = cell / (w1 * w2) - m0, d1 = (cell / w2) % w1 - m1, d2 = cell % w2 - m2;
-        int t0 = b0 + d0, t1 = b1 + d1, t2 = b2 + d2;
-        int s0 = floordiv_i(t0, nb0), s1 = floordiv_i(t1, nb1), s2 = floordiv_i(t2, nb2);
-        int id = ((t0 - s0 * nb0) * nb1 + (t1 - s1 * nb1)) * nb2 + (t2 - s2 * nb2);
-        int start = bin_start[s.bin_off + id], end = bin_start[s.bin_off + id + 1];
-        for (int q = start + lane; q < end; q += 32) {
-            int j = bin_atoms[q];
-            int4 bj = abin[j];
+    // Cells are handled NB_CELLS at a time: their (start, count, shift) are fetched by one
+    // thread each, the counts are scanned, and then the candidates of all those cells form ONE
+    // flat index space dealt over the threads.  Every thread so has several independent
+    // chains of dependent loads in flight (bin_atoms -> abin/pos) instead of walking cell by
+    // cell, which is what this latency-bound kernel needs.
+    for (int c0 = 0; c0 < nscan; c0 += NB_CELLS) {
+        const int nc = min(NB_CELLS, nscan - c0);
+        __syncthreads();
+        for (int t = tid; t < NB_CELLS; t += NB_THREADS) {
+            int cnt = 0;
+            if (t < nc) {
+                const int cell = c0 + t;
+                const int d0 = cell / (w1 * w2) - m0, d1 = (cell / w2) % w1 - m1, d2 = cell % w2 - m2;
+                const int t0 = b0 + d0, t1 = b1 + d1, t2 = b2 + d2;
+                const int s0 = floordiv_i(t0, nb0), s1 = floordiv_i(t1, nb1), s2 = floordiv_i(t2, nb2);
+                const int id = ((t0 - s0 * nb0) * nb1 + (t1 - s1 * nb1)) * nb2 + (t2 - s2 * nb2);
+                double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+                if (prune) {   // slab gaps (negative: inside); only worth it when many image cells are scanned
+                    g0 = fmax((double)t0 - fb0, fb0 - (double)(t0 + 1)) * bw0;
+                    g1 = fmax((double)t1 - fb1, fb1 - (double)(t1 + 1)) * bw1;
+                    g2 = fmax((double)t2 - fb2, fb2 - (double)(t2 + 1)) * bw2;
+                }
+                const int start = bin_start[s.bin_off + id];
+                cnt = (g0 > rprune || g1 > rprune || g2 > rprune) ? 0 : bin_start[s.bin_off + id + 1] - start;
+                c_start[t] = start;
+                c_shift[t] = make_int4(s0, s1, s2, 0);
+            }
+            c_off[t] = cnt;
+        }
+        __syncthreads();
+        if (wid == 0) {  // exclusive scan of the NB_CELLS counts by one warp (NB_CELLS / 32 per lane)
+            int run = 0;
+            for (int base = 0; base < NB_CELLS; base += 32) {
+                const int v = c_off[base + lane];
+                int x = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+                c_off[base + lane] = run + x - v;
+                run += __shfl_sync(0xffffffffu, x, 31);
+            }
+            if (lane == 0) c_off[NB_CELLS] = run;
+        }
+        __syncthreads();
+        const int total = c_off[NB_CELLS];
+        for (int cand = tid; cand < total; cand += NB_THREADS) {
+            int lo = 0, hi = nc;  // cell of this candidate: last cell with c_off <= cand
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (c_off[mid] <= cand) lo = mid; else hi = mid; }
+            const int j = bin_atoms[c_start[lo] + (cand - c_off[lo])];
+            const int4 sh = c_shift[lo];
+            const int4 bj = abin[j];
             // shift between wrapped coordinates -> shift of the caller's coordinates
-            int n1 = s0 - bj.y + bi.y, n2 = s1 - bj.z + bi.z, n3 = s2 - bj.w + bi.w;
+            const int n1 = sh.x - bj.y + bi.y, n2 = sh.y - bj.z + bi.z, n3 = sh.z - bj.w + bi.w;
             if (j == i && n1 == 0 && n2 == 0 && n3 == 0) continue;
             if (abs(n1) > na0 || abs(n2) > na1 || abs(n3) > na2) continue;
             double ox, oy, oz;
-            double dis = image_distance(pos, ntot, j, lat, n1, n2, n3, xi, yi, zi, ox, oy, oz);
+            const double dis = image_distance(pos, ntot, j, lat, n1, n2, n3, xi, yi, zi, ox, oy, oz);
             if (dis > rcut) continue;
             if (dis < 0.5) atomicAdd(&nclose, 1);
             dmin = fmin(dmin, dis);
-            int p = atomicAdd(&nkeys, 1);
+            const int p = atomicAdd(&nkeys, 1);
             if (p < NB_MAXLIST) keys[p] = nbr_key(j - aoff, n1, n2, n3);
         }
     }
@@ -249,11 +375,17 @@ void launch_neighbor_build(cudaStream_t st, const StructDev *structs, const int 
                            int *bin_count, int *bin_start, int *bin_atoms, uint64_t *nbr_keys, int *nbr_cnt,
                            double *min_dis, DevFlags *flags, const DomainDev &dom, unsigned char *role, int *active,
                            long *launches) {
-    cudaMemsetAsync(bin_count, 0, sizeof(int) * (size_t)nbins_total, st);
-    int tb = 256, gb = (ntot + tb - 1) / tb;
-    k_bin<<<gb, tb, 0, st>>>(structs, sid, pos, ntot, abin, arank, bin_count, dom, role, dom.enabled ? active : nullptr, flags);
-    k_scan_bins<<<1, 1024, 0, st>>>(bin_count, bin_start, nbins_total);
-    k_fill_bins<<<gb, tb, 0, st>>>(structs, sid, abin, arank, bin_start, ntot, bin_atoms);
+    if (ntot <= 8192 && nbins_total <= SMALL_NBINS) {
+        k_bin_small<<<1, 1024, 0, st>>>(structs, sid, pos, ntot, nbins_total, abin, bin_start, bin_atoms, dom, role,
+                                        dom.enabled ? active : nullptr, flags);
+        if (launches) *launches -= 2;   // one launch instead of three
+    } else {
+        cudaMemsetAsync(bin_count, 0, sizeof(int) * (size_t)nbins_total, st);
+        int tb = 256, gb = (ntot + tb - 1) / tb;
+        k_bin<<<gb, tb, 0, st>>>(structs, sid, pos, ntot, abin, arank, bin_count, dom, role, dom.enabled ? active : nullptr, flags);
+        k_scan_bins<<<1, 1024, 0, st>>>(bin_count, bin_start, nbins_total);
+        k_fill_bins<<<gb, tb, 0, st>>>(structs, sid, abin, arank, bin_start, ntot, bin_atoms);
+    }
     k_neigh<<<ntot, NB_THREADS, 0, st>>>(structs, sid, pos, abin, bin_start, bin_atoms, ntot, rcut, cap,
                                           nbr_keys, nbr_cnt, min_dis, flags, dom.enabled ? active : nullptr);
     if (launches) *launches += 4;
