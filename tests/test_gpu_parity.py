@@ -328,3 +328,119 @@ def test_entry_points_restore_the_callers_device(golden_frames):
     assert torch.cuda.current_device() == 0
     assert torch.zeros(1, device="cuda").device.index == 0
     c.close()
+
+
+# ---------------------------------------------------------------------------
+# edge cases of the reference's behaviour (SURVEY.md 5 "failure detection", App. A)
+# ---------------------------------------------------------------------------
+def test_isolated_atoms_and_tiny_structures(ctx, shipped_pot):
+    """No neighbours at all (P = 0), a dimer, and a single atom in a small cell that only
+    sees its own images."""
+    big = np.eye(3) * 40.0
+    for pos, z in ((np.array([[1.0, 2.0, 3.0]]), [6]),
+                   (np.array([[0.0, 0.0, 0.0], [1.4, 0.2, -0.3]]), [6, 5]),
+                   (np.array([[0.0, 0.0, 0.0], [1.4, 0.2, -0.3], [20.0, 20.0, 20.0]]), [6, 5, 6])):
+        z = np.array(z, np.int32)
+        _cmp(ctx.evaluate(z, big, pos, 6.0, True), shipped_pot.calc_dense(z, big, pos, 6.0, True))
+    small = np.array([[3.1, 0.0, 0.0], [0.4, 2.9, 0.0], [-0.3, 0.5, 3.3]])     # nabc = (2,3,2): self images only
+    z = np.array([6], np.int32)
+    want = shipped_pot.calc_dense(z, small, np.array([[0.2, 0.1, 0.3]]), 6.0, True)
+    got = ctx.evaluate(z, small, np.array([[0.2, 0.1, 0.3]]), 6.0, True)
+    _cmp(got, want)
+    assert np.abs(got["forces"]).max() < 1e-9               # a lattice of one atom: no net force, but a stress
+    assert np.abs(got["stress"]).max() > 1.0
+
+
+def test_rcut_other_than_the_sf_cutoffs(ctx, shipped_pot, bc_structure):
+    """rcut = 4.5 hides neighbours the 5 and 6 A functions would use (gap_calc.f90:101);
+    rcut = 7 lists neighbours no function uses."""
+    cell, pos = sheared(bc_structure["cell"], bc_structure["positions"])
+    z = bc_structure["numbers"].astype(np.int32)
+    for rcut in (4.5, 7.0):
+        _cmp(ctx.evaluate(z, cell, pos, rcut, True), shipped_pot.calc_sparse(z, cell, pos, rcut, True))
+
+
+def test_unwrapped_positions_parity(ctx, shipped_pot, bc_structure):
+    """Atoms shifted by whole lattice vectors: the reference's +-nabc window loses
+    neighbours; results must follow the reference, not physics."""
+    cell, pos = sheared(bc_structure["cell"], bc_structure["positions"])
+    pos = pos.copy(); pos[3] += 2 * cell[0] - cell[2]; pos[17] -= cell[1]
+    z = bc_structure["numbers"].astype(np.int32)
+    want = shipped_pot.calc_dense(z, cell, pos, 6.0, True)
+    _cmp(ctx.evaluate(z, cell, pos, 6.0, True), want)
+    wrapped = shipped_pot.calc_dense(z, cell, sheared(bc_structure["cell"], bc_structure["positions"])[1], 6.0, False)
+    assert abs(want["energy"] - wrapped["energy"]) > 1e-3
+
+
+def test_error_reporting(ctx, golden_frames, tmp_path, monkeypatch):
+    import gapcu
+    g = golden_frames
+    z = g["numbers"].copy().astype(np.int32); z[5] = 14           # species absent from gap_parameters
+    with pytest.raises(gapcu.GapcuError) as e:
+        ctx.evaluate(z, g["cell"][0], g["positions"][0], 6.0, True)
+    assert e.value.code == -3
+    dense = np.eye(3) * 2.7                                       # > 1000 neighbours within 6 A: reference stops
+    pos = np.array([[i, j, k] for i in range(3) for j in range(3) for k in range(3)], float) * 0.9 + 0.1
+    with pytest.raises(gapcu.GapcuError) as e:
+        ctx.evaluate(np.full(27, 6, np.int32), dense, pos, 6.0, True)
+    assert e.value.code == -2 and "max_neighbor" in str(e.value)
+    # the context stays usable after an error
+    r = ctx.evaluate(g["numbers"], g["cell"][0], g["positions"][0], 6.0, True)
+    assert abs(r["energy"] - g["energy"][0]) <= E_TOL * abs(g["energy"][0])
+    # Fortran-style entry point: message + STOP in the reference; with GAPCU_ERRORS=return NaNs come back
+    monkeypatch.chdir(tmp_path)                                   # no gap_parameters here
+    monkeypatch.setenv("GAPCU_ERRORS", "return")
+    import libgap.libgap as m
+    ene, force, stress, var = m.fgap_calc(g["numbers"], g["cell"][0], g["positions"][0], np.ones(66), np.zeros((129, 66)),
+                                          np.zeros((129, 129)), np.zeros(129), 6.0, True)
+    assert np.isnan(ene) and np.isnan(force).all()
+    assert "gap_parameters file does not exist!" in gapcu.lib().gapcu_last_error().decode()
+
+
+def test_maximum_neighbour_count(shipped_pot):
+    """Close to the reference's limit of 1000 neighbours per atom (gap_calc.f90:68): 8 atoms
+    in a 2.05 A cube see ~840 neighbours each; the kernels switch to their large-list
+    configuration (shared accumulators, several triplet-list chunks)."""
+    import gapcu
+    cell = np.eye(3) * 2.05
+    pos = np.array([[i, j, k] for i in range(2) for j in range(2) for k in range(2)], float) * 1.02 + 0.05
+    pos += np.random.default_rng(9).normal(0, 0.03, pos.shape)
+    z = np.array([6, 5, 6, 6, 5, 6, 6, 6], np.int32)
+    want = shipped_pot.calc_sparse(z, cell, pos, 6.0, True, stats=True)
+    assert 700 * 8 < want["stats"][0] <= 1000 * 8
+    c = gapcu.Context(0)
+    c.load_potential(os.path.join(GOLDEN, "gap_parameters"))
+    _cmp(c.evaluate(z, cell, pos, 6.0, True), want)
+    c.close()
+
+
+def test_neighbour_capacity_grows_on_demand(shipped_pot):
+    """A sparse structure first (small learned capacity), then a dense one in the same
+    context: the overflow is detected on the device and the pass re-run."""
+    import gapcu
+    c = gapcu.Context(0)
+    c.load_potential(os.path.join(GOLDEN, "gap_parameters"))
+    sparse_cell = np.eye(3) * 30.0
+    pos = np.random.default_rng(5).uniform(0, 30, (40, 3))
+    z = np.full(40, 6, np.int32)
+    _cmp(c.evaluate(z, sparse_cell, pos, 6.0, True), shipped_pot.calc_sparse(z, sparse_cell, pos, 6.0, True))
+    dense_cell = np.eye(3) * 7.2
+    fr = np.random.default_rng(6).uniform(0, 1, (40, 3))
+    while True:                                                 # 40 atoms in 373 A^3: ~100 neighbours each... make it denser
+        cell2 = np.eye(3) * 6.4
+        p2 = fr @ cell2
+        break
+    want = shipped_pot.calc_sparse(z, cell2, p2, 6.0, True)
+    _cmp(c.evaluate(z, cell2, p2, 6.0, True), want)
+    c.close()
+
+
+def test_batch_lgrad_false_and_mixed_sizes(ctx, shipped_pot):
+    structs = [random_candidate(3300 + i, 4 + 9 * i, 6 + 9 * i, species=(5, 6)) for i in range(5)]
+    ctx.set_structures([s[2] for s in structs], [s[0] for s in structs], [s[1] for s in structs], 6.0)
+    ctx.compute(False)
+    e, f, s = ctx.fetch()
+    assert not f.any() and not s.any()
+    for i, (cell, pos, z) in enumerate(structs):
+        w = shipped_pot.calc_sparse(z, cell, pos, 6.0, False)["energy"]
+        assert abs(e[i] - w) <= E_TOL * abs(w)
