@@ -217,10 +217,19 @@ def run_ours(args):
                  "split_stage_ms_per_step": {k: v / args.steps for k, v in st_split.items()}}
     t_desc = (stages["descriptor_forward"] + stages["gpr_dmma"] + stages["descriptor_backward"]) / args.steps * 1e-3
     achieved = (w_desc + w_gpr) / t_desc / 1e12
+    traffic, ncu_extra = None, {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        ncu_extra = {"fp64_pipe_active_pct": tj["fp64_pipe_active_pct"], "issue_slots_busy_pct": tj["issue_slots_busy_pct"],
+                     "source": tj["source"]}
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {"bound": "fp64", "kernel": "k_centre<fused> (wACSF forward + in-CTA GPR + backward, one launch per step)",
                 "achieved": achieved, "peak": dfma, "unit": "TFLOP/s", "frac": achieved / dfma if dfma else None,
                 "peak_source": "DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
-                "dmma_peak_tflops": dmma, "traffic": None,
+                "dmma_peak_tflops": dmma, "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu)",
+                "ncu": ncu_extra,
                 "flops_per_step": w_desc + w_gpr, "flops_desc": w_desc, "flops_gpr": w_gpr, "seconds_per_step": t_desc,
                 "gpr_dmma": split_gpr,
                 "stage_ms_per_step": {k: v / args.steps for k, v in stages.items()}}
