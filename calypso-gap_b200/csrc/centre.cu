@@ -430,7 +430,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                     const double cosv = (ra2 + rb2 - rjk2) * 0.5 * s_ir[ra] * s_ir[rb];
                     const double ssum = ra2 + rb2 + rjk2;
                     const double ww = s_w[ra] * s_w[rb];
-                    const double rjk = rjk2 > 0.0 ? rjk2 * rsqrt(rjk2) : 0.0;
+                    const double rjk = rjk2 * rsqrt_pos(fmax(rjk2, 1e-300));
                     double sn, cs;
                     sincos_0pi(rjk * pirc, &sn, &cs);
                     const double phi = fcc[ra] * fcc[rb] * (0.5 * (cs + 1.0));
@@ -494,7 +494,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             const double xb = s_x[rb], yb = s_x[pcap + rb], zb = s_x[2 * pcap + rb];
             const double rja = s_r[ra], rkb = s_r[rb], ira = s_ir[ra], irb = s_ir[rb];
             const double rjk2 = pair_dist2(xa, ya, za, xb, yb, zb);
-            const double irjk = rsqrt(rjk2);
+            const double irjk = rsqrt_pos(rjk2);
             const double rjk = rjk2 * irjk;
             const double ra2 = rja * rja, rb2 = rkb * rkb;
             const double cosv = (ra2 + rb2 - rjk2) * 0.5 * ira * irb;
@@ -601,10 +601,16 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         {
             const int kslab = (D + NW - 1) / NW, k0 = wid * kslab, k1 = min(D, k0 + kslab);
             for (int j = lane; j < Mp; j += 32) {
-                double s0 = 0.0;
-                const double *col = a.gpr_MtT + j;
-                for (int k = k0; k < k1; k++) { const double d0 = s_xs[k] - col[(size_t)k * Mp]; s0 = fma(d0, d0, s0); }
-                part[wid * Mp + j] = s0;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                const double *col = a.gpr_MtT + (size_t)k0 * Mp + j;
+                int k = k0;
+                for (; k + 3 < k1; k += 4, col += 4 * (size_t)Mp) {   // four independent chains, loads issued together
+                    const double m0 = __ldg(col), m1 = __ldg(col + Mp), m2 = __ldg(col + 2 * (size_t)Mp), m3 = __ldg(col + 3 * (size_t)Mp);
+                    const double d0 = s_xs[k] - m0, d1 = s_xs[k + 1] - m1, d2 = s_xs[k + 2] - m2, d3 = s_xs[k + 3] - m3;
+                    s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
+                }
+                for (; k < k1; k++, col += Mp) { const double d0 = s_xs[k] - __ldg(col); s0 = fma(d0, d0, s0); }
+                part[wid * Mp + j] = (s0 + s1) + (s2 + s3);
             }
         }
         __syncthreads();
@@ -631,9 +637,16 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             for (int k = lane; k < D; k += 32) {
                 const double xk = s_xs[k];
                 const double *row = a.gpr_Mt + k;
-                double a0 = 0.0;
-                for (int j = j0; j < j1; j++) a0 = fma(s_W[j], xk - row[(size_t)j * Dp], a0);
-                part[wid * D + k] = a0;       // W was consumed into registers/s_W; part is reused with stride D
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                const double *rp = row + (size_t)j0 * Dp;
+                int j = j0;
+                for (; j + 3 < j1; j += 4, rp += 4 * (size_t)Dp) {
+                    const double m0 = __ldg(rp), m1 = __ldg(rp + Dp), m2 = __ldg(rp + 2 * (size_t)Dp), m3 = __ldg(rp + 3 * (size_t)Dp);
+                    a0 = fma(s_W[j], xk - m0, a0); a1 = fma(s_W[j + 1], xk - m1, a1);
+                    a2 = fma(s_W[j + 2], xk - m2, a2); a3 = fma(s_W[j + 3], xk - m3, a3);
+                }
+                for (; j < j1; j++, rp += Dp) a0 = fma(s_W[j], xk - __ldg(rp), a0);
+                part[wid * D + k] = (a0 + a1) + (a2 + a3);   // part is reused with stride D
             }
         }
         __syncthreads();

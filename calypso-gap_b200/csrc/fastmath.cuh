@@ -104,4 +104,19 @@ GAPCU_HD void sincos_0pi(double y, double *sn, double *cs) {
     *cs = odd ? -s : cc;
 }
 
+#if defined(__CUDACC__)
+// 1/sqrt(x) for normal positive x: hardware seed (rsqrt.approx.ftz.f64, ~2^-22) refined by two
+// Newton steps (y <- y + y*(1 - x y^2)/2): ~1 ulp, 10 instructions instead of the ~35 of the
+// library routine, which also handles zero / denormal / infinite arguments.
+__device__ __forceinline__ double rsqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x * y, y, 1.0);
+    y = fma(y * 0.5, e, y);
+    e = fma(-x * y, y, 1.0);
+    y = fma(y * 0.5, e, y);
+    return y;
+}
+#endif
+
 }  // namespace gapcu
