@@ -621,12 +621,11 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
         GprDev g;
         g.M = c->M; g.Mp = c->Mp; g.D = c->D; g.Dp = c->Dp; g.Mt = c->d_Mt.p; g.MtT = c->d_MtT.p; g.mn = c->d_mn.p;
         g.coeff = c->d_coeff.p; g.cmean = c->d_cmean.p; g.itheta = c->d_itheta.p;
-        int nslice = 1, mslice = c->Mp;
-        gpr_slicing(c->ntot, c->Mp, &nslice, &mslice);
-        CU(c->d_epart.ensure((size_t)nslice * c->ntot));
-        CU(c->d_accpart.ensure((size_t)nslice * c->ntot * c->Dp));
-        if (launch_gpr(c->stream, g, c->d_G.p, c->ntot, c->d_eatom.p, c->d_dEdG.p, c->d_epart.p, c->d_accpart.p, nslice,
-                       mslice, &c->launches))
+        const int max_slices = gpr_max_slices(c->ntot, c->Mp);
+        CU(c->d_epart.ensure((size_t)max_slices * c->ntot));
+        CU(c->d_accpart.ensure((size_t)max_slices * c->ntot * c->Dp));
+        if (launch_gpr(c->stream, g, c->d_G.p, c->ntot, c->d_eatom.p, c->d_dEdG.p, c->d_epart.p, c->d_accpart.p,
+                       max_slices, c->d_exp2.p, &c->launches))
             return fail(GAPCU_ELIMIT, "unsupported descriptor length for the GPR kernel");
         CU(cudaGetLastError());
         if (ev) CU(cudaEventRecord(ev[3], c->stream));

@@ -19,11 +19,12 @@
 // k index enumerate the sparse points in the order (2t) then (2t+1).
 #include <cstdint>
 
+#include "fastmath.cuh"
 #include "launch.cuh"
 
 namespace gapcu {
 
-constexpr int GPR_WARPS = 4;   // 32 atoms per CTA share one staged tile of the sparse set
+constexpr int GPR_WARPS = 8;   // 64 atoms per CTA share the staged tiles of the sparse set
 constexpr int GPR_TS = 16;     // sparse points per staged tile
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
@@ -31,40 +32,69 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
-// row stride (doubles) of the staged tile: == 4 (mod 16) makes the GEMM 1 fragment loads
-// (8 rows x 4 consecutive doubles per half warp pair) hit 16 distinct bank pairs
-__host__ __device__ constexpr int gpr_ldt(int Dp) { return Dp + ((20 - Dp % 16) % 16); }
+// Row stride (doubles) of the shared-memory matrices: == 4 (mod 16).  A half warp of a
+// fragment load touches 4 rows x 4 consecutive doubles; with this stride those 16 doubles
+// fall into 16 distinct bank pairs.
+__host__ __device__ constexpr int gpr_ld(int Dp) { return Dp + ((20 - Dp % 16) % 16); }
 
-// NT = number of 8-wide descriptor tiles (Dp = 8*NT).  grid = (ceil(N/32), M slices).
-// Every CTA handles 32 atoms x one slice of the sparse set and writes PARTIAL sums
+// Column n of GEMM 1's 8-wide output tile is sparse row rowmap(n) = {0,1,2,3,5,4,7,6}[n] of
+// the staged tile.  GEMM 2 reads the rows rowmap(2t+e), t = 0..3, in one instruction: with
+// this permutation they are distinct mod 4 for e = 0 and e = 1 (as are rowmap(0..3) and
+// rowmap(4..7) for GEMM 1), so every fragment load of both GEMMs is bank-conflict free.
+__device__ __forceinline__ int gpr_rowmap(int n) { return n < 4 ? n : (n ^ 1); }
+
+// NT = number of 8-wide descriptor tiles (Dp = 8*NT).  grid = (ceil(N/64), M slices).
+// Every CTA handles 64 atoms x one slice of the sparse set and writes PARTIAL sums
 // (E over the slice, W*m' over the slice); k_gpr_combine adds the slices in fixed order.
+// Tiles of 16 sparse points are double buffered with cp.async: tile i+1 streams in while
+// tile i is consumed by the DMMAs.
 template <int NT>
 __global__ void __launch_bounds__(32 * GPR_WARPS)
 k_gpr(GprDev p, const double *__restrict__ G, int ntot, int mslice, double *__restrict__ epart,
-      double *__restrict__ accpart) {
+      double *__restrict__ accpart, const double *__restrict__ t32g) {
     extern __shared__ __align__(16) double sm[];
     constexpr int Dp = 8 * NT;
-    constexpr int LDX = Dp + 1;
-    constexpr int LDT = gpr_ldt(Dp);
-    double *xs_all = sm;                               // [GPR_WARPS][8][LDX]
-    double *tile = sm + GPR_WARPS * 8 * LDX;           // [GPR_TS][LDT]; 32*LDX doubles is a multiple of 16 bytes
+    constexpr int LD = gpr_ld(Dp);
+    double *xs_all = sm;                                  // [GPR_WARPS][8][LD]
+    double *tiles = sm + GPR_WARPS * 8 * LD;              // [2][GPR_TS][LD]
+    double *s_t32 = tiles + 2 * GPR_TS * LD;              // [32] exp table
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    double *xs = xs_all + (size_t)wid * 8 * LDX;
+    double *xs = xs_all + (size_t)wid * 8 * LD;
     const int row0 = (blockIdx.x * GPR_WARPS + wid) * 8;
+    const int sp_begin = blockIdx.y * mslice, sp_end = min(p.Mp, sp_begin + mslice);
+    const int ntiles = (sp_end - sp_begin + GPR_TS - 1) / GPR_TS;
+    auto stage = [&](int tile_idx, int buf) {
+        const char *src = (const char *)(p.Mt + (size_t)(sp_begin + tile_idx * GPR_TS) * Dp);
+        double *dst = tiles + (size_t)buf * GPR_TS * LD;
+        for (int idx = tid; idx < GPR_TS * (Dp / 2); idx += 32 * GPR_WARPS) {
+            const int r = idx / (Dp / 2), c2 = idx - r * (Dp / 2);
+            cp_async16(dst + r * LD + 2 * c2, src + (size_t)idx * 16);
+        }
+        cp_async_commit();
+    };
+    if (ntiles > 0) stage(0, 0);
+    if (tid < 32) s_t32[tid] = t32g[tid];
     // scaled, centred descriptors of this warp's 8 atoms
     for (int k = lane; k < Dp; k += 32) {
         const double it = p.itheta[k], cm = p.cmean[k];
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             const int row = row0 + r;
-            xs[r * LDX + k] = (row < ntot && k < p.D) ? (G[(size_t)row * p.D + k] - cm) * it : 0.0;
+            xs[r * LD + k] = (row < ntot && k < p.D) ? (G[(size_t)row * p.D + k] - cm) * it : 0.0;
         }
     }
     __syncwarp();
     double xn = 0.0;
-    for (int k = t; k < Dp; k += 4) { const double v = xs[g * LDX + k]; xn += v * v; }
+    for (int k = t; k < Dp; k += 4) { const double v = xs[g * LD + k]; xn += v * v; }
     xn += __shfl_xor_sync(0xffffffffu, xn, 1);
     xn += __shfl_xor_sync(0xffffffffu, xn, 2);
 
@@ -72,39 +102,36 @@ k_gpr(GprDev p, const double *__restrict__ G, int ntot, int mslice, double *__re
 #pragma unroll
     for (int n = 0; n < NT; n++) acc[n][0] = acc[n][1] = 0.0;
     double esum = 0.0;
-    const int sp_begin = blockIdx.y * mslice, sp_end = min(p.Mp, sp_begin + mslice);
-    for (int sp0 = sp_begin; sp0 < sp_end; sp0 += GPR_TS) {
-        __syncthreads();  // the previous tile has been consumed by every warp
-        {   // stage GPR_TS rows of the scaled sparse set, 16 bytes per thread and step
-            const double2 *src = (const double2 *)(p.Mt + (size_t)sp0 * Dp);
-            for (int idx = tid; idx < GPR_TS * (Dp / 2); idx += 32 * GPR_WARPS) {
-                const int r = idx / (Dp / 2), c2 = idx - r * (Dp / 2);
-                *(double2 *)(tile + r * LDT + 2 * c2) = src[idx];
-            }
-        }
-        __syncthreads();
+    const int rg = gpr_rowmap(g);                             // tile row feeding GEMM 1's column n = g
+    const int r0 = gpr_rowmap(2 * t), r1 = gpr_rowmap(2 * t + 1);   // rows behind this lane's two C columns
+    for (int i = 0; i < ntiles; i++) {
+        if (i + 1 < ntiles) { stage(i + 1, (i + 1) & 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();                                       // tile i is complete for every thread
+        const double *tile = tiles + (size_t)(i & 1) * GPR_TS * LD;
+        const int sp0 = sp_begin + i * GPR_TS;
         // GEMM 1: S(8 atoms x 16 sparse) over the descriptor index; one A fragment feeds both 8-wide halves
         double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
-        const double *xrow = xs + g * LDX + t;              // A(row=g, k=t)
-        const double *m0 = tile + g * LDT + t;              // B(k=t, n=g) = tile[g][4ks+t]
-        const double *m1 = m0 + 8 * LDT;
+        const double *xrow = xs + g * LD + t;                  // A(row=g, k=t)
+        const double *m0 = tile + rg * LD + t;                 // B(k=t, n=g) = tile[rowmap(g)][4ks+t]
+        const double *m1 = m0 + 8 * LD;
 #pragma unroll 4
         for (int ks = 0; ks < 2 * NT; ks++) {
             const double av = xrow[4 * ks];
             dmma884(c00, c01, av, m0[4 * ks]);
             dmma884(c10, c11, av, m1[4 * ks]);
         }
-        const int col = sp0 + 2 * t;
-        const double w00 = exp(-0.5 * (xn + __ldg(p.mn + col) - 2.0 * c00)) * __ldg(p.coeff + col);
-        const double w01 = exp(-0.5 * (xn + __ldg(p.mn + col + 1) - 2.0 * c01)) * __ldg(p.coeff + col + 1);
-        const double w10 = exp(-0.5 * (xn + __ldg(p.mn + col + 8) - 2.0 * c10)) * __ldg(p.coeff + col + 8);
-        const double w11 = exp(-0.5 * (xn + __ldg(p.mn + col + 9) - 2.0 * c11)) * __ldg(p.coeff + col + 9);
+        const int ca = sp0 + r0, cb = sp0 + r1;                // sparse points of this lane's C columns
+        const double w00 = exp_neg(fmax(-0.5 * (xn + __ldg(p.mn + ca) - 2.0 * c00), -700.0), s_t32) * __ldg(p.coeff + ca);
+        const double w01 = exp_neg(fmax(-0.5 * (xn + __ldg(p.mn + cb) - 2.0 * c01), -700.0), s_t32) * __ldg(p.coeff + cb);
+        const double w10 = exp_neg(fmax(-0.5 * (xn + __ldg(p.mn + ca + 8) - 2.0 * c10), -700.0), s_t32) * __ldg(p.coeff + ca + 8);
+        const double w11 = exp_neg(fmax(-0.5 * (xn + __ldg(p.mn + cb + 8) - 2.0 * c11), -700.0), s_t32) * __ldg(p.coeff + cb + 8);
         esum += (w00 + w01) + (w10 + w11);
         // GEMM 2: acc(8 atoms x Dp) += W(8 x 16 sparse) * tile(16 sparse x Dp).  The C fragment of
-        // GEMM 1 (row g, columns 2t, 2t+1) is used as the A operand as is: k-step j enumerates
-        // the sparse points (2t) resp. (2t+1), so B(k=t, n=g) = tile[2t(+1)][8n+g].
-        const double *b0 = tile + (2 * t) * LDT + g;
-        const double *b1 = b0 + LDT, *b2 = b0 + 8 * LDT, *b3 = b2 + LDT;
+        // GEMM 1 (row g, columns 2t, 2t+1) is used as the A operand as is: k-step e enumerates the
+        // sparse rows rowmap(2t+e), so B(k=t, n=g) = tile[rowmap(2t+e)][8n+g].
+        const double *b0 = tile + r0 * LD + g, *b1 = tile + r1 * LD + g;
+        const double *b2 = b0 + 8 * LD, *b3 = b1 + 8 * LD;
 #pragma unroll
         for (int n = 0; n < NT; n++) {
             dmma884(acc[n][0], acc[n][1], w00, b0[8 * n]);
@@ -112,6 +139,7 @@ k_gpr(GprDev p, const double *__restrict__ G, int ntot, int mslice, double *__re
             dmma884(acc[n][0], acc[n][1], w10, b2[8 * n]);
             dmma884(acc[n][0], acc[n][1], w11, b3[8 * n]);
         }
+        __syncthreads();                                       // every warp is done with this buffer
     }
     esum += __shfl_xor_sync(0xffffffffu, esum, 1);
     esum += __shfl_xor_sync(0xffffffffu, esum, 2);
@@ -174,37 +202,51 @@ void launch_gpr_prepare(cudaStream_t st, int M, int D, const double *mm_c_order,
     k_gpr_prepare<<<1, 256, 0, st>>>(M, D, mm_c_order, theta, coeff, Mp, Dp, Mt, MtT, mn, coeff_p, cmean, itheta);
 }
 
+static int gpr_sms() {
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    return sms;
+}
+
+// upper bound of the number of sparse-set slices launch_gpr may use (sizes the partial buffers)
+int gpr_max_slices(int ntot, int Mp) {
+    const int row_ctas = (ntot + 8 * GPR_WARPS - 1) / (8 * GPR_WARPS);
+    const int tiles = (Mp + GPR_TS - 1) / GPR_TS;
+    int want = (8 * gpr_sms() + row_ctas - 1) / row_ctas;
+    return want < 1 ? 1 : (want > tiles ? tiles : want);
+}
+
 template <int NT>
-static int launch_gpr_nt(cudaStream_t st, const GprDev &g, const double *G, int ntot, int nslice, int mslice,
-                         double *epart, double *accpart) {
+static int launch_gpr_nt(cudaStream_t st, const GprDev &g, const double *G, int ntot, int max_slices, double *epart,
+                         double *accpart, const double *t32, int *nslice_out) {
     constexpr int Dp = 8 * NT;
-    const size_t sm = sizeof(double) * (GPR_WARPS * 8 * (Dp + 1) + GPR_TS * gpr_ldt(Dp));
+    const size_t sm = sizeof(double) * (GPR_WARPS * 8 * gpr_ld(Dp) + 2 * GPR_TS * gpr_ld(Dp) + 32);
     if (cudaFuncSetAttribute((const void *)k_gpr<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
         return -1;
-    dim3 grid((ntot + 8 * GPR_WARPS - 1) / (8 * GPR_WARPS), nslice);
-    k_gpr<NT><<<grid, 32 * GPR_WARPS, sm, st>>>(g, G, ntot, mslice, epart, accpart);
+    // slice the sparse set so that the grid is a whole number of waves of resident CTAs
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gpr<NT>, 32 * GPR_WARPS, sm) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int slots = gpr_sms() * per_sm;
+    const int row_ctas = (ntot + 8 * GPR_WARPS - 1) / (8 * GPR_WARPS);
+    const int tiles = (g.Mp + GPR_TS - 1) / GPR_TS;
+    int want = slots / row_ctas;                     // one full wave
+    if (want < 1) want = 1;
+    if (want > tiles) want = tiles;
+    if (want > max_slices) want = max_slices;
+    const int tps = (tiles + want - 1) / want;       // tiles per slice
+    const int nslice = (tiles + tps - 1) / tps;
+    dim3 grid(row_ctas, nslice);
+    k_gpr<NT><<<grid, 32 * GPR_WARPS, sm, st>>>(g, G, ntot, tps * GPR_TS, epart, accpart, t32);
+    *nslice_out = nslice;
     return 0;
 }
 
-// how the sparse set is sliced over blockIdx.y: enough CTAs to fill the device at small N
-void gpr_slicing(int ntot, int Mp, int *nslice, int *mslice) {
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-    const int row_ctas = (ntot + 8 * GPR_WARPS - 1) / (8 * GPR_WARPS);
-    int want = (2 * sms + row_ctas - 1) / row_ctas;          // about two CTAs per SM
-    const int tiles = (Mp + GPR_TS - 1) / GPR_TS;
-    want = want < 1 ? 1 : (want > tiles ? tiles : want);
-    const int tps = (tiles + want - 1) / want;               // tiles per slice
-    *mslice = tps * GPR_TS;
-    *nslice = (tiles + tps - 1) / tps;
-}
-
 int launch_gpr(cudaStream_t st, const GprDev &g, const double *G, int ntot, double *eatom, double *dEdG,
-               double *epart, double *accpart, int nslice, int mslice, long *launches) {
+               double *epart, double *accpart, int max_slices, const double *t32, long *launches) {
     if (launches) *launches += 2;
-    int rc = -1;
+    int rc = -1, nslice = 1;
     switch (g.Dp / 8) {
-#define CASE(n) case n: rc = launch_gpr_nt<n>(st, g, G, ntot, nslice, mslice, epart, accpart); break;
+#define CASE(n) case n: rc = launch_gpr_nt<n>(st, g, G, ntot, max_slices, epart, accpart, t32, &nslice); break;
         CASE(2) CASE(4) CASE(6) CASE(8) CASE(9) CASE(10) CASE(12) CASE(14) CASE(16) CASE(20) CASE(24) CASE(28) CASE(32)
 #undef CASE
         default: return -1;

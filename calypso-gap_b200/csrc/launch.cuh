@@ -38,9 +38,9 @@ struct GprDev {
     const double *cmean;     // [Dp]
     const double *itheta;    // [Dp]      1/theta, zero padded
 };
-void gpr_slicing(int ntot, int Mp, int *nslice, int *mslice);
+int gpr_max_slices(int ntot, int Mp);
 int launch_gpr(cudaStream_t st, const GprDev &g, const double *G, int ntot, double *eatom, double *dEdG,
-               double *epart, double *accpart, int nslice, int mslice, long *launches);
+               double *epart, double *accpart, int max_slices, const double *t32, long *launches);
 void launch_gpr_prepare(cudaStream_t st, int M, int D, const double *mm_c_order, const double *theta,
                         const double *coeff, int Mp, int Dp, double *Mt, double *MtT, double *mn,
                         double *coeff_p, double *cmean, double *itheta);
