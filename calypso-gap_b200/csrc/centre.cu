@@ -43,7 +43,12 @@
 
 namespace gapcu {
 
-constexpr int CT = 256;  // threads per centre CTA (measured: 384 threads x 2 CTAs/SM is no faster, barrier stalls grow)
+#define GRP_BEGIN(a, c) (a).cls.grp_begin[c]   // first group of class c / one past its last group
+
+#ifndef GAPCU_CT
+#define GAPCU_CT 256
+#endif
+constexpr int CT = GAPCU_CT;  // threads per centre CTA (measured: 384 threads x 2 CTAs/SM is no faster, barrier stalls grow)
 constexpr int NW = CT / 32;
 constexpr int MAXG = 4;  // alpha groups of one class handled per forward pass (register accumulators)
 
@@ -177,7 +182,9 @@ template <int MODE>
 __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i, unsigned char *smem, const bool first) {
     constexpr bool FWD = MODE != MODE_BWD, BWD = MODE != MODE_FWD, FUSED = MODE == MODE_FUSED;
     const PlanDev &pl = a.plan;
-    const int ncls = pl.ncls, D = pl.D, nsf = pl.nsf, pcap = a.pcap, lcap = a.lcap;
+    // (compile-time specialisation of ncls / nsf / group table / pcap was measured: no gain, -1 % .. +4 %)
+    const int ncls = pl.ncls, D = pl.D, nsf = pl.nsf, pcap = a.pcap;
+    const int lcap = a.lcap;
     const SmemLayout &L = a.lay;
     double *s_t32 = (double *)(smem + L.t32);
     double *s_t2 = (double *)(smem + L.t2);       // class thresholds padded with -1 (never passes)
@@ -293,7 +300,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         }
     }
     __syncthreads();
-    if (FWD && tid < ncls && a.cls.grp_begin[tid + 1] > a.cls.grp_begin[tid]) {
+    if (FWD && tid < ncls && GRP_BEGIN(a, tid + 1) > GRP_BEGIN(a, tid)) {
         // sum_c Q_c of SURVEY.md 8(d): candidate pairs of every angular cutoff class
         unsigned long long pc = 0;
         for (int s = 0; s < P; s++) pc += (s_nc[s] > tid);
@@ -324,12 +331,19 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 if (lim) {
                     const double rjk2 = pair_dist2(s_x[ra], s_x[pcap + ra], s_x[2 * pcap + ra], s_x[rb], s_x[pcap + rb],
                                                    s_x[2 * pcap + rb]);
-                    // thresholds descend: the classes with rjk2 <= t2[c] are a prefix; count it by bisection
+                    // thresholds descend: the classes with rjk2 <= t2[c] are a prefix.  Up to 8 classes:
+                    // independent compares against constant-bank operands (no loads, no dependent
+                    // chain; measured -1.7 %); more: bisection over the shared-memory copy.
                     int lo = 0;
+                    if (ncls <= 8) {
 #pragma unroll
-                    for (int step = MAXC_DEV / 2; step; step >>= 1)
-                        if (rjk2 <= s_t2[lo + step - 1]) lo += step;
-                    if (lo == MAXC_DEV - 1 && rjk2 <= s_t2[MAXC_DEV - 1]) lo = MAXC_DEV;
+                        for (int c = 0; c < 8; c++) lo += (c < ncls && rjk2 <= a.cls.t2[c]);
+                    } else {
+#pragma unroll
+                        for (int step = MAXC_DEV / 2; step; step >>= 1)
+                            if (rjk2 <= s_t2[lo + step - 1]) lo += step;
+                        if (lo == MAXC_DEV - 1 && rjk2 <= s_t2[MAXC_DEV - 1]) lo = MAXC_DEV;
+                    }
                     bk = min(lo, lim);
                     if (!((angmask >> bk) & 1u)) bk = 0;
                 }
@@ -374,7 +388,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             if (count_work && lane == 0) {
                 wk_trip += ctl->nkept;
                 for (int c = 0; c < ncls; c++) {
-                    const int g0 = a.cls.grp_begin[c], g1 = a.cls.grp_begin[c + 1];
+                    const int g0 = GRP_BEGIN(a, c), g1 = GRP_BEGIN(a, c + 1);
                     if (g1 > g0) {
                         int nf = 0;
                         for (int g = g0; g < g1; g++) nf += (g_iplus[g] >= 0) + (g_iminus[g] >= 0);
@@ -408,7 +422,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
     auto forward_list = [&]() {
         int rot = 0;  // items dealt so far: the next class continues the round robin where this one stopped
         for (int c = 0; c < ncls; c++) {
-            const int g0 = a.cls.grp_begin[c], g1 = a.cls.grp_begin[c + 1];
+            const int g0 = GRP_BEGIN(a, c), g1 = GRP_BEGIN(a, c + 1);
             const int n_c = ctl->npre[c];
             if (g0 == g1 || n_c == 0) continue;
             const int myrank = (tid - rot + CT) % CT;   // this thread's position in the deal for class c
@@ -503,7 +517,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             const double u1 = irb - cosv * ira, u2 = ira - cosv * irb, u3 = -rjk * ira * irb;
             double cij = 0.0, cik = 0.0, cjk = 0.0;
             for (int c = 0; c < v; c++) {
-                const int g0 = a.cls.grp_begin[c], g1 = a.cls.grp_begin[c + 1];
+                const int g0 = GRP_BEGIN(a, c), g1 = GRP_BEGIN(a, c + 1);
                 if (g0 == g1) continue;
                 const double pirc = a.cls.pirc[c];
                 double sn, cs;
@@ -514,7 +528,19 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 const double fab = fa * fb, phi = fab * fjk;
                 // S1 = sum gamma e lam, T0 = sum gamma e, S3 = sum alpha gamma e (1 + lam cos)
                 double S1 = 0.0, T0 = 0.0, S3 = 0.0;
-                for (int gg = g0; gg < g1; gg++) {
+                // two groups per trip: their exponentials are independent chains (ILP; measured -7 %)
+                int gg = g0;
+                for (; gg + 1 < g1; gg += 2) {
+                    const double al0 = s_galpha[gg], al1 = s_galpha[gg + 1];
+                    const double e0 = exp_arg(-al0 * ssum, s_t32, a.exp_clamp), e1 = exp_arg(-al1 * ssum, s_t32, a.exp_clamp);
+                    const double4 gd0 = *(const double4 *)(s_gd + 4 * gg), gd1 = *(const double4 *)(s_gd + 4 * gg + 4);
+                    const double t00 = e0 * fma(ww, gd0.y, gd0.x), t01 = e0 * fma(ww, gd0.w, gd0.z);
+                    const double t10 = e1 * fma(ww, gd1.y, gd1.x), t11 = e1 * fma(ww, gd1.w, gd1.z);
+                    T0 += t00 + t10;
+                    S1 += t01 + t11;
+                    S3 = fma(al0, fma(cosv, t01, t00), fma(al1, fma(cosv, t11, t10), S3));
+                }
+                if (gg < g1) {
                     const double al = s_galpha[gg];
                     const double e = exp_arg(-al * ssum, s_t32, a.exp_clamp);
                     const double4 gd = *(const double4 *)(s_gd + 4 * gg);   // DU, DW, DUL, DWL
@@ -754,8 +780,8 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
 // Persistent CTAs: as many as fit the device, each pulling centre atoms from a queue
 // ordered by descending neighbour count (longest first), so that 1000 centres on 296
 // resident CTAs do not cost four full waves and the heavy centres do not form the tail.
-template <int MODE>
-__global__ void __launch_bounds__(CT, 3) k_centre(const CentreArgs a) {
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(CT, MINB) k_centre(const CentreArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_next;
     bool first = true;
@@ -781,21 +807,26 @@ __global__ void __launch_bounds__(CT, 3) k_centre(const CentreArgs a) {
     }
 }
 
-template <int MODE>
-static int launch_mode(cudaStream_t st, const CentreArgs &a_in) {
+template <int MODE, int MINB>
+static int launch_mode_b(cudaStream_t st, const CentreArgs &a_in) {
     CentreArgs a = a_in;
     a.lay = make_layout(a, MODE);
     const size_t sm = (size_t)a.lay.total;
     if (sm > 227 * 1024) return -1;
-    if (cudaFuncSetAttribute((const void *)k_centre<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
+    if (cudaFuncSetAttribute((const void *)k_centre<MODE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
         return -2;
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_centre<MODE>, CT, sm) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_centre<MODE, MINB>, CT, sm) != cudaSuccess || per_sm < 1) per_sm = 1;
     const int grid = a.ntot < sms * per_sm ? a.ntot : sms * per_sm;
-    k_centre<MODE><<<grid, CT, sm, st>>>(a);
+    k_centre<MODE, MINB><<<grid, CT, sm, st>>>(a);
     return 0;
+}
+
+template <int MODE>
+static int launch_mode(cudaStream_t st, const CentreArgs &a) {
+    return (a.variant & 8) ? launch_mode_b<MODE, 2>(st, a) : launch_mode_b<MODE, 3>(st, a);
 }
 
 int launch_forward(cudaStream_t st, const CentreArgs &a, long *launches) {

@@ -529,6 +529,7 @@ static int make_centre_args(gapcu_ctx *c, int lgrad, CentreArgs *out, bool *fuse
     a.nbr_keys = c->d_keys.p; a.nbr_cnt = c->d_nbr_cnt.p; a.order = c->d_order.p; a.n_centres = &c->d_flags.p->n_centres; a.exp2_table = c->d_exp2.p;
     a.ntot = c->ntot; a.cap = c->cap; a.pcap = c->pcap; a.lgrad = lgrad;
     a.exp_clamp = c->exp_clamp;
+    { static int var = -1; if (var < 0) { const char *e = getenv("GAPCU_VARIANT"); var = e ? atoi(e) : 0; } a.variant = var; }
     a.G = c->d_G.p; a.dEdG = c->d_dEdG.p; a.dEdG_out = c->d_dEdG.p; a.eatom = c->d_eatom.p;
     a.fpair = c->d_fpair.p; a.gself = c->d_gself.p; a.vir = c->d_vir.p;
     a.gpr_M = c->M; a.gpr_Mp = c->Mp; a.gpr_Dp = c->Dp; a.gpr_Mt = c->d_Mt.p; a.gpr_MtT = c->d_MtT.p;
@@ -545,7 +546,7 @@ static int make_centre_args(gapcu_ctx *c, int lgrad, CentreArgs *out, bool *fuse
         const int q = c->pcap * (c->pcap - 1) / 2;
         const int want = std::min(8192, std::max(2048, round_up(q, 32)));
         const int mode = fused ? 2 : 1;
-        const size_t targets[3] = {74 * 1024, 112 * 1024, 220 * 1024};   // 3, 2, 1 CTAs per SM
+        const size_t targets[3] = {(size_t)((a.variant & 8) ? 112 : 74) * 1024, 112 * 1024, 220 * 1024};   // 3, 2, 1 CTAs per SM
         const int lmin[3] = {3584, 3072, 1024};
         bool ok = false;
         for (int t = 0; t < 3 && !ok; t++)

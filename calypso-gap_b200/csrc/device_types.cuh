@@ -107,6 +107,7 @@ struct CentreArgs {
     int npa;                    // private accumulator sets in backward: NW, or 1 (= shared + atomics)
     int lgrad;
     int exp_clamp;              // 1: exponent arguments may fall below -700 and are clamped
+    int variant;                // experiment switches (environment GAPCU_VARIANT), 0 in production
     double *G;                  // [NT][D]   descriptors out (forward / fused; may be null in fused)
     const double *dEdG;         // [NT][D]   backward in (MODE_BWD)
     double *dEdG_out;           // [NT][D]   fused: dE/dG out (may be null)

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, "lib", "libgapcu.so")
+LIBPATH = os.environ.get("GAPCU_LIB", os.path.join(HERE, "lib", "libgapcu.so"))   # GAPCU_LIB: alternative build (A/B timing)
 NSTAGE = 8
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
