@@ -448,17 +448,22 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                     double sn, cs;
                     sincos_0pi(rjk * pirc, &sn, &cs);
                     const double phi = fcc[ra] * fcc[rb] * (0.5 * (cs + 1.0));
-#pragma unroll
-                    for (int g = 0; g < MAXG; g++) {
-                        if (g < ng) {
-                            const double pe = phi * exp_arg(-s_galpha[gb + g] * ssum, s_t32, a.exp_clamp);
-                            const double pw = pe * ww;
-                            acc[g][0] += pe;
-                            acc[g][1] = fma(pe, cosv, acc[g][1]);
-                            acc[g][2] += pw;
-                            acc[g][3] = fma(pw, cosv, acc[g][3]);
-                        }
-                    }
+                    // groups in pairs without a branch between their exponentials, so the two
+                    // dependent chains interleave (same trick as in the backward loop)
+                    auto one = [&](double (&ac)[4], int g) {
+                        const double pe = phi * exp_arg(-s_galpha[gb + g] * ssum, s_t32, a.exp_clamp);
+                        const double pw = pe * ww;
+                        ac[0] += pe; ac[1] = fma(pe, cosv, ac[1]); ac[2] += pw; ac[3] = fma(pw, cosv, ac[3]);
+                    };
+                    auto two = [&](double (&a0)[4], double (&a1)[4], int g) {
+                        const double e0 = exp_arg(-s_galpha[gb + g] * ssum, s_t32, a.exp_clamp);
+                        const double e1 = exp_arg(-s_galpha[gb + g + 1] * ssum, s_t32, a.exp_clamp);
+                        const double pe0 = phi * e0, pe1 = phi * e1, pw0 = pe0 * ww, pw1 = pe1 * ww;
+                        a0[0] += pe0; a0[1] = fma(pe0, cosv, a0[1]); a0[2] += pw0; a0[3] = fma(pw0, cosv, a0[3]);
+                        a1[0] += pe1; a1[1] = fma(pe1, cosv, a1[1]); a1[2] += pw1; a1[3] = fma(pw1, cosv, a1[3]);
+                    };
+                    if (ng >= 2) two(acc[0], acc[1], 0); else one(acc[0], 0);
+                    if (ng >= 4) two(acc[2], acc[3], 2); else if (ng == 3) one(acc[2], 2);
                 }
                 if (__any_sync(0xffffffffu, myrank < n_c)) {
 #pragma unroll
