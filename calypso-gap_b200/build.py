@@ -19,10 +19,11 @@ OBJ = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
-CU_SOURCES = ["neigh.cu", "centre.cu", "gpr.cu", "gather.cu", "microbench.cu", "context.cu"]
+CU_SOURCES = ["neigh.cu", "centre.cu", "centre_p128.cu", "centre_p256.cu", "centre_p512.cu", "centre_p1024.cu", "gpr.cu", "gather.cu",
+              "microbench.cu", "context.cu"]
 CPP_SOURCES = ["potential.cpp"]
 C_SOURCES = ["fortran_shim.c"]
-HEADERS = ["device_types.cuh", "fastmath.cuh", "geom.cuh", "launch.cuh", "potential.hpp", os.path.join("..", "..", "include", "gapcu.h")]
+HEADERS = ["device_types.cuh", "centre_impl.cuh", "fastmath.cuh", "geom.cuh", "launch.cuh", "potential.hpp", os.path.join("..", "..", "include", "gapcu.h")]
 
 
 def _newer(target, deps):
@@ -42,6 +43,7 @@ def build_libgapcu(force=False, verbose_ptxas=False):
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     objs = []
+    cmds = []
     for src in CU_SOURCES:
         s, o = os.path.join(CSRC, src), os.path.join(OBJ, src + ".o")
         if force or _newer(o, [s] + hdrs):
@@ -49,8 +51,12 @@ def build_libgapcu(force=False, verbose_ptxas=False):
                    "-c", s, "-o", o]
             if verbose_ptxas:
                 cmd.insert(1, "-Xptxas=-v")
-            _run(cmd)
+            cmds.append(cmd)
         objs.append(o)
+    if cmds:   # the translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(cmds), os.cpu_count() or 1)) as ex:
+            list(ex.map(_run, cmds))
     for src in CPP_SOURCES:
         s, o = os.path.join(CSRC, src), os.path.join(OBJ, src + ".o")
         if force or _newer(o, [s] + hdrs):

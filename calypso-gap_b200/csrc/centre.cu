@@ -1,78 +1,26 @@
-// centre.cu -- the per-centre wACSF kernel (K2 forward, K4 backward, or both fused
-// with an in-CTA GPR): one CTA per centre atom.
-//
-// What is computed (reference loops wacsf.f90:65-795):
-//   radial  type 1  G = sum_j exp(-a r^2) fc(r)            wacsf.f90:69-162
-//           type 3  G = sum_j exp(-4 (r-rs)^2) fc(r)       wacsf.f90:436-527
-//   angular type 2/4  G = sum_{j<k} (1 +- cos) exp(-a (rij^2+rik^2+rjk^2)) fc fc fc
-//                                                          wacsf.f90:169-432, 534-791
-//   each in an unweighted channel ii and a species-weighted channel ii+nsf, then
-//   (fused mode) e_i and dE/dG from the sparse GPR (gap_calc.f90:143-166), then the
-//   chain rule dE/dG * dG/dr (gap_calc.f90:177-203) WITHOUT the reference's dense
-//   dxdy(D,N,N,3): the geometry is recomputed and contracted on the fly, leaving
-//   per neighbour slot dE_i/dx_slot, plus dE_i/dx_i and the centre's strs sums.
-//
-// Structure per centre (all orders fixed -> results are bit-reproducible):
-//   1. stage neighbours in shared memory: absolute image coordinates (reference
-//      arithmetic, geom.cuh), r, 1/r, weight, and fc/fc' for each cutoff class
-//      the neighbour belongs to (classes = distinct cutoffs, descending, so the
-//      classes of a distance are a prefix);
-//   2. radial functions: one thread per neighbour, warp-shuffle sums;
-//   3. triplet list: all pairs q=(a<b) of the flat triangular index are tested ONCE
-//      with the exact reference arithmetic (squared-distance thresholds equivalent
-//      to the reference's sqrt(..) > cutoff); survivors carry their "bucket" = number
-//      of classes they belong to; a deterministic counting sort orders them by bucket
-//      (descending), so the items of class c are the prefix S[0 .. npre[c]);
-//   4. forward: class-outer loop over that prefix, per-thread register accumulators
-//      per (class, alpha) group [sum pe, sum pe*cos, and the two weighted sums; the
-//      lambda=+-1 functions are (sum pe +- sum pe*cos)], one warp reduction per class;
-//   5. (fused) GPR for this atom in the CTA: difference form, no cancellation;
-//   6. backward: warps take batches of 32 triplets of the SAME bucket; per class one
-//      sincos and per (class, alpha) one exp: the sum over symmetry functions is
-//      folded into four per-centre constants per group (sum du, sum dw, sum lam*du,
-//      sum lam*dw), so there is no inner loop over functions; the three leg scalars
-//      go to per-warp private accumulators (dE/dx_j = A_j d_j - V_j) with in-warp
-//      conflict serialisation: no atomics anywhere.
-#include <cstdint>
-#include <cstring>
-
-#include "device_types.cuh"
-#include "fastmath.cuh"
-#include "geom.cuh"
-#include "launch.cuh"
+// centre.cu -- host side of the per-centre wACSF kernel: shared-memory layout and dispatch to
+// the capacity-specialised instances (centre_impl.cuh, centre_p*.cu).
+#include "centre_impl.cuh"
 
 namespace gapcu {
 
-#define GRP_BEGIN(a, c) (a).cls.grp_begin[c]   // first group of class c / one past its last group
-
-#ifndef GAPCU_CT
-#define GAPCU_CT 256
-#endif
-constexpr int CT = GAPCU_CT;  // threads per centre CTA (measured: 384 threads x 2 CTAs/SM is no faster, barrier stalls grow)
-constexpr int NW = CT / 32;
-constexpr int MAXG = 4;  // alpha groups of one class handled per forward pass (register accumulators)
-
-enum { MODE_FWD = 0, MODE_BWD = 1, MODE_FUSED = 2 };
+// neighbour capacity of the instance that serves a runtime capacity
+static int pcap_template(int pcap) { return pcap <= 128 ? 128 : pcap <= 256 ? 256 : pcap <= 512 ? 512 : 1024; }
 
 static SmemLayout make_layout(const CentreArgs &a, int mode) {
     SmemLayout L;
-    int o = 0;
+    memset(&L, 0, sizeof L);
+    const int pt = pcap_template(a.pcap), D = a.plan.D;
+    int o = hot_bytes(pt, a.plan.ncls);   // Hot<PCAP>: neighbour records, gradient accumulator, class counts, fc tables
     auto take = [&](long bytes) { int r = o; o += (int)((bytes + 15) & ~15l); return r; };
-    const int pcap = a.pcap, D = a.plan.D;
+    take(0);
     const bool bwd = mode != MODE_FWD, fwd = mode != MODE_BWD, fused = mode == MODE_FUSED;
     L.t32 = take(8 * 32);
     L.t2 = take(8 * MAXC_DEV);
     L.galpha = take(8 * (a.plan.n_grp + 1));
     L.gd = bwd ? take(8 * 4 * (a.plan.n_grp + 1)) : 0;
-    L.x = take(8 * 3 * pcap);
-    L.r = take(8 * pcap);
-    L.ir = take(8 * pcap);
-    L.w = take(8 * pcap);
-    L.fc = take(8 * a.plan.ncls * pcap);
-    L.dfc = bwd ? take(8 * a.plan.ncls * pcap) : 0;
     L.sG = fused ? take(8 * D) : 0;
     L.sdu = bwd ? take(8 * D) : 0;
-    L.acc = bwd ? take(8 * 3 * pcap) : 0;
     L.red = take(8 * NW * 16);
     L.S = take(4 * (a.lcap + 32));
     // scratch region, three lives: [U | gw] while lists are built and the forward runs,
@@ -81,7 +29,7 @@ static SmemLayout make_layout(const CentreArgs &a, int mode) {
     const long scr_fwd = scr_u + (fwd ? 8l * NW * D : 0);
     const long gpr_part = 8l * NW * (a.gpr_Mp > D ? a.gpr_Mp : D);
     const long scr_gpr = fused ? gpr_part + 8l * (D + a.gpr_Mp + 8) : 0;
-    const long scr_pa = (bwd && a.npa > 1) ? 8l * a.npa * 3 * pcap : 8l * CT;
+    const long scr_pa = (bwd && a.npa > 1) ? 8l * a.npa * 3 * pt : 8l * CT;
     long scr = scr_fwd > scr_pa ? scr_fwd : scr_pa;
     if (scr_gpr > scr) scr = scr_gpr;
     L.scratch = take(scr);
@@ -90,7 +38,6 @@ static SmemLayout make_layout(const CentreArgs &a, int mode) {
     L.sW = L.xs + 8 * ((D + 1) & ~1);
     L.ctl = take(4 * 512);
     L.rad = take(16 * (a.plan.n_rad + 1));
-    L.nc = take(pcap);
     L.total = o;
     return L;
 }
@@ -99,752 +46,28 @@ size_t centre_smem_bytes(const CentreArgs &a, int mode) { return (size_t)make_la
 int centre_warps() { return NW; }
 size_t centre_stash_words(const CentreArgs &a, int chunks, int ctas) { return (size_t)ctas * chunks * (size_t)(a.lcap + 32 + 512); }
 
-// control block in shared memory
-struct Ctl {
-    int cntw[NW];               // kept items per warp segment
-    int hw[NW][MAXC_DEV + 1];   // kept items per (warp, bucket)
-    int basew[NW][MAXC_DEV + 1];// running output position per (warp, bucket)
-    int tot[MAXC_DEV + 1];      // items per bucket
-    int npre[MAXC_DEV + 1];     // items with bucket > c  (prefix length of class c)
-    int obase[MAXC_DEV + 1];    // start of order slot o (bucket ncls-o) in S
-    int ocnt[MAXC_DEV + 1];
-    int obq[MAXC_DEV + 1];      // batches of order slot o
-    int obp[MAXC_DEV + 2];      // first batch of order slot o
-    int TB, nkept;
-};
-static_assert(sizeof(Ctl) <= 4 * 512, "Ctl does not fit");
-static_assert(sizeof(Ctl) <= 4 * 512, "Ctl does not fit its stash slot");
-
-// exp(x), x <= 0; clamp only when the potential can produce arguments below -700
-__device__ __forceinline__ double exp_arg(double x, const double *T32, int clamp) {
-    if (clamp) x = fmax(x, -700.0);
-    return exp_neg(x, T32);
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// Sum four per-lane values over the warp with 6 instead of 20 value shuffles: after the
-// call the lanes with (lane>>3) == k hold the total of v_k.
-__device__ __forceinline__ double warp_sum4(double v0, double v1, double v2, double v3, int lane) {
-    const bool hi16 = lane & 16, hi8 = lane & 8;
-    // lanes with bit4 = 0 keep (v0, v1), the others (v2, v3); each gets the partner's copy
-    double k0 = hi16 ? v2 : v0, k1 = hi16 ? v3 : v1;
-    const double s0 = hi16 ? v0 : v2, s1 = hi16 ? v1 : v3;
-    k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-    k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-    double k = hi8 ? k1 : k0;
-    const double s = hi8 ? k0 : k1;
-    k += __shfl_xor_sync(0xffffffffu, s, 8);
-    k += __shfl_xor_sync(0xffffffffu, k, 4);
-    k += __shfl_xor_sync(0xffffffffu, k, 2);
-    k += __shfl_xor_sync(0xffffffffu, k, 1);
-    return k;
-}
-
-// pair index q -> (a < b), q = b(b-1)/2 + a
-__device__ __forceinline__ void tri_decode(int q, int &a, int &b) {
-    int bb = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)q)) * 0.5f);
-    if (bb * (bb - 1) / 2 > q) bb--;
-    if ((bb + 1) * bb / 2 <= q) bb++;
-    b = bb;
-    a = q - bb * (bb - 1) / 2;
-}
-
-// add a 3-vector to a [3][pcap] accumulator at index idx.  Private (per warp) set: lanes
-// that hit the same idx take turns in lane order (deterministic, no atomics).  Shared set
-// (very long neighbour lists only): shared-memory atomics.
-__device__ __forceinline__ void scatter3(double *pa, int pcap, int idx, double v0, double v1, double v2,
-                                         unsigned amask, unsigned ltmask, bool priv) {
-    if (priv) {
-        const unsigned peers = __match_any_sync(amask, idx);
-        const int rank = __popc(peers & ltmask);
-        const int maxr = __reduce_max_sync(amask, rank);
-        for (int r = 0; r <= maxr; r++) {
-            if (rank == r) {
-                pa[idx] += v0;
-                pa[pcap + idx] += v1;
-                pa[2 * pcap + idx] += v2;
-            }
-            __syncwarp(amask);
-        }
-    } else {
-        atomicAdd(&pa[idx], v0);
-        atomicAdd(&pa[pcap + idx], v1);
-        atomicAdd(&pa[2 * pcap + idx], v2);
-    }
-}
-
-template <int MODE>
-__device__ __forceinline__ void process_centre(const CentreArgs &a, const int i, unsigned char *smem, const bool first) {
-    constexpr bool FWD = MODE != MODE_BWD, BWD = MODE != MODE_FWD, FUSED = MODE == MODE_FUSED;
-    const PlanDev &pl = a.plan;
-    // (compile-time specialisation of ncls / nsf / group table / pcap was measured: no gain, -1 % .. +4 %)
-    const int ncls = pl.ncls, D = pl.D, nsf = pl.nsf, pcap = a.pcap;
-    const int lcap = a.lcap;
-    const SmemLayout &L = a.lay;
-    double *s_t32 = (double *)(smem + L.t32);
-    double *s_t2 = (double *)(smem + L.t2);       // class thresholds padded with -1 (never passes)
-    double *s_galpha = (double *)(smem + L.galpha);
-    double *s_gd = (double *)(smem + L.gd);      // [n_grp][4]: DU, DW, DUL, DWL (backward)
-    double *s_x = (double *)(smem + L.x);        // [3][pcap]
-    double *s_r = (double *)(smem + L.r);
-    double *s_ir = (double *)(smem + L.ir);
-    double *s_w = (double *)(smem + L.w);
-    double *s_fc = (double *)(smem + L.fc);      // [ncls][pcap]
-    double *s_dfc = (double *)(smem + L.dfc);
-    double *s_gw = (double *)(smem + L.gw);      // [NW][D] per-warp partial descriptors
-    double *s_G = (double *)(smem + L.sG);
-    double *s_du = (double *)(smem + L.sdu);     // dE/dG of this centre
-    double *s_xs = (double *)(smem + L.xs);
-    double *s_W = (double *)(smem + L.sW);
-    double *s_acc = (double *)(smem + L.acc);    // [3][pcap]: dE_i/dx of every neighbour slot
-    double *s_red = (double *)(smem + L.red);
-    uint32_t *s_S = (uint32_t *)(smem + L.S);
-    uint32_t *s_U = (uint32_t *)(smem + L.scratch);
-    double *s_pa = (double *)(smem + L.scratch);  // [NW][3][pcap] (aliases U; live only in backward phase B)
-    Ctl *ctl = (Ctl *)(smem + L.ctl);
-    int2 *s_radi = (int2 *)(smem + L.rad);        // per radial function: (ii, cls | type<<16)
-    double *s_radp = (double *)(smem + L.rad + 8 * (pl.n_rad + 1));
-    unsigned char *s_nc = smem + L.nc;
-
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned ltmask = (1u << lane) - 1u;
-    const int P = a.nbr_cnt[i];
-    if (P > pcap || P > a.cap) {  // host re-runs with a larger capacity
-        if (tid == 0) atomicExch(&a.flags->overflow, 1);
-        return;
-    }
-    const StructDev &sd = a.structs[a.sid[i]];
-    const int ntot = a.ntot;
-    const int *g_iplus = pl.itab + pl.o_grp_iplus, *g_iminus = pl.itab + pl.o_grp_iminus;
-
-    // ---- 0: tables (centre independent: loaded once per persistent CTA) ----------------
-    if (first) {
-        if (tid < 32) s_t32[tid] = a.exp2_table[tid];
-        if (tid < MAXC_DEV) s_t2[tid] = tid < ncls ? a.cls.t2[tid] : -1.0;
-        for (int t = tid; t < pl.n_grp; t += CT) s_galpha[t] = pl.dtab[pl.o_grp_alpha + t];
-        for (int t = tid; t < pl.n_rad; t += CT) {
-            s_radi[t] = make_int2(pl.itab[pl.o_rad_ii + t], pl.itab[pl.o_rad_cls + t] | (pl.itab[pl.o_rad_type + t] << 16));
-            s_radp[t] = pl.dtab[pl.o_rad_p + t];
-        }
-    }
-    if (FWD) for (int t = tid; t < NW * D; t += CT) s_gw[t] = 0.0;
-    if (MODE == MODE_BWD) for (int t = tid; t < D; t += CT) s_du[t] = a.dEdG[(size_t)i * D + t];
-    __shared__ double s_lat[9];
-    if (tid < 9) s_lat[tid] = sd.lat[tid];
-    __syncthreads();
-
-    const double xi = a.pos[i], yi = a.pos[ntot + i], zi = a.pos[2 * ntot + i];
-    unsigned long long wk_pc = 0, wk_rad = 0;
-
-    // ---- 1: stage neighbours (a: geometry per neighbour, b: fc/fc' per (neighbour, class)) ----
-    for (int s = tid; s < P; s += CT) {
-        double ox, oy, oz, dis, wj;
-        if (a.nbr_table) {
-            // CAR2ACSF: image position, distance and weight as the caller tabulated them (wacsf.f90:80-84)
-            const size_t NA = (size_t)ntot, ld = (size_t)a.table_ld;
-            const double *T = a.nbr_table + i + NA * s;
-            ox = T[0]; oy = T[NA * ld]; oz = T[2 * NA * ld]; dis = T[3 * NA * ld]; wj = T[4 * NA * ld];
-        } else {
-            int jl, n1, n2, n3;
-            nbr_unkey(a.nbr_keys[(size_t)i * a.cap + s], jl, n1, n2, n3);
-            const int j = sd.atom_off + jl;
-            dis = image_distance(a.pos, ntot, j, s_lat, n1, n2, n3, xi, yi, zi, ox, oy, oz);
-            wj = a.wgt[j];
-        }
-        s_x[s] = ox; s_x[pcap + s] = oy; s_x[2 * pcap + s] = oz;
-        s_r[s] = dis;
-        s_ir[s] = 1.0 / dis;
-        s_w[s] = wj;
-        int nc = 0;
-        while (nc < ncls && !(dis > a.cls.rc[nc])) nc++;  // reference: "if (rij.gt.cutoff) cycle"
-        s_nc[s] = (unsigned char)nc;
-        wk_pc += nc;
-    }
-    __syncthreads();
-    const int P32 = (P + 31) & ~31;
-    for (int t = tid; t < ncls * P32; t += CT) {
-        const int c = t / P32, s = t - c * P32;
-        if (s < P && c < s_nc[s]) {
-            double sn, cs;
-            sincos_0pi(s_r[s] * a.cls.pirc[c], &sn, &cs);
-            s_fc[c * pcap + s] = 0.5 * (cs + 1.0);
-            if (BWD) s_dfc[c * pcap + s] = -0.5 * a.cls.pirc[c] * sn;
-        }
-    }
-    __syncthreads();
-    // ---- 2: radial forward: one warp task per function, lanes over neighbours ----------
-    if (FWD) {
-        for (int q = wid; q < pl.n_rad; q += NW) {
-            const int2 ri = s_radi[q];
-            const int c = ri.y & 0xffff;
-            const double prm = s_radp[q];
-            const bool t1 = (ri.y >> 16) == 1;
-            double gu = 0.0, gwt = 0.0;
-            for (int s = lane; s < P; s += 32) {
-                if (c < s_nc[s]) {
-                    const double dis = s_r[s];
-                    const double d = t1 ? dis : dis - prm;
-                    const double g = exp_arg((t1 ? -prm : -4.0) * d * d, s_t32, a.exp_clamp) * s_fc[c * pcap + s];
-                    gu += g;
-                    gwt = fma(g, s_w[s], gwt);
-                    wk_rad++;
-                }
-            }
-            gu = warp_sum(gu); gwt = warp_sum(gwt);
-            if (lane == 0) { s_gw[wid * D + ri.x] += gu; s_gw[wid * D + ri.x + nsf] += gwt; }
-        }
-    }
-    __syncthreads();
-    if (FWD && tid < ncls && GRP_BEGIN(a, tid + 1) > GRP_BEGIN(a, tid)) {
-        // sum_c Q_c of SURVEY.md 8(d): candidate pairs of every angular cutoff class
-        unsigned long long pc = 0;
-        for (int s = 0; s < P; s++) pc += (s_nc[s] > tid);
-        atomicAdd(&a.flags->work[8], pc * (pc - 1) / 2);
-    }
-
-    // ---- 3: triplet list builder (phase A + deterministic counting sort) ----------
-    const uint32_t angmask = a.cls.angmask;
-    const int Q = P * (P - 1) / 2;
-    const int nchunk = (angmask && Q > 0) ? (Q + lcap - 1) / lcap : 0;
-    const int qchunk = nchunk ? ((Q + nchunk - 1) / nchunk + 31) & ~31 : 0;
-    unsigned long long wk_trip = 0, wk_tc = 0, wk_tsf = 0;
-
-    auto build_list = [&](int q0, int q1, bool count_work) {
-        const int n = q1 - q0;
-        const int R = (((n + NW - 1) / NW) + 31) & ~31;  // per-warp contiguous sub-range
-        const int wq0 = q0 + wid * R, wq1 = min(q1, wq0 + R);
-        uint32_t *seg = s_U + wid * R;
-        int cnt = 0;
-        if (lane <= ncls) ctl->hw[wid][lane] = 0;
-        __syncwarp();
-        int ra = 0, rb = 1;
-        if (wq0 + lane < wq1) tri_decode(wq0 + lane, ra, rb);
-        for (int qb = wq0; qb < wq1; qb += 32) {
-            int bk = 0;
-            if (qb + lane < wq1) {
-                const int lim = min((int)s_nc[ra], (int)s_nc[rb]);
-                if (lim) {
-                    const double rjk2 = pair_dist2(s_x[ra], s_x[pcap + ra], s_x[2 * pcap + ra], s_x[rb], s_x[pcap + rb],
-                                                   s_x[2 * pcap + rb]);
-                    // thresholds descend: the classes with rjk2 <= t2[c] are a prefix.  Up to 8 classes:
-                    // independent compares against constant-bank operands (no loads, no dependent
-                    // chain; measured -1.7 %); more: bisection over the shared-memory copy.
-                    int lo = 0;
-                    if (ncls <= 8) {
-#pragma unroll
-                        for (int c = 0; c < 8; c++) lo += (c < ncls && rjk2 <= a.cls.t2[c]);
-                    } else {
-#pragma unroll
-                        for (int step = MAXC_DEV / 2; step; step >>= 1)
-                            if (rjk2 <= s_t2[lo + step - 1]) lo += step;
-                        if (lo == MAXC_DEV - 1 && rjk2 <= s_t2[MAXC_DEV - 1]) lo = MAXC_DEV;
-                    }
-                    bk = min(lo, lim);
-                    if (!((angmask >> bk) & 1u)) bk = 0;
-                }
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, bk > 0);
-            if (bk > 0) {
-                seg[cnt + __popc(m & ltmask)] = (uint32_t)ra | ((uint32_t)rb << 10) | ((uint32_t)bk << 20);
-                const unsigned peers = __match_any_sync(m, bk);
-                if ((peers & ltmask) == 0) ctl->hw[wid][bk] += __popc(peers);  // one lane per bucket present
-            }
-            __syncwarp();
-            cnt += __popc(m);
-            // next pair of this lane: q += 32
-            ra += 32;
-            while (ra >= rb) { ra -= rb; rb++; }
-        }
-        if (lane == 0) ctl->cntw[wid] = cnt;
-        __syncthreads();
-        if (wid == 0) {
-            // lane o <-> bucket v = ncls - o (heavy buckets first); totals over warps, then an
-            // exclusive scan over the lanes gives every bucket its place in S
-            const int o = lane, v = ncls - lane;
-            int t = 0;
-            if (o < ncls)
-                for (int w = 0; w < NW; w++) { const int h = ctl->hw[w][v]; ctl->basew[w][v] = t; t += h; }
-            const int nb = (t + 31) >> 5;
-            int off = t, bp = nb;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int yo = __shfl_up_sync(0xffffffffu, off, d), yb = __shfl_up_sync(0xffffffffu, bp, d);
-                if (lane >= d) { off += yo; bp += yb; }
-            }
-            // off/bp are inclusive sums over order slots 0..o
-            if (o < ncls) {
-                ctl->tot[v] = t;
-                ctl->obase[o] = off - t; ctl->ocnt[o] = t; ctl->obq[o] = nb; ctl->obp[o] = bp - nb;
-                for (int w = 0; w < NW; w++) ctl->basew[w][v] += off - t;
-                ctl->npre[v - 1] = off;   // items with bucket > v-1, i.e. bucket >= v: slots 0..o
-            }
-            if (o == ncls - 1 || (ncls == 0 && o == 0)) { ctl->obp[ncls] = bp; ctl->TB = bp; ctl->nkept = off; }
-            __syncwarp();
-            if (count_work && lane == 0) {
-                wk_trip += ctl->nkept;
-                for (int c = 0; c < ncls; c++) {
-                    const int g0 = GRP_BEGIN(a, c), g1 = GRP_BEGIN(a, c + 1);
-                    if (g1 > g0) {
-                        int nf = 0;
-                        for (int g = g0; g < g1; g++) nf += (g_iplus[g] >= 0) + (g_iminus[g] >= 0);
-                        wk_tc += ctl->npre[c];
-                        wk_tsf += (unsigned long long)ctl->npre[c] * nf;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        for (int t0 = 0; t0 < cnt; t0 += 32) {
-            const int t = t0 + lane;
-            const bool act = t < cnt;
-            const unsigned am = __ballot_sync(0xffffffffu, act);
-            if (act) {
-                const uint32_t it = seg[t];
-                const int v = it >> 20;
-                const unsigned peers = __match_any_sync(am, v);
-                const int rank = __popc(peers & ltmask);
-                const int base = ctl->basew[wid][v];
-                s_S[base + rank] = it;
-                __syncwarp(am);
-                if (rank == 0) ctl->basew[wid][v] = base + __popc(peers);
-            }
-            __syncwarp();
-        }
-        __syncthreads();
-    };
-
-    // ---- 4: forward over the sorted list ----------------------------------------------
-    auto forward_list = [&]() {
-        int rot = 0;  // items dealt so far: the next class continues the round robin where this one stopped
-        for (int c = 0; c < ncls; c++) {
-            const int g0 = GRP_BEGIN(a, c), g1 = GRP_BEGIN(a, c + 1);
-            const int n_c = ctl->npre[c];
-            if (g0 == g1 || n_c == 0) continue;
-            const int myrank = (tid - rot + CT) % CT;   // this thread's position in the deal for class c
-            rot = (rot + n_c) % CT;
-            const double pirc = a.cls.pirc[c];
-            const double *fcc = s_fc + c * pcap;
-            for (int gb = g0; gb < g1; gb += MAXG) {
-                const int ng = min(MAXG, g1 - gb);
-                double acc[MAXG][4];
-#pragma unroll
-                for (int g = 0; g < MAXG; g++) acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.0;
-                for (int t = myrank; t < n_c; t += CT) {
-                    const uint32_t it = s_S[t];
-                    const int ra = it & 1023, rb = (it >> 10) & 1023;
-                    const double rjk2 = pair_dist2(s_x[ra], s_x[pcap + ra], s_x[2 * pcap + ra], s_x[rb], s_x[pcap + rb],
-                                                   s_x[2 * pcap + rb]);
-                    const double rja = s_r[ra], rkb = s_r[rb];
-                    const double ra2 = rja * rja, rb2 = rkb * rkb;
-                    const double cosv = (ra2 + rb2 - rjk2) * 0.5 * s_ir[ra] * s_ir[rb];
-                    const double ssum = ra2 + rb2 + rjk2;
-                    const double ww = s_w[ra] * s_w[rb];
-                    const double rjk = rjk2 * rsqrt_pos(fmax(rjk2, 1e-300));
-                    double sn, cs;
-                    sincos_0pi(rjk * pirc, &sn, &cs);
-                    const double phi = fcc[ra] * fcc[rb] * (0.5 * (cs + 1.0));
-                    // groups in pairs without a branch between their exponentials, so the two
-                    // dependent chains interleave (same trick as in the backward loop)
-                    auto one = [&](double (&ac)[4], int g) {
-                        const double pe = phi * exp_arg(-s_galpha[gb + g] * ssum, s_t32, a.exp_clamp);
-                        const double pw = pe * ww;
-                        ac[0] += pe; ac[1] = fma(pe, cosv, ac[1]); ac[2] += pw; ac[3] = fma(pw, cosv, ac[3]);
-                    };
-                    auto two = [&](double (&a0)[4], double (&a1)[4], int g) {
-                        const double e0 = exp_arg(-s_galpha[gb + g] * ssum, s_t32, a.exp_clamp);
-                        const double e1 = exp_arg(-s_galpha[gb + g + 1] * ssum, s_t32, a.exp_clamp);
-                        const double pe0 = phi * e0, pe1 = phi * e1, pw0 = pe0 * ww, pw1 = pe1 * ww;
-                        a0[0] += pe0; a0[1] = fma(pe0, cosv, a0[1]); a0[2] += pw0; a0[3] = fma(pw0, cosv, a0[3]);
-                        a1[0] += pe1; a1[1] = fma(pe1, cosv, a1[1]); a1[2] += pw1; a1[3] = fma(pw1, cosv, a1[3]);
-                    };
-                    if (ng >= 2) two(acc[0], acc[1], 0); else one(acc[0], 0);
-                    if (ng >= 4) two(acc[2], acc[3], 2); else if (ng == 3) one(acc[2], 2);
-                }
-                if (__any_sync(0xffffffffu, myrank < n_c)) {
-#pragma unroll
-                    for (int g = 0; g < MAXG; g++) {
-                        if (g < ng) {
-                            // lanes 0,8,16,24 end up with sum pe, sum pe*cos, sum w*pe, sum w*pe*cos
-                            const double tot = warp_sum4(acc[g][0], acc[g][1], acc[g][2], acc[g][3], lane);
-                            const double oth = __shfl_xor_sync(0xffffffffu, tot, 8);  // the cos partner / the plain partner
-                            if ((lane & 7) == 0) {
-                                const int ip = g_iplus[gb + g], im = g_iminus[gb + g];
-                                double *gw = s_gw + wid * D + ((lane & 16) ? nsf : 0);
-                                // lane&8 == 0: tot = plain sum, oth = cos sum -> lambda=+1 ; else the lambda=-1 one
-                                if (!(lane & 8)) { if (ip >= 0) gw[ip] += tot + oth; }
-                                else { if (im >= 0) gw[im] += oth - tot; }
-                            }
-                        }
-                    }
-                }
-            }
-        }
-    };
-
-    // ---- 6: backward over the sorted list -----------------------------------------------
-    auto backward_list = [&]() {
-        const bool priv = a.npa > 1;
-        double *pa = priv ? s_pa + (size_t)wid * 3 * pcap : s_acc;
-        if (priv) {
-            for (int t = lane; t < 3 * pcap; t += 32) pa[t] = 0.0;
-            __syncwarp();
-        }
-        const int TB = ctl->TB;
-        int o = 0;
-        // batches are ordered heavy bucket first; deal them 0..NW-1, NW-1..0, 0..NW-1, ... so that
-        // every warp gets a similar mix (fixed assignment: keeps the summation order reproducible)
-        for (int round = 0; round * NW < TB; round++) {
-            const int g = round * NW + ((round & 1) ? NW - 1 - wid : wid);
-            if (g >= TB) continue;
-            while (o + 1 < ncls && g >= ctl->obp[o + 1]) o++;
-            const int v = ncls - o, q = g - ctl->obp[o], Qb = ctl->obq[o], n = ctl->ocnt[o];
-            const int idx = lane * Qb + q;  // lanes far apart in the list -> mostly distinct rows
-            const bool act = idx < n;
-            const unsigned am = __ballot_sync(0xffffffffu, act);
-            if (!act) continue;
-            const uint32_t it = s_S[ctl->obase[o] + idx];
-            const int ra = it & 1023, rb = (it >> 10) & 1023;
-            const double xa = s_x[ra], ya = s_x[pcap + ra], za = s_x[2 * pcap + ra];
-            const double xb = s_x[rb], yb = s_x[pcap + rb], zb = s_x[2 * pcap + rb];
-            const double rja = s_r[ra], rkb = s_r[rb], ira = s_ir[ra], irb = s_ir[rb];
-            const double rjk2 = pair_dist2(xa, ya, za, xb, yb, zb);
-            const double irjk = rsqrt_pos(rjk2);
-            const double rjk = rjk2 * irjk;
-            const double ra2 = rja * rja, rb2 = rkb * rkb;
-            const double cosv = (ra2 + rb2 - rjk2) * 0.5 * ira * irb;
-            const double ssum = ra2 + rb2 + rjk2;
-            const double ww = s_w[ra] * s_w[rb];
-            const double u1 = irb - cosv * ira, u2 = ira - cosv * irb, u3 = -rjk * ira * irb;
-            double cij = 0.0, cik = 0.0, cjk = 0.0;
-            for (int c = 0; c < v; c++) {
-                const int g0 = GRP_BEGIN(a, c), g1 = GRP_BEGIN(a, c + 1);
-                if (g0 == g1) continue;
-                const double pirc = a.cls.pirc[c];
-                double sn, cs;
-                sincos_0pi(rjk * pirc, &sn, &cs);
-                const double fjk = 0.5 * (cs + 1.0), dfjk = -0.5 * pirc * sn;
-                const double fa = s_fc[c * pcap + ra], fb = s_fc[c * pcap + rb];
-                const double dfa = s_dfc[c * pcap + ra], dfb = s_dfc[c * pcap + rb];
-                const double fab = fa * fb, phi = fab * fjk;
-                // S1 = sum gamma e lam, T0 = sum gamma e, S3 = sum alpha gamma e (1 + lam cos)
-                double S1 = 0.0, T0 = 0.0, S3 = 0.0;
-                // two groups per trip: their exponentials are independent chains (ILP; measured -7 %)
-                int gg = g0;
-                for (; gg + 1 < g1; gg += 2) {
-                    const double al0 = s_galpha[gg], al1 = s_galpha[gg + 1];
-                    const double e0 = exp_arg(-al0 * ssum, s_t32, a.exp_clamp), e1 = exp_arg(-al1 * ssum, s_t32, a.exp_clamp);
-                    const double4 gd0 = *(const double4 *)(s_gd + 4 * gg), gd1 = *(const double4 *)(s_gd + 4 * gg + 4);
-                    const double t00 = e0 * fma(ww, gd0.y, gd0.x), t01 = e0 * fma(ww, gd0.w, gd0.z);
-                    const double t10 = e1 * fma(ww, gd1.y, gd1.x), t11 = e1 * fma(ww, gd1.w, gd1.z);
-                    T0 += t00 + t10;
-                    S1 += t01 + t11;
-                    S3 = fma(al0, fma(cosv, t01, t00), fma(al1, fma(cosv, t11, t10), S3));
-                }
-                if (gg < g1) {
-                    const double al = s_galpha[gg];
-                    const double e = exp_arg(-al * ssum, s_t32, a.exp_clamp);
-                    const double4 gd = *(const double4 *)(s_gd + 4 * gg);   // DU, DW, DUL, DWL
-                    const double t0 = e * fma(ww, gd.y, gd.x), t1 = e * fma(ww, gd.w, gd.z);
-                    T0 += t0;
-                    S1 += t1;
-                    S3 = fma(al, fma(cosv, t1, t0), S3);
-                }
-                const double S2 = fma(cosv, S1, T0);  // sum gamma e (1 + lam cos)
-                const double pS1 = phi * S1, pS3 = 2.0 * phi * S3;
-                cij += pS1 * u1 - pS3 * rja + S2 * (dfa * fb * fjk);
-                cik += pS1 * u2 - pS3 * rkb + S2 * (fa * dfb * fjk);
-                cjk += pS1 * u3 - pS3 * rjk + S2 * (fab * dfjk);
-            }
-            // dE/dx_j = (gij+gjk) d_j - gjk d_k ; dE/dx_k = (gik+gjk) d_k - gjk d_j
-            const double gij = cij * ira, gik = cik * irb, gjk = cjk * irjk;
-            const double dxa = xa - xi, dya = ya - yi, dza = za - zi, dxb = xb - xi, dyb = yb - yi, dzb = zb - zi;
-            const double ga = gij + gjk, gb = gik + gjk;
-            scatter3(pa, pcap, ra, fma(ga, dxa, -gjk * dxb), fma(ga, dya, -gjk * dyb), fma(ga, dza, -gjk * dzb), am, ltmask, priv);
-            scatter3(pa, pcap, rb, fma(gb, dxb, -gjk * dxa), fma(gb, dyb, -gjk * dya), fma(gb, dzb, -gjk * dza), am, ltmask, priv);
-        }
-        __syncthreads();
-        if (priv) {
-            for (int t = tid; t < 3 * pcap; t += CT) {
-                double v = 0.0;
-#pragma unroll
-                for (int w = 0; w < NW; w++) v += s_pa[(size_t)w * 3 * pcap + t];
-                s_acc[t] += v;
-            }
-            __syncthreads();
-        }
-    };
-
-    // ---- drive the phases ---------------------------------------------------------------
-    bool list_ready = false, list_stashed = false;
-    if (FWD) {
-        const bool stash = FUSED && nchunk > 1 && a.list_scratch && nchunk <= a.list_scratch_chunks;
-        for (int ch = 0; ch < nchunk; ch++) {
-            build_list(ch * qchunk, min(Q, (ch + 1) * qchunk), true);
-            if (stash) {
-                // keep the sorted list of this chunk (L2 resident) for the backward pass
-                uint32_t *dst = a.list_scratch + ((size_t)blockIdx.x * a.list_scratch_chunks + ch) * (size_t)(lcap + 32 + 512);
-                const int n = ctl->nkept;
-                for (int t = tid; t < n; t += CT) dst[t] = s_S[t];
-                const int *cs = (const int *)ctl;
-                for (int t = tid; t < (int)(sizeof(Ctl) / 4); t += CT) dst[lcap + 32 + t] = (uint32_t)cs[t];
-            }
-            forward_list();
-            __syncthreads();
-        }
-        list_ready = (nchunk == 1);
-        list_stashed = stash;
-        __syncthreads();
-        // per-warp partial sums -> descriptors (fixed order)
-        for (int k = tid; k < D; k += CT) {
-            double v = 0.0;
-#pragma unroll
-            for (int w = 0; w < NW; w++) v += s_gw[w * D + k];
-            if (FUSED) s_G[k] = v;
-            if (a.G) a.G[(size_t)i * D + k] = v;
-        }
-        // work counters
-        unsigned long long v0 = wk_pc, v1 = wk_rad;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); }
-        if (lane == 0) { atomicAdd(&a.flags->work[2], v0); atomicAdd(&a.flags->work[7], v1); }
-        if (tid == 0) {
-            atomicAdd(&a.flags->work[0], 1ull);
-            atomicAdd(&a.flags->work[1], (unsigned long long)P);
-            atomicAdd(&a.flags->work[3], (unsigned long long)Q);
-            atomicAdd(&a.flags->work[4], wk_trip);
-            atomicAdd(&a.flags->work[5], wk_tc);
-            atomicAdd(&a.flags->work[6], wk_tsf);
-        }
-    }
-    if (FUSED) {
-        // ---- 5: sparse GPR of this atom (gap_calc.f90:143-166), difference form ----------
-        __syncthreads();
-        const int M = a.gpr_M, Mp = a.gpr_Mp, Dp = a.gpr_Dp;
-        for (int k = tid; k < D; k += CT) s_xs[k] = (s_G[k] - a.gpr_cmean[k]) * a.gpr_itheta[k];
-        __syncthreads();
-        // squared distances: warp w sums its slab of descriptor components for every sparse point
-        double *part = (double *)(smem + L.scratch);          // [NW][Mp] partial sums (gw/U are dead by now)
-        {
-            const int kslab = (D + NW - 1) / NW, k0 = wid * kslab, k1 = min(D, k0 + kslab);
-            for (int j = lane; j < Mp; j += 32) {
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                const double *col = a.gpr_MtT + (size_t)k0 * Mp + j;
-                int k = k0;
-                for (; k + 3 < k1; k += 4, col += 4 * (size_t)Mp) {   // four independent chains, loads issued together
-                    const double m0 = __ldg(col), m1 = __ldg(col + Mp), m2 = __ldg(col + 2 * (size_t)Mp), m3 = __ldg(col + 3 * (size_t)Mp);
-                    const double d0 = s_xs[k] - m0, d1 = s_xs[k + 1] - m1, d2 = s_xs[k + 2] - m2, d3 = s_xs[k + 3] - m3;
-                    s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
-                }
-                for (; k < k1; k++, col += Mp) { const double d0 = s_xs[k] - __ldg(col); s0 = fma(d0, d0, s0); }
-                part[wid * Mp + j] = (s0 + s1) + (s2 + s3);
-            }
-        }
-        __syncthreads();
-        double esum = 0.0;
-        for (int j = tid; j < Mp; j += CT) {
-            double sacc = 0.0;
-#pragma unroll
-            for (int w = 0; w < NW; w++) sacc += part[w * Mp + j];
-            const double wv = (j < M) ? exp_arg(-0.5 * sacc, s_t32, 1) * a.gpr_coeff[j] : 0.0;
-            s_W[j] = wv;
-            esum += wv;
-        }
-        esum = warp_sum(esum);
-        if (lane == 0) s_red[wid] = esum;
-        __syncthreads();
-        if (tid == 0) {
-            double e = 0.0;
-            for (int w = 0; w < NW; w++) e += s_red[w];
-            a.eatom[i] = e;
-        }
-        // dE/dG_k = -(1/theta_k) sum_j W_j (x'_k - m'_jk): warp w takes a slab of sparse points, lanes over k
-        {
-            const int jslab = (M + NW - 1) / NW, j0 = wid * jslab, j1 = min(M, j0 + jslab);
-            for (int k = lane; k < D; k += 32) {
-                const double xk = s_xs[k];
-                const double *row = a.gpr_Mt + k;
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                const double *rp = row + (size_t)j0 * Dp;
-                int j = j0;
-                for (; j + 3 < j1; j += 4, rp += 4 * (size_t)Dp) {
-                    const double m0 = __ldg(rp), m1 = __ldg(rp + Dp), m2 = __ldg(rp + 2 * (size_t)Dp), m3 = __ldg(rp + 3 * (size_t)Dp);
-                    a0 = fma(s_W[j], xk - m0, a0); a1 = fma(s_W[j + 1], xk - m1, a1);
-                    a2 = fma(s_W[j + 2], xk - m2, a2); a3 = fma(s_W[j + 3], xk - m3, a3);
-                }
-                for (; j < j1; j++, rp += Dp) a0 = fma(s_W[j], xk - __ldg(rp), a0);
-                part[wid * D + k] = (a0 + a1) + (a2 + a3);   // part is reused with stride D
-            }
-        }
-        __syncthreads();
-        for (int k2 = tid; k2 < D; k2 += CT) {
-            double acc = 0.0;
-#pragma unroll
-            for (int w = 0; w < NW; w++) acc += part[w * D + k2];
-            const double v = -a.gpr_itheta[k2] * acc;
-            s_du[k2] = v;
-            if (a.dEdG_out) a.dEdG_out[(size_t)i * D + k2] = v;
-        }
-        __syncthreads();
-    }
-    if (BWD) {
-        if (!a.lgrad) return;
-        // per (class, alpha) group: sums of dE/dG over its functions
-        for (int g = tid; g < pl.n_grp; g += CT) {
-            const int ip = g_iplus[g], im = g_iminus[g];
-            const double dup = ip >= 0 ? s_du[ip] : 0.0, dwp = ip >= 0 ? s_du[ip + nsf] : 0.0;
-            const double dum = im >= 0 ? s_du[im] : 0.0, dwm = im >= 0 ? s_du[im + nsf] : 0.0;
-            s_gd[4 * g] = dup + dum; s_gd[4 * g + 1] = dwp + dwm; s_gd[4 * g + 2] = dup - dum; s_gd[4 * g + 3] = dwp - dwm;
-        }
-        // radial backward: thread (neighbour, part); part p takes the functions q = p, p+nparts, ...
-        {
-            const int nparts = P32 <= CT ? min(CT / P32, 8) : 1;
-            const int stride = P32 <= CT ? P32 : CT;       // neighbours covered per sweep
-            double *part = s_pa;  // [nparts][stride] scratch, <= CT doubles (free until backward_list)
-            const int p = tid / stride, s0 = tid - p * stride;
-            for (int sb = 0; sb < P32; sb += stride) {
-                const int s = sb + s0;
-                double cacc = 0.0;
-                if (p < nparts && s < P) {
-                    const double dis = s_r[s], wj = s_w[s];
-                    const int nc = s_nc[s];
-                    for (int q = p; q < pl.n_rad; q += nparts) {
-                        const int2 ri = s_radi[q];
-                        const int c = ri.y & 0xffff;
-                        if (c >= nc) continue;
-                        double arg, dgf;
-                        if ((ri.y >> 16) == 1) { const double al = s_radp[q]; arg = -al * dis * dis; dgf = -2.0 * al * dis; }
-                        else { const double d = dis - s_radp[q]; arg = -4.0 * d * d; dgf = -8.0 * d; }
-                        const double dg = exp_arg(arg, s_t32, a.exp_clamp) * fma(dgf, s_fc[c * pcap + s], s_dfc[c * pcap + s]);
-                        cacc = fma(s_du[ri.x] + wj * s_du[ri.x + nsf], dg, cacc);
-                    }
-                }
-                if (p < nparts) part[p * stride + s0] = cacc;
-                __syncthreads();
-                if (tid < stride && sb + tid < pcap) {
-                    double v = 0.0;
-                    for (int pp = 0; pp < nparts; pp++) v += part[pp * stride + tid];
-                    const int s2 = sb + tid;
-                    const bool in = s2 < P;
-                    const double g = in ? v * s_ir[s2] : 0.0;     // (dE/dr) / r
-                    s_acc[s2] = in ? g * (s_x[s2] - xi) : 0.0;
-                    s_acc[pcap + s2] = in ? g * (s_x[pcap + s2] - yi) : 0.0;
-                    s_acc[2 * pcap + s2] = in ? g * (s_x[2 * pcap + s2] - zi) : 0.0;
-                }
-                __syncthreads();
-            }
-            for (int s2 = P32 + tid; s2 < pcap; s2 += CT) {
-                s_acc[s2] = 0.0; s_acc[pcap + s2] = 0.0; s_acc[2 * pcap + s2] = 0.0;
-            }
-        }
-        __syncthreads();
-        for (int ch = 0; ch < nchunk; ch++) {
-            if (list_stashed) {
-                const uint32_t *src = a.list_scratch + ((size_t)blockIdx.x * a.list_scratch_chunks + ch) * (size_t)(lcap + 32 + 512);
-                int *cs = (int *)ctl;
-                for (int t = tid; t < (int)(sizeof(Ctl) / 4); t += CT) cs[t] = (int)src[lcap + 32 + t];
-                __syncthreads();
-                const int n = ctl->nkept;
-                for (int t = tid; t < n; t += CT) s_S[t] = src[t];
-                __syncthreads();
-            } else if (!list_ready) {
-                build_list(ch * qchunk, min(Q, (ch + 1) * qchunk), false);
-            }
-            backward_list();
-        }
-        // ---- epilogue: per neighbour gradient, centre gradient, strs contraction ----------
-        double acc9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // gself xyz, vir xx xy xz yy yz zz
-        for (int s = tid; s < P; s += CT) {
-            const double dx = s_x[s] - xi, dy = s_x[pcap + s] - yi, dz = s_x[2 * pcap + s] - zi;
-            const double gx = s_acc[s], gy = s_acc[pcap + s], gz = s_acc[2 * pcap + s];
-            double *fp = a.fpair + ((size_t)i * a.cap + s) * 3;
-            fp[0] = gx; fp[1] = gy; fp[2] = gz;
-            acc9[0] -= gx; acc9[1] -= gy; acc9[2] -= gz;
-            acc9[3] += dx * gx; acc9[4] += dx * gy; acc9[5] += dx * gz;
-            acc9[6] += dy * gy; acc9[7] += dy * gz; acc9[8] += dz * gz;
-        }
-#pragma unroll
-        for (int q = 0; q < 9; q++) {
-            const double v = warp_sum(acc9[q]);
-            if (lane == 0) s_red[wid * 16 + q] = v;
-        }
-        __syncthreads();
-        if (tid < 9) {
-            double v = 0.0;
-            for (int w = 0; w < NW; w++) v += s_red[w * 16 + tid];
-            if (tid < 3) a.gself[(size_t)i * 3 + tid] = v;
-            else a.vir[(size_t)i * 6 + (tid - 3)] = v;
-        }
-    }
-}
-
-// Persistent CTAs: as many as fit the device, each pulling centre atoms from a queue
-// ordered by descending neighbour count (longest first), so that 1000 centres on 296
-// resident CTAs do not cost four full waves and the heavy centres do not form the tail.
-template <int MODE, int MINB>
-__global__ void __launch_bounds__(CT, MINB) k_centre(const CentreArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_next;
-    bool first = true;
-    unsigned long long t0 = 0;
-    if (threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
-    for (;;) {
-        __syncthreads();  // everybody is done with the previous centre's shared memory
-        if (threadIdx.x == 0) s_next = atomicAdd(&a.flags->queue[MODE], 1);
-        __syncthreads();
-        const int n = s_next;
-        if (n >= (a.n_centres ? *a.n_centres : a.ntot)) break;
-        process_centre<MODE>(a, a.order ? a.order[n] : n, smem, first);
-        first = false;
-    }
-    if (threadIdx.x == 0) {
-        unsigned long long t1;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-        atomicMax(&a.flags->t_start_min, ~t0);   // flags start zeroed: minima are kept as maxima of the complement
-        atomicMax(&a.flags->t_exit_min, ~t1);
-        atomicMax(&a.flags->t_exit_max, t1);
-        atomicAdd(&a.flags->t_busy_sum, t1 - t0);
-        atomicAdd(&a.flags->n_ctas, 1ull);
-    }
-}
-
-template <int MODE, int MINB>
-static int launch_mode_b(cudaStream_t st, const CentreArgs &a_in) {
+static int launch_mode(cudaStream_t st, const CentreArgs &a_in, int mode) {
     CentreArgs a = a_in;
-    a.lay = make_layout(a, MODE);
-    const size_t sm = (size_t)a.lay.total;
-    if (sm > 227 * 1024) return -1;
-    if (cudaFuncSetAttribute((const void *)k_centre<MODE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
-        return -2;
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-    int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_centre<MODE, MINB>, CT, sm) != cudaSuccess || per_sm < 1) per_sm = 1;
-    const int grid = a.ntot < sms * per_sm ? a.ntot : sms * per_sm;
-    k_centre<MODE, MINB><<<grid, CT, sm, st>>>(a);
-    return 0;
-}
-
-template <int MODE>
-static int launch_mode(cudaStream_t st, const CentreArgs &a) {
-    return (a.variant & 8) ? launch_mode_b<MODE, 2>(st, a) : launch_mode_b<MODE, 3>(st, a);
+    a.lay = make_layout(a, mode);
+    switch (pcap_template(a.pcap)) {
+        case 128: return launch_centre_p128(st, a, mode);
+        case 256: return launch_centre_p256(st, a, mode);
+        case 512: return launch_centre_p512(st, a, mode);
+        default: return launch_centre_p1024(st, a, mode);
+    }
 }
 
 int launch_forward(cudaStream_t st, const CentreArgs &a, long *launches) {
     if (launches) *launches += 1;
-    return launch_mode<MODE_FWD>(st, a);
+    return launch_mode(st, a, MODE_FWD);
 }
 int launch_backward(cudaStream_t st, const CentreArgs &a, long *launches) {
     if (launches) *launches += 1;
-    return launch_mode<MODE_BWD>(st, a);
+    return launch_mode(st, a, MODE_BWD);
 }
 int launch_fused(cudaStream_t st, const CentreArgs &a, long *launches) {
     if (launches) *launches += 1;
-    return launch_mode<MODE_FUSED>(st, a);
+    return launch_mode(st, a, MODE_FUSED);
 }
 
 }  // namespace gapcu
