@@ -79,12 +79,6 @@ struct Ctl {
 };
 static_assert(sizeof(Ctl) <= 4 * 512, "Ctl does not fit its slot");
 
-// exp(x), x <= 0; clamp only when the potential can produce arguments below -700
-__device__ __forceinline__ double exp_arg(double x, const double *T32, int clamp) {
-    if (clamp) x = fmax(x, -700.0);
-    return exp_neg(x, T32);
-}
-
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -257,7 +251,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 if (c < NCB(s)) {
                     const double dis = NB2(s, 1).y;
                     const double d = t1 ? dis : dis - prm;
-                    const double g = exp_arg((t1 ? -prm : -4.0) * d * d, s_t32, a.exp_clamp) * FCV(c, s);
+                    const double g = exp_neg((t1 ? -prm : -4.0) * d * d, s_t32) * FCV(c, s);
                     gu += g;
                     gwt = fma(g, NB2(s, 2).y, gwt);
                     wk_rad++;
@@ -309,7 +303,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 int lo = 0;
                 if (packed) {
 #pragma unroll
-                    for (int c = 0; c < 8; c++) lo += (c < ncls && rjk2 <= a.cls.t2[c]);
+                    for (int c = 0; c < 8; c++) lo += (rjk2 <= a.cls.t2[c]);   // absent classes hold -1
                 } else {
 #pragma unroll
                     for (int step = MAXC_DEV / 2; step; step >>= 1)
@@ -413,6 +407,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             const int myrank = (tid - rot + CT) % CT;   // this thread's position in the deal for class c
             rot = (rot + n_c) % CT;
             const double pirc = a.cls.pirc[c];
+            const unsigned char *fcc = smem + H::FCD + c * (PCAP * 16);   // fc of class c: record stride 16 bytes
             for (int gb = g0; gb < g1; gb += MAXG) {
                 const int ng = min(MAXG, g1 - gb);
                 double acc[MAXG][4];
@@ -431,17 +426,17 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                     const double rjk = rjk2 * rsqrt_pos(fmax(rjk2, 1e-300));
                     double sn, cs;
                     sincos_0pi(rjk * pirc, &sn, &cs);
-                    const double phi = FCV(c, ra) * FCV(c, rb) * (0.5 * (cs + 1.0));
+                    const double phi = *(const double *)(fcc + ra * 16) * *(const double *)(fcc + rb * 16) * (0.5 * (cs + 1.0));
                     // groups in pairs without a branch between their exponentials, so the two
                     // dependent chains interleave (same trick as in the backward loop)
                     auto one = [&](double (&ac)[4], int g) {
-                        const double pe = phi * exp_arg(-s_galpha[gb + g] * ssum, s_t32, a.exp_clamp);
+                        const double pe = phi * exp_neg(-s_galpha[gb + g] * ssum, s_t32);
                         const double pw = pe * ww;
                         ac[0] += pe; ac[1] = fma(pe, cosv, ac[1]); ac[2] += pw; ac[3] = fma(pw, cosv, ac[3]);
                     };
                     auto two = [&](double (&a0)[4], double (&a1)[4], int g) {
-                        const double e0 = exp_arg(-s_galpha[gb + g] * ssum, s_t32, a.exp_clamp);
-                        const double e1 = exp_arg(-s_galpha[gb + g + 1] * ssum, s_t32, a.exp_clamp);
+                        const double e0 = exp_neg(-s_galpha[gb + g] * ssum, s_t32);
+                        const double e1 = exp_neg(-s_galpha[gb + g + 1] * ssum, s_t32);
                         const double pe0 = phi * e0, pe1 = phi * e1, pw0 = pe0 * ww, pw1 = pe1 * ww;
                         a0[0] += pe0; a0[1] = fma(pe0, cosv, a0[1]); a0[2] += pw0; a0[3] = fma(pw0, cosv, a0[3]);
                         a1[0] += pe1; a1[1] = fma(pe1, cosv, a1[1]); a1[2] += pw1; a1[3] = fma(pw1, cosv, a1[3]);
@@ -521,7 +516,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 int gg = g0;
                 for (; gg + 1 < g1; gg += 2) {
                     const double al0 = s_galpha[gg], al1 = s_galpha[gg + 1];
-                    const double e0 = exp_arg(-al0 * ssum, s_t32, a.exp_clamp), e1 = exp_arg(-al1 * ssum, s_t32, a.exp_clamp);
+                    const double e0 = exp_neg(-al0 * ssum, s_t32), e1 = exp_neg(-al1 * ssum, s_t32);
                     const double4 gd0 = *(const double4 *)(s_gd + 4 * gg), gd1 = *(const double4 *)(s_gd + 4 * gg + 4);
                     const double t00 = e0 * fma(ww, gd0.y, gd0.x), t01 = e0 * fma(ww, gd0.w, gd0.z);
                     const double t10 = e1 * fma(ww, gd1.y, gd1.x), t11 = e1 * fma(ww, gd1.w, gd1.z);
@@ -531,7 +526,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 }
                 if (gg < g1) {
                     const double al = s_galpha[gg];
-                    const double e = exp_arg(-al * ssum, s_t32, a.exp_clamp);
+                    const double e = exp_neg(-al * ssum, s_t32);
                     const double4 gd = *(const double4 *)(s_gd + 4 * gg);   // DU, DW, DUL, DWL
                     const double t0 = e * fma(ww, gd.y, gd.x), t1 = e * fma(ww, gd.w, gd.z);
                     T0 += t0;
@@ -634,7 +629,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             double sacc = 0.0;
 #pragma unroll
             for (int w = 0; w < NW; w++) sacc += part[w * Mp + j];
-            const double wv = (j < M) ? exp_arg(-0.5 * sacc, s_t32, 1) * a.gpr_coeff[j] : 0.0;
+            const double wv = (j < M) ? exp_neg(-0.5 * sacc, s_t32) * a.gpr_coeff[j] : 0.0;
             s_W[j] = wv;
             esum += wv;
         }
@@ -704,7 +699,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                         if ((ri.y >> 16) == 1) { const double al = s_radp[q]; arg = -al * dis * dis; dgf = -2.0 * al * dis; }
                         else { const double d = dis - s_radp[q]; arg = -4.0 * d * d; dgf = -8.0 * d; }
                         const double2 fd = FCD2(c, s);
-                        const double dg = exp_arg(arg, s_t32, a.exp_clamp) * fma(dgf, fd.x, fd.y);
+                        const double dg = exp_neg(arg, s_t32) * fma(dgf, fd.x, fd.y);
                         cacc = fma(s_du[ri.x] + wj * s_du[ri.x + nsf], dg, cacc);
                     }
                 }

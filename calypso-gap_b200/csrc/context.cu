@@ -87,7 +87,6 @@ struct gapcu_ctx {
     int M = 0, D = 0, Mp = 0, Dp = 0;
     std::vector<double> h_theta, h_mm, h_coeff;  // cached GPR data (C order)
     DBuf<double> d_mm_raw, d_theta_raw, d_coeff_raw, d_Mt, d_MtT, d_mn, d_coeff, d_cmean, d_itheta, d_exp2;
-    int exp_clamp = 0;
     int pipeline = 0;  // 0 auto, 1 split (K2 -> DMMA K3 -> K4), 2 fused single centre kernel
     // ---- structures
     int nstruct = 0, ntot = 0, nbins = 0;
@@ -136,6 +135,7 @@ struct gapcu_ctx {
         ClassTab t;
         memset(&t, 0, sizeof t);
         for (int c = 0; c < plan.ncls; c++) { t.rc[c] = plan.rc[c]; t.t2[c] = plan.t2[c]; t.pirc[c] = plan.pirc[c]; }
+        for (int c = plan.ncls; c < MAXC_DEV; c++) t.t2[c] = -1.0;   // no squared distance passes an absent class
         for (int c = 0; c <= MAXC_DEV; c++) t.grp_begin[c] = plan.grp_begin[c];
         t.angmask = plan.ang_prefix_mask;
         return t;
@@ -220,17 +220,10 @@ static int set_sf(gapcu_ctx *c, const std::vector<int> &z, const std::vector<dou
     if (c->plan.n_unknown)
         fprintf(stdout, " Unknown function type in gap_parameters (%d functions left at zero)\n", c->plan.n_unknown);
     c->z = z; c->w = w;
-    {   // can any exponent argument -alpha*(rij^2+rik^2+rjk^2) / -alpha*r^2 / -4 (r-rs)^2 drop below -700?
-        double worst = 0.0;
-        for (size_t i = 0; i < ntype.size(); i++) {
-            const double rc2 = cutoff[i] * cutoff[i];
-            if (ntype[i] == 1) worst = std::max(worst, std::fabs(alpha[i]) * rc2);
-            if (ntype[i] == 2 || ntype[i] == 4) worst = std::max(worst, std::fabs(alpha[i]) * 3.0 * rc2);
-            if (ntype[i] == 3) worst = std::max(worst, 4.0 * std::max(rc2, alpha[i] * alpha[i]));
-            if ((ntype[i] == 1 || ntype[i] == 2 || ntype[i] == 4) && alpha[i] < 0.0) return fail(GAPCU_ELIMIT, "negative symmetry-function alpha is not supported");
-        }
-        c->exp_clamp = worst > 690.0;
-    }
+    // exponent arguments -alpha*(rij^2+rik^2+rjk^2), -alpha*r^2, -4 (r-rs)^2 must be <= 0 (exp_neg, fastmath.cuh;
+    // arbitrarily negative ones are fine: the result saturates at ~2^-1021)
+    for (size_t i = 0; i < ntype.size(); i++)
+        if ((ntype[i] == 1 || ntype[i] == 2 || ntype[i] == 4) && alpha[i] < 0.0) return fail(GAPCU_ELIMIT, "negative symmetry-function alpha is not supported");
     CU(c->d_itab.ensure(c->plan.itab.size() + 1));
     CU(c->d_dtab.ensure(c->plan.dtab.size() + 1));
     CU(cudaMemcpyAsync(c->d_itab.p, c->plan.itab.data(), sizeof(int) * c->plan.itab.size(), cudaMemcpyHostToDevice, c->stream));
@@ -528,7 +521,6 @@ static int make_centre_args(gapcu_ctx *c, int lgrad, CentreArgs *out, bool *fuse
     a.structs = c->d_structs.p; a.sid = c->d_sid.p; a.pos = c->d_pos.p; a.wgt = c->d_wgt.p;
     a.nbr_keys = c->d_keys.p; a.nbr_cnt = c->d_nbr_cnt.p; a.order = c->d_order.p; a.n_centres = &c->d_flags.p->n_centres; a.exp2_table = c->d_exp2.p;
     a.ntot = c->ntot; a.cap = c->cap; a.pcap = c->pcap; a.lgrad = lgrad;
-    a.exp_clamp = c->exp_clamp;
     { static int var = -1; if (var < 0) { const char *e = getenv("GAPCU_VARIANT"); var = e ? atoi(e) : 0; } a.variant = var; }
     a.G = c->d_G.p; a.dEdG = c->d_dEdG.p; a.dEdG_out = c->d_dEdG.p; a.eatom = c->d_eatom.p;
     a.fpair = c->d_fpair.p; a.gself = c->d_gself.p; a.vir = c->d_vir.p;

@@ -73,7 +73,7 @@ struct PlanDev {
 // Cutoff-class tables, passed by value in the kernel parameters (constant bank).
 struct ClassTab {
     double rc[MAXC_DEV];    // class cutoff, descending
-    double t2[MAXC_DEV];    // largest x with sqrt_rn(x) <= rc
+    double t2[MAXC_DEV];    // largest x with sqrt_rn(x) <= rc; -1 for absent classes
     double pirc[MAXC_DEV];  // PI_REF / rc
     int grp_begin[MAXC_DEV + 1];
     uint32_t angmask;       // bit b: some class c < b holds angular functions
@@ -106,7 +106,6 @@ struct CentreArgs {
     int list_scratch_chunks;
     int npa;                    // private accumulator sets in backward: NW, or 1 (= shared + atomics)
     int lgrad;
-    int exp_clamp;              // 1: exponent arguments may fall below -700 and are clamped
     int variant;                // experiment switches (environment GAPCU_VARIANT), 0 in production
     double *G;                  // [NT][D]   descriptors out (forward / fused; may be null in fused)
     const double *dEdG;         // [NT][D]   backward in (MODE_BWD)

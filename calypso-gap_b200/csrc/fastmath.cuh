@@ -4,10 +4,12 @@
 // cos/sin(pi~ r/Rc) with r <= Rc.  The CUDA library versions carry range checks,
 // huge-argument reduction and denormal handling that are dead weight here (ncu:
 // ~50 SASS instructions per exp, ~70 per sincos).  These versions keep full double
-// accuracy (<= ~2 ulp; tests/test_fastmath.py checks them against libm on the host
-// with the same source) on the restricted domains:
-//   exp_neg(x)      -700 <= x <= 0  (callers clamp the argument when it can be lower)
-//   sincos_0pi(y)   0 <= y <= 3.3
+// accuracy (<= ~2 ulp; tests/test_boundary_cpu.py::test_fastmath_host_versions checks
+// them against libm on the host with the same source) on the restricted domains:
+//   exp_neg(x)      x <= 0; arguments below about -708 return a value <= 2^-1021 instead
+//                   of a denormal or zero (one integer max on the exponent, no FP clamp)
+//   sincos_0pi(y)   0 <= y <= 3.3: no quadrant logic, both functions are polynomials in
+//                   t = y - pi/2 (sin y = cos t, cos y = -sin t)
 #pragma once
 #include <math.h>
 #include <string.h>
@@ -36,15 +38,16 @@ static inline void fill_exp2_table(double *t) {
     0.008333333333333333,     /* 4  1/5!                          */                         \
     0.041666666666666664,     /* 5  1/4!                          */                         \
     0.16666666666666666,      /* 6  1/3!                          */                         \
-    0.6366197723675814,       /* 7  2/pi                          */                         \
-    -1.5707963267948912,      /* 8  -pi/2 high                    */                         \
-    -5.390302858158119e-15,   /* 9  -pi/2 low                     */                         \
-    2.8114572543455206e-15, -7.647163731819816e-13, 1.6059043836821613e-10, /* 10-12 sin */  \
-    -2.505210838544172e-08, 2.7557319223985893e-06, -0.0001984126984126984, /* 13-15     */  \
-    0.008333333333333333, -0.16666666666666666,                             /* 16-17     */  \
-    4.779477332387385e-14, -1.1470745597729725e-11, 2.08767569878681e-09,   /* 18-20 cos */  \
-    -2.755731922398589e-07, 2.48015873015873e-05, -0.001388888888888889,    /* 21-23     */  \
-    0.041666666666666664                                                    /* 24        */
+    -1.5707963267948966,      /* 7  -pi/2 high                    */                         \
+    -6.123233995736766e-17,   /* 8  -pi/2 low                     */                         \
+    /* 9-18: sin t = t + t^3 (S1 + S2 z + ... + S10 z^9), z = t^2 (Taylor; next term < 2e-18 on |t| <= 1.73) */ \
+    -0.16666666666666666, 0.008333333333333333, -0.0001984126984126984, 2.7557319223985893e-06,   \
+    -2.505210838544172e-08, 1.6059043836821613e-10, -7.647163731819816e-13, 2.8114572543455206e-15, \
+    -8.22063524662433e-18, 1.9572941063391263e-20,                                                 \
+    /* 19-28: cos t = 1 - z/2 + z^2 (C2 + C3 z + ... + C11 z^9) */                                \
+    0.041666666666666664, -0.001388888888888889, 2.48015873015873e-05, -2.755731922398589e-07,     \
+    2.08767569878681e-09, -1.1470745597729725e-11, 4.779477332387385e-14, -1.5619206968586225e-16, \
+    4.110317623312165e-19, -8.896791392450574e-22
 
 #if defined(__CUDACC__)
 __constant__ double gapcu_kc_dev[] = {GAPCU_KC_LIST};
@@ -56,16 +59,25 @@ static const double gapcu_kc_host[] = {GAPCU_KC_LIST};
 #define KC(i) gapcu_kc_host[i]
 #endif
 
-// exp(x) for -700 <= x <= 0 (callers clamp).  x = (32 m + j) ln2/32 + r, |r| <= ln2/64:
+// exp(x) for x <= 0.  x = (32 m + j) ln2/32 + r, |r| <= ln2/64:
 // exp(x) = 2^m * T[j] * (1 + r + r^2/2! + ... + r^6/6!)        (next term < 4e-18)
+// Two integer clamps replace the FP one: the high word of x is capped at that of -1e7 (as
+// unsigned integers, larger means more negative), and m is kept >= -1021 so that the
+// exponent field cannot wrap; results that should underflow come out as <= 2^-1021.
 GAPCU_HD double exp_neg(double x, const double *T32) {
     const double MAGIC = 6755399441055744.0;             // 1.5 * 2^52: rounds to nearest integer
+    unsigned long long xb;
+    memcpy(&xb, &x, sizeof xb);
+    unsigned int xh = (unsigned int)(xb >> 32);
+    xh = xh < 0xc16312d0u ? xh : 0xc16312d0u;            // x >= -1e7 (one integer min)
+    xb = ((unsigned long long)xh << 32) | (xb & 0xffffffffull);
+    memcpy(&x, &xb, sizeof x);
     const double kd = fma(x, KC(0), MAGIC);
     const double kf = kd - MAGIC;
     long long kbits;
     memcpy(&kbits, &kd, sizeof kbits);
     const int ki = (int)(unsigned int)kbits;             // low word of kd holds the integer (two's complement)
-    double r = fma(kf, KC(1), x);                        // k*hi is exact
+    double r = fma(kf, KC(1), x);                        // k*hi is exact for |k| < 2^17, accurate enough beyond
     r = fma(kf, KC(2), r);
     double p = fma(r, KC(3), KC(4));
     p = fma(p, r, KC(5));
@@ -74,34 +86,32 @@ GAPCU_HD double exp_neg(double x, const double *T32) {
     p = fma(p, r * r, r);                                // expm1(r)
     const double t = T32[ki & 31];
     double y = fma(t, p, t);
+    int m = ki >> 5;
+    m = m > -1021 ? m : -1021;
     unsigned long long yb;
     memcpy(&yb, &y, sizeof yb);
-    yb += (unsigned long long)(unsigned int)((ki >> 5) << 20) << 32;  // * 2^m on the high word (y in [1,2.1), m >= -1010)
+    yb += (unsigned long long)(unsigned int)(m << 20) << 32;  // * 2^m on the high word (y in [1,2.1))
     memcpy(&y, &yb, sizeof y);
     return y;
 }
 
-// sin(y), cos(y) for 0 <= y <= 3.3: quadrant q in {0,1,2}, t = y - q*pi/2 in [-pi/4, pi/4]
+// sin(y), cos(y) for 0 <= y <= 3.3 through t = y - pi/2 in [-1.571, 1.73]
 GAPCU_HD void sincos_0pi(double y, double *sn, double *cs) {
-    const double q = rint(y * KC(7));
-    double t = fma(q, KC(8), y);                         // q*hi exact
-    t = fma(q, KC(9), t);
-    const double z = t * t, z2 = z * z, z4 = z2 * z2;
-    // Estrin evaluation: four independent pairs per polynomial instead of one 8-long chain
-    const double s01 = fma(z, KC(16), KC(17)), s23 = fma(z, KC(14), KC(15));
-    const double s45 = fma(z, KC(12), KC(13)), s67 = fma(z, KC(10), KC(11));
+    const double t = (y + KC(7)) + KC(8);
+    const double z = t * t, z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
+    // Estrin evaluation: independent pairs instead of one 10-long chain per polynomial
+    const double s01 = fma(z, KC(10), KC(9)), s23 = fma(z, KC(12), KC(11)), s45 = fma(z, KC(14), KC(13));
+    const double s67 = fma(z, KC(16), KC(15)), s89 = fma(z, KC(18), KC(17));
     double s = fma(z4, fma(z2, s67, s45), fma(z2, s23, s01));
-    s = fma(s * z, t, t);                                // sin(t)
-    const double c01 = fma(z, -0.5, 1.0), c23 = fma(z, KC(23), KC(24));
-    const double c45 = fma(z, KC(21), KC(22)), c67 = fma(z, KC(19), KC(20));
-    const double c03 = fma(z2, c23, c01), c47 = fma(z2, c67, c45);
-    double c = fma(z4, fma(z4, KC(18), c47), c03);       // cos(t): degree 8 in z
-    // q = 0: (s, c); q = 1: (c, -s); q = 2: (-s, -c)
-    const bool odd = (q == 1.0);
-    const bool two = (q == 2.0);
-    const double ss = two ? -s : s, cc = two ? -c : c;
-    *sn = odd ? c : ss;
-    *cs = odd ? -s : cc;
+    s = fma(z8, s89, s);
+    s = fma(t * z, s, t);                                // sin(t)
+    const double c01 = fma(z, KC(20), KC(19)), c23 = fma(z, KC(22), KC(21)), c45 = fma(z, KC(24), KC(23));
+    const double c67 = fma(z, KC(26), KC(25)), c89 = fma(z, KC(28), KC(27));
+    double c = fma(z4, fma(z2, c67, c45), fma(z2, c23, c01));
+    c = fma(z8, c89, c);
+    c = fma(z2, c, fma(z, -0.5, 1.0));                   // cos(t)
+    *sn = c;
+    *cs = -s;
 }
 
 #if defined(__CUDACC__)

@@ -122,10 +122,10 @@ k_gpr(GprDev p, const double *__restrict__ G, int ntot, int mslice, double *__re
             dmma884(c10, c11, av, m1[4 * ks]);
         }
         const int ca = sp0 + r0, cb = sp0 + r1;                // sparse points of this lane's C columns
-        const double w00 = exp_neg(fmax(-0.5 * (xn + __ldg(p.mn + ca) - 2.0 * c00), -700.0), s_t32) * __ldg(p.coeff + ca);
-        const double w01 = exp_neg(fmax(-0.5 * (xn + __ldg(p.mn + cb) - 2.0 * c01), -700.0), s_t32) * __ldg(p.coeff + cb);
-        const double w10 = exp_neg(fmax(-0.5 * (xn + __ldg(p.mn + ca + 8) - 2.0 * c10), -700.0), s_t32) * __ldg(p.coeff + ca + 8);
-        const double w11 = exp_neg(fmax(-0.5 * (xn + __ldg(p.mn + cb + 8) - 2.0 * c11), -700.0), s_t32) * __ldg(p.coeff + cb + 8);
+        const double w00 = exp_neg(-0.5 * (xn + __ldg(p.mn + ca) - 2.0 * c00), s_t32) * __ldg(p.coeff + ca);
+        const double w01 = exp_neg(-0.5 * (xn + __ldg(p.mn + cb) - 2.0 * c01), s_t32) * __ldg(p.coeff + cb);
+        const double w10 = exp_neg(-0.5 * (xn + __ldg(p.mn + ca + 8) - 2.0 * c10), s_t32) * __ldg(p.coeff + ca + 8);
+        const double w11 = exp_neg(-0.5 * (xn + __ldg(p.mn + cb + 8) - 2.0 * c11), s_t32) * __ldg(p.coeff + cb + 8);
         esum += (w00 + w01) + (w10 + w11);
         // GEMM 2: acc(8 atoms x Dp) += W(8 x 16 sparse) * tile(16 sparse x Dp).  The C fragment of
         // GEMM 1 (row g, columns 2t, 2t+1) is used as the A operand as is: k-step e enumerates the

@@ -141,7 +141,11 @@ def test_fastmath_host_versions(tmp_path):
     xs = -np.concatenate([rng.uniform(0, 700, 20000), rng.uniform(0, 5, 20000), [0.0, 1e-300, 700.0]])
     got = np.array([L.fm_exp(x) for x in xs])
     assert (np.abs(got - np.exp(xs)) <= 4.5e-16 * np.exp(xs)).all()
+    # below the normal range the result is a harmless tiny number (<= 2^-1021), never NaN / inf / garbage
+    for x in (-709.0, -800.0, -1e4, -1e7, -1e12, -1e300, -np.inf):
+        v = L.fm_exp(x)
+        assert 0.0 <= v <= 2.0 ** -1020
     s, c = C.c_double(), C.c_double()
     for y in np.concatenate([rng.uniform(0, 3.3, 20000), [0.0, np.pi / 2, 3.141592654]]):
         L.fm_sc(y, C.byref(s), C.byref(c))
-        assert abs(s.value - np.sin(y)) < 3e-16 and abs(c.value - np.cos(y)) < 3e-16
+        assert abs(s.value - np.sin(y)) < 4e-16 and abs(c.value - np.cos(y)) < 4e-16   # absolute: what fc / fc' need
