@@ -606,11 +606,15 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         const int M = a.gpr_M, Mp = a.gpr_Mp, Dp = a.gpr_Dp;
         for (int k = tid; k < D; k += CT) s_xs[k] = (s_G[k] - a.gpr_cmean[k]) * a.gpr_itheta[k];
         __syncthreads();
-        // squared distances: warp w sums its slab of descriptor components for every sparse point
-        double *part = (double *)(smem + L.scratch);          // [NW][Mp] partial sums (gw/U are dead by now)
+        // squared distances: thread (sparse point j, slab h of the descriptor components); as many
+        // slabs as the CTA has threads for, so that a thread runs a long loop instead of a short one
+        double *part = (double *)(smem + L.scratch);          // [slabs <= NW][Mp] partial sums (gw/U are dead by now)
+        const int nsA = max(1, min(CT / Mp, NW));
         {
-            const int kslab = (D + NW - 1) / NW, k0 = wid * kslab, k1 = min(D, k0 + kslab);
-            for (int j = lane; j < Mp; j += 32) {
+            const int kslab = (D + nsA - 1) / nsA;
+            for (int item = tid; item < Mp * nsA; item += CT) {
+                const int h = item / Mp, j = item - h * Mp;
+                const int k0 = h * kslab, k1 = min(D, k0 + kslab);
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
                 const double *col = a.gpr_MtT + (size_t)k0 * Mp + j;
                 int k = k0;
@@ -620,15 +624,14 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                     s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
                 }
                 for (; k < k1; k++, col += Mp) { const double d0 = s_xs[k] - __ldg(col); s0 = fma(d0, d0, s0); }
-                part[wid * Mp + j] = (s0 + s1) + (s2 + s3);
+                part[h * Mp + j] = (s0 + s1) + (s2 + s3);
             }
         }
         __syncthreads();
         double esum = 0.0;
         for (int j = tid; j < Mp; j += CT) {
             double sacc = 0.0;
-#pragma unroll
-            for (int w = 0; w < NW; w++) sacc += part[w * Mp + j];
+            for (int h = 0; h < nsA; h++) sacc += part[h * Mp + j];
             const double wv = (j < M) ? exp_neg(-0.5 * sacc, s_t32) * a.gpr_coeff[j] : 0.0;
             s_W[j] = wv;
             esum += wv;
@@ -641,14 +644,16 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             for (int w = 0; w < NW; w++) e += s_red[w];
             a.eatom[i] = e;
         }
-        // dE/dG_k = -(1/theta_k) sum_j W_j (x'_k - m'_jk): warp w takes a slab of sparse points, lanes over k
+        // dE/dG_k = -(1/theta_k) sum_j W_j (x'_k - m'_jk): thread (component k, slab h of the sparse points)
+        const int nsB = max(1, min(CT / D, NW));
         {
-            const int jslab = (M + NW - 1) / NW, j0 = wid * jslab, j1 = min(M, j0 + jslab);
-            for (int k = lane; k < D; k += 32) {
+            const int jslab = (M + nsB - 1) / nsB;
+            for (int item = tid; item < D * nsB; item += CT) {
+                const int h = item / D, k = item - h * D;
+                const int j0 = h * jslab, j1 = min(M, j0 + jslab);
                 const double xk = s_xs[k];
-                const double *row = a.gpr_Mt + k;
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                const double *rp = row + (size_t)j0 * Dp;
+                const double *rp = a.gpr_Mt + k + (size_t)j0 * Dp;
                 int j = j0;
                 for (; j + 3 < j1; j += 4, rp += 4 * (size_t)Dp) {
                     const double m0 = __ldg(rp), m1 = __ldg(rp + Dp), m2 = __ldg(rp + 2 * (size_t)Dp), m3 = __ldg(rp + 3 * (size_t)Dp);
@@ -656,14 +661,13 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                     a2 = fma(s_W[j + 2], xk - m2, a2); a3 = fma(s_W[j + 3], xk - m3, a3);
                 }
                 for (; j < j1; j++, rp += Dp) a0 = fma(s_W[j], xk - __ldg(rp), a0);
-                part[wid * D + k] = (a0 + a1) + (a2 + a3);   // part is reused with stride D
+                part[h * D + k] = (a0 + a1) + (a2 + a3);   // part is reused with stride D
             }
         }
         __syncthreads();
         for (int k2 = tid; k2 < D; k2 += CT) {
             double acc = 0.0;
-#pragma unroll
-            for (int w = 0; w < NW; w++) acc += part[w * D + k2];
+            for (int h = 0; h < nsB; h++) acc += part[h * D + k2];
             const double v = -a.gpr_itheta[k2] * acc;
             s_du[k2] = v;
             if (a.dEdG_out) a.dEdG_out[(size_t)i * D + k2] = v;

@@ -95,7 +95,8 @@ struct gapcu_ctx {
     std::vector<int> h_natoms;
     DBuf<StructDev> d_structs;
     DBuf<int> d_sid, d_arank, d_bin_count, d_bin_start, d_bin_atoms, d_nbr_cnt, d_order;
-    DBuf<int4> d_abin;
+    DBuf<int4> d_abin, d_sabin;   // per atom / in bin order: (bin | atom, wrap offsets)
+    DBuf<double> d_spos;          // coordinates in bin order
     DBuf<double> d_pos, d_wgt, d_G, d_dEdG, d_eatom, d_fpair, d_gself, d_vir, d_force, d_out8, d_mindis, d_epart, d_accpart;
     DBuf<uint64_t> d_keys;
     DBuf<uint32_t> d_stash;
@@ -196,7 +197,7 @@ extern "C" void gapcu_ctx_destroy(gapcu_ctx *c) {
     c->d_itab.release(); c->d_dtab.release(); c->d_mm_raw.release(); c->d_theta_raw.release(); c->d_coeff_raw.release();
     c->d_Mt.release(); c->d_MtT.release(); c->d_exp2.release(); c->d_mn.release(); c->d_coeff.release(); c->d_cmean.release(); c->d_itheta.release();
     c->d_structs.release(); c->d_sid.release(); c->d_arank.release(); c->d_bin_count.release(); c->d_bin_start.release();
-    c->d_bin_atoms.release(); c->d_nbr_cnt.release(); c->d_order.release(); c->d_abin.release(); c->d_pos.release(); c->d_wgt.release();
+    c->d_bin_atoms.release(); c->d_nbr_cnt.release(); c->d_order.release(); c->d_abin.release(); c->d_sabin.release(); c->d_spos.release(); c->d_pos.release(); c->d_wgt.release();
     c->d_G.release(); c->d_dEdG.release(); c->d_eatom.release(); c->d_fpair.release(); c->d_gself.release();
     c->d_vir.release(); c->d_force.release(); c->d_out8.release(); c->d_mindis.release(); c->d_keys.release();
     c->d_stash.release(); c->d_epart.release(); c->d_accpart.release(); c->d_flags.release(); c->d_flush.release(); c->d_role.release(); c->d_active.release();
@@ -389,7 +390,7 @@ static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, con
     }
     // ---- device buffers
     CU(c->d_structs.ensure(nstruct)); CU(c->d_sid.ensure(NT)); CU(c->d_pos.ensure(3 * NT)); CU(c->d_wgt.ensure(NT));
-    CU(c->d_abin.ensure(NT)); CU(c->d_arank.ensure(NT)); CU(c->d_bin_count.ensure(c->nbins + 1));
+    CU(c->d_abin.ensure(NT)); CU(c->d_sabin.ensure(NT)); CU(c->d_spos.ensure(3 * NT)); CU(c->d_arank.ensure(NT)); CU(c->d_bin_count.ensure(c->nbins + 1));
     CU(c->d_bin_start.ensure(c->nbins + 2)); CU(c->d_bin_atoms.ensure(NT)); CU(c->d_nbr_cnt.ensure(NT)); CU(c->d_order.ensure(NT));
     CU(c->d_flags.ensure(1)); CU(c->d_out8.ensure(8 * (size_t)nstruct)); CU(c->d_force.ensure(3 * NT));
     CU(c->d_mindis.ensure(NT)); CU(c->d_role.ensure(NT)); CU(c->d_active.ensure(NT));
@@ -498,7 +499,7 @@ static int ensure_work_buffers(gapcu_ctx *c) {
 
 static int run_neighbors(gapcu_ctx *c, bool with_keys, bool with_min) {
     launch_neighbor_build(c->stream, c->d_structs.p, c->d_sid.p, c->d_pos.p, c->ntot, c->nbins, c->rcut, c->cap,
-                          c->d_abin.p, c->d_arank.p, c->d_bin_count.p, c->d_bin_start.p, c->d_bin_atoms.p,
+                          c->d_abin.p, c->d_arank.p, c->d_bin_count.p, c->d_bin_start.p, c->d_bin_atoms.p, c->d_sabin.p, c->d_spos.p,
                           with_keys ? c->d_keys.p : nullptr, c->d_nbr_cnt.p, with_min ? c->d_mindis.p : nullptr,
                           c->d_flags.p, c->dom, c->d_role.p, c->d_active.p, &c->launches);
     CU(cudaGetLastError());

@@ -13,9 +13,9 @@ constexpr int MAX_NEIGHBOR_REF_DEV = 1000;  // gap_calc.f90:68
 // neigh.cu
 void launch_neighbor_build(cudaStream_t st, const StructDev *structs, const int *sid, const double *pos,
                            int ntot, int nbins_total, double rcut, int cap, int4 *abin, int *arank,
-                           int *bin_count, int *bin_start, int *bin_atoms, uint64_t *nbr_keys, int *nbr_cnt,
-                           double *min_dis, DevFlags *flags, const DomainDev &dom, unsigned char *role, int *active,
-                           long *launches);
+                           int *bin_count, int *bin_start, int *bin_atoms, int4 *sabin, double *spos, uint64_t *nbr_keys,
+                           int *nbr_cnt, double *min_dis, DevFlags *flags, const DomainDev &dom, unsigned char *role,
+                           int *active, long *launches);
 
 void launch_order(cudaStream_t st, const int *nbr_cnt, int ntot, int *order, const unsigned char *role,
                   DevFlags *flags, long *launches);

@@ -104,12 +104,19 @@ __global__ void k_scan_bins(const int *bin_count, int *bin_start, int nb) {
     if (threadIdx.x == 0) bin_start[nb] = carry;
 }
 
-__global__ void k_fill_bins(const StructDev *structs, const int *sid, const int4 *abin, const int *arank,
-                            const int *bin_start, int ntot, int *bin_atoms) {
+// Besides the permutation bin_atoms, the atoms' records are copied into bin order (sabin: atom
+// index + wrap offsets, spos: coordinates), so that k_neigh reads the candidates of a cell as
+// contiguous, independent loads instead of a chain bin_atoms -> abin -> pos.
+__global__ void k_fill_bins(const StructDev *structs, const int *sid, const double *pos, const int4 *abin, const int *arank,
+                            const int *bin_start, int ntot, int *bin_atoms, int4 *sabin, double *spos) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ntot) return;
     const StructDev &s = structs[sid[i]];
-    bin_atoms[bin_start[s.bin_off + abin[i].x] + arank[i]] = i;
+    const int4 b = abin[i];
+    const int slot = bin_start[s.bin_off + b.x] + arank[i];
+    bin_atoms[slot] = i;
+    sabin[slot] = make_int4(i, b.y, b.z, b.w);
+    spos[slot] = pos[i]; spos[ntot + slot] = pos[ntot + i]; spos[2 * ntot + slot] = pos[2 * ntot + i];
 }
 
 // Small batches: bin, scan and fill in ONE single-CTA kernel (shared-memory counters) instead
@@ -117,7 +124,8 @@ __global__ void k_fill_bins(const StructDev *structs, const int *sid, const int4
 constexpr int SMALL_NBINS = 4096;
 __global__ void __launch_bounds__(1024)
 k_bin_small(const StructDev *structs, const int *sid, const double *pos, int ntot, int nbins_total, int4 *abin,
-            int *bin_start, int *bin_atoms, DomainDev dom, unsigned char *role, int *active, DevFlags *flags) {
+            int *bin_start, int *bin_atoms, int4 *sabin, double *spos, DomainDev dom, unsigned char *role, int *active,
+            DevFlags *flags) {
     __shared__ int cnt[SMALL_NBINS + 1];
     __shared__ int wsum[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -177,7 +185,11 @@ k_bin_small(const StructDev *structs, const int *sid, const double *pos, int nto
     __syncthreads();
     for (int i = tid; i < ntot; i += 1024) {
         const StructDev &s = structs[sid[i]];
-        bin_atoms[atomicAdd(&cnt[s.bin_off + abin[i].x], 1)] = i;
+        const int4 b = abin[i];
+        const int slot = atomicAdd(&cnt[s.bin_off + b.x], 1);
+        bin_atoms[slot] = i;
+        sabin[slot] = make_int4(i, b.y, b.z, b.w);
+        spos[slot] = pos[i]; spos[ntot + slot] = pos[ntot + i]; spos[2 * ntot + slot] = pos[2 * ntot + i];
     }
 }
 
@@ -185,7 +197,7 @@ k_bin_small(const StructDev *structs, const int *sid, const double *pos, int nto
 // reference test, sort into reference order, store keys (+ optional min distance).
 __global__ void __launch_bounds__(NB_THREADS)
 k_neigh(const StructDev *structs, const int *sid, const double *pos, const int4 *abin,
-        const int *bin_start, const int *bin_atoms, int ntot, double rcut, int cap,
+        const int *bin_start, const int4 *sabin, const double *spos, int ntot, double rcut, int cap,
         uint64_t *nbr_keys, int *nbr_cnt, double *min_dis, DevFlags *flags, const int *active) {
     __shared__ uint64_t keys[NB_MAXLIST];
     __shared__ int nkeys, nclose;
@@ -267,23 +279,39 @@ k_neigh(const StructDev *structs, const int *sid, const double *pos, const int4 
         }
         __syncthreads();
         const int total = c_off[NB_CELLS];
-        for (int cand = tid; cand < total; cand += NB_THREADS) {
+        // two candidates per trip: both records are requested before either is tested
+        struct Cand { int4 bj, sh; double x, y, z; bool ok; };
+        auto fetch = [&](int cand, Cand &r) {
+            r.ok = cand < total;
+            if (!r.ok) return;
             int lo = 0, hi = nc;  // cell of this candidate: last cell with c_off <= cand
             while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (c_off[mid] <= cand) lo = mid; else hi = mid; }
-            const int j = bin_atoms[c_start[lo] + (cand - c_off[lo])];
-            const int4 sh = c_shift[lo];
-            const int4 bj = abin[j];
+            const int slot = c_start[lo] + (cand - c_off[lo]);
+            r.bj = sabin[slot];                          // (atom, wrap offsets) and coordinates in bin order:
+            r.x = spos[slot]; r.y = spos[ntot + slot]; r.z = spos[2 * ntot + slot];   // independent loads
+            r.sh = c_shift[lo];
+        };
+        auto test = [&](const Cand &r) {
+            if (!r.ok) return;
+            const int j = r.bj.x;
             // shift between wrapped coordinates -> shift of the caller's coordinates
-            const int n1 = sh.x - bj.y + bi.y, n2 = sh.y - bj.z + bi.z, n3 = sh.z - bj.w + bi.w;
-            if (j == i && n1 == 0 && n2 == 0 && n3 == 0) continue;
-            if (abs(n1) > na0 || abs(n2) > na1 || abs(n3) > na2) continue;
+            const int n1 = r.sh.x - r.bj.y + bi.y, n2 = r.sh.y - r.bj.z + bi.z, n3 = r.sh.z - r.bj.w + bi.w;
+            if (j == i && n1 == 0 && n2 == 0 && n3 == 0) return;
+            if (abs(n1) > na0 || abs(n2) > na1 || abs(n3) > na2) return;
             double ox, oy, oz;
-            const double dis = image_distance(pos, ntot, j, lat, n1, n2, n3, xi, yi, zi, ox, oy, oz);
-            if (dis > rcut) continue;
+            const double dis = image_distance_xyz(r.x, r.y, r.z, lat, n1, n2, n3, xi, yi, zi, ox, oy, oz);
+            if (dis > rcut) return;
             if (dis < 0.5) atomicAdd(&nclose, 1);
             dmin = fmin(dmin, dis);
             const int p = atomicAdd(&nkeys, 1);
             if (p < NB_MAXLIST) keys[p] = nbr_key(j - aoff, n1, n2, n3);
+        };
+        for (int cand = tid; cand < total; cand += 2 * NB_THREADS) {
+            Cand ca, cb;
+            fetch(cand, ca);
+            fetch(cand + NB_THREADS, cb);
+            test(ca);
+            test(cb);
         }
     }
     if (min_dis) {
@@ -372,21 +400,21 @@ void launch_order(cudaStream_t st, const int *nbr_cnt, int ntot, int *order, con
 // ---- host launchers ------------------------------------------------------
 void launch_neighbor_build(cudaStream_t st, const StructDev *structs, const int *sid, const double *pos,
                            int ntot, int nbins_total, double rcut, int cap, int4 *abin, int *arank,
-                           int *bin_count, int *bin_start, int *bin_atoms, uint64_t *nbr_keys, int *nbr_cnt,
-                           double *min_dis, DevFlags *flags, const DomainDev &dom, unsigned char *role, int *active,
-                           long *launches) {
+                           int *bin_count, int *bin_start, int *bin_atoms, int4 *sabin, double *spos, uint64_t *nbr_keys,
+                           int *nbr_cnt, double *min_dis, DevFlags *flags, const DomainDev &dom, unsigned char *role,
+                           int *active, long *launches) {
     if (ntot <= 8192 && nbins_total <= SMALL_NBINS) {
-        k_bin_small<<<1, 1024, 0, st>>>(structs, sid, pos, ntot, nbins_total, abin, bin_start, bin_atoms, dom, role,
-                                        dom.enabled ? active : nullptr, flags);
+        k_bin_small<<<1, 1024, 0, st>>>(structs, sid, pos, ntot, nbins_total, abin, bin_start, bin_atoms, sabin, spos, dom,
+                                        role, dom.enabled ? active : nullptr, flags);
         if (launches) *launches -= 2;   // one launch instead of three
     } else {
         cudaMemsetAsync(bin_count, 0, sizeof(int) * (size_t)nbins_total, st);
         int tb = 256, gb = (ntot + tb - 1) / tb;
         k_bin<<<gb, tb, 0, st>>>(structs, sid, pos, ntot, abin, arank, bin_count, dom, role, dom.enabled ? active : nullptr, flags);
         k_scan_bins<<<1, 1024, 0, st>>>(bin_count, bin_start, nbins_total);
-        k_fill_bins<<<gb, tb, 0, st>>>(structs, sid, abin, arank, bin_start, ntot, bin_atoms);
+        k_fill_bins<<<gb, tb, 0, st>>>(structs, sid, pos, abin, arank, bin_start, ntot, bin_atoms, sabin, spos);
     }
-    k_neigh<<<ntot, NB_THREADS, 0, st>>>(structs, sid, pos, abin, bin_start, bin_atoms, ntot, rcut, cap,
+    k_neigh<<<ntot, NB_THREADS, 0, st>>>(structs, sid, pos, abin, bin_start, sabin, spos, ntot, rcut, cap,
                                           nbr_keys, nbr_cnt, min_dis, flags, dom.enabled ? active : nullptr);
     if (launches) *launches += 4;
 }
