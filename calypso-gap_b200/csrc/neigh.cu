@@ -195,7 +195,7 @@ k_bin_small(const StructDev *structs, const int *sid, const double *pos, int nto
 
 // One CTA per centre atom: gather candidates from the surrounding bins, apply the
 // reference test, sort into reference order, store keys (+ optional min distance).
-__global__ void __launch_bounds__(NB_THREADS)
+__global__ void __launch_bounds__(NB_THREADS, 8)
 k_neigh(const StructDev *structs, const int *sid, const double *pos, const int4 *abin,
         const int *bin_start, const int4 *sabin, const double *spos, int ntot, double rcut, int cap,
         uint64_t *nbr_keys, int *nbr_cnt, double *min_dis, DevFlags *flags, const int *active) {
@@ -279,39 +279,52 @@ k_neigh(const StructDev *structs, const int *sid, const double *pos, const int4 
         }
         __syncthreads();
         const int total = c_off[NB_CELLS];
-        // two candidates per trip: both records are requested before either is tested
-        struct Cand { int4 bj, sh; double x, y, z; bool ok; };
-        auto fetch = [&](int cand, Cand &r) {
-            r.ok = cand < total;
-            if (!r.ok) return;
-            int lo = 0, hi = nc;  // cell of this candidate: last cell with c_off <= cand
-            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (c_off[mid] <= cand) lo = mid; else hi = mid; }
-            const int slot = c_start[lo] + (cand - c_off[lo]);
+        // Every thread takes a contiguous run of the flat candidate index: one cell lookup per run
+        // instead of one per candidate, then it walks (cells are crossed rarely); the record of
+        // the next candidate is requested before the current one is tested.
+        struct Cand { int4 bj; double x, y, z; };
+        auto load = [&](int slot) {
+            Cand r;
             r.bj = sabin[slot];                          // (atom, wrap offsets) and coordinates in bin order:
             r.x = spos[slot]; r.y = spos[ntot + slot]; r.z = spos[2 * ntot + slot];   // independent loads
-            r.sh = c_shift[lo];
+            return r;
         };
-        auto test = [&](const Cand &r) {
-            if (!r.ok) return;
-            const int j = r.bj.x;
-            // shift between wrapped coordinates -> shift of the caller's coordinates
-            const int n1 = r.sh.x - r.bj.y + bi.y, n2 = r.sh.y - r.bj.z + bi.z, n3 = r.sh.z - r.bj.w + bi.w;
-            if (j == i && n1 == 0 && n2 == 0 && n3 == 0) return;
-            if (abs(n1) > na0 || abs(n2) > na1 || abs(n3) > na2) return;
-            double ox, oy, oz;
-            const double dis = image_distance_xyz(r.x, r.y, r.z, lat, n1, n2, n3, xi, yi, zi, ox, oy, oz);
-            if (dis > rcut) return;
-            if (dis < 0.5) atomicAdd(&nclose, 1);
-            dmin = fmin(dmin, dis);
-            const int p = atomicAdd(&nkeys, 1);
-            if (p < NB_MAXLIST) keys[p] = nbr_key(j - aoff, n1, n2, n3);
-        };
-        for (int cand = tid; cand < total; cand += 2 * NB_THREADS) {
-            Cand ca, cb;
-            fetch(cand, ca);
-            fetch(cand + NB_THREADS, cb);
-            test(ca);
-            test(cb);
+        const int per = (total + NB_THREADS - 1) / NB_THREADS;
+        int cand = tid * per;
+        const int cend = min(total, cand + per);
+        if (cand < cend) {
+            int lo = 0, hi = nc;  // cell of the first candidate: last cell with c_off <= cand
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (c_off[mid] <= cand) lo = mid; else hi = mid; }
+            int slot = c_start[lo] + (cand - c_off[lo]);
+            int cell_end = c_off[lo + 1];
+            int4 sh = c_shift[lo];
+            Cand r = load(slot);
+            for (; cand < cend; cand++) {
+                const Cand cur = r;
+                const int4 csh = sh;
+                if (cand + 1 < cend) {
+                    slot++;
+                    if (cand + 1 >= cell_end) {   // next candidate lives in a later (non-empty) cell
+                        do lo++; while (c_off[lo + 1] <= cand + 1);
+                        slot = c_start[lo] + (cand + 1 - c_off[lo]);
+                        cell_end = c_off[lo + 1];
+                        sh = c_shift[lo];
+                    }
+                    r = load(slot);
+                }
+                const int j = cur.bj.x;
+                // shift between wrapped coordinates -> shift of the caller's coordinates
+                const int n1 = csh.x - cur.bj.y + bi.y, n2 = csh.y - cur.bj.z + bi.z, n3 = csh.z - cur.bj.w + bi.w;
+                if (j == i && n1 == 0 && n2 == 0 && n3 == 0) continue;
+                if (abs(n1) > na0 || abs(n2) > na1 || abs(n3) > na2) continue;
+                double ox, oy, oz;
+                const double dis = image_distance_xyz(cur.x, cur.y, cur.z, lat, n1, n2, n3, xi, yi, zi, ox, oy, oz);
+                if (dis > rcut) continue;
+                if (dis < 0.5) atomicAdd(&nclose, 1);
+                dmin = fmin(dmin, dis);
+                const int p = atomicAdd(&nkeys, 1);
+                if (p < NB_MAXLIST) keys[p] = nbr_key(j - aoff, n1, n2, n3);
+            }
         }
     }
     if (min_dis) {
@@ -337,6 +350,27 @@ k_neigh(const StructDev *structs, const int *sid, const double *pos, const int4 
     // bitonic sort of the keys (padded to a power of two with +inf keys)
     int n2 = 1;
     while (n2 < count) n2 <<= 1;
+    if (n2 <= NB_THREADS) {
+        // one key per thread: compare-exchange distances below 32 go through warp shuffles,
+        // only the few larger ones through shared memory
+        uint64_t key = tid < count ? keys[tid] : ~0ull;
+        for (int k = 2; k <= n2; k <<= 1)
+            for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                uint64_t other;
+                if (jj >= 32) {
+                    __syncthreads();
+                    keys[tid] = key;
+                    __syncthreads();
+                    other = keys[tid ^ jj];
+                } else {
+                    other = __shfl_xor_sync(0xffffffffu, key, jj);
+                }
+                const bool keep_min = ((tid & jj) == 0) == ((tid & k) == 0);
+                key = keep_min ? (key < other ? key : other) : (key < other ? other : key);
+            }
+        if (tid < count) nbr_keys[(size_t)i * cap + tid] = key;
+        return;
+    }
     for (int p = count + tid; p < n2; p += NB_THREADS) keys[p] = ~0ull;
     __syncthreads();
     for (int k = 2; k <= n2; k <<= 1)

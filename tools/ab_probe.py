@@ -16,7 +16,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "--child":
     c.set_structures(z, cell, pos, 6.0)
     c.time_compute(10, True, 0, stages=False)
     ms, st, _ = c.time_compute(100, True, 0, stages=True)
-    print("RESULT %.4f %.4f" % (ms / 100, st["descriptor_forward"] / 100))
+    print("RESULT %.4f %.4f %.4f %.4f" % (ms / 100, st["descriptor_forward"] / 100, st["neighbor_build"] / 100, st["force_gather_reduce"] / 100))
     sys.exit(0)
 variants = sys.argv[1:] or ["0", "1"]
 res = {v: [] for v in variants}
@@ -33,4 +33,5 @@ for rep in range(3):
                 res[v].append(tuple(float(x) for x in line.split()[1:]))
 for v in variants:
     steps = sorted(r[0] for r in res[v]); cen = sorted(r[1] for r in res[v])
-    print("variant %s: step ms median %.4f (min %.4f)  centre kernel ms median %.4f (min %.4f)" % (v, steps[len(steps) // 2], steps[0], cen[len(cen) // 2], cen[0]))
+    nb = sorted(r[2] for r in res[v]); ga = sorted(r[3] for r in res[v])
+    print("variant %s: step ms median %.4f (min %.4f)  centre kernel ms median %.4f (min %.4f)  neighbours %.4f  gather %.4f" % (v, steps[len(steps) // 2], steps[0], cen[len(cen) // 2], cen[0], nb[len(nb) // 2], ga[len(ga) // 2]))
