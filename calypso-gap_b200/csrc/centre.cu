@@ -5,12 +5,12 @@
 namespace gapcu {
 
 // neighbour capacity of the instance that serves a runtime capacity
-static int pcap_template(int pcap) { return pcap <= 128 ? 128 : pcap <= 256 ? 256 : pcap <= 512 ? 512 : 1024; }
+int centre_pcap_template(int pcap) { return pcap <= 128 ? 128 : pcap <= 256 ? 256 : pcap <= 512 ? 512 : 1024; }
 
 static SmemLayout make_layout(const CentreArgs &a, int mode) {
     SmemLayout L;
     memset(&L, 0, sizeof L);
-    const int pt = pcap_template(a.pcap), D = a.plan.D;
+    const int pt = centre_pcap_template(a.pcap), D = a.plan.D;
     int o = hot_bytes(pt, a.plan.ncls);   // Hot<PCAP>: neighbour records, gradient accumulator, class counts, fc tables
     auto take = [&](long bytes) { int r = o; o += (int)((bytes + 15) & ~15l); return r; };
     take(0);
@@ -49,7 +49,9 @@ size_t centre_stash_words(const CentreArgs &a, int chunks, int ctas) { return (s
 static int launch_mode(cudaStream_t st, const CentreArgs &a_in, int mode) {
     CentreArgs a = a_in;
     a.lay = make_layout(a, mode);
-    switch (pcap_template(a.pcap)) {
+    const int pt = centre_pcap_template(a.pcap);
+    a.queue_slot = mode * 4 + (pt == 128 ? 0 : pt == 256 ? 1 : pt == 512 ? 2 : 3);
+    switch (centre_pcap_template(a.pcap)) {
         case 128: return launch_centre_p128(st, a, mode);
         case 256: return launch_centre_p256(st, a, mode);
         case 512: return launch_centre_p512(st, a, mode);

@@ -779,12 +779,14 @@ __global__ void __launch_bounds__(CT, 3) k_centre(const CentreArgs a) {
     bool first = true;
     unsigned long long t0 = 0;
     if (threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    const int q_begin = a.q_begin ? *a.q_begin : 0;
+    const int q_end = a.q_end ? *a.q_end : (a.n_centres ? *a.n_centres : a.ntot);
     for (;;) {
         __syncthreads();  // everybody is done with the previous centre's shared memory
-        if (threadIdx.x == 0) s_next = atomicAdd(&a.flags->queue[MODE], 1);
+        if (threadIdx.x == 0) s_next = q_begin + atomicAdd(&a.flags->queue[a.queue_slot], 1);
         __syncthreads();
         const int n = s_next;
-        if (n >= (a.n_centres ? *a.n_centres : a.ntot)) break;
+        if (n >= q_end) break;
         process_centre<MODE, PCAP>(a, a.order ? a.order[n] : n, first);
         first = false;
     }

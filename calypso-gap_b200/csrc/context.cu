@@ -97,6 +97,8 @@ struct gapcu_ctx {
     DBuf<int> d_sid, d_arank, d_bin_count, d_bin_start, d_bin_atoms, d_nbr_cnt, d_order;
     DBuf<int4> d_abin, d_sabin;   // per atom / in bin order: (bin | atom, wrap offsets)
     DBuf<double> d_spos;          // coordinates in bin order
+    DBuf<double> d_finpart;       // per (structure, chunk) partial sums of E and the strs contraction
+    int max_natoms = 0;           // largest structure of the batch
     DBuf<double> d_pos, d_wgt, d_G, d_dEdG, d_eatom, d_fpair, d_gself, d_vir, d_force, d_out8, d_mindis, d_epart, d_accpart;
     DBuf<uint64_t> d_keys;
     DBuf<uint32_t> d_stash;
@@ -197,7 +199,7 @@ extern "C" void gapcu_ctx_destroy(gapcu_ctx *c) {
     c->d_itab.release(); c->d_dtab.release(); c->d_mm_raw.release(); c->d_theta_raw.release(); c->d_coeff_raw.release();
     c->d_Mt.release(); c->d_MtT.release(); c->d_exp2.release(); c->d_mn.release(); c->d_coeff.release(); c->d_cmean.release(); c->d_itheta.release();
     c->d_structs.release(); c->d_sid.release(); c->d_arank.release(); c->d_bin_count.release(); c->d_bin_start.release();
-    c->d_bin_atoms.release(); c->d_nbr_cnt.release(); c->d_order.release(); c->d_abin.release(); c->d_sabin.release(); c->d_spos.release(); c->d_pos.release(); c->d_wgt.release();
+    c->d_bin_atoms.release(); c->d_nbr_cnt.release(); c->d_order.release(); c->d_abin.release(); c->d_sabin.release(); c->d_spos.release(); c->d_finpart.release(); c->d_pos.release(); c->d_wgt.release();
     c->d_G.release(); c->d_dEdG.release(); c->d_eatom.release(); c->d_fpair.release(); c->d_gself.release();
     c->d_vir.release(); c->d_force.release(); c->d_out8.release(); c->d_mindis.release(); c->d_keys.release();
     c->d_stash.release(); c->d_epart.release(); c->d_accpart.release(); c->d_flags.release(); c->d_flush.release(); c->d_role.release(); c->d_active.release();
@@ -494,6 +496,9 @@ static int ensure_work_buffers(gapcu_ctx *c) {
     CU(c->d_keys.ensure(NT * c->cap));
     CU(c->d_G.ensure(NT * c->D)); CU(c->d_dEdG.ensure(NT * c->D)); CU(c->d_eatom.ensure(NT));
     CU(c->d_fpair.ensure(NT * c->cap * 3)); CU(c->d_gself.ensure(NT * 3)); CU(c->d_vir.ensure(NT * 6));
+    c->max_natoms = 0;
+    for (const StructDev &sd : c->h_structs) c->max_natoms = std::max(c->max_natoms, sd.natoms);
+    CU(c->d_finpart.ensure((size_t)std::max(1, c->nstruct) * finalize_chunks(c->max_natoms) * 8));
     return 0;
 }
 
@@ -514,14 +519,14 @@ static int read_flags(gapcu_ctx *c) {
 
 // kernel arguments of the centre kernel for the context's current state; picks the pipeline
 // and the shared-memory budget (triplet-list capacity, private accumulator sets)
-static int make_centre_args(gapcu_ctx *c, int lgrad, CentreArgs *out, bool *fused_out) {
+static int make_centre_args(gapcu_ctx *c, int lgrad, int pcap, CentreArgs *out, bool *fused_out) {
     CentreArgs a;
     memset(&a, 0, sizeof a);
     a.plan = c->plan_dev();
     a.cls = c->class_tab();
     a.structs = c->d_structs.p; a.sid = c->d_sid.p; a.pos = c->d_pos.p; a.wgt = c->d_wgt.p;
     a.nbr_keys = c->d_keys.p; a.nbr_cnt = c->d_nbr_cnt.p; a.order = c->d_order.p; a.n_centres = &c->d_flags.p->n_centres; a.exp2_table = c->d_exp2.p;
-    a.ntot = c->ntot; a.cap = c->cap; a.pcap = c->pcap; a.lgrad = lgrad;
+    a.ntot = c->ntot; a.cap = c->cap; a.pcap = pcap; a.lgrad = lgrad;
     { static int var = -1; if (var < 0) { const char *e = getenv("GAPCU_VARIANT"); var = e ? atoi(e) : 0; } a.variant = var; }
     a.G = c->d_G.p; a.dEdG = c->d_dEdG.p; a.dEdG_out = c->d_dEdG.p; a.eatom = c->d_eatom.p;
     a.fpair = c->d_fpair.p; a.gself = c->d_gself.p; a.vir = c->d_vir.p;
@@ -536,7 +541,7 @@ static int make_centre_args(gapcu_ctx *c, int lgrad, CentreArgs *out, bool *fuse
     // footprint that lets 3 CTAs share an SM (the kernel is latency bound: more resident
     // warps matter more than building the triplet list in one chunk), then 2, then 1.
     {
-        const int q = c->pcap * (c->pcap - 1) / 2;
+        const int q = pcap * (pcap - 1) / 2;
         const int want = std::min(8192, std::max(2048, round_up(q, 32)));
         const int mode = fused ? 2 : 1;
         const size_t targets[3] = {(size_t)((a.variant & 8) ? 112 : 74) * 1024, 112 * 1024, 220 * 1024};   // 3, 2, 1 CTAs per SM
@@ -601,16 +606,39 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
     launch_order(c->stream, c->d_nbr_cnt.p, c->ntot, c->d_order.p, c->d_role.p, c->d_flags.p, &c->launches);
     CU(cudaGetLastError());
     if (ev) CU(cudaEventRecord(ev[1], c->stream));
-    CentreArgs a;
+    // Capacity tiers: `order` lists the centres by descending neighbour count, so the centres
+    // that need the 1024 / 512 / 256-neighbour instance of the kernel are a prefix; each tier is
+    // served by its own instance (own shared-memory footprint, hence own residency): a few crowded
+    // atoms of a heterogeneous batch no longer dictate the footprint of all the others.
+    struct Tier { CentreArgs a; };
+    std::vector<Tier> tiers;
     bool fused = false;
-    if ((rc = make_centre_args(c, lgrad, &a, &fused))) return rc;
+    {
+        const int top = centre_pcap_template(c->pcap);
+        DevFlags *F = c->d_flags.p;
+        for (int cap = top; cap >= 128; cap >>= 1) {
+            const int idx = cap == 128 ? 0 : cap == 256 ? 1 : cap == 512 ? 2 : 3;
+            Tier t;
+            if ((rc = make_centre_args(c, lgrad, cap == top ? c->pcap : cap, &t.a, &fused))) return rc;
+            t.a.q_begin = cap == top ? nullptr : &F->n_gt[idx];
+            t.a.q_end = cap == 128 ? &F->n_centres : &F->n_gt[idx - 1];
+            tiers.push_back(t);
+        }
+        for (Tier &t : tiers)   // a later tier may have grown (moved) the shared list-parking buffer
+            if (t.a.list_scratch) t.a.list_scratch = c->d_stash.p;
+    }
+    const char *too_big = "centre kernel needs more shared memory than an SM has";
     if (fused) {
-        if (launch_fused(c->stream, a, &c->launches)) return fail(GAPCU_ELIMIT, "centre kernel needs more shared memory than an SM has");
-        CU(cudaGetLastError());
+        for (Tier &t : tiers) {
+            if (launch_fused(c->stream, t.a, &c->launches)) return fail(GAPCU_ELIMIT, too_big);
+            CU(cudaGetLastError());
+        }
         if (ev) { CU(cudaEventRecord(ev[2], c->stream)); CU(cudaEventRecord(ev[3], c->stream)); CU(cudaEventRecord(ev[4], c->stream)); }
     } else {
-        if (launch_forward(c->stream, a, &c->launches)) return fail(GAPCU_ELIMIT, "centre kernel needs more shared memory than an SM has");
-        CU(cudaGetLastError());
+        for (Tier &t : tiers) {
+            if (launch_forward(c->stream, t.a, &c->launches)) return fail(GAPCU_ELIMIT, too_big);
+            CU(cudaGetLastError());
+        }
         if (ev) CU(cudaEventRecord(ev[2], c->stream));
         GprDev g;
         g.M = c->M; g.Mp = c->Mp; g.D = c->D; g.Dp = c->Dp; g.Mt = c->d_Mt.p; g.MtT = c->d_MtT.p; g.mn = c->d_mn.p;
@@ -623,15 +651,16 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
             return fail(GAPCU_ELIMIT, "unsupported descriptor length for the GPR kernel");
         CU(cudaGetLastError());
         if (ev) CU(cudaEventRecord(ev[3], c->stream));
-        if (lgrad) {
-            if (launch_backward(c->stream, a, &c->launches)) return fail(GAPCU_ELIMIT, "centre kernel needs more shared memory than an SM has");
-            CU(cudaGetLastError());
-        }
+        if (lgrad)
+            for (Tier &t : tiers) {
+                if (launch_backward(c->stream, t.a, &c->launches)) return fail(GAPCU_ELIMIT, too_big);
+                CU(cudaGetLastError());
+            }
         if (ev) CU(cudaEventRecord(ev[4], c->stream));
     }
     launch_gather(c->stream, c->d_structs.p, c->nstruct, c->d_sid.p, c->ntot, c->cap, c->d_keys.p, c->d_nbr_cnt.p,
                   c->d_fpair.p, c->d_gself.p, c->d_vir.p, c->d_eatom.p, lgrad, c->d_force.p, c->d_out8.p, c->d_role.p,
-                  c->dom.enabled ? c->d_active.p : nullptr, c->d_flags.p, &c->launches);
+                  c->dom.enabled ? c->d_active.p : nullptr, c->d_flags.p, c->d_finpart.p, c->max_natoms, &c->launches);
     CU(cudaGetLastError());
     if (c->dom.enabled && c->nccl_comm) {
         // ghost-force return and the (E, stress) partial sums: one sum over ranks each
@@ -1035,7 +1064,7 @@ extern "C" int gapcu_car2acsf_table(int na, int max_neighbor, int nf, const doub
         return bail(fail(GAPCU_ECUDA, "upload failed"));
     CentreArgs a;
     bool fused = false;
-    if ((rc = make_centre_args(c, 1, &a, &fused))) return bail(rc);
+    if ((rc = make_centre_args(c, 1, c->pcap, &a, &fused))) return bail(rc);
     a.nbr_table = d_table.p; a.table_ld = max_neighbor; a.order = nullptr; a.n_centres = nullptr; a.lgrad = 1;
     auto run = [&](bool backward) -> int {
         if (cudaMemsetAsync(c->d_flags.p, 0, sizeof(DevFlags), c->stream) != cudaSuccess) return fail(GAPCU_ECUDA, "memset failed");

@@ -49,7 +49,8 @@ struct DevFlags {
     int close_pairs;     // pairs closer than 0.5 A (reference prints a warning)
     int n_active;        // atoms with role >= 1 (decomposed runs)
     int n_centres;       // atoms with role == 2
-    int queue[4];        // work-queue heads of the persistent centre kernels (one per mode)
+    int n_gt[4];         // centres with more than 128 / 256 / 512 / 1024 neighbours: the capacity tiers' places in `order`
+    int queue[16];       // work-queue heads of the persistent centre kernels (mode * 4 + tier)
     unsigned long long work[10];  // see gapcu_ctx_work_counters
     // persistent centre kernel, nanoseconds of %globaltimer: earliest start, earliest / latest
     // exit and the sum of the CTAs' busy times (load-balance diagnostics)
@@ -99,6 +100,9 @@ struct CentreArgs {
     int table_ld;
     const int *order;           // [NT] centres by descending neighbour count (null: natural order)
     const int *n_centres;       // device count of entries in `order` (null: ntot)
+    // capacity tier served by this launch: entries [*q_begin, *q_end) of `order` (null: 0 / all), own queue head
+    const int *q_begin, *q_end;
+    int queue_slot;
     const double *exp2_table;   // [32] 2^(j/32)
     int ntot, cap, pcap;        // pcap: shared-memory neighbour capacity (>= max count)
     int lcap;                   // triplet-list capacity per chunk

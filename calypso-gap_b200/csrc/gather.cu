@@ -77,16 +77,35 @@ k_gather(const StructDev *structs, const int *sid, int ntot, int cap, const uint
     }
 }
 
-// One CTA per structure: E = sum e_i (gap_calc.f90:154), stress from the strs
-// contraction (gap_calc.f90:189-203) in the output order of :221-226.
+// E = sum e_i (gap_calc.f90:154) and the strs contraction (gap_calc.f90:189-203), in two fixed-order
+// levels: CTA (chunk, structure) sums FIN_CHUNK atoms, then one warp per structure adds the
+// chunks in order and writes the outputs in the order of gap_calc.f90:221-226.  A single CTA per
+// structure (the first version) costs ~0.1 ms on a 100k-atom cell.
+constexpr int FIN_CHUNK = 2048;
+
+// s = (E, then (xx, xy, xz, yy, yz, zz) of sum delta_a * dE/dx_b); stress = -that / (6.24219e-3 * V)
+__device__ __forceinline__ void write_out8(const double *s, const StructDev &sd, double *o) {
+    o[0] = s[0];
+    const double f = (1.0 / GPA2EVPANG) / sd.volume;
+    o[1] = -s[1] * f;  // xx
+    o[2] = -s[4] * f;  // yy
+    o[3] = -s[6] * f;  // zz
+    o[4] = -s[2] * f;  // xy
+    o[5] = -s[5] * f;  // yz
+    o[6] = -s[3] * f;  // xz
+    o[7] = 0.0;        // variance (gap_calc.f90:206)
+}
+
 __global__ void __launch_bounds__(256)
-k_finalize(const StructDev *structs, const double *eatom, const double *vir, int lgrad, double *out8,
-           const unsigned char *role) {
+k_finalize_partial(const StructDev *structs, const double *eatom, const double *vir, int lgrad, double *partial,
+                   int nchunk, const unsigned char *role, double *out8) {
     __shared__ double red[8][7];
-    const StructDev &sd = structs[blockIdx.x];
+    __shared__ double tot[8];
+    const StructDev &sd = structs[blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int t0 = blockIdx.x * FIN_CHUNK, t1 = min(sd.natoms, t0 + FIN_CHUNK);
     double v[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int t = tid; t < sd.natoms; t += 256) {
+    for (int t = t0 + tid; t < t1; t += 256) {
         const int i = sd.atom_off + t;
         if (role && role[i] != 2) continue;   // decomposed run: partial sums over this rank's centres
         v[0] += eatom[i];
@@ -102,25 +121,34 @@ k_finalize(const StructDev *structs, const double *eatom, const double *vir, int
         if (lane == 0) red[wid][q] = x;
     }
     __syncthreads();
-    if (tid == 0) {
-        double s[7];
-        for (int q = 0; q < 7; q++) {
-            double x = 0.0;
-            for (int w = 0; w < 8; w++) x += red[w][q];
-            s[q] = x;
-        }
-        double *o = out8 + (size_t)blockIdx.x * 8;
-        o[0] = s[0];
-        const double f = (1.0 / GPA2EVPANG) / sd.volume;
-        // s[1..6] = (xx, xy, xz, yy, yz, zz) of sum delta_a * dE/dx_b ; stress = -that * f
-        o[1] = -s[1] * f;  // xx
-        o[2] = -s[4] * f;  // yy
-        o[3] = -s[6] * f;  // zz
-        o[4] = -s[2] * f;  // xy
-        o[5] = -s[5] * f;  // yz
-        o[6] = -s[3] * f;  // xz
-        o[7] = 0.0;        // variance (gap_calc.f90:206)
+    if (tid < 7) {
+        double x = 0.0;
+        for (int w = 0; w < 8; w++) x += red[w][tid];
+        partial[((size_t)blockIdx.y * nchunk + blockIdx.x) * 8 + tid] = x;
+        tot[tid] = x;
     }
+    if (nchunk == 1) {   // small structures: this CTA already holds the totals, no second launch
+        __syncthreads();
+        if (tid == 0) write_out8(tot, sd, out8 + (size_t)blockIdx.y * 8);
+    }
+}
+
+__global__ void __launch_bounds__(32)
+k_finalize(const StructDev *structs, const double *partial, int nchunk, double *out8) {
+    __shared__ double s[8];
+    const StructDev &sd = structs[blockIdx.x];
+    const int lane = threadIdx.x;
+    const int used = (sd.natoms + FIN_CHUNK - 1) / FIN_CHUNK;   // chunks of this structure (the others were not written)
+    if (lane < 7) {
+        const double *p = partial + (size_t)blockIdx.x * nchunk * 8 + lane;
+        double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+        int c = 0;
+        for (; c + 3 < used; c += 4) { x0 += p[8 * c]; x1 += p[8 * c + 8]; x2 += p[8 * c + 16]; x3 += p[8 * c + 24]; }
+        for (; c < used; c++) x0 += p[8 * c];
+        s[lane] = (x0 + x1) + (x2 + x3);
+    }
+    __syncwarp();
+    if (lane == 0) write_out8(s, sd, out8 + (size_t)blockIdx.x * 8);
 }
 
 // dE/dG := unit vector e_k for every atom (CAR2ACSF export: one backward pass per descriptor)
@@ -133,18 +161,23 @@ void launch_onehot(cudaStream_t st, double *dEdG, int ntot, int D, int k) {
     k_onehot<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dEdG, ntot, D, k);
 }
 
+int finalize_chunks(int max_natoms) { return max_natoms > 0 ? (max_natoms + FIN_CHUNK - 1) / FIN_CHUNK : 1; }
+
 void launch_gather(cudaStream_t st, const StructDev *structs, int nstruct, const int *sid, int ntot, int cap,
                    const uint64_t *nbr_keys, const int *nbr_cnt, const double *fpair, const double *gself,
                    const double *vir, const double *eatom, int lgrad, double *force_soa, double *out8,
-                   const unsigned char *role, const int *active, const DevFlags *flags, long *launches) {
+                   const unsigned char *role, const int *active, const DevFlags *flags, double *partial, int max_natoms,
+                   long *launches) {
     cudaMemsetAsync(force_soa, 0, sizeof(double) * 3 * (size_t)ntot, st);
     if (lgrad) {
         k_gather<<<ntot, GT, 0, st>>>(structs, sid, ntot, cap, nbr_keys, nbr_cnt, fpair, gself, force_soa, role, active,
                                        flags);
         if (launches) *launches += 1;
     }
-    k_finalize<<<nstruct, 256, 0, st>>>(structs, eatom, vir, lgrad, out8, role);
-    if (launches) *launches += 1;
+    const int nchunk = finalize_chunks(max_natoms);
+    k_finalize_partial<<<dim3(nchunk, nstruct), 256, 0, st>>>(structs, eatom, vir, lgrad, partial, nchunk, role, out8);
+    if (nchunk > 1) k_finalize<<<nstruct, 32, 0, st>>>(structs, partial, nchunk, out8);
+    if (launches) *launches += nchunk > 1 ? 2 : 1;
 }
 
 }  // namespace gapcu

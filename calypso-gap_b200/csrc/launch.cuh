@@ -23,6 +23,7 @@ void launch_order(cudaStream_t st, const int *nbr_cnt, int ntot, int *order, con
 // centre.cu  (mode: 0 forward, 1 backward, 2 fused forward + GPR + backward)
 size_t centre_smem_bytes(const CentreArgs &a, int mode);
 int centre_warps();
+int centre_pcap_template(int pcap);   // capacity of the kernel instance that serves `pcap` neighbours: 128, 256, 512 or 1024
 size_t centre_stash_words(const CentreArgs &a, int chunks, int ctas);
 int launch_forward(cudaStream_t st, const CentreArgs &a, long *launches);
 int launch_backward(cudaStream_t st, const CentreArgs &a, long *launches);
@@ -49,7 +50,9 @@ void launch_gpr_prepare(cudaStream_t st, int M, int D, const double *mm_c_order,
 void launch_gather(cudaStream_t st, const StructDev *structs, int nstruct, const int *sid, int ntot, int cap,
                    const uint64_t *nbr_keys, const int *nbr_cnt, const double *fpair, const double *gself,
                    const double *vir, const double *eatom, int lgrad, double *force_soa, double *out8,
-                   const unsigned char *role, const int *active, const DevFlags *flags, long *launches);
+                   const unsigned char *role, const int *active, const DevFlags *flags, double *partial, int max_natoms,
+                   long *launches);
+int finalize_chunks(int max_natoms);   // partial needs nstruct * finalize_chunks(max_natoms) * 8 doubles
 
 void launch_onehot(cudaStream_t st, double *dEdG, int ntot, int D, int k);
 

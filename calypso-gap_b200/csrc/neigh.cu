@@ -418,6 +418,11 @@ __global__ void __launch_bounds__(1024) k_order_by_count(const int *nbr_cnt, int
     hist[tid] = excl;
     __syncthreads();
     if (tid == NB_MAXLIST - 1) flags->n_centres = excl + v;   // total number of owned atoms
+    // thread of key(count c) holds the number of centres with more than c neighbours
+    if (tid == NB_MAXLIST - 128) flags->n_gt[0] = excl;
+    if (tid == NB_MAXLIST - 256) flags->n_gt[1] = excl;
+    if (tid == NB_MAXLIST - 512) flags->n_gt[2] = excl;
+    if (tid == 0) flags->n_gt[3] = 0;
     for (int i = tid; i < ntot; i += 1024) {
         if (role && role[i] != 2) continue;
         const int key = NB_MAXLIST - min(max(nbr_cnt[i], 1), NB_MAXLIST);   // 0..1023 (0 and 1 neighbours share a key)
