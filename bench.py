@@ -229,13 +229,30 @@ def run_ours(args):
                      "source": tj["source"]}
     except (OSError, KeyError, ValueError):
         pass
+    # the two HBM/latency-bound passes beside it: algorithmic bytes (positions, 8-byte list
+    # entries written once / read once, 24-byte pair gradients, forces) over their stage times
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs"
+    except (OSError, KeyError, ValueError):
+        hbm_peak, hbm_src = 6456.2, "fallback (B200_PROFILING.md)"
+    pbar = work["pairs"] / max(work["atoms"], 1.0)
+    b_k1 = natoms * (24 + 4 + 8 * pbar + 4)
+    b_k5 = natoms * (8 * pbar + 24 * pbar + 24 + 72 + 8)
+    t_k1 = stages["neighbor_build"] / args.steps * 1e-3
+    t_k5 = stages["force_gather_reduce"] / args.steps * 1e-3
+    hbm_passes = {"peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
+                  "neighbor_build": {"bytes": b_k1, "achieved": b_k1 / t_k1 / 1e9, "frac": b_k1 / t_k1 / 1e9 / hbm_peak},
+                  "force_gather_reduce": {"bytes": b_k5, "achieved": b_k5 / t_k5 / 1e9, "frac": b_k5 / t_k5 / 1e9 / hbm_peak},
+                  "note": "both passes are launch/latency bound at 1000 atoms (a few hundred KB per pass); they reach "
+                          "their bandwidth regime only on 10^5-atom inputs (BASELINE.md section 5)"}
     roofline = {"bound": "fp64", "kernel": "k_centre<fused> (wACSF forward + in-CTA GPR + backward, one launch per step)",
                 "achieved": achieved, "peak": dfma, "unit": "TFLOP/s", "frac": achieved / dfma if dfma else None,
                 "peak_source": "DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                 "dmma_peak_tflops": dmma, "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu)",
                 "ncu": ncu_extra,
                 "flops_per_step": w_desc + w_gpr, "flops_desc": w_desc, "flops_gpr": w_gpr, "seconds_per_step": t_desc,
-                "gpr_dmma": split_gpr,
+                "gpr_dmma": split_gpr, "hbm_passes": hbm_passes,
                 "stage_ms_per_step": {k: v / args.steps for k, v in stages.items()}}
     # ---- CPU baseline: the reference's algorithm (dense oracle) on the same structure ---
     cpu = cpu_reference(1, sample_centres=min(natoms, args.cpu_centres), repeats=1)

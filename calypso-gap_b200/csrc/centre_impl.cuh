@@ -500,6 +500,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             const double ww = aiw.y * biw.y;
             const double u1 = irb - cosv * ira, u2 = ira - cosv * irb, u3 = -rjk * ira * irb;
             double cij = 0.0, cik = 0.0, cjk = 0.0;
+#pragma unroll 2
             for (int c = 0; c < v; c++) {
                 const int g0 = GRP_BEGIN(a, c), g1 = GRP_BEGIN(a, c + 1);
                 if (g0 == g1) continue;
