@@ -414,6 +414,32 @@ def test_maximum_neighbour_count(shipped_pot):
     c.close()
 
 
+def test_capacity_tiers_in_one_batch(ctx, shipped_pot):
+    """A batch whose structures need different instances of the centre kernel (<= 128, <= 256,
+    <= 512 and <= 1024 neighbours per atom): every tier of the count-ordered centre list is
+    served by its own launch; all of them must agree with the oracle."""
+    rng = np.random.default_rng(21)
+    structs = []
+    for edge, n in ((9.0, 40), (6.0, 40), (5.2, 40), (2.05, 8)):   # ~50, ~165, ~265, ~840 neighbours per atom
+        if n == 8:
+            pos = np.array([[i, j, k] for i in range(2) for j in range(2) for k in range(2)], float) * 1.02 + 0.05
+            pos += rng.normal(0, 0.03, pos.shape)
+        else:
+            g = np.stack(np.meshgrid(*[np.arange(4)] * 3, indexing="ij"), -1).reshape(-1, 3)[:n]
+            pos = (g + 0.5) * (edge / 4) + rng.normal(0, 0.05, (n, 3))
+        structs.append((np.eye(3) * edge, pos, rng.choice(np.array([5, 6], np.int32), n)))
+    ctx.set_structures([t[2] for t in structs], [t[0] for t in structs], [t[1] for t in structs], 6.0)
+    ctx.compute(True)
+    e, f, s = ctx.fetch()
+    off, counts = 0, []
+    for i, (cell, pos, z) in enumerate(structs):
+        want = shipped_pot.calc_sparse(z, cell, pos, 6.0, True, stats=True)
+        counts.append(want["stats"][0] / len(pos))
+        _cmp({"energy": e[i], "forces": f[off:off + len(pos)], "stress": s[i]}, want)
+        off += len(pos)
+    assert counts[0] <= 128 < counts[1] <= 256 < counts[2] <= 512 < counts[3]
+
+
 def test_neighbour_capacity_grows_on_demand(shipped_pot):
     """A sparse structure first (small learned capacity), then a dense one in the same
     context: the overflow is detected on the device and the pass re-run."""
