@@ -112,6 +112,11 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        # stdout carries exactly one JSON line (rank 0).  The image sets NCCL_DEBUG=VERSION, whose banner
+        # NCCL prints to stdout and only redirects from level WARN on: same information, sent to stderr
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     os.environ["GAPCU_DEVICE"] = str(local)   # device of the Fortran-style entry points (gapcu_calc) on this rank
