@@ -408,25 +408,75 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             rot = (rot + n_c) % CT;
             const double pirc = a.cls.pirc[c];
             const unsigned char *fcc = smem + H::FCD + c * (PCAP * 16);   // fc of class c: record stride 16 bytes
+            // per item: geometry, fc product and the angle; shared by the loops below
+            struct Item { double phi, cosv, ssum, ww; };
+            auto prep = [&](int t) {
+                const uint32_t it = s_S[t];
+                const int ra = it & 1023, rb = (it >> 10) & 1023;
+                const double2 axy = NB2(ra, 0), azr = NB2(ra, 1), aiw = NB2(ra, 2);
+                const double2 bxy = NB2(rb, 0), bzr = NB2(rb, 1), biw = NB2(rb, 2);
+                const double rjk2 = dist2_fma(axy.x - bxy.x, axy.y - bxy.y, azr.x - bzr.x);
+                const double ra2 = azr.y * azr.y, rb2 = bzr.y * bzr.y;
+                Item x;
+                x.cosv = (ra2 + rb2 - rjk2) * 0.5 * aiw.x * biw.x;
+                x.ssum = ra2 + rb2 + rjk2;
+                x.ww = aiw.y * biw.y;
+                const double rjk = rjk2 * rsqrt_pos(fmax(rjk2, 1e-300));
+                double sn, cs;
+                sincos_0pi(rjk * pirc, &sn, &cs);
+                x.phi = *(const double *)(fcc + ra * 16) * *(const double *)(fcc + rb * 16) * (0.5 * (cs + 1.0));
+                return x;
+            };
+            if (g1 - g0 <= 2) {
+                // one or two exponents in this class (the usual case): TWO triplets per thread and trip,
+                // i.e. four independent exponential chains in flight -- the kernel is latency bound
+                const int ng = g1 - g0;
+                const double al0 = s_galpha[g0], al1 = s_galpha[g1 - 1];
+                double acc[2][4];
+#pragma unroll
+                for (int g = 0; g < 2; g++) acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.0;
+                auto add = [&](const Item &x, double e0, double e1) {
+                    const double pe0 = x.phi * e0, pe1 = x.phi * e1, pw0 = pe0 * x.ww, pw1 = pe1 * x.ww;
+                    acc[0][0] += pe0; acc[0][1] = fma(pe0, x.cosv, acc[0][1]); acc[0][2] += pw0; acc[0][3] = fma(pw0, x.cosv, acc[0][3]);
+                    acc[1][0] += pe1; acc[1][1] = fma(pe1, x.cosv, acc[1][1]); acc[1][2] += pw1; acc[1][3] = fma(pw1, x.cosv, acc[1][3]);
+                };
+                int t = myrank;
+                for (; t + CT < n_c; t += 2 * CT) {
+                    const Item x = prep(t), y = prep(t + CT);
+                    const double ex0 = exp_neg(-al0 * x.ssum, s_t32), ey0 = exp_neg(-al0 * y.ssum, s_t32);
+                    const double ex1 = exp_neg(-al1 * x.ssum, s_t32), ey1 = exp_neg(-al1 * y.ssum, s_t32);
+                    add(x, ex0, ex1);
+                    add(y, ey0, ey1);
+                }
+                if (t < n_c) {
+                    const Item x = prep(t);
+                    add(x, exp_neg(-al0 * x.ssum, s_t32), exp_neg(-al1 * x.ssum, s_t32));
+                }
+                if (__any_sync(0xffffffffu, myrank < n_c)) {
+#pragma unroll
+                    for (int g = 0; g < 2; g++) {
+                        if (g < ng) {   // with a single exponent acc[1] duplicates acc[0] and is dropped
+                            const double tot = warp_sum4(acc[g][0], acc[g][1], acc[g][2], acc[g][3], lane);
+                            const double oth = __shfl_xor_sync(0xffffffffu, tot, 8);
+                            if ((lane & 7) == 0) {
+                                const int ip = g_iplus[g0 + g], im = g_iminus[g0 + g];
+                                double *gw = s_gw + wid * D + ((lane & 16) ? nsf : 0);
+                                if (!(lane & 8)) { if (ip >= 0) gw[ip] += tot + oth; }
+                                else { if (im >= 0) gw[im] += oth - tot; }
+                            }
+                        }
+                    }
+                }
+                continue;
+            }
             for (int gb = g0; gb < g1; gb += MAXG) {
                 const int ng = min(MAXG, g1 - gb);
                 double acc[MAXG][4];
 #pragma unroll
                 for (int g = 0; g < MAXG; g++) acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.0;
                 for (int t = myrank; t < n_c; t += CT) {
-                    const uint32_t it = s_S[t];
-                    const int ra = it & 1023, rb = (it >> 10) & 1023;
-                    const double2 axy = NB2(ra, 0), azr = NB2(ra, 1), aiw = NB2(ra, 2);
-                    const double2 bxy = NB2(rb, 0), bzr = NB2(rb, 1), biw = NB2(rb, 2);
-                    const double rjk2 = dist2_fma(axy.x - bxy.x, axy.y - bxy.y, azr.x - bzr.x);
-                    const double ra2 = azr.y * azr.y, rb2 = bzr.y * bzr.y;
-                    const double cosv = (ra2 + rb2 - rjk2) * 0.5 * aiw.x * biw.x;
-                    const double ssum = ra2 + rb2 + rjk2;
-                    const double ww = aiw.y * biw.y;
-                    const double rjk = rjk2 * rsqrt_pos(fmax(rjk2, 1e-300));
-                    double sn, cs;
-                    sincos_0pi(rjk * pirc, &sn, &cs);
-                    const double phi = *(const double *)(fcc + ra * 16) * *(const double *)(fcc + rb * 16) * (0.5 * (cs + 1.0));
+                    const Item x = prep(t);
+                    const double phi = x.phi, cosv = x.cosv, ssum = x.ssum, ww = x.ww;
                     // groups in pairs without a branch between their exponentials, so the two
                     // dependent chains interleave (same trick as in the backward loop)
                     auto one = [&](double (&ac)[4], int g) {
