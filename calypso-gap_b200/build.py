@@ -19,7 +19,7 @@ OBJ = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
-CU_SOURCES = ["neigh.cu", "centre.cu", "centre_p128.cu", "centre_p256.cu", "centre_p512.cu", "centre_p1024.cu", "gpr.cu", "gather.cu",
+CU_SOURCES = ["neigh.cu", "centre.cu", "centre_p128.cu", "centre_p256.cu", "centre_p512.cu", "centre_p1024.cu", "gpr.cu", "gather.cu", "variance.cu",
               "microbench.cu", "context.cu"]
 CPP_SOURCES = ["potential.cpp"]
 C_SOURCES = ["fortran_shim.c"]

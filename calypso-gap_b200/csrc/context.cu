@@ -734,6 +734,32 @@ extern "C" int gapcu_ctx_fetch_descriptors(gapcu_ctx *c, double *xx, double *ded
     return 0;
 }
 
+extern "C" int gapcu_ctx_variance(gapcu_ctx *c, const double *qmm, double *variance, double *covf) {
+    if (!c || !c->computed) return fail(GAPCU_EARG, "nothing computed");
+    if (!qmm || !variance) return fail(GAPCU_EARG, "qmm and variance are required");
+    DeviceGuard dg_(c->device);
+    int rc = finish_pass(c);
+    if (rc) return rc;
+    const size_t M = (size_t)c->M, NT = (size_t)c->ntot;
+    DBuf<double> d_q, d_covf, d_var;
+    auto bail = [&](int r) { d_q.release(); d_covf.release(); d_var.release(); return r; };
+    if (d_q.ensure(M * M) != cudaSuccess || d_covf.ensure(NT) != cudaSuccess || d_var.ensure(c->nstruct) != cudaSuccess)
+        return bail(fail(GAPCU_ECUDA, "out of device memory for the variance pass"));
+    if (cudaMemcpyAsync(d_q.p, qmm, sizeof(double) * M * M, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+        return bail(fail(GAPCU_ECUDA, "upload of QMM failed"));
+    if (launch_variance(c->stream, c->d_structs.p, c->nstruct, c->ntot, c->d_G.p, c->D, c->M, c->Mp, c->Dp, c->d_Mt.p,
+                        c->d_cmean.p, c->d_itheta.p, d_q.p, d_covf.p, d_var.p))
+        return bail(fail(GAPCU_ELIMIT, "sparse set too large for the variance kernel's shared memory"));
+    c->launches += 2;
+    std::vector<double> h_var(c->nstruct);
+    bool ok = cudaMemcpyAsync(h_var.data(), d_var.p, sizeof(double) * c->nstruct, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
+    if (ok && covf) ok = cudaMemcpyAsync(covf, d_covf.p, sizeof(double) * NT, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+    if (!ok) return bail(fail(GAPCU_ECUDA, "variance pass failed"));
+    for (int s = 0; s < c->nstruct; s++) variance[s] = h_var[s];
+    return bail(0);
+}
+
 extern "C" int gapcu_ctx_fetch_neighbors(gapcu_ctx *c, int cap, int *count, int *idx, int *shift, double *dis) {
     if (!c || !c->computed) return fail(GAPCU_EARG, "nothing computed");
     DeviceGuard dg_(c->device);

@@ -56,6 +56,11 @@ int finalize_chunks(int max_natoms);   // partial needs nstruct * finalize_chunk
 
 void launch_onehot(cudaStream_t st, double *dEdG, int ntot, int D, int k);
 
+// variance.cu
+int launch_variance(cudaStream_t st, const StructDev *structs, int nstruct, int ntot, const double *G, int D, int M, int Mp,
+                    int Dp, const double *Mt, const double *cmean, const double *itheta, const double *qmm, double *covf,
+                    double *variance);
+
 // microbench.cu
 void launch_fp64_peaks(cudaStream_t st, double *dfma_tflops, double *dmma_tflops);
 

@@ -26,7 +26,7 @@ SYMBOLS = [
     "gapcu_device_count", "gapcu_ctx_create", "gapcu_ctx_destroy", "gapcu_ctx_load_potential",
     "gapcu_ctx_set_potential", "gapcu_ctx_set_pipeline", "gapcu_nccl_unique_id", "gapcu_ctx_nccl_init",
     "gapcu_ctx_set_domain", "gapcu_ctx_set_structures", "gapcu_ctx_compute", "gapcu_ctx_fetch",
-    "gapcu_ctx_fetch_descriptors", "gapcu_ctx_fetch_neighbors", "gapcu_ctx_time_compute", "gapcu_stage_name",
+    "gapcu_ctx_fetch_descriptors", "gapcu_ctx_variance", "gapcu_ctx_fetch_neighbors", "gapcu_ctx_time_compute", "gapcu_stage_name",
     "gapcu_ctx_work_counters", "gapcu_ctx_balance", "gapcu_fp64_peaks",
 ]
 FORTRAN_SYMBOLS = ["fgap_calc_", "fgap_read_", "fget_bond_", "car2acsf_", "write_array_2dim_"]
@@ -158,6 +158,16 @@ class Context:
         xx = np.zeros((nt, des_len)); dedg = np.zeros((nt, des_len)); eat = np.zeros(nt)
         _check(lib().gapcu_ctx_fetch_descriptors(self.h, xx.ctypes.data, dedg.ctypes.data, eat.ctypes.data))
         return xx, dedg, eat
+
+    def variance(self, qmm):
+        """Predictive variance of the last compute for a caller-supplied QMM (M x M): returns
+        (VARIANCE per structure, covf per atom); formula of gap_calc.f90:207-210."""
+        q = np.asfortranarray(qmm, dtype=np.float64)
+        nt = int(self.natoms.sum())
+        var = np.zeros(len(self.natoms)); covf = np.zeros(nt)
+        lib().gapcu_ctx_variance.argtypes = [_vp, _vp, _vp, _vp]
+        _check(lib().gapcu_ctx_variance(self.h, q.ctypes.data, var.ctypes.data, covf.ctypes.data))
+        return var, covf
 
     def neighbors(self, cap=1000):
         nt = int(self.natoms.sum())

@@ -122,6 +122,13 @@ int gapcu_ctx_compute(gapcu_ctx *ctx, int lgrad);
 int gapcu_ctx_fetch(gapcu_ctx *ctx, double *ene, double *force, double *stress);
 /* Descriptors / dE/dG / atomic energies of the last compute ([sum natoms][des_len], C order). */
 int gapcu_ctx_fetch_descriptors(gapcu_ctx *ctx, double *xx, double *dedg, double *eatom);
+/* Predictive variance of the last compute (additive).  The reference carries the
+ * formula commented out and returns VARIANCE = 0 (gappy/libgap/gap_calc.f90:205-210), which the
+ * drop-in entry points above keep doing; this entry point evaluates it for callers that hold QMM:
+ *     covf(i) = delta - ckm(i,:) . matmul(QMM, ckm(i,:)),  VARIANCE = sum_i covf(i) / na,
+ * ckm = GET_COV (gap_calc.f90:268-288), delta = 1 (gap_calc.f90:8).
+ * qmm: QMM(nsparseX, nsparseX) in Fortran order; variance[nstruct]; covf[sum natoms] or NULL. */
+int gapcu_ctx_variance(gapcu_ctx *ctx, const double *qmm, double *variance, double *covf);
 /* Neighbour lists of the last compute in reference order (j, n1, n2, n3):
  * count[ntot], idx[ntot][cap] (index within the structure), shift[ntot][cap][3],
  * dis[ntot][cap].  Returns the largest count, or a negative code. */

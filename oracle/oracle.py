@@ -176,6 +176,15 @@ class Potential:
         """Same arithmetic in O(N) memory (validated against calc_dense)."""
         return self._calc(False, species, lat, pos, rcut, lgrad, max_nb, desc, stats)
 
+    def variance(self, xx, qmm, delta=1.0):
+        """The predictive variance the reference carries commented out (gap_calc.f90:205-210):
+        covf(i) = delta - ckm(i,:) . matmul(qmm, ckm(i,:)), VARIANCE = sum(covf) / na, with
+        ckm = GET_COV (gap_calc.f90:268-288).  xx: descriptors [na, des_len] of calc_*(desc=True)."""
+        d = (np.asarray(xx)[:, None, :] - self.mm[None, :, :]) / self.theta
+        ckm = delta * np.exp(-0.5 * (d * d).sum(-1))
+        covf = delta - np.einsum("ij,jl,il->i", ckm, np.asarray(qmm, float), ckm)
+        return float(covf.sum() / len(covf)), covf
+
     def car2acsf_dense(self, species, lat, pos, rcut=6.0, lgrad=True):
         species = np.ascontiguousarray(species, np.int32)
         lat = np.ascontiguousarray(lat, np.float64); pos = np.ascontiguousarray(pos, np.float64)

@@ -414,6 +414,30 @@ def test_maximum_neighbour_count(shipped_pot):
     c.close()
 
 
+def test_predictive_variance_entry_point(ctx, shipped_pot, bc_structure):
+    """the variance formula the reference carries commented out
+    (gap_calc.f90:205-210), for a caller-supplied QMM; checked against the numpy restatement in
+    the oracle on two structures of one batch.  The drop-in outputs keep VARIANCE = 0."""
+    pot = shipped_pot
+    d = (pot.mm[:, None, :] - pot.mm[None, :, :]) / pot.theta
+    kmm = np.exp(-0.5 * (d * d).sum(-1))
+    qmm = np.linalg.inv(kmm + 1e-3 * np.eye(len(kmm)))          # a realistic inverse sparse covariance
+    qmm += 1e-3 * np.random.default_rng(3).normal(size=qmm.shape) * np.abs(qmm).mean()   # not exactly symmetric
+    z, cell, pos = bc_structure["numbers"].astype(np.int32), bc_structure["cell"], bc_structure["positions"]
+    (cell2, pos2), z2 = sheared(cell, pos), z
+    ctx.set_structures([z, z2], [cell, cell2], [pos, pos2], 6.0)
+    ctx.compute(True)
+    var, covf = ctx.variance(qmm)
+    off = 0
+    for s, (zz, cc, pp) in enumerate(((z, cell, pos), (z2, cell2, pos2))):
+        want = pot.calc_sparse(zz, cc, pp, 6.0, False, desc=True)
+        v_ref, covf_ref = pot.variance(want["xx"], qmm)
+        scale = max(1.0, np.abs(covf_ref).max())
+        assert np.abs(covf[off:off + len(pp)] - covf_ref).max() <= 1e-9 * scale
+        assert abs(var[s] - v_ref) <= 1e-9 * scale
+        off += len(pp)
+
+
 def test_capacity_tiers_in_one_batch(ctx, shipped_pot):
     """A batch whose structures need different instances of the centre kernel (<= 128, <= 256,
     <= 512 and <= 1024 neighbours per atom): every tier of the count-ordered centre list is
