@@ -20,6 +20,7 @@ static SmemLayout make_layout(const CentreArgs &a, int mode) {
     L.galpha = take(8 * (a.plan.n_grp + 1));
     L.gd = bwd ? take(8 * 4 * (a.plan.n_grp + 1)) : 0;
     L.sG = fused ? take(8 * D) : 0;
+    L.gx = (fused && a.cs > 1) ? take(8 * D) : 0;
     L.sdu = bwd ? take(8 * D) : 0;
     L.red = take(8 * NW * 16);
     L.S = take(4 * (a.lcap + 32));

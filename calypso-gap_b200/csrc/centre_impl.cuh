@@ -35,7 +35,18 @@
 //      sum lam*dw), so there is no inner loop over functions; the three leg scalars
 //      go to per-warp private accumulators (dE/dx_j = A_j d_j - V_j) with in-warp
 //      conflict serialisation: no atomics anywhere.
+//
+// Thread-block clusters (template CS = 1, 2 or 4 CTAs per centre): when a launch has fewer
+// centres than the device has CTA slots (a 64-atom MD cell uses 64 of 444), CS CTAs of one
+// cluster share a centre.  Every CTA stages the neighbours, then takes 1/CS of the pair
+// range (own triplet list, own forward sums, own backward accumulators) and 1/CS of the
+// radial functions; the partial descriptors are exchanged through distributed shared memory
+// (each CTA adds the CS partial vectors in rank order, so all hold the same bits), the small
+// GPR is evaluated by every CTA, and rank 0 adds the CS gradient accumulators in rank order
+// and writes the centre's outputs.  Three cluster barriers per centre.
 #pragma once
+#include <cooperative_groups.h>
+
 #include <cstdint>
 #include <cstring>
 
@@ -45,6 +56,7 @@
 #include "launch.cuh"
 
 namespace gapcu {
+namespace cg = cooperative_groups;
 
 #define GRP_BEGIN(a, c) (a).cls.grp_begin[c]   // first group of class c / one past its last group
 
@@ -143,9 +155,12 @@ extern __shared__ __align__(16) unsigned char smem[];   // dynamic shared memory
 // is always taken with pair_dist2, the reference's arithmetic)
 __device__ __forceinline__ double dist2_fma(double dx, double dy, double dz) { return fma(dz, dz, fma(dy, dy, dx * dx)); }
 
-template <int MODE, int PCAP>
+template <int MODE, int PCAP, int CS>
 __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i, const bool first) {
     constexpr bool FWD = MODE != MODE_BWD, BWD = MODE != MODE_FWD, FUSED = MODE == MODE_FUSED;
+    // rank of this CTA among the CS CTAs that share centre i; lead = the one that writes the outputs
+    const int crank = CS > 1 ? (int)cg::this_cluster().block_rank() : 0;
+    const bool lead = crank == 0;
     using H = Hot<PCAP>;
     // neighbour record s: (x, y) (z, r) (1/r, w); class pair (c, s): (fc, fc')
 #define NB2(s, k) (*(double2 *)(smem + H::NB + (s) * 48 + (k) * 16))
@@ -163,6 +178,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
     double *s_gd = (double *)(smem + L.gd);      // [n_grp][4]: DU, DW, DUL, DWL (backward)
     double *s_gw = (double *)(smem + L.gw);      // [NW][D] per-warp partial descriptors
     double *s_G = (double *)(smem + L.sG);
+    double *s_gx = (double *)(smem + L.gx);      // this CTA's partial descriptors, read by its cluster peers (CS > 1)
     double *s_du = (double *)(smem + L.sdu);     // dE/dG of this centre
     double *s_xs = (double *)(smem + L.xs);
     double *s_W = (double *)(smem + L.sW);
@@ -177,10 +193,6 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned ltmask = (1u << lane) - 1u;
     const int P = a.nbr_cnt[i];
-    if (P > PCAP || P > a.cap) {  // host re-runs with a larger capacity
-        if (tid == 0) atomicExch(&a.flags->overflow, 1);
-        return;
-    }
     const StructDev &sd = a.structs[a.sid[i]];
     const int ntot = a.ntot;
     const int *g_iplus = pl.itab + pl.o_grp_iplus, *g_iminus = pl.itab + pl.o_grp_iminus;
@@ -194,6 +206,10 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             s_radi[t] = make_int2(pl.itab[pl.o_rad_ii + t], pl.itab[pl.o_rad_cls + t] | (pl.itab[pl.o_rad_type + t] << 16));
             s_radp[t] = pl.dtab[pl.o_rad_p + t];
         }
+    }
+    if (P > PCAP || P > a.cap) {  // host re-runs with a larger capacity (checked after the tables are in place: `first` is spent)
+        if (tid == 0) atomicExch(&a.flags->overflow, 1);
+        return;
     }
     if (FWD) for (int t = tid; t < NW * D; t += CT) s_gw[t] = 0.0;
     if (MODE == MODE_BWD) for (int t = tid; t < D; t += CT) s_du[t] = a.dEdG[(size_t)i * D + t];
@@ -225,7 +241,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         int nc = 0;
         while (nc < ncls && !(dis > a.cls.rc[nc])) nc++;  // reference: "if (rij.gt.cutoff) cycle"
         NCB(s) = (unsigned char)nc;
-        wk_pc += nc;
+        if (lead) wk_pc += nc;
     }
     __syncthreads();
     const int P32 = (P + 31) & ~31;
@@ -241,7 +257,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
     __syncthreads();
     // ---- 2: radial forward: one warp task per function, lanes over neighbours ----------
     if (FWD) {
-        for (int q = wid; q < pl.n_rad; q += NW) {
+        for (int q = wid + NW * crank; q < pl.n_rad; q += NW * CS) {   // the cluster's CTAs share the functions
             const int2 ri = s_radi[q];
             const int c = ri.y & 0xffff;
             const double prm = s_radp[q];
@@ -262,7 +278,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         }
     }
     __syncthreads();
-    if (FWD && tid < ncls && GRP_BEGIN(a, tid + 1) > GRP_BEGIN(a, tid)) {
+    if (FWD && lead && tid < ncls && GRP_BEGIN(a, tid + 1) > GRP_BEGIN(a, tid)) {
         // sum_c Q_c of SURVEY.md 8(d): candidate pairs of every angular cutoff class
         unsigned long long pc = 0;
         for (int s = 0; s < P; s++) pc += (NCB(s) > tid);
@@ -271,7 +287,11 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
 
     // ---- 3: triplet list builder (phase A + deterministic counting sort) ----------
     const uint32_t angmask = a.cls.angmask;
-    const int Q = P * (P - 1) / 2;
+    // pair range of this CTA: the whole triangle, or one of CS contiguous parts of it
+    const int Qall = P * (P - 1) / 2;
+    const int qpart = CS > 1 ? ((Qall + CS - 1) / CS + 31) & ~31 : Qall;
+    const int Qlo = min(Qall, crank * qpart), Qhi = min(Qall, Qlo + qpart);
+    const int Q = Qhi - Qlo;
     const int nchunk = (angmask && Q > 0) ? (Q + lcap - 1) / lcap : 0;
     const int qchunk = nchunk ? ((Q + nchunk - 1) / nchunk + 31) & ~31 : 0;
     unsigned long long wk_trip = 0, wk_tc = 0, wk_tsf = 0;
@@ -614,7 +634,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
     if (FWD) {
         const bool stash = FUSED && nchunk > 1 && a.list_scratch && nchunk <= a.list_scratch_chunks;
         for (int ch = 0; ch < nchunk; ch++) {
-            build_list(ch * qchunk, min(Q, (ch + 1) * qchunk), true);
+            build_list(Qlo + ch * qchunk, min(Qhi, Qlo + (ch + 1) * qchunk), true);
             if (stash) {
                 // keep the sorted list of this chunk (L2 resident) for the backward pass
                 uint32_t *dst = a.list_scratch + ((size_t)blockIdx.x * a.list_scratch_chunks + ch) * (size_t)(lcap + 32 + 512);
@@ -634,8 +654,21 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             double v = 0.0;
 #pragma unroll
             for (int w = 0; w < NW; w++) v += s_gw[w * D + k];
+            if (CS > 1) { s_gx[k] = v; continue; }
             if (FUSED) s_G[k] = v;
             if (a.G) a.G[(size_t)i * D + k] = v;
+        }
+        if (CS > 1) {
+            // partial descriptors of the cluster's CTAs, added in rank order by every CTA
+            cg::cluster_group cl = cg::this_cluster();
+            cl.sync();
+            for (int k = tid; k < D; k += CT) {
+                double v = 0.0;
+#pragma unroll
+                for (int r = 0; r < CS; r++) v += cl.map_shared_rank(s_gx, r)[k];
+                if (FUSED) s_G[k] = v;
+                if (lead && a.G) a.G[(size_t)i * D + k] = v;
+            }
         }
         // work counters
         unsigned long long v0 = wk_pc, v1 = wk_rad;
@@ -643,9 +676,11 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         for (int o = 16; o; o >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); }
         if (lane == 0) { atomicAdd(&a.flags->work[2], v0); atomicAdd(&a.flags->work[7], v1); }
         if (tid == 0) {
-            atomicAdd(&a.flags->work[0], 1ull);
-            atomicAdd(&a.flags->work[1], (unsigned long long)P);
-            atomicAdd(&a.flags->work[3], (unsigned long long)Q);
+            if (lead) {
+                atomicAdd(&a.flags->work[0], 1ull);
+                atomicAdd(&a.flags->work[1], (unsigned long long)P);
+                atomicAdd(&a.flags->work[3], (unsigned long long)Qall);
+            }
             atomicAdd(&a.flags->work[4], wk_trip);
             atomicAdd(&a.flags->work[5], wk_tc);
             atomicAdd(&a.flags->work[6], wk_tsf);
@@ -693,7 +728,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         if (tid == 0) {
             double e = 0.0;
             for (int w = 0; w < NW; w++) e += s_red[w];
-            a.eatom[i] = e;
+            if (lead) a.eatom[i] = e;
         }
         // dE/dG_k = -(1/theta_k) sum_j W_j (x'_k - m'_jk): thread (component k, slab h of the sparse points)
         const int nsB = max(1, min(CT / D, NW));
@@ -721,7 +756,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             for (int h = 0; h < nsB; h++) acc += part[h * D + k2];
             const double v = -a.gpr_itheta[k2] * acc;
             s_du[k2] = v;
-            if (a.dEdG_out) a.dEdG_out[(size_t)i * D + k2] = v;
+            if (lead && a.dEdG_out) a.dEdG_out[(size_t)i * D + k2] = v;
         }
         __syncthreads();
     }
@@ -746,7 +781,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 if (p < nparts && s < P) {
                     const double dis = NB2(s, 1).y, wj = NB2(s, 2).y;
                     const int nc = NCB(s);
-                    for (int q = p; q < pl.n_rad; q += nparts) {
+                    for (int q = p + nparts * crank; q < pl.n_rad; q += nparts * CS) {
                         const int2 ri = s_radi[q];
                         const int c = ri.y & 0xffff;
                         if (c >= nc) continue;
@@ -787,15 +822,27 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 for (int t = tid; t < n; t += CT) s_S[t] = src[t];
                 __syncthreads();
             } else if (!list_ready) {
-                build_list(ch * qchunk, min(Q, (ch + 1) * qchunk), false);
+                build_list(Qlo + ch * qchunk, min(Qhi, Qlo + (ch + 1) * qchunk), false);
             }
             backward_list();
         }
         // ---- epilogue: per neighbour gradient, centre gradient, strs contraction ----------
+        if (CS > 1) {
+            cg::this_cluster().sync();   // every CTA's accumulator is final; the lead adds them in rank order
+            if (!lead) return;
+        }
         double acc9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // gself xyz, vir xx xy xz yy yz zz
         for (int s = tid; s < P; s += CT) {
             const double dx = NB2(s, 0).x - xi, dy = NB2(s, 0).y - yi, dz = NB2(s, 1).x - zi;
-            const double gx = s_acc[s], gy = s_acc[PCAP + s], gz = s_acc[2 * PCAP + s];
+            double gx = s_acc[s], gy = s_acc[PCAP + s], gz = s_acc[2 * PCAP + s];
+            if (CS > 1) {
+                cg::cluster_group cl = cg::this_cluster();
+#pragma unroll
+                for (int r = 1; r < CS; r++) {
+                    const double *ra = cl.map_shared_rank(s_acc, r);
+                    gx += ra[s]; gy += ra[PCAP + s]; gz += ra[2 * PCAP + s];
+                }
+            }
             double *fp = a.fpair + ((size_t)i * a.cap + s) * 3;
             fp[0] = gx; fp[1] = gy; fp[2] = gz;
             acc9[0] -= gx; acc9[1] -= gy; acc9[2] -= gz;
@@ -824,7 +871,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
 // Persistent CTAs: as many as fit the device, each pulling centre atoms from a queue
 // ordered by descending neighbour count (longest first), so that 1000 centres on 444
 // resident CTAs do not cost full waves and the heavy centres do not form the tail.
-template <int MODE, int PCAP>
+template <int MODE, int PCAP, int CS>
 __global__ void __launch_bounds__(CT, 3) k_centre(const CentreArgs a) {
     __shared__ int s_next;
     bool first = true;
@@ -833,12 +880,25 @@ __global__ void __launch_bounds__(CT, 3) k_centre(const CentreArgs a) {
     const int q_begin = a.q_begin ? *a.q_begin : 0;
     const int q_end = a.q_end ? *a.q_end : (a.n_centres ? *a.n_centres : a.ntot);
     for (;;) {
-        __syncthreads();  // everybody is done with the previous centre's shared memory
-        if (threadIdx.x == 0) s_next = q_begin + atomicAdd(&a.flags->queue[a.queue_slot], 1);
-        __syncthreads();
+        // everybody (CS > 1: every CTA of the cluster, whose shared memory the lead reads) is done
+        // with the previous centre; the lead then pulls the next one for the whole cluster
+        if (CS > 1) {
+            cg::cluster_group cl = cg::this_cluster();
+            cl.sync();
+            if (cl.block_rank() == 0 && threadIdx.x == 0) {
+                const int nx = q_begin + atomicAdd(&a.flags->queue[a.queue_slot], 1);
+#pragma unroll
+                for (int r = 0; r < CS; r++) *cl.map_shared_rank(&s_next, r) = nx;
+            }
+            cl.sync();
+        } else {
+            __syncthreads();
+            if (threadIdx.x == 0) s_next = q_begin + atomicAdd(&a.flags->queue[a.queue_slot], 1);
+            __syncthreads();
+        }
         const int n = s_next;
         if (n >= q_end) break;
-        process_centre<MODE, PCAP>(a, a.order ? a.order[n] : n, first);
+        process_centre<MODE, PCAP, CS>(a, a.order ? a.order[n] : n, first);
         first = false;
     }
     if (threadIdx.x == 0) {
@@ -853,19 +913,34 @@ __global__ void __launch_bounds__(CT, 3) k_centre(const CentreArgs a) {
 }
 
 // launch k_centre<MODE, PCAP> on the persistent grid; a.lay must be the layout for (MODE, PCAP)
-template <int MODE, int PCAP>
+template <int MODE, int PCAP, int CS>
 int launch_centre(cudaStream_t st, const CentreArgs &a) {
     const size_t sm = (size_t)a.lay.total;
     if (sm > 227 * 1024) return -1;
-    if (cudaFuncSetAttribute((const void *)k_centre<MODE, PCAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
+    if (cudaFuncSetAttribute((const void *)k_centre<MODE, PCAP, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
         return -2;
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-    int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_centre<MODE, PCAP>, CT, sm) != cudaSuccess || per_sm < 1) per_sm = 1;
-    const int grid = a.ntot < sms * per_sm ? a.ntot : sms * per_sm;
-    k_centre<MODE, PCAP><<<grid, CT, sm, st>>>(a);
-    return 0;
+    if (CS == 1) {
+        int per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_centre<MODE, PCAP, CS>, CT, sm) != cudaSuccess || per_sm < 1) per_sm = 1;
+        const int grid = a.ntot < sms * per_sm ? a.ntot : sms * per_sm;
+        k_centre<MODE, PCAP, CS><<<grid, CT, sm, st>>>(a);
+        return 0;
+    }
+    // CS CTAs per centre: a persistent grid of whole clusters
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(CS * sms, 1, 1); cfg.blockDim = dim3(CT, 1, 1); cfg.dynamicSmemBytes = sm; cfg.stream = st;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, k_centre<MODE, PCAP, CS>, &cfg) != cudaSuccess || ncl < 1) return -3;
+    const int clusters = a.ntot < ncl ? a.ntot : ncl;
+    cfg.gridDim = dim3(CS * clusters, 1, 1);
+    return cudaLaunchKernelEx(&cfg, k_centre<MODE, PCAP, CS>, a) == cudaSuccess ? 0 : -4;
 }
 
 // one translation unit per capacity (centre_p*.cu) defines these
@@ -874,12 +949,16 @@ int launch_centre_p256(cudaStream_t st, const CentreArgs &a, int mode);
 int launch_centre_p512(cudaStream_t st, const CentreArgs &a, int mode);
 int launch_centre_p1024(cudaStream_t st, const CentreArgs &a, int mode);
 
+// the split pipeline (forward / backward launches) always runs one CTA per centre; the fused
+// kernel also exists with 2 and 4 CTAs per centre (a.cs, chosen by the host for small launches)
 #define GAPCU_CENTRE_INSTANCE(PC)                                                         \
     namespace gapcu {                                                                     \
     int launch_centre_p##PC(cudaStream_t st, const CentreArgs &a, int mode) {             \
-        if (mode == MODE_FWD) return launch_centre<MODE_FWD, PC>(st, a);                  \
-        if (mode == MODE_BWD) return launch_centre<MODE_BWD, PC>(st, a);                  \
-        return launch_centre<MODE_FUSED, PC>(st, a);                                      \
+        if (mode == MODE_FWD) return launch_centre<MODE_FWD, PC, 1>(st, a);               \
+        if (mode == MODE_BWD) return launch_centre<MODE_BWD, PC, 1>(st, a);               \
+        if (a.cs == 2) return launch_centre<MODE_FUSED, PC, 2>(st, a);                    \
+        if (a.cs == 4) return launch_centre<MODE_FUSED, PC, 4>(st, a);                    \
+        return launch_centre<MODE_FUSED, PC, 1>(st, a);                                   \
     }                                                                                     \
     }
 

@@ -88,6 +88,7 @@ struct gapcu_ctx {
     std::vector<double> h_theta, h_mm, h_coeff;  // cached GPR data (C order)
     DBuf<double> d_mm_raw, d_theta_raw, d_coeff_raw, d_Mt, d_MtT, d_mn, d_coeff, d_cmean, d_itheta, d_exp2;
     int pipeline = 0;  // 0 auto, 1 split (K2 -> DMMA K3 -> K4), 2 fused single centre kernel
+    int cluster = 0;   // CTAs per centre of the fused kernel: 0 auto, 1, 2 or 4
     // ---- structures
     int nstruct = 0, ntot = 0, nbins = 0;
     double rcut = 0.0;
@@ -189,6 +190,7 @@ extern "C" gapcu_ctx *gapcu_ctx_create(int device) {
         return nullptr;
     }
     if (const char *e = getenv("GAPCU_PIPELINE")) c->pipeline = !strcmp(e, "split") ? 1 : !strcmp(e, "fused") ? 2 : 0;
+    if (const char *e = getenv("GAPCU_CLUSTER")) { const int v = atoi(e); c->cluster = (v == 1 || v == 2 || v == 4) ? v : 0; }
     return c;
 }
 
@@ -295,6 +297,13 @@ extern "C" int gapcu_ctx_load_potential(gapcu_ctx *c, const char *path) {
     return gapcu_ctx_set_potential(c, (int)pf.z.size(), pf.z.data(), pf.w.data(), (int)pf.ntype.size(), pf.ntype.data(),
                                    pf.alpha.data(), pf.cutoff.data(), pf.nsparse, pf.des_len, pf.theta.data(),
                                    pf.mm.data(), pf.coeff.data());
+}
+
+extern "C" int gapcu_ctx_set_cluster(gapcu_ctx *c, int ctas_per_centre) {
+    if (!c || !(ctas_per_centre == 0 || ctas_per_centre == 1 || ctas_per_centre == 2 || ctas_per_centre == 4))
+        return fail(GAPCU_EARG, "CTAs per centre must be 0 (automatic), 1, 2 or 4");
+    c->cluster = ctas_per_centre;
+    return 0;
 }
 
 extern "C" int gapcu_ctx_set_pipeline(gapcu_ctx *c, int mode) {
@@ -519,9 +528,10 @@ static int read_flags(gapcu_ctx *c) {
 
 // kernel arguments of the centre kernel for the context's current state; picks the pipeline
 // and the shared-memory budget (triplet-list capacity, private accumulator sets)
-static int make_centre_args(gapcu_ctx *c, int lgrad, int pcap, CentreArgs *out, bool *fused_out) {
+static int make_centre_args(gapcu_ctx *c, int lgrad, int pcap, CentreArgs *out, bool *fused_out, int cs = 1) {
     CentreArgs a;
     memset(&a, 0, sizeof a);
+    a.cs = cs;
     a.plan = c->plan_dev();
     a.cls = c->class_tab();
     a.structs = c->d_structs.p; a.sid = c->d_sid.p; a.pos = c->d_pos.p; a.wgt = c->d_wgt.p;
@@ -619,7 +629,22 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
         for (int cap = top; cap >= 128; cap >>= 1) {
             const int idx = cap == 128 ? 0 : cap == 256 ? 1 : cap == 512 ? 2 : 3;
             Tier t;
-            if ((rc = make_centre_args(c, lgrad, cap == top ? c->pcap : cap, &t.a, &fused))) return rc;
+            // CTAs per centre (thread-block cluster of the fused kernel): a launch with fewer centres
+            // than CTA slots spreads every centre over 2 or 4 CTAs.  The host knows the number of
+            // centres of a tier only as an upper bound (the number of atoms); gapcu_ctx_set_cluster /
+            // GAPCU_CLUSTER=1|2|4 overrides.
+            int cs = 1;
+            {
+                const int forced = c->cluster;
+                if (!c->sm_count) cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
+                const int slots = c->sm_count * (cap == 128 ? 3 : cap == 256 ? 2 : 1);   // resident CTAs of this tier's instance
+                if (forced == 1 || forced == 2 || forced == 4) cs = forced;
+                // no tier can hold more centres than there are atoms.  Measured on B200 (tools/cluster_probe.py):
+                // the split pays while the CTAs of a launch do not have to share SMs more than two at a time
+                else if (c->ntot * 4 <= c->sm_count) cs = 4;
+                else if (c->ntot <= c->sm_count && c->ntot * 2 <= slots) cs = 2;
+            }
+            if ((rc = make_centre_args(c, lgrad, cap == top ? c->pcap : cap, &t.a, &fused, cs))) return rc;
             t.a.q_begin = cap == top ? nullptr : &F->n_gt[idx];
             t.a.q_end = cap == 128 ? &F->n_centres : &F->n_gt[idx - 1];
             tiers.push_back(t);

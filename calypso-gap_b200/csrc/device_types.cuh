@@ -82,7 +82,7 @@ struct ClassTab {
 
 // shared-memory layout of the centre kernel (byte offsets), computed on the host
 struct SmemLayout {
-    int t32, t2, galpha, gd, x, r, ir, w, fc, dfc, gw, sG, sdu, xs, sW, acc, red, S, scratch, ctl, rad, nc, total;
+    int t32, t2, galpha, gd, x, r, ir, w, fc, dfc, gw, sG, gx, sdu, xs, sW, acc, red, S, scratch, ctl, rad, nc, total;
 };
 
 // Everything the per-centre kernel needs.
@@ -111,6 +111,7 @@ struct CentreArgs {
     int npa;                    // private accumulator sets in backward: NW, or 1 (= shared + atomics)
     int lgrad;
     int variant;                // experiment switches (environment GAPCU_VARIANT), 0 in production
+    int cs;                     // CTAs per centre (thread-block cluster size of the fused kernel): 1, 2 or 4
     double *G;                  // [NT][D]   descriptors out (forward / fused; may be null in fused)
     const double *dEdG;         // [NT][D]   backward in (MODE_BWD)
     double *dEdG_out;           // [NT][D]   fused: dE/dG out (may be null)

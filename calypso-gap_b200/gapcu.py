@@ -24,7 +24,7 @@ _lib = None
 SYMBOLS = [
     "gapcu_last_error", "gapcu_calc", "gapcu_read", "gapcu_bond", "gapcu_car2acsf_table", "gapcu_print_last_error",
     "gapcu_device_count", "gapcu_ctx_create", "gapcu_ctx_destroy", "gapcu_ctx_load_potential",
-    "gapcu_ctx_set_potential", "gapcu_ctx_set_pipeline", "gapcu_nccl_unique_id", "gapcu_ctx_nccl_init",
+    "gapcu_ctx_set_potential", "gapcu_ctx_set_pipeline", "gapcu_ctx_set_cluster", "gapcu_nccl_unique_id", "gapcu_ctx_nccl_init",
     "gapcu_ctx_set_domain", "gapcu_ctx_set_structures", "gapcu_ctx_compute", "gapcu_ctx_fetch",
     "gapcu_ctx_fetch_descriptors", "gapcu_ctx_variance", "gapcu_ctx_fetch_neighbors", "gapcu_ctx_time_compute", "gapcu_stage_name",
     "gapcu_ctx_work_counters", "gapcu_ctx_balance", "gapcu_fp64_peaks",
@@ -55,6 +55,7 @@ def lib():
         L.gapcu_ctx_set_structures.argtypes = [_vp, C.c_int, _ip, _ip, _dp, _dp, C.c_double]
         L.gapcu_ctx_compute.argtypes = [_vp, C.c_int]
         L.gapcu_ctx_set_pipeline.argtypes = [_vp, C.c_int]
+        L.gapcu_ctx_set_cluster.argtypes = [_vp, C.c_int]
         L.gapcu_nccl_unique_id.argtypes = [C.c_char_p]
         L.gapcu_ctx_nccl_init.argtypes = [_vp, C.c_int, C.c_int, C.c_char_p]
         L.gapcu_ctx_set_domain.argtypes = [_vp] + [C.c_int] * 6
@@ -129,6 +130,10 @@ class Context:
     def set_pipeline(self, mode):
         """'auto' | 'split' (K2 -> DMMA GPR -> K4) | 'fused' (one centre kernel)."""
         _check(lib().gapcu_ctx_set_pipeline(self.h, {"auto": 0, "split": 1, "fused": 2}[mode]))
+
+    def set_cluster(self, ctas_per_centre):
+        """CTAs (one thread-block cluster) per centre atom in the fused kernel: 0 = automatic, 1, 2, 4."""
+        _check(lib().gapcu_ctx_set_cluster(self.h, int(ctas_per_centre)))
 
     def nccl_init(self, world, rank, unique_id):
         _check(lib().gapcu_ctx_nccl_init(self.h, int(world), int(rank), unique_id))

@@ -98,6 +98,14 @@ int gapcu_ctx_set_potential(gapcu_ctx *ctx, int nspecies, const int *z, const do
  * settable with the environment variable GAPCU_PIPELINE=split|fused. */
 int gapcu_ctx_set_pipeline(gapcu_ctx *ctx, int mode);
 
+/* CTAs per centre atom of the fused kernel (a thread-block cluster shares one centre: each CTA
+ * takes a part of the neighbour-pair range, partial descriptors and gradients are combined
+ * through distributed shared memory in rank order).  0 = automatic (default: 2 or 4 when the
+ * launch has fewer centres than the device has SMs, e.g. the 64-atom cells of an MD run;
+ * otherwise 1), or 1, 2, 4.  Also settable with GAPCU_CLUSTER=1|2|4.  Results differ from the
+ * one-CTA evaluation only by summation order (~1e-15 relative). */
+int gapcu_ctx_set_cluster(gapcu_ctx *ctx, int ctas_per_centre);
+
 /* Spatial decomposition of ONE large structure over the ranks of a node (SURVEY.md 8(e),
  * BASELINE config 4).  Every rank holds all positions; the cell is cut into g0 x g1 x g2
  * bricks in fractional coordinates; this rank evaluates the centres of brick (m0,m1,m2),

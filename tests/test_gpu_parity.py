@@ -494,3 +494,50 @@ def test_batch_lgrad_false_and_mixed_sizes(ctx, shipped_pot):
     for i, (cell, pos, z) in enumerate(structs):
         w = shipped_pot.calc_sparse(z, cell, pos, 6.0, False)["energy"]
         assert abs(e[i] - w) <= E_TOL * abs(w)
+
+
+@pytest.mark.parametrize("cs", [1, 2, 4])
+def test_cluster_sizes_agree(shipped_pot, golden_frames, cs):
+    """1, 2 or 4 CTAs (one thread-block cluster) per centre atom: the pair range, the radial
+    functions and the gradient accumulators are split over the cluster and recombined through
+    distributed shared memory in rank order.  Every setting must meet the gates against the
+    golden trajectory and the oracle (64-atom cell, a self-image cell, the four capacity tiers
+    incl. chunked triplet lists and ~840 neighbours per atom), be bit-reproducible, and the
+    default (automatic) choice must give the same numbers as the explicit one it selects."""
+    import gapcu
+    c = gapcu.Context(0)
+    c.set_cluster(cs)
+    c.load_potential(os.path.join(GOLDEN, "gap_parameters"))
+    g = golden_frames
+    r = c.evaluate(g["numbers"], g["cell"][3], g["positions"][3], 6.0, True)
+    _cmp(r, {"energy": g["energy"][3], "forces": g["forces"][3], "stress": g["stress"][3]})
+    r2 = c.evaluate(g["numbers"], g["cell"][3], g["positions"][3], 6.0, True)
+    assert r2["energy"] == r["energy"] and np.array_equal(r2["forces"], r["forces"]) and np.array_equal(r2["stress"], r["stress"])
+    assert np.array_equal(c.evaluate(g["numbers"], g["cell"][3], g["positions"][3], 6.0, False)["forces"], np.zeros((64, 3)))
+    cell, pos, z = random_candidate(3001, species=(5, 6))
+    _cmp(c.evaluate(z, cell, pos, 6.0, True), shipped_pot.calc_sparse(z, cell, pos, 6.0, True))
+    rng = np.random.default_rng(22)
+    structs = []
+    for edge, n in ((9.0, 30), (6.0, 30), (5.2, 20), (2.05, 8)):
+        if n == 8:
+            p = np.array([[i, j, k] for i in range(2) for j in range(2) for k in range(2)], float) * 1.02 + 0.05
+            p += rng.normal(0, 0.03, p.shape)
+        else:
+            gr = np.stack(np.meshgrid(*[np.arange(4)] * 3, indexing="ij"), -1).reshape(-1, 3)[:n]
+            p = (gr + 0.5) * (edge / 4) + rng.normal(0, 0.05, (n, 3))
+        structs.append((np.eye(3) * edge, p, rng.choice(np.array([5, 6], np.int32), n)))
+    c.set_structures([t[2] for t in structs], [t[0] for t in structs], [t[1] for t in structs], 6.0)
+    c.compute(True)
+    e, f, s = c.fetch()
+    off = 0
+    for i, (cl, p, zz) in enumerate(structs):
+        _cmp({"energy": e[i], "forces": f[off:off + len(p)], "stress": s[i]}, shipped_pot.calc_sparse(zz, cl, p, 6.0, True))
+        off += len(p)
+    if cs == 2:
+        # 64 centres on 148 SMs: the automatic choice is two CTAs per centre
+        a = gapcu.Context(0)
+        a.load_potential(os.path.join(GOLDEN, "gap_parameters"))
+        ra = a.evaluate(g["numbers"], g["cell"][3], g["positions"][3], 6.0, True)
+        assert ra["energy"] == r["energy"] and np.array_equal(ra["forces"], r["forces"])
+        a.close()
+    c.close()

@@ -9,7 +9,8 @@ import gapcu  # noqa: E402
 from structures import cubic_supercell  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-cell, pos, z = cubic_supercell(10, 10, 10)
+dims = tuple(int(x) for x in sys.argv[2:5]) if len(sys.argv) >= 5 else (10, 10, 10)
+cell, pos, z = cubic_supercell(*dims)
 c = gapcu.Context(0)
 c.load_potential(os.path.join(ROOT, "bench_data", "gap_parameters_c2"))
 c.set_structures(z, cell, pos, 6.0)
