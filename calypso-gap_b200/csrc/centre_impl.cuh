@@ -361,13 +361,16 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         }
         if (lane == 0) ctl->cntw[wid] = cnt;
         __syncthreads();
-        if (wid == 0) {
+        {
             // lane o <-> bucket v = ncls - o (heavy buckets first); totals over warps, then an
-            // exclusive scan over the lanes gives every bucket its place in S
+            // exclusive scan over the lanes gives every bucket its place in S.  Every warp does
+            // this (cheap) scan for itself and keeps only its own row of running positions, so
+            // the scatter below needs no second block barrier; warp 0 also publishes the list's
+            // control block, which is read after the barrier that ends build_list.
             const int o = lane, v = ncls - lane;
-            int t = 0;
+            int t = 0, before = 0;   // items of bucket v in all warps / in the warps before this one
             if (o < ncls)
-                for (int w = 0; w < NW; w++) { const int h = ctl->hw[w][v]; ctl->basew[w][v] = t; t += h; }
+                for (int w = 0; w < NW; w++) { const int h = ctl->hw[w][v]; before = w == wid ? t : before; t += h; }
             const int nb = (t + 31) >> 5;
             int off = t, bp = nb;
 #pragma unroll
@@ -376,15 +379,17 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 if (lane >= d) { off += yo; bp += yb; }
             }
             // off/bp are inclusive sums over order slots 0..o
-            if (o < ncls) {
-                ctl->tot[v] = t;
-                ctl->obase[o] = off - t; ctl->ocnt[o] = t; ctl->obq[o] = nb; ctl->obp[o] = bp - nb;
-                for (int w = 0; w < NW; w++) ctl->basew[w][v] += off - t;
-                ctl->npre[v - 1] = off;   // items with bucket > v-1, i.e. bucket >= v: slots 0..o
+            if (o < ncls) ctl->basew[wid][v] = off - t + before;
+            if (wid == 0) {
+                if (o < ncls) {
+                    ctl->tot[v] = t;
+                    ctl->obase[o] = off - t; ctl->ocnt[o] = t; ctl->obq[o] = nb; ctl->obp[o] = bp - nb;
+                    ctl->npre[v - 1] = off;   // items with bucket > v-1, i.e. bucket >= v: slots 0..o
+                }
+                if (o == ncls - 1 || (ncls == 0 && o == 0)) { ctl->obp[ncls] = bp; ctl->TB = bp; ctl->nkept = off; }
             }
-            if (o == ncls - 1 || (ncls == 0 && o == 0)) { ctl->obp[ncls] = bp; ctl->TB = bp; ctl->nkept = off; }
             __syncwarp();
-            if (count_work && lane == 0) {
+            if (wid == 0 && count_work && lane == 0) {
                 wk_trip += ctl->nkept;
                 for (int c = 0; c < ncls; c++) {
                     const int g0 = GRP_BEGIN(a, c), g1 = GRP_BEGIN(a, c + 1);
@@ -397,7 +402,6 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 }
             }
         }
-        __syncthreads();
         for (int t0 = 0; t0 < cnt; t0 += 32) {
             const int t = t0 + lane;
             const bool act = t < cnt;

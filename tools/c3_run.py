@@ -9,6 +9,7 @@ algorithm's CPU time on the first K structures (--cpu K; oracle, test infrastruc
 parity check of the first K structures against the oracle (--check K)."""
 import json
 import os
+import pickle
 import sys
 import time
 from multiprocessing import Pool
@@ -42,11 +43,25 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    # every rank generates only what it needs to know the costs: all cells and atom counts are
-    # needed for the partition, so the structures are generated once per rank in parallel
+    # rank 0 generates the batch on all host cores and hands it to the other ranks of the node
+    # (the partition needs every cell and atom count)
     t0 = time.time()
-    with Pool(min(os.cpu_count() or 1, 32) // max(1, world) or 1) as pool:
-        structs = pool.map(_make, range(nstruct), chunksize=16)
+    share = "/dev/shm/c3_structs_%d_%s.pkl" % (nstruct, os.environ.get("MASTER_PORT", "0"))
+    if rank == 0:
+        with Pool(min(os.cpu_count() or 1, 64)) as pool:
+            structs = pool.map(_make, range(nstruct), chunksize=8)
+        if world > 1:
+            with open(share + ".tmp", "wb") as fh:
+                pickle.dump(structs, fh)
+            os.replace(share + ".tmp", share)
+    if world > 1:
+        dist.barrier()
+        if rank:
+            with open(share, "rb") as fh:
+                structs = pickle.load(fh)
+        dist.barrier()
+        if rank == 0:
+            os.remove(share)
     t_gen = time.time() - t0
     costs = [batch.estimate_cost(len(p), abs(np.linalg.det(c))) for c, p, _ in structs]
     mine = batch.partition(costs, world)[rank]
