@@ -923,10 +923,21 @@ std::mutex g_mu;
 gapcu_ctx *g_ctx = nullptr;
 struct FileId { dev_t dev = 0; ino_t ino = 0; off_t size = -1; long mt_s = 0, mt_ns = 0; } g_file;
 
+// devices of the drop-in entry points (gapcu_set_devices); empty: GAPCU_DEVICE or device 0
+std::vector<int> g_devices;
+// gapcu_calc_batch: one context per device, each with the whole ./gap_parameters loaded
+struct BatchSlot { int device = -1; gapcu_ctx *ctx = nullptr; FileId file; };
+std::vector<BatchSlot> g_batch;
+
+int default_device() {
+    if (!g_devices.empty()) return g_devices[0];
+    if (const char *e = getenv("GAPCU_DEVICE")) return atoi(e);
+    return 0;
+}
+
 int default_ctx(gapcu_ctx **out) {
     if (!g_ctx) {
-        int dev = 0;
-        if (const char *e = getenv("GAPCU_DEVICE")) dev = atoi(e);
+        const int dev = default_device();
         g_ctx = gapcu_ctx_create(dev);
         if (!g_ctx) return g_err.find("no CUDA device") != std::string::npos ? GAPCU_ENODEV : GAPCU_ECUDA;
     }
@@ -1015,6 +1026,112 @@ extern "C" int gapcu_calc(int na, const int *species, const double *lat, const d
     for (int q = 0; q < 6; q++) stress[q] = h_out[1 + q];
     memcpy(force, h_f, b_f);
     if (variance) *variance = 0.0;  // gap_calc.f90:206
+    return 0;
+}
+
+extern "C" int gapcu_set_devices(int n, const int *devices) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const int have = gapcu_device_count();
+    if (have <= 0) return fail(GAPCU_ENODEV, "no CUDA device: gapcu has no CPU fallback");
+    if (n < 0 || (n > 0 && !devices)) return fail(GAPCU_EARG, "bad device list");
+    std::vector<int> want(devices, devices + n);
+    for (size_t k = 0; k < want.size(); k++) {
+        if (want[k] < 0 || want[k] >= have) return fail(GAPCU_EARG, "device " + std::to_string(want[k]) + " does not exist");
+        for (size_t q = 0; q < k; q++)
+            if (want[q] == want[k]) return fail(GAPCU_EARG, "device " + std::to_string(want[k]) + " listed twice");
+    }
+    g_devices = want;
+    // contexts on devices that are no longer wanted go away; the others keep their state
+    if (g_ctx && g_ctx->device != default_device()) { gapcu_ctx_destroy(g_ctx); g_ctx = nullptr; g_file = FileId(); }
+    for (BatchSlot &b : g_batch) if (b.ctx) gapcu_ctx_destroy(b.ctx);
+    g_batch.clear();
+    return 0;
+}
+
+// A CALYPSO-style batch through the drop-in side channel: the potential (SF table AND GPR
+// block) is ./gap_parameters, as for FGAP_READ + FGAP_CALC; the structures are independent,
+// so they are dealt to the devices by estimated cost and every device runs its shard as one
+// batched launch sequence on its own context and stream, with no inter-device traffic.
+extern "C" int gapcu_calc_batch(int nstruct, const int *natoms, const int *species, const double *lat, const double *pos,
+                                double rcut, int lgrad, double *ene, double *force, double *stress) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (nstruct <= 0 || !natoms || !species || !lat || !pos) return fail(GAPCU_EARG, "bad batch arguments");
+    for (int s = 0; s < nstruct; s++) if (natoms[s] <= 0) return fail(GAPCU_EARG, "a structure of the batch has no atoms");
+    if (gapcu_device_count() <= 0) return fail(GAPCU_ENODEV, "no CUDA device: gapcu has no CPU fallback");
+    std::vector<int> devs = g_devices;
+    if (devs.empty()) devs.push_back(default_device());
+    if (g_batch.size() != devs.size()) {
+        for (BatchSlot &b : g_batch) if (b.ctx) gapcu_ctx_destroy(b.ctx);
+        g_batch.assign(devs.size(), BatchSlot());
+    }
+    struct stat st;
+    if (stat("gap_parameters", &st) != 0) return fail(GAPCU_EFILE, "gap_parameters file does not exist!");
+    for (size_t d = 0; d < devs.size(); d++) {
+        BatchSlot &b = g_batch[d];
+        if (!b.ctx) { b.ctx = gapcu_ctx_create(devs[d]); b.device = devs[d]; b.file = FileId(); }
+        if (!b.ctx) return GAPCU_ECUDA;
+        const bool same = b.ctx->have_sf && b.ctx->have_gpr && st.st_dev == b.file.dev && st.st_ino == b.file.ino &&
+                          st.st_size == b.file.size && st.st_mtim.tv_sec == b.file.mt_s && st.st_mtim.tv_nsec == b.file.mt_ns;
+        if (!same) {
+            int rc = gapcu_ctx_load_potential(b.ctx, "gap_parameters");
+            if (rc) return rc;
+            b.file.dev = st.st_dev; b.file.ino = st.st_ino; b.file.size = st.st_size;
+            b.file.mt_s = st.st_mtim.tv_sec; b.file.mt_ns = st.st_mtim.tv_nsec;
+        }
+    }
+    // greedy longest-processing-time deal by N * P^2 (P = mean neighbour count; the triplet work dominates)
+    const int nd = (int)devs.size();
+    std::vector<size_t> off(nstruct + 1, 0);
+    for (int s = 0; s < nstruct; s++) off[s + 1] = off[s] + (size_t)natoms[s];
+    std::vector<double> cost(nstruct);
+    for (int s = 0; s < nstruct; s++) {
+        const double *L = lat + 9 * (size_t)s;
+        const double vol = std::fabs(L[0] * (L[4] * L[8] - L[5] * L[7]) - L[1] * (L[3] * L[8] - L[5] * L[6]) + L[2] * (L[3] * L[7] - L[4] * L[6]));
+        const double p = 4.0 / 3.0 * 3.141592653589793 * rcut * rcut * rcut * natoms[s] / std::max(vol, 1e-30);
+        cost[s] = natoms[s] * p * p;
+    }
+    std::vector<int> order(nstruct);
+    for (int s = 0; s < nstruct; s++) order[s] = s;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+    std::vector<std::vector<int>> shard(nd);
+    std::vector<double> load(nd, 0.0);
+    for (int s : order) {
+        int best = 0;
+        for (int d = 1; d < nd; d++) if (load[d] < load[best]) best = d;
+        shard[best].push_back(s);
+        load[best] += cost[s];
+    }
+    struct Packed { std::vector<int> na, sp; std::vector<double> lat, pos, e, f, s; };
+    std::vector<Packed> pk(nd);
+    for (int d = 0; d < nd; d++) {
+        std::sort(shard[d].begin(), shard[d].end());
+        if (shard[d].empty()) continue;
+        Packed &k = pk[d];
+        for (int s : shard[d]) {
+            k.na.push_back(natoms[s]);
+            k.sp.insert(k.sp.end(), species + off[s], species + off[s + 1]);
+            k.lat.insert(k.lat.end(), lat + 9 * (size_t)s, lat + 9 * (size_t)s + 9);
+            k.pos.insert(k.pos.end(), pos + 3 * off[s], pos + 3 * off[s + 1]);
+        }
+        int rc = gapcu_ctx_set_structures(g_batch[d].ctx, (int)k.na.size(), k.na.data(), k.sp.data(), k.lat.data(), k.pos.data(), rcut);
+        if (!rc) rc = gapcu_ctx_compute(g_batch[d].ctx, lgrad ? 1 : 0);   // asynchronous: the devices run side by side
+        if (rc) return rc;
+    }
+    for (int d = 0; d < nd; d++) {
+        if (shard[d].empty()) continue;
+        Packed &k = pk[d];
+        k.e.resize(k.na.size()); k.f.resize(k.pos.size()); k.s.resize(6 * k.na.size());
+        int rc = gapcu_ctx_fetch(g_batch[d].ctx, k.e.data(), k.f.data(), k.s.data());
+        if (rc) return rc;
+        size_t fo = 0;
+        for (size_t q = 0; q < shard[d].size(); q++) {
+            const int s = shard[d][q];
+            if (ene) ene[s] = k.e[q];
+            if (stress) memcpy(stress + 6 * (size_t)s, k.s.data() + 6 * q, 6 * sizeof(double));
+            if (force) memcpy(force + 3 * off[s], k.f.data() + fo, 3 * sizeof(double) * natoms[s]);
+            fo += 3 * (size_t)natoms[s];
+        }
+    }
     return 0;
 }
 

@@ -23,6 +23,7 @@ _lib = None
 # every symbol include/gapcu.h declares (tests check the library exports them all)
 SYMBOLS = [
     "gapcu_last_error", "gapcu_calc", "gapcu_read", "gapcu_bond", "gapcu_car2acsf_table", "gapcu_print_last_error",
+    "gapcu_set_devices", "gapcu_calc_batch",
     "gapcu_device_count", "gapcu_ctx_create", "gapcu_ctx_destroy", "gapcu_ctx_load_potential",
     "gapcu_ctx_set_potential", "gapcu_ctx_set_pipeline", "gapcu_ctx_set_cluster", "gapcu_nccl_unique_id", "gapcu_ctx_nccl_init",
     "gapcu_ctx_set_domain", "gapcu_ctx_set_structures", "gapcu_ctx_compute", "gapcu_ctx_fetch",
@@ -67,6 +68,8 @@ def lib():
         L.gapcu_fp64_peaks.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.gapcu_calc.argtypes = [C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_double, C.c_int,
                                  _vp, _vp, _vp, _vp]
+        L.gapcu_set_devices.argtypes = [C.c_int, _vp]
+        L.gapcu_calc_batch.argtypes = [C.c_int, _vp, _vp, _vp, _vp, C.c_double, C.c_int, _vp, _vp, _vp]
         L.gapcu_bond.argtypes = [C.c_int, _vp, _vp, _vp, C.c_double, C.POINTER(C.c_double)]
         _lib = L
     return _lib
@@ -205,6 +208,27 @@ class Context:
         a = C.c_double(); b = C.c_double()
         _check(lib().gapcu_fp64_peaks(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+
+def set_devices(devices):
+    """Devices of the drop-in entry points (gapcu_calc on the first, gapcu_calc_batch over all)."""
+    d = np.ascontiguousarray(list(devices), np.int32)
+    _check(lib().gapcu_set_devices(len(d), d.ctypes.data))
+
+
+def calc_batch(species_list, lat_list, pos_list, rcut=6.0, lgrad=True):
+    """Independent structures through the drop-in side channel (./gap_parameters in the working
+    directory holds the whole potential), sharded over the devices of set_devices().  Returns
+    (energies[ns], list of forces[n_i, 3], stresses[ns, 6])."""
+    natoms = np.array([len(p) for p in pos_list], np.int32)
+    species = np.ascontiguousarray(np.concatenate([np.asarray(s).ravel() for s in species_list]), np.int32)
+    lat = np.ascontiguousarray(np.stack([np.asarray(l, np.float64) for l in lat_list]))
+    pos = np.ascontiguousarray(np.concatenate([np.asarray(p, np.float64).reshape(-1, 3) for p in pos_list]))
+    ene = np.zeros(len(natoms)); force = np.zeros((int(natoms.sum()), 3)); stress = np.zeros((len(natoms), 6))
+    _check(lib().gapcu_calc_batch(len(natoms), natoms.ctypes.data, species.ctypes.data, lat.ctypes.data, pos.ctypes.data,
+                                  float(rcut), int(bool(lgrad)), ene.ctypes.data, force.ctypes.data, stress.ctypes.data))
+    offs = np.concatenate([[0], np.cumsum(natoms)])
+    return ene, [force[offs[k]:offs[k + 1]] for k in range(len(natoms))], stress
 
 
 def nccl_unique_id():

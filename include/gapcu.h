@@ -73,6 +73,23 @@ int gapcu_bond(int na, const double *lat, const int *elements, const double *pos
 int gapcu_car2acsf_table(int na, int max_neighbor, int nf, const double *pos, const double *neighbor,
                          const int *neighbor_count, int lgrad, double *xx, double *dxdy, double *strs);
 
+/* ---- additive drop-in entry points (same ./gap_parameters side channel) --- */
+
+/* Devices used by the entry points of this section and the previous one (default: device
+ * GAPCU_DEVICE or 0).  gapcu_calc / gapcu_bond / gapcu_car2acsf_table run on devices[0];
+ * gapcu_calc_batch shards over all of them.  n = 0 restores the default. */
+int gapcu_set_devices(int n, const int *devices);
+
+/* A batch of independent structures, CALYPSO-search style (what gappy/tools/cgg2.py:111-115
+ * does with one process per structure): nstruct structures in the C-order layout of
+ * gapcu_ctx_set_structures, the potential -- SF table AND GPR block -- read from
+ * ./gap_parameters (parsed once per device, re-read when the file changes).  Structures are
+ * dealt to the devices by estimated cost, every device evaluates its shard as one batched
+ * launch sequence, concurrently, with no inter-device communication.  ene[nstruct],
+ * force[sum natoms][3], stress[nstruct][6] (xx yy zz xy yz xz, GPa); any may be NULL. */
+int gapcu_calc_batch(int nstruct, const int *natoms, const int *species, const double *lat, const double *pos,
+                     double rcut, int lgrad, double *ene, double *force, double *stress);
+
 /* prints gapcu_last_error() on stdout the way the reference prints before STOP */
 void gapcu_print_last_error(void);
 

@@ -541,3 +541,42 @@ def test_cluster_sizes_agree(shipped_pot, golden_frames, cs):
         assert ra["energy"] == r["energy"] and np.array_equal(ra["forces"], r["forces"])
         a.close()
     c.close()
+
+
+def test_calc_batch_dropin_entry_point(shipped_pot, golden_frames, bc_structure, monkeypatch):
+    """gapcu_calc_batch: independent structures through the reference's side channel (the whole
+    potential is ./gap_parameters), dealt to the devices of gapcu_set_devices.  Results must equal
+    the one-structure evaluations to rounding (same kernels, same per-structure reductions) and
+    meet the gates against the oracle; with two devices the shards run side by side."""
+    import gapcu
+    monkeypatch.chdir(GOLDEN)
+    g = golden_frames
+    structs = [(g["numbers"], g["cell"][0], g["positions"][0]), (bc_structure["numbers"], bc_structure["cell"], bc_structure["positions"])]
+    for seed in (3000, 3002, 3003):
+        cell, pos, z = random_candidate(seed, species=(5, 6))
+        structs.append((z, cell, pos))
+    one = gapcu.Context(0)
+    one.load_potential("gap_parameters")
+    singles = [one.evaluate(z, cell, pos, 6.0, True) for z, cell, pos in structs]
+    one.close()
+    device_sets = [[0]] + ([[0, 1], [1]] if gapcu.device_count() >= 2 else [])
+    try:
+        for devs in device_sets:
+            gapcu.set_devices(devs)
+            e, f, s = gapcu.calc_batch([t[0] for t in structs], [t[1] for t in structs], [t[2] for t in structs], 6.0, True)
+            for k, (z, cell, pos) in enumerate(structs):
+                # not bit for bit: a lone 64-atom structure is spread over two CTAs per centre, the batch is not
+                assert abs(e[k] - singles[k]["energy"]) <= 1e-13 * abs(e[k])
+                assert np.abs(f[k] - singles[k]["forces"]).max() <= 1e-12 * np.abs(f[k]).max()
+                assert np.abs(s[k] - singles[k]["stress"]).max() <= 1e-12 * np.abs(s[k]).max()
+                if k >= 2:
+                    _cmp({"energy": e[k], "forces": f[k], "stress": s[k]}, shipped_pot.calc_sparse(z, cell, pos, 6.0, True))
+            _cmp({"energy": e[0], "forces": f[0], "stress": s[0]}, {"energy": g["energy"][0], "forces": g["forces"][0], "stress": g["stress"][0]})
+            e0, f0, _ = gapcu.calc_batch([t[0] for t in structs], [t[1] for t in structs], [t[2] for t in structs], 6.0, False)
+            assert np.array_equal(e0, e) and all(not fk.any() for fk in f0)
+        with pytest.raises(gapcu.GapcuError):
+            gapcu.set_devices([gapcu.device_count()])
+        with pytest.raises(gapcu.GapcuError):
+            gapcu.set_devices([0, 0])
+    finally:
+        gapcu.set_devices([])
