@@ -357,7 +357,9 @@ static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, con
         for (int d = 0; d < 3; d++) {
             sd.nabc[d] = ci.nabc[d];
             sd.nbin[d] = ci.nbin[d];
-            sd.mscan[d] = (ci.nbin[d] > 1) ? 1 : ci.nabc[d] + 1;
+            // layers of bins scanned either side (potential.cpp:make_cell; the bin count may have been reduced above)
+            const double w = sd.spacing[d] / ci.nbin[d], full = rcut * (1.0 + 1e-9);
+            sd.mscan[d] = w >= full ? 1 : w >= 0.5 * full ? 2 : ci.nabc[d] + 1;
         }
         sd.atom_off = aoff; sd.natoms = natoms[s]; sd.bin_off = boff; sd.nbins = (int)cells;
         aoff += natoms[s]; boff += (int)cells;

@@ -19,11 +19,27 @@ constexpr double GPA2EVPANG = 6.24219e-3;  // gap_calc.f90:9
 
 constexpr int GT = 128;  // threads per atom in k_gather: one mirror lookup per thread for P <= 128
 
+// arguments of the per-structure reduction that rides along in k_gather's grid (see below)
+struct FinArgs {
+    const double *eatom, *vir;
+    double *partial, *out8;
+    int lgrad, nchunk, nstruct;
+};
+__device__ void finalize_partial(const StructDev *structs, const FinArgs &f, const unsigned char *role, int chunk, int st);
+
+// Grid: ntot CTAs gather the forces (one atom each), followed by nchunk * nstruct CTAs that
+// reduce E and the strs contraction per structure.  Both parts read only what the centre
+// kernel wrote, so they share one launch (a separate launch costs ~7 us on small inputs).
 __global__ void __launch_bounds__(GT)
 k_gather(const StructDev *structs, const int *sid, int ntot, int cap, const uint64_t *nbr_keys,
          const int *nbr_cnt, const double *fpair, const double *gself, double *force,
-         const unsigned char *role, const int *active, const DevFlags *flags) {
+         const unsigned char *role, const int *active, const DevFlags *flags, const int ngather, const FinArgs fin) {
     __shared__ double red[GT / 32][3];
+    if ((int)blockIdx.x >= ngather) {
+        const int r = blockIdx.x - ngather;
+        finalize_partial(structs, fin, role, r % fin.nchunk, r / fin.nchunk);
+        return;
+    }
     const int slot_i = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (slot_i >= (active ? flags->n_active : ntot)) return;
@@ -96,16 +112,17 @@ __device__ __forceinline__ void write_out8(const double *s, const StructDev &sd,
     o[7] = 0.0;        // variance (gap_calc.f90:206)
 }
 
-__global__ void __launch_bounds__(256)
-k_finalize_partial(const StructDev *structs, const double *eatom, const double *vir, int lgrad, double *partial,
-                   int nchunk, const unsigned char *role, double *out8) {
-    __shared__ double red[8][7];
+__device__ void finalize_partial(const StructDev *structs, const FinArgs &f, const unsigned char *role, const int chunk, const int st) {
+    __shared__ double red[GT / 32][7];
     __shared__ double tot[8];
-    const StructDev &sd = structs[blockIdx.y];
+    const StructDev &sd = structs[st];
+    const double *eatom = f.eatom, *vir = f.vir;
+    double *partial = f.partial, *out8 = f.out8;
+    const int lgrad = f.lgrad, nchunk = f.nchunk;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int t0 = blockIdx.x * FIN_CHUNK, t1 = min(sd.natoms, t0 + FIN_CHUNK);
+    const int t0 = chunk * FIN_CHUNK, t1 = min(sd.natoms, t0 + FIN_CHUNK);
     double v[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int t = t0 + tid; t < t1; t += 256) {
+    for (int t = t0 + tid; t < t1; t += GT) {
         const int i = sd.atom_off + t;
         if (role && role[i] != 2) continue;   // decomposed run: partial sums over this rank's centres
         v[0] += eatom[i];
@@ -123,13 +140,13 @@ k_finalize_partial(const StructDev *structs, const double *eatom, const double *
     __syncthreads();
     if (tid < 7) {
         double x = 0.0;
-        for (int w = 0; w < 8; w++) x += red[w][tid];
-        partial[((size_t)blockIdx.y * nchunk + blockIdx.x) * 8 + tid] = x;
+        for (int w = 0; w < GT / 32; w++) x += red[w][tid];
+        partial[((size_t)st * nchunk + chunk) * 8 + tid] = x;
         tot[tid] = x;
     }
     if (nchunk == 1) {   // small structures: this CTA already holds the totals, no second launch
         __syncthreads();
-        if (tid == 0) write_out8(tot, sd, out8 + (size_t)blockIdx.y * 8);
+        if (tid == 0) write_out8(tot, sd, out8 + (size_t)st * 8);
     }
 }
 
@@ -169,13 +186,12 @@ void launch_gather(cudaStream_t st, const StructDev *structs, int nstruct, const
                    const unsigned char *role, const int *active, const DevFlags *flags, double *partial, int max_natoms,
                    long *launches) {
     cudaMemsetAsync(force_soa, 0, sizeof(double) * 3 * (size_t)ntot, st);
-    if (lgrad) {
-        k_gather<<<ntot, GT, 0, st>>>(structs, sid, ntot, cap, nbr_keys, nbr_cnt, fpair, gself, force_soa, role, active,
-                                       flags);
-        if (launches) *launches += 1;
-    }
     const int nchunk = finalize_chunks(max_natoms);
-    k_finalize_partial<<<dim3(nchunk, nstruct), 256, 0, st>>>(structs, eatom, vir, lgrad, partial, nchunk, role, out8);
+    FinArgs fin;
+    fin.eatom = eatom; fin.vir = vir; fin.partial = partial; fin.out8 = out8; fin.lgrad = lgrad; fin.nchunk = nchunk; fin.nstruct = nstruct;
+    const int ngather = lgrad ? ntot : 0;   // without gradients only the reduction CTAs run
+    k_gather<<<ngather + nchunk * nstruct, GT, 0, st>>>(structs, sid, ntot, cap, nbr_keys, nbr_cnt, fpair, gself, force_soa, role,
+                                                         active, flags, ngather, fin);
     if (nchunk > 1) k_finalize<<<nstruct, 32, 0, st>>>(structs, partial, nchunk, out8);
     if (launches) *launches += nchunk > 1 ? 2 : 1;
 }

@@ -211,13 +211,18 @@ CellInfo make_cell(const double *L, double rcut) {
     for (int c = 0; c < 3; c++) {
         double len = std::sqrt(ci.inv[c] * ci.inv[c] + ci.inv[3 + c] * ci.inv[3 + c] + ci.inv[6 + c] * ci.inv[6 + c]);
         double spacing = 1.0 / len;                       // interplanar spacing along direction c
-        int nb = (int)std::floor(spacing / (rcut * (1.0 + 1e-9)));
+        // Bins at least rcut/2 thick, two neighbour layers: atoms whose bins differ by d layers are at
+        // least (d-1) bin widths apart along this direction, so d <= 2 covers rcut; the 5x5x5 block of
+        // half-size bins holds ~3.7 rcut-spheres of candidates instead of the ~6.4 of 3x3x3 full-size ones
+        // (k_neigh tests every candidate with the reference's arithmetic, so candidates are its cost).
+        const double half = 0.5 * rcut * (1.0 + 1e-9), full = rcut * (1.0 + 1e-9);
+        int nb = (int)std::floor(spacing / half);
         if (nb < 1) nb = 1;
         if (nb > 1024) nb = 1024;
         ci.nbin[c] = nb;
-        // bins at least rcut thick need one neighbour layer; a single thin bin is
-        // scanned over every image the reference would visit (plus one for safety)
-        ci.mscan[c] = (spacing / nb >= rcut * (1.0 + 1e-9)) ? 1 : ci.nabc[c] + 1;
+        // a single thinner bin is scanned over every image the reference would visit (plus one for safety)
+        const double w = spacing / nb;
+        ci.mscan[c] = w >= full ? 1 : w >= half ? 2 : ci.nabc[c] + 1;
     }
     return ci;
 }
