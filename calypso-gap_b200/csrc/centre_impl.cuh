@@ -554,6 +554,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         for (int round = 0; round * NW < TB; round++) {
             const int g = round * NW + ((round & 1) ? NW - 1 - wid : wid);
             if (g >= TB) continue;
+            __syncwarp();   // orders this batch's accumulator reads after the previous batch's writes for lanes that sat that one out
             while (o + 1 < ncls && g >= ctl->obp[o + 1]) o++;
             const int v = ncls - o, q = g - ctl->obp[o], Qb = ctl->obq[o], n = ctl->ocnt[o];
             const int idx = lane * Qb + q;  // lanes far apart in the list -> mostly distinct rows
