@@ -289,8 +289,11 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
     const uint32_t angmask = a.cls.angmask;
     // pair range of this CTA: the whole triangle, or one of CS contiguous parts of it
     const int Qall = P * (P - 1) / 2;
-    const int qpart = CS > 1 ? ((Qall + CS - 1) / CS + 31) & ~31 : Qall;
-    const int Qlo = min(Qall, crank * qpart), Qhi = min(Qall, Qlo + qpart);
+    int Qlo = 0, Qhi = Qall;
+    if constexpr (CS > 1) {
+        const int qpart = ((Qall + CS - 1) / CS + 31) & ~31;
+        Qlo = min(Qall, crank * qpart); Qhi = min(Qall, Qlo + qpart);
+    }
     const int Q = Qhi - Qlo;
     const int nchunk = (angmask && Q > 0) ? (Q + lcap - 1) / lcap : 0;
     const int qchunk = nchunk ? ((Q + nchunk - 1) / nchunk + 31) & ~31 : 0;
@@ -361,16 +364,13 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         }
         if (lane == 0) ctl->cntw[wid] = cnt;
         __syncthreads();
-        {
+        if (wid == 0) {
             // lane o <-> bucket v = ncls - o (heavy buckets first); totals over warps, then an
-            // exclusive scan over the lanes gives every bucket its place in S.  Every warp does
-            // this (cheap) scan for itself and keeps only its own row of running positions, so
-            // the scatter below needs no second block barrier; warp 0 also publishes the list's
-            // control block, which is read after the barrier that ends build_list.
+            // exclusive scan over the lanes gives every bucket its place in S
             const int o = lane, v = ncls - lane;
-            int t = 0, before = 0;   // items of bucket v in all warps / in the warps before this one
+            int t = 0;
             if (o < ncls)
-                for (int w = 0; w < NW; w++) { const int h = ctl->hw[w][v]; before = w == wid ? t : before; t += h; }
+                for (int w = 0; w < NW; w++) { const int h = ctl->hw[w][v]; ctl->basew[w][v] = t; t += h; }
             const int nb = (t + 31) >> 5;
             int off = t, bp = nb;
 #pragma unroll
@@ -379,17 +379,15 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 if (lane >= d) { off += yo; bp += yb; }
             }
             // off/bp are inclusive sums over order slots 0..o
-            if (o < ncls) ctl->basew[wid][v] = off - t + before;
-            if (wid == 0) {
-                if (o < ncls) {
-                    ctl->tot[v] = t;
-                    ctl->obase[o] = off - t; ctl->ocnt[o] = t; ctl->obq[o] = nb; ctl->obp[o] = bp - nb;
-                    ctl->npre[v - 1] = off;   // items with bucket > v-1, i.e. bucket >= v: slots 0..o
-                }
-                if (o == ncls - 1 || (ncls == 0 && o == 0)) { ctl->obp[ncls] = bp; ctl->TB = bp; ctl->nkept = off; }
+            if (o < ncls) {
+                ctl->tot[v] = t;
+                ctl->obase[o] = off - t; ctl->ocnt[o] = t; ctl->obq[o] = nb; ctl->obp[o] = bp - nb;
+                for (int w = 0; w < NW; w++) ctl->basew[w][v] += off - t;
+                ctl->npre[v - 1] = off;   // items with bucket > v-1, i.e. bucket >= v: slots 0..o
             }
+            if (o == ncls - 1 || (ncls == 0 && o == 0)) { ctl->obp[ncls] = bp; ctl->TB = bp; ctl->nkept = off; }
             __syncwarp();
-            if (wid == 0 && count_work && lane == 0) {
+            if (count_work && lane == 0) {
                 wk_trip += ctl->nkept;
                 for (int c = 0; c < ncls; c++) {
                     const int g0 = GRP_BEGIN(a, c), g1 = GRP_BEGIN(a, c + 1);
@@ -402,6 +400,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 }
             }
         }
+        __syncthreads();
         for (int t0 = 0; t0 < cnt; t0 += 32) {
             const int t = t0 + lane;
             const bool act = t < cnt;
@@ -659,11 +658,14 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             double v = 0.0;
 #pragma unroll
             for (int w = 0; w < NW; w++) v += s_gw[w * D + k];
-            if (CS > 1) { s_gx[k] = v; continue; }
-            if (FUSED) s_G[k] = v;
-            if (a.G) a.G[(size_t)i * D + k] = v;
+            if constexpr (CS > 1) {
+                s_gx[k] = v;
+            } else {
+                if (FUSED) s_G[k] = v;
+                if (a.G) a.G[(size_t)i * D + k] = v;
+            }
         }
-        if (CS > 1) {
+        if constexpr (CS > 1) {
             // partial descriptors of the cluster's CTAs, added in rank order by every CTA
             cg::cluster_group cl = cg::this_cluster();
             cl.sync();
@@ -832,7 +834,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             backward_list();
         }
         // ---- epilogue: per neighbour gradient, centre gradient, strs contraction ----------
-        if (CS > 1) {
+        if constexpr (CS > 1) {
             cg::this_cluster().sync();   // every CTA's accumulator is final; the lead adds them in rank order
             if (!lead) return;
         }
@@ -840,7 +842,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         for (int s = tid; s < P; s += CT) {
             const double dx = NB2(s, 0).x - xi, dy = NB2(s, 0).y - yi, dz = NB2(s, 1).x - zi;
             double gx = s_acc[s], gy = s_acc[PCAP + s], gz = s_acc[2 * PCAP + s];
-            if (CS > 1) {
+            if constexpr (CS > 1) {
                 cg::cluster_group cl = cg::this_cluster();
 #pragma unroll
                 for (int r = 1; r < CS; r++) {
@@ -887,7 +889,7 @@ __global__ void __launch_bounds__(CT, 3) k_centre(const CentreArgs a) {
     for (;;) {
         // everybody (CS > 1: every CTA of the cluster, whose shared memory the lead reads) is done
         // with the previous centre; the lead then pulls the next one for the whole cluster
-        if (CS > 1) {
+        if constexpr (CS > 1) {
             cg::cluster_group cl = cg::this_cluster();
             cl.sync();
             if (cl.block_rank() == 0 && threadIdx.x == 0) {

@@ -27,20 +27,20 @@ struct FinArgs {
 };
 __device__ void finalize_partial(const StructDev *structs, const FinArgs &f, const unsigned char *role, int chunk, int st);
 
-// Grid: ntot CTAs gather the forces (one atom each), followed by nchunk * nstruct CTAs that
-// reduce E and the strs contraction per structure.  Both parts read only what the centre
-// kernel wrote, so they share one launch (a separate launch costs ~7 us on small inputs).
+// Grid: nchunk * nstruct CTAs that reduce E and the strs contraction per structure (first, so
+// that they do not form a tail), then ntot CTAs that gather the forces (one atom each).  Both
+// parts read only what the centre kernel wrote, so they share one launch (a separate launch
+// costs ~7 us on small inputs).
 __global__ void __launch_bounds__(GT)
 k_gather(const StructDev *structs, const int *sid, int ntot, int cap, const uint64_t *nbr_keys,
          const int *nbr_cnt, const double *fpair, const double *gself, double *force,
-         const unsigned char *role, const int *active, const DevFlags *flags, const int ngather, const FinArgs fin) {
+         const unsigned char *role, const int *active, const DevFlags *flags, const int nfin, const FinArgs fin) {
     __shared__ double red[GT / 32][3];
-    if ((int)blockIdx.x >= ngather) {
-        const int r = blockIdx.x - ngather;
-        finalize_partial(structs, fin, role, r % fin.nchunk, r / fin.nchunk);
+    if ((int)blockIdx.x < nfin) {
+        finalize_partial(structs, fin, role, blockIdx.x % fin.nchunk, blockIdx.x / fin.nchunk);
         return;
     }
-    const int slot_i = blockIdx.x;
+    const int slot_i = blockIdx.x - nfin;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (slot_i >= (active ? flags->n_active : ntot)) return;
     const int i = active ? active[slot_i] : slot_i;
@@ -190,8 +190,8 @@ void launch_gather(cudaStream_t st, const StructDev *structs, int nstruct, const
     FinArgs fin;
     fin.eatom = eatom; fin.vir = vir; fin.partial = partial; fin.out8 = out8; fin.lgrad = lgrad; fin.nchunk = nchunk; fin.nstruct = nstruct;
     const int ngather = lgrad ? ntot : 0;   // without gradients only the reduction CTAs run
-    k_gather<<<ngather + nchunk * nstruct, GT, 0, st>>>(structs, sid, ntot, cap, nbr_keys, nbr_cnt, fpair, gself, force_soa, role,
-                                                         active, flags, ngather, fin);
+    k_gather<<<nchunk * nstruct + ngather, GT, 0, st>>>(structs, sid, ntot, cap, nbr_keys, nbr_cnt, fpair, gself, force_soa, role,
+                                                         active, flags, nchunk * nstruct, fin);
     if (nchunk > 1) k_finalize<<<nstruct, 32, 0, st>>>(structs, partial, nchunk, out8);
     if (launches) *launches += nchunk > 1 ? 2 : 1;
 }
