@@ -12,6 +12,7 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -46,7 +47,9 @@ template <class T>
 struct DBuf {
     T *p = nullptr;
     size_t n = 0;
+    bool view = false;   // p points into another allocation (the results block): not owned
     cudaError_t ensure(size_t want) {
+        if (view) return want <= n ? cudaSuccess : cudaErrorInvalidValue;
         if (want <= n) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; n = 0;
@@ -55,7 +58,7 @@ struct DBuf {
         if (e == cudaSuccess) n = grow;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p && !view) cudaFree(p); p = nullptr; n = 0; }
 };
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -105,6 +108,9 @@ struct gapcu_ctx {
     DBuf<uint32_t> d_stash;
     int sm_count = 0;
     DBuf<DevFlags> d_flags;
+    // flags | out8 | force live in ONE allocation so that a call reads its results back with one copy
+    DBuf<unsigned char> d_results;
+    size_t res_o_out = 0, res_o_f = 0;   // byte offsets of out8 and force in d_results
     DBuf<unsigned char> d_flush;
     // ---- spatial decomposition over ranks + NCCL (loaded lazily with dlopen)
     DomainDev dom = {0, {1, 1, 1}, {0, 0, 0}, {0.0, 0.0, 0.0}};
@@ -146,7 +152,7 @@ struct gapcu_ctx {
     }
     int pin(size_t bytes) {
         if (bytes <= h_pin_bytes) return 0;
-        if (h_pin) cudaFreeHost(h_pin);
+        if (h_pin) { cudaStreamSynchronize(stream); cudaFreeHost(h_pin); }   // pending copies may still read the old buffer
         h_pin = nullptr; h_pin_bytes = 0;
         size_t grow = bytes + bytes / 4 + 4096;
         if (cudaMallocHost(&h_pin, grow) != cudaSuccess) return -1;
@@ -154,6 +160,19 @@ struct gapcu_ctx {
         return 0;
     }
 };
+
+static_assert(sizeof(DevFlags) <= 512, "DevFlags outgrew its slot in the results block");
+static cudaError_t ensure_results(gapcu_ctx *c, size_t nstruct, size_t NT) {
+    const size_t o_out = 512, o_f = o_out + ((64 * nstruct + 255) & ~(size_t)255), total = o_f + 24 * NT;
+    cudaError_t e = c->d_results.ensure(total);
+    if (e != cudaSuccess) return e;
+    c->d_flags.view = c->d_out8.view = c->d_force.view = true;
+    c->d_flags.p = (DevFlags *)c->d_results.p; c->d_flags.n = 1;
+    c->d_out8.p = (double *)(c->d_results.p + o_out); c->d_out8.n = 8 * nstruct;
+    c->d_force.p = (double *)(c->d_results.p + o_f); c->d_force.n = 3 * NT;
+    c->res_o_out = o_out; c->res_o_f = o_f;
+    return cudaSuccess;
+}
 
 // ---------------------------------------------------------------------------
 // context life cycle
@@ -204,7 +223,7 @@ extern "C" void gapcu_ctx_destroy(gapcu_ctx *c) {
     c->d_bin_atoms.release(); c->d_nbr_cnt.release(); c->d_order.release(); c->d_abin.release(); c->d_sabin.release(); c->d_spos.release(); c->d_finpart.release(); c->d_pos.release(); c->d_wgt.release();
     c->d_G.release(); c->d_dEdG.release(); c->d_eatom.release(); c->d_fpair.release(); c->d_gself.release();
     c->d_vir.release(); c->d_force.release(); c->d_out8.release(); c->d_mindis.release(); c->d_keys.release();
-    c->d_stash.release(); c->d_epart.release(); c->d_accpart.release(); c->d_flags.release(); c->d_flush.release(); c->d_role.release(); c->d_active.release();
+    c->d_stash.release(); c->d_epart.release(); c->d_accpart.release(); c->d_flags.release(); c->d_results.release(); c->d_flush.release(); c->d_role.release(); c->d_active.release();
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->stage_ev_init) for (auto &e : c->stage_ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -405,7 +424,7 @@ static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, con
     CU(c->d_structs.ensure(nstruct)); CU(c->d_sid.ensure(NT)); CU(c->d_pos.ensure(3 * NT)); CU(c->d_wgt.ensure(NT));
     CU(c->d_abin.ensure(NT)); CU(c->d_sabin.ensure(NT)); CU(c->d_spos.ensure(3 * NT)); CU(c->d_arank.ensure(NT)); CU(c->d_bin_count.ensure(c->nbins + 1));
     CU(c->d_bin_start.ensure(c->nbins + 2)); CU(c->d_bin_atoms.ensure(NT)); CU(c->d_nbr_cnt.ensure(NT)); CU(c->d_order.ensure(NT));
-    CU(c->d_flags.ensure(1)); CU(c->d_out8.ensure(8 * (size_t)nstruct)); CU(c->d_force.ensure(3 * NT));
+    CU(ensure_results(c, (size_t)nstruct, NT));
     CU(c->d_mindis.ensure(NT)); CU(c->d_role.ensure(NT)); CU(c->d_active.ensure(NT));
     CU(cudaMemcpyAsync(c->d_structs.p, hp + o_structs, b_structs, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_sid.p, h_sid, b_sid, cudaMemcpyHostToDevice, c->stream));
@@ -727,17 +746,29 @@ extern "C" int gapcu_ctx_fetch(gapcu_ctx *c, double *ene, double *force, double 
     if (!c) return fail(GAPCU_EARG, "null context");
     if (!c->computed) return fail(GAPCU_EARG, "nothing computed");
     DeviceGuard dg_(c->device);
-    int rc = finish_pass(c);
-    if (rc) return rc;
+    // flags, per-structure outputs and forces come back in one copy; if a neighbour list overflowed
+    // (the count grew since the capacity was learned) the pass is re-run with a larger capacity
+    const size_t NT = (size_t)c->ntot;
+    const size_t b_f = sizeof(double) * 3 * NT;
+    double *h_out = nullptr, *h_f = nullptr;
+    for (int attempt = 0;; attempt++) {
+        const size_t bytes = force ? c->res_o_f + b_f : c->res_o_f;
+        if (c->pin(c->res_o_f + b_f)) return fail(GAPCU_ECUDA, "cudaMallocHost failed");
+        CU(cudaMemcpyAsync(c->h_pin, c->d_results.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->h_flags = *(const DevFlags *)c->h_pin;
+        h_out = (double *)((char *)c->h_pin + c->res_o_out); h_f = (double *)((char *)c->h_pin + c->res_o_f);
+        if (c->h_flags.too_many)
+            return fail(GAPCU_ENEIGH, "Atoms neighbor: " + std::to_string(c->h_flags.maxcount) + " large than max_neighbor 1000");
+        if (!c->h_flags.overflow) break;
+        if (attempt >= 3) return fail(GAPCU_ECUDA, "neighbour capacity did not converge");
+        c->cap = std::max(c->cap, std::min(1024, round_up(c->h_flags.maxcount + 16, 32)));
+        c->pcap_known = false;
+        int rc = enqueue_pass(c, c->last_lgrad, nullptr);
+        if (rc) return rc;
+    }
     if (c->h_flags.close_pairs)
         fprintf(stdout, " Warning: The distance of two atoms is very small (%d pairs below 0.5)\n", c->h_flags.close_pairs);
-    const size_t NT = (size_t)c->ntot;
-    size_t b_out = sizeof(double) * 8 * c->nstruct, b_f = sizeof(double) * 3 * NT;
-    if (c->pin(b_out + b_f + 512)) return fail(GAPCU_ECUDA, "cudaMallocHost failed");
-    double *h_out = (double *)c->h_pin, *h_f = h_out + 8 * (size_t)c->nstruct;
-    CU(cudaMemcpyAsync(h_out, c->d_out8.p, b_out, cudaMemcpyDeviceToHost, c->stream));
-    if (force) CU(cudaMemcpyAsync(h_f, c->d_force.p, b_f, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
     for (int s = 0; s < c->nstruct; s++) {
         if (ene) ene[s] = h_out[8 * s];
         if (stress) for (int q = 0; q < 6; q++) stress[6 * s + q] = h_out[8 * s + 1 + q];
@@ -973,6 +1004,11 @@ extern "C" int gapcu_calc(int na, const int *species, const double *lat, const d
                           int lgrad, double *ene, double *force, double *stress, double *variance) {
     (void)qmm;
     std::lock_guard<std::mutex> lk(g_mu);
+    // GAPCU_TRACE=1: host-side time stamps of this call's phases on stderr (development aid)
+    static const bool trace = getenv("GAPCU_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point tp[6];
+    auto stamp = [&](int k) { if (trace) tp[k] = std::chrono::steady_clock::now(); };
+    stamp(0);
     gapcu_ctx *c = nullptr;
     int rc = default_ctx(&c);
     if (rc) return rc;
@@ -1000,17 +1036,18 @@ extern "C" int gapcu_calc(int na, const int *species, const double *lat, const d
     }
     double lat_c[9];
     for (int r = 0; r < 3; r++) for (int col = 0; col < 3; col++) lat_c[r * 3 + col] = lat[r + 3 * col];
+    stamp(1);
     if ((rc = set_structures_impl(c, 1, &na, species, lat_c, pos, true, rcut, true))) return rc;
+    stamp(2);
     if ((rc = enqueue_pass(c, lgrad ? 1 : 0, nullptr))) return rc;
+    stamp(3);
     // results: flags | out8 | force SoA (= Fortran FORCE(NA,3)) in one batch, one synchronisation
     size_t b_f = sizeof(double) * 3 * (size_t)na;
-    if (c->pin(sizeof(DevFlags) + 64 + b_f + 64)) return fail(GAPCU_ECUDA, "cudaMallocHost failed");
+    if (c->pin(c->res_o_f + b_f)) return fail(GAPCU_ECUDA, "cudaMallocHost failed");
     DevFlags *h_fl = (DevFlags *)c->h_pin;
-    double *h_out = (double *)((char *)c->h_pin + ((sizeof(DevFlags) + 63) & ~(size_t)63)), *h_f = h_out + 8;
+    double *h_out = (double *)((char *)c->h_pin + c->res_o_out), *h_f = (double *)((char *)c->h_pin + c->res_o_f);
     for (int attempt = 0;; attempt++) {
-        CU(cudaMemcpyAsync(h_fl, c->d_flags.p, sizeof(DevFlags), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(h_out, c->d_out8.p, sizeof(double) * 8, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(h_f, c->d_force.p, b_f, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(c->h_pin, c->d_results.p, c->res_o_f + b_f, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
         c->h_flags = *h_fl;
         if (c->h_flags.too_many)
@@ -1024,10 +1061,17 @@ extern "C" int gapcu_calc(int na, const int *species, const double *lat, const d
     }
     if (c->h_flags.close_pairs)
         fprintf(stdout, " Warning: The distance of two atoms is very small (%d pairs below 0.5)\n", c->h_flags.close_pairs);
+    stamp(4);
     *ene = h_out[0];
     for (int q = 0; q < 6; q++) stress[q] = h_out[1 + q];
     memcpy(force, h_f, b_f);
     if (variance) *variance = 0.0;  // gap_calc.f90:206
+    stamp(5);
+    if (trace) {
+        auto us = [&](int a, int b) { return std::chrono::duration<double, std::micro>(tp[b] - tp[a]).count(); };
+        fprintf(stderr, "gapcu_calc trace (us): potential check %.1f | set_structures + H2D %.1f | enqueue %.1f | D2H + wait %.1f | copy out %.1f | total %.1f\n",
+                us(0, 1), us(1, 2), us(2, 3), us(3, 4), us(4, 5), us(0, 5));
+    }
     return 0;
 }
 
@@ -1220,7 +1264,7 @@ extern "C" int gapcu_car2acsf_table(int na, int max_neighbor, int nf, const doub
     std::vector<int> h_sid(NA, 0);
     std::vector<unsigned char> h_role(NA, 2);
     CU(c->d_structs.ensure(1)); CU(c->d_sid.ensure(NA)); CU(c->d_pos.ensure(3 * NA)); CU(c->d_wgt.ensure(NA));
-    CU(c->d_nbr_cnt.ensure(NA)); CU(c->d_flags.ensure(1)); CU(c->d_role.ensure(NA)); CU(c->d_order.ensure(NA));
+    CU(c->d_nbr_cnt.ensure(NA)); CU(ensure_results(c, 1, NA)); CU(c->d_role.ensure(NA)); CU(c->d_order.ensure(NA));
     CU(d_table.ensure(NA * max_neighbor * 6));
     if ((rc = ensure_work_buffers(c))) { d_table.release(); return rc; }
     auto bail = [&](int code) { d_table.release(); return code; };
