@@ -184,12 +184,17 @@ def run_ours(args):
     pos_steps = [np.asfortranarray(pos + rng.normal(0.0, 0.01, pos.shape)) for _ in range(max(args.steps, args.warmup, 3))]
     step_no = [0]
 
+    # raw addresses taken once: a compiled host driver passes plain pointers, it does not build
+    # numpy ctypes views inside its MD loop
+    pos_ptrs = [p.ctypes.data for p in pos_steps]
+    p_z, p_lat, p_th, p_mm, p_co = zi.ctypes.data, latf.ctypes.data, th.ctypes.data, mmf.ctypes.data, co.ctypes.data
+    p_e, p_f, p_s, p_v = C.addressof(e_out), f_out.ctypes.data, s_out.ctypes.data, C.addressof(v_out)
+    calc = L.gapcu_calc
+
     def e2e_step():
-        posf = pos_steps[step_no[0] % len(pos_steps)]
+        p_pos = pos_ptrs[step_no[0] % len(pos_ptrs)]
         step_no[0] += 1
-        rc = L.gapcu_calc(natoms, zi.ctypes.data, latf.ctypes.data, posf.ctypes.data, M, D, th.ctypes.data,
-                          mmf.ctypes.data, None, co.ctypes.data, RCUT, 1, C.addressof(e_out), f_out.ctypes.data,
-                          s_out.ctypes.data, C.addressof(v_out))
+        rc = calc(natoms, p_z, p_lat, p_pos, M, D, p_th, p_mm, None, p_co, RCUT, 1, p_e, p_f, p_s, p_v)
         assert rc == 0, L.gapcu_last_error()
         return e_out.value, f_out
 
@@ -207,7 +212,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = natoms * args.steps * world / float(t.item())
     h2d = 24 * natoms + 8 * natoms + 4 * natoms + 208   # pos + species weights + structure ids + cell record
-    d2h = 24 * natoms + 64 + 96                          # forces + (E, stress, variance) + flags/counters
+    d2h = 24 * natoms + 512 + 256                        # one copy: flags/counters slot, (E, stress, variance) slot, forces
 
     if rank != 0:
         if world > 1:

@@ -92,6 +92,7 @@ struct gapcu_ctx {
     DBuf<double> d_mm_raw, d_theta_raw, d_coeff_raw, d_Mt, d_MtT, d_mn, d_coeff, d_cmean, d_itheta, d_exp2;
     int pipeline = 0;  // 0 auto, 1 split (K2 -> DMMA K3 -> K4), 2 fused single centre kernel
     int cluster = 0;   // CTAs per centre of the fused kernel: 0 auto, 1, 2 or 4
+    bool direct_ok = false;   // every structure is small enough for k_neigh_direct (set_structures)
     // ---- structures
     int nstruct = 0, ntot = 0, nbins = 0;
     double rcut = 0.0;
@@ -352,6 +353,7 @@ static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, con
     c->h_natoms.assign(natoms, natoms + nstruct);
     int boff = 0, aoff = 0;
     double max_density = 0.0;
+    bool direct = true;   // all structures small enough for the direct neighbour kernel
     for (int s = 0; s < nstruct; s++) {
         CellInfo ci = make_cell(lat_c + 9 * (size_t)s, rcut);
         if (!(ci.volume > 0.0)) return fail(GAPCU_EARG, "singular lattice");
@@ -381,10 +383,12 @@ static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, con
             sd.mscan[d] = w >= full ? 1 : w >= 0.5 * full ? 2 : ci.nabc[d] + 1;
         }
         sd.atom_off = aoff; sd.natoms = natoms[s]; sd.bin_off = boff; sd.nbins = (int)cells;
+        if ((long)natoms[s] * (2 * ci.nabc[0] + 1) * (2 * ci.nabc[1] + 1) * (2 * ci.nabc[2] + 1) > neighbor_direct_max_candidates()) direct = false;
         aoff += natoms[s]; boff += (int)cells;
         max_density = std::max(max_density, natoms[s] / ci.volume);
     }
     c->nstruct = nstruct; c->ntot = (int)ntot; c->nbins = boff; c->rcut = rcut;
+    c->direct_ok = direct && !getenv("GAPCU_NO_DIRECT");   // GAPCU_NO_DIRECT: always the cell list (A/B and tests)
     const size_t NT = (size_t)ntot;
     // ---- pack host staging: structs | sid | pos SoA | wgt
     size_t b_structs = sizeof(StructDev) * nstruct, b_sid = sizeof(int) * NT, b_pos = sizeof(double) * 3 * NT,
@@ -532,11 +536,15 @@ static int ensure_work_buffers(gapcu_ctx *c) {
     return 0;
 }
 
-static int run_neighbors(gapcu_ctx *c, bool with_keys, bool with_min) {
+// small undecomposed cells take the direct neighbour kernel, which also orders the centres
+static bool neighbors_direct(const gapcu_ctx *c) { return c->direct_ok && !c->dom.enabled; }
+
+static int run_neighbors(gapcu_ctx *c, bool with_keys, bool with_min, bool with_order = false) {
     launch_neighbor_build(c->stream, c->d_structs.p, c->d_sid.p, c->d_pos.p, c->ntot, c->nbins, c->rcut, c->cap,
                           c->d_abin.p, c->d_arank.p, c->d_bin_count.p, c->d_bin_start.p, c->d_bin_atoms.p, c->d_sabin.p, c->d_spos.p,
                           with_keys ? c->d_keys.p : nullptr, c->d_nbr_cnt.p, with_min ? c->d_mindis.p : nullptr,
-                          c->d_flags.p, c->dom, c->d_role.p, c->d_active.p, &c->launches);
+                          c->d_flags.p, c->dom, c->d_role.p, c->d_active.p, with_order ? c->d_order.p : nullptr,
+                          neighbors_direct(c), &c->launches);
     CU(cudaGetLastError());
     return 0;
 }
@@ -617,7 +625,7 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
     }
     CU(cudaMemsetAsync(c->d_flags.p, 0, sizeof(DevFlags), c->stream));
     if (ev) CU(cudaEventRecord(ev[0], c->stream));
-    if ((rc = run_neighbors(c, true, false))) return rc;
+    if ((rc = run_neighbors(c, true, false, true))) return rc;
     if (!c->pcap_known) {
         // first pass for this kind of input: learn the largest neighbour count
         for (int attempt = 0; attempt < 4; attempt++) {
@@ -629,12 +637,13 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
             c->cap = std::min(1024, round_up(c->h_flags.maxcount + 16, 32));
             if ((rc = ensure_work_buffers(c))) return rc;
             CU(cudaMemsetAsync(c->d_flags.p, 0, sizeof(DevFlags), c->stream));
-            if ((rc = run_neighbors(c, true, false))) return rc;
+            if ((rc = run_neighbors(c, true, false, true))) return rc;
         }
         c->pcap = std::min(c->cap, std::max(32, round_up(c->h_flags.maxcount + 8, 32)));
         c->pcap_known = true;
     }
-    launch_order(c->stream, c->d_nbr_cnt.p, c->ntot, c->d_order.p, c->d_role.p, c->d_flags.p, &c->launches);
+    if (!neighbors_direct(c))
+        launch_order(c->stream, c->d_nbr_cnt.p, c->ntot, c->d_order.p, c->d_role.p, c->d_flags.p, &c->launches);
     CU(cudaGetLastError());
     if (ev) CU(cudaEventRecord(ev[1], c->stream));
     // Capacity tiers: `order` lists the centres by descending neighbour count, so the centres
@@ -669,6 +678,9 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
             t.a.q_begin = cap == top ? nullptr : &F->n_gt[idx];
             t.a.q_end = cap == 128 ? &F->n_centres : &F->n_gt[idx - 1];
             tiers.push_back(t);
+            // a launch with at most one centre per SM gains nothing from the leaner instances: the top
+            // one serves every centre and the (mostly empty) lower tiers are not launched
+            if (cap == top && top <= 256 && c->ntot <= c->sm_count) { tiers.back().a.q_end = &F->n_centres; break; }
         }
         for (Tier &t : tiers)   // a later tier may have grown (moved) the shared list-parking buffer
             if (t.a.list_scratch) t.a.list_scratch = c->d_stash.p;

@@ -55,6 +55,7 @@ struct DevFlags {
     // persistent centre kernel, nanoseconds of %globaltimer: earliest start, earliest / latest
     // exit and the sum of the CTAs' busy times (load-balance diagnostics)
     unsigned long long t_start_min, t_exit_min, t_exit_max, t_busy_sum, n_ctas;
+    int ticket;          // CTAs of k_neigh_direct that are done (the last one orders the centres)
 };
 
 constexpr int MAXC_DEV = 16;  // distinct cutoffs (classes) supported

@@ -15,7 +15,10 @@ void launch_neighbor_build(cudaStream_t st, const StructDev *structs, const int 
                            int ntot, int nbins_total, double rcut, int cap, int4 *abin, int *arank,
                            int *bin_count, int *bin_start, int *bin_atoms, int4 *sabin, double *spos, uint64_t *nbr_keys,
                            int *nbr_cnt, double *min_dis, DevFlags *flags, const DomainDev &dom, unsigned char *role,
-                           int *active, long *launches);
+                           int *active, int *order, bool direct, long *launches);
+// direct = true: every structure has natoms * (image window) <= neighbor_direct_max_candidates() and the
+// cell is not decomposed; then one kernel builds the lists AND fills `order` (no launch_order needed)
+int neighbor_direct_max_candidates();
 
 void launch_order(cudaStream_t st, const int *nbr_cnt, int ntot, int *order, const unsigned char *role,
                   DevFlags *flags, long *launches);

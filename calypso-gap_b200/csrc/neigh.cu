@@ -390,44 +390,155 @@ k_neigh(const StructDev *structs, const int *sid, const double *pos, const int4 
 
 // Centres ordered by descending neighbour count (counting sort; single CTA).  The order
 // only schedules the persistent centre kernel; results do not depend on it.
-__global__ void __launch_bounds__(1024) k_order_by_count(const int *nbr_cnt, int ntot, int *order,
-                                                        const unsigned char *role, DevFlags *flags) {
-    __shared__ int hist[NB_MAXLIST + 2];
-    __shared__ int wsum[32];
+// The body works for any CTA size NT that divides 1024: thread t owns the NT-th part of the 1024
+// keys.  hist: NB_MAXLIST + 2 ints, wsum: 32 ints of shared memory.
+template <int NT>
+__device__ void order_body(const int *nbr_cnt, int ntot, int *order, const unsigned char *role, DevFlags *flags, int *hist, int *wsum) {
+    constexpr int PER = 1024 / NT;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int t = tid; t < NB_MAXLIST + 2; t += 1024) hist[t] = 0;
+    for (int t = tid; t < NB_MAXLIST + 2; t += NT) hist[t] = 0;
     __syncthreads();
-    for (int i = tid; i < ntot; i += 1024)
+    for (int i = tid; i < ntot; i += NT)
         if (!role || role[i] == 2) atomicAdd(&hist[NB_MAXLIST - min(max(nbr_cnt[i], 1), NB_MAXLIST)], 1);
     __syncthreads();
-    // exclusive scan of the 1024 keys (one per thread), key 0 = largest count
-    int v = hist[tid], x = v;
+    // exclusive scan of the 1024 keys (PER consecutive keys per thread), key 0 = largest count
+    int loc[PER], v = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { loc[k] = hist[tid * PER + k]; v += loc[k]; }
+    int x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
     if (lane == 31) wsum[wid] = x;
     __syncthreads();
     if (wid == 0) {
-        int s = wsum[lane];
+        int s = lane < NT / 32 ? wsum[lane] : 0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
         wsum[lane] = s;
     }
     __syncthreads();
-    const int excl = (wid ? wsum[wid - 1] : 0) + x - v;
+    int excl = (wid ? wsum[wid - 1] : 0) + x - v;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const int key = tid * PER + k;
+        hist[key] = excl;
+        // the owner of key(count c) knows the number of centres with more than c neighbours
+        if (key == NB_MAXLIST - 128) flags->n_gt[0] = excl;
+        if (key == NB_MAXLIST - 256) flags->n_gt[1] = excl;
+        if (key == NB_MAXLIST - 512) flags->n_gt[2] = excl;
+        if (key == 0) flags->n_gt[3] = 0;
+        excl += loc[k];
+        if (key == NB_MAXLIST - 1) flags->n_centres = excl;   // total number of owned atoms
+    }
     __syncthreads();
-    hist[tid] = excl;
-    __syncthreads();
-    if (tid == NB_MAXLIST - 1) flags->n_centres = excl + v;   // total number of owned atoms
-    // thread of key(count c) holds the number of centres with more than c neighbours
-    if (tid == NB_MAXLIST - 128) flags->n_gt[0] = excl;
-    if (tid == NB_MAXLIST - 256) flags->n_gt[1] = excl;
-    if (tid == NB_MAXLIST - 512) flags->n_gt[2] = excl;
-    if (tid == 0) flags->n_gt[3] = 0;
-    for (int i = tid; i < ntot; i += 1024) {
+    for (int i = tid; i < ntot; i += NT) {
         if (role && role[i] != 2) continue;
         const int key = NB_MAXLIST - min(max(nbr_cnt[i], 1), NB_MAXLIST);   // 0..1023 (0 and 1 neighbours share a key)
         order[atomicAdd(&hist[key], 1)] = i;
     }
+}
+
+__global__ void __launch_bounds__(1024) k_order_by_count(const int *nbr_cnt, int ntot, int *order,
+                                                        const unsigned char *role, DevFlags *flags) {
+    __shared__ int hist[NB_MAXLIST + 2];
+    __shared__ int wsum[32];
+    order_body<1024>(nbr_cnt, ntot, order, role, flags, hist, wsum);
+}
+
+// Small cells (an MD cell of tens of atoms): the reference's own double loop, one CTA per centre.
+// Candidate c = (j, n1, n2, n3) in the reference's loop order (gap_calc.f90:90-96: j, then n1, n2,
+// n3, the last fastest) IS the sorted order of the keys, so every thread tests a contiguous run of
+// at most 32 candidates, keeps a bit mask, and one block-wide prefix sum places the survivors:
+// no cell list, no sort, no atomics on the list.  Raw (unwrapped) positions and the +-nabc window,
+// exactly as in the reference.  The CTA that finishes last orders the centres by neighbour count
+// for the centre kernel (a handful of atoms: an own launch would cost more than the work).
+constexpr int DIRECT_MAX_CANDIDATES = 32 * NB_THREADS;
+__global__ void __launch_bounds__(NB_THREADS)
+k_neigh_direct(const StructDev *structs, const int *sid, const double *pos, int ntot, double rcut, int cap,
+               uint64_t *nbr_keys, int *nbr_cnt, double *min_dis, DevFlags *flags, int *order, unsigned char *role) {
+    __shared__ double lat[9];
+    __shared__ int wcnt[NB_THREADS / 32], wclose[NB_THREADS / 32];
+    __shared__ double wmin[NB_THREADS / 32];
+    __shared__ int hist[NB_MAXLIST + 2 + 32];
+    __shared__ int s_last;
+    const int i = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const StructDev &s = structs[sid[i]];
+    if (tid < 9) lat[tid] = s.lat[tid];
+    __syncthreads();
+    const double xi = pos[i], yi = pos[ntot + i], zi = pos[2 * ntot + i];
+    const int na0 = s.nabc[0], na1 = s.nabc[1], na2 = s.nabc[2];
+    const int w2 = 2 * na2 + 1, w12 = (2 * na1 + 1) * w2, W = (2 * na0 + 1) * w12;
+    const int aoff = s.atom_off, il = i - aoff;
+    const int total = s.natoms * W;
+    const int per = (total + NB_THREADS - 1) / NB_THREADS;   // <= 32 (host checks DIRECT_MAX_CANDIDATES)
+    const int c0 = tid * per, c1 = min(total, c0 + per);
+    unsigned mask = 0;
+    int nclose = 0;
+    double dmin = 1e300;
+    if (c0 < c1) {
+        int jl = c0 / W, w = c0 - jl * W;
+        double xj = pos[aoff + jl], yj = pos[ntot + aoff + jl], zj = pos[2 * ntot + aoff + jl];
+        for (int c = c0; c < c1; c++) {
+            const int n1 = w / w12 - na0, r = w % w12, n2 = r / w2 - na1, n3 = r % w2 - na2;
+            if (!(jl == il && n1 == 0 && n2 == 0 && n3 == 0)) {
+                double ox, oy, oz;
+                const double dis = image_distance_xyz(xj, yj, zj, lat, n1, n2, n3, xi, yi, zi, ox, oy, oz);
+                if (!(dis > rcut)) {
+                    mask |= 1u << (c - c0);
+                    nclose += dis < 0.5;
+                    dmin = fmin(dmin, dis);
+                }
+            }
+            if (++w == W && c + 1 < c1) {
+                w = 0; jl++;
+                xj = pos[aoff + jl]; yj = pos[ntot + aoff + jl]; zj = pos[2 * ntot + aoff + jl];
+            }
+        }
+    }
+    // block-wide exclusive prefix sum of the kept counts
+    const int mine = __popc(mask);
+    int x = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    int ncl = nclose;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { ncl += __shfl_xor_sync(0xffffffffu, ncl, o); dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o)); }
+    if (lane == 31) wcnt[wid] = x;
+    if (lane == 0) { wclose[wid] = ncl; wmin[wid] = dmin; }
+    __syncthreads();
+    int base = x - mine, count = 0;
+#pragma unroll
+    for (int w = 0; w < NB_THREADS / 32; w++) { if (w < wid) base += wcnt[w]; count += wcnt[w]; }
+    if (tid == 0) {
+        nbr_cnt[i] = count;
+        if (role) role[i] = 2;
+        atomicMax(&flags->maxcount, count);
+        if (count > MAX_NEIGHBOR_REF_DEV) atomicExch(&flags->too_many, 1);
+        if (count > cap) atomicExch(&flags->overflow, 1);
+        int nc = 0;
+        double m = wmin[0];
+        for (int w = 0; w < NB_THREADS / 32; w++) { nc += wclose[w]; m = fmin(m, wmin[w]); }
+        if (nc) atomicAdd(&flags->close_pairs, nc);
+        if (min_dis) min_dis[i] = m;
+    }
+    if (nbr_keys != nullptr && count <= cap) {
+        uint64_t *dst = nbr_keys + (size_t)i * cap + base;
+        for (unsigned m = mask; m; m &= m - 1) {
+            const int c = c0 + __ffs(m) - 1;
+            const int jl = c / W, w = c - jl * W;
+            const int n1 = w / w12 - na0, r = w % w12, n2 = r / w2 - na1, n3 = r % w2 - na2;
+            *dst++ = nbr_key(jl, n1, n2, n3);
+        }
+    }
+    if (!order) return;
+    __threadfence();          // this centre's count is visible before its ticket
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&flags->ticket, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    order_body<NB_THREADS>(nbr_cnt, ntot, order, role, flags, hist, hist + NB_MAXLIST + 2);
 }
 
 void launch_order(cudaStream_t st, const int *nbr_cnt, int ntot, int *order, const unsigned char *role,
@@ -437,11 +548,19 @@ void launch_order(cudaStream_t st, const int *nbr_cnt, int ntot, int *order, con
 }
 
 // ---- host launchers ------------------------------------------------------
+int neighbor_direct_max_candidates() { return DIRECT_MAX_CANDIDATES; }
+
 void launch_neighbor_build(cudaStream_t st, const StructDev *structs, const int *sid, const double *pos,
                            int ntot, int nbins_total, double rcut, int cap, int4 *abin, int *arank,
                            int *bin_count, int *bin_start, int *bin_atoms, int4 *sabin, double *spos, uint64_t *nbr_keys,
                            int *nbr_cnt, double *min_dis, DevFlags *flags, const DomainDev &dom, unsigned char *role,
-                           int *active, long *launches) {
+                           int *active, int *order, bool direct, long *launches) {
+    if (direct) {
+        // small cells: one launch does what binning, cell scan, sort and centre ordering do otherwise
+        k_neigh_direct<<<ntot, NB_THREADS, 0, st>>>(structs, sid, pos, ntot, rcut, cap, nbr_keys, nbr_cnt, min_dis, flags, order, role);
+        if (launches) *launches += 1;
+        return;
+    }
     if (ntot <= 8192 && nbins_total <= SMALL_NBINS) {
         k_bin_small<<<1, 1024, 0, st>>>(structs, sid, pos, ntot, nbins_total, abin, bin_start, bin_atoms, sabin, spos, dom,
                                         role, dom.enabled ? active : nullptr, flags);

@@ -580,3 +580,53 @@ def test_calc_batch_dropin_entry_point(shipped_pot, golden_frames, bc_structure,
             gapcu.set_devices([0, 0])
     finally:
         gapcu.set_devices([])
+
+
+def test_direct_and_cell_list_neighbour_builds_agree(oracle, bc_structure, golden_frames, monkeypatch):
+    """Small cells use the direct neighbour kernel (the reference's own double loop: no cell list, no
+    sort; the last CTA orders the centres), everything else the cell list with half-size bins.  Both
+    must give the oracle's lists bit for bit (counts, indices, shifts, distance bits) on wrapped,
+    sheared, unwrapped and tie cases, and the same energies/forces."""
+    import gapcu
+    cases = []
+    cell, pos = sheared(bc_structure["cell"], bc_structure["positions"])
+    z = bc_structure["numbers"].astype(np.int32)
+    cases.append((z, cell, pos))
+    p2 = pos.copy(); p2[3] += 2 * cell[0] - cell[2]; p2[17] -= cell[1]
+    cases.append((z, cell, p2))
+    cases.append((np.full(8, 6, np.int32), np.eye(3) * 4.0,
+                  np.array([[0, 0, 0], [2, 0, 0], [0, 2, 0], [2, 2, 0], [0, 0, 2], [2, 0, 2], [0, 2, 2], [2, 2, 2.0]])))
+    g = golden_frames
+    cases.append((g["numbers"].astype(np.int32), g["cell"][5], g["positions"][5]))
+    results = {}
+    for mode in ("direct", "cells"):
+        if mode == "cells":
+            monkeypatch.setenv("GAPCU_NO_DIRECT", "1")
+        else:
+            monkeypatch.delenv("GAPCU_NO_DIRECT", raising=False)
+        c = gapcu.Context(0)
+        c.load_potential(os.path.join(GOLDEN, "gap_parameters"))
+        out = []
+        for zz, cl, pp in cases:
+            r = c.evaluate(zz, cl, pp, 6.0, True)
+            got, want = c.neighbors(1000), oracle.neighbors(cl, pp, 6.0)
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b), mode
+            out.append(r)
+        results[mode] = out
+        c.close()
+    for a, b in zip(results["direct"], results["cells"]):
+        assert a["energy"] == b["energy"] and np.array_equal(a["forces"], b["forces"]) and np.array_equal(a["stress"], b["stress"])
+    # the min-distance entry point (FGET_BOND) goes through the same two builds
+    for mode in ("direct", "cells"):
+        if mode == "cells":
+            monkeypatch.setenv("GAPCU_NO_DIRECT", "1")
+        else:
+            monkeypatch.delenv("GAPCU_NO_DIRECT", raising=False)
+        import ctypes as C
+        for zz, cl, pp in cases[:2]:
+            latf, posf = np.asfortranarray(cl, dtype=np.float64), np.asfortranarray(pp, dtype=np.float64)
+            out = C.c_double()
+            assert gapcu.lib().gapcu_bond(len(zz), latf.ctypes.data, np.ascontiguousarray(zz, np.int32).ctypes.data,
+                                          posf.ctypes.data, 6.0, C.byref(out)) == 0
+            assert out.value == oracle.get_bond(cl, pp, 6.0)
