@@ -123,6 +123,14 @@ def test_no_gpu_means_loud_failure():
             "try:\n    gapcu.Context(0); print('CREATED')\nexcept gapcu.GapcuError as e:\n    print('ERR', e.code)\n") % os.path.join(ROOT, "calypso-gap_b200")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120).stdout
     assert "ERR -6" in out and "CREATED" not in out
+    # the drop-in batch entry points as well (gapcu_set_devices, gapcu_calc_batch)
+    code = ("import sys, os; os.environ['CUDA_VISIBLE_DEVICES']=''; sys.path.insert(0, %r); import gapcu, numpy as np\n"
+            "os.chdir(%r)\n"
+            "for f in (lambda: gapcu.set_devices([0]), lambda: gapcu.calc_batch([np.array([6, 6], np.int32)], [np.eye(3) * 5], [np.zeros((2, 3))])):\n"
+            "    try:\n        f(); print('RAN')\n    except gapcu.GapcuError as e:\n        print('ERR', e.code)\n") % (
+                os.path.join(ROOT, "calypso-gap_b200"), GOLDEN)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120).stdout
+    assert out.count("ERR -6") == 2 and "RAN" not in out
 
 
 def test_fastmath_host_versions(tmp_path):
