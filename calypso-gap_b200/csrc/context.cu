@@ -9,7 +9,9 @@
 //   K5  gather.cu   force gather (mirror-pair lookup) + per-structure E / stress
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -1193,13 +1195,84 @@ extern "C" int gapcu_calc_batch(int nstruct, const int *natoms, const int *speci
     return 0;
 }
 
+// Zero-fill of a large caller buffer (FGAP_READ's INVCMM = 0 on 4000 x 4000 doubles, gap_calc.f90:361,
+// which the reference's ASE calculator pays on every MD step because it builds a fresh Calculator
+// per step, gappy/ASE/gap_calc.py:41).  The f2py wrapper hands over a freshly allocated array: 128 MB
+// of an anonymous private mapping whose pages were never touched and therefore read as zero.
+// Writing zeros into them costs ~35 ms of page faults; instead the kernel's page map is consulted
+// and only pages that are present or swapped (i.e. that may hold data) are cleared.  Anything that
+// is not provably a private anonymous mapping, and any failure on the way, falls back to memset.
+static void zero_fill(void *ptr, size_t bytes) {
+    const size_t PAGE = (size_t)sysconf(_SC_PAGESIZE);
+    if (bytes < (8u << 20) || PAGE == 0) { memset(ptr, 0, bytes); return; }
+    const uintptr_t a0 = (uintptr_t)ptr, a1 = a0 + bytes;
+    const uintptr_t p0 = (a0 + PAGE - 1) / PAGE * PAGE, p1 = a1 / PAGE * PAGE;   // whole pages inside
+    // the range must be covered by writable, private mappings without a backing file (inode 0);
+    // numpy's madvise(MADV_HUGEPAGE) on the aligned interior splits an allocation into several
+    bool anon = false;
+    if (FILE *mf = fopen("/proc/self/maps", "r")) {
+        char line[512];
+        uintptr_t cur = a0;
+        while (fgets(line, sizeof line, mf)) {
+            unsigned long lo = 0, hi = 0, inode = 0;
+            char perms[8] = {0};
+            if (sscanf(line, "%lx-%lx %7s %*x %*s %lu", &lo, &hi, perms, &inode) != 4) continue;
+            if (hi <= cur) continue;
+            if (lo > cur || inode != 0 || perms[1] != 'w' || perms[3] != 'p') break;   // hole or not anonymous
+            cur = hi;
+            if (cur >= a1) { anon = true; break; }
+        }
+        fclose(mf);
+    }
+    int fd = anon ? open("/proc/self/pagemap", O_RDONLY) : -1;
+    if (fd < 0 || p1 <= p0) { if (fd >= 0) close(fd); memset(ptr, 0, bytes); return; }
+    memset(ptr, 0, p0 - a0);
+    memset((void *)p1, 0, a1 - p1);
+    std::vector<uint64_t> ent(8192);
+    bool ok = true;
+    for (uintptr_t pg = p0; pg < p1 && ok;) {
+        const size_t n = std::min<size_t>(ent.size(), (p1 - pg) / PAGE);
+        const ssize_t got = pread(fd, ent.data(), n * 8, (off_t)(pg / PAGE * 8));
+        if (got != (ssize_t)(n * 8)) { ok = false; memset((void *)pg, 0, p1 - pg); break; }
+        for (size_t k = 0; k < n;) {
+            if (!(ent[k] >> 62)) { k++; continue; }          // bit 63 present, bit 62 swapped: neither -> still zero
+            size_t e = k + 1;
+            while (e < n && (ent[e] >> 62)) e++;
+            memset((void *)(pg + k * PAGE), 0, (e - k) * PAGE);
+            k = e;
+        }
+        pg += n * PAGE;
+    }
+    close(fd);
+}
+
 extern "C" int gapcu_read(const char *path, int *nsparsex, int *des_len, double *theta, int theta_cap, double *mm,
                           int mm_ld, int mm_cols, double *invcmm, int invcmm_ld, double *coeff, int coeff_cap) {
-    PotentialFile pf;
-    try {
-        pf = read_gap_parameters(path ? path : "gap_parameters");
-    } catch (const std::exception &e) {
-        return fail(GAPCU_EFILE, e.what());
+    // the parse is cached by the file's identity (the reference's ASE calculator re-reads it every step)
+    static std::mutex mu;
+    static PotentialFile pf;
+    static std::string pf_path;
+    static FileId pf_id;
+    std::lock_guard<std::mutex> lk(mu);
+    const char *fname = path ? path : "gap_parameters";
+    struct stat st;
+    const bool have_stat = stat(fname, &st) == 0;
+    char full[4096];
+    const std::string key = (have_stat && realpath(fname, full)) ? std::string(full) : std::string();
+    const bool same = have_stat && !key.empty() && key == pf_path && st.st_dev == pf_id.dev && st.st_ino == pf_id.ino &&
+                      st.st_size == pf_id.size && st.st_mtim.tv_sec == pf_id.mt_s && st.st_mtim.tv_nsec == pf_id.mt_ns;
+    if (!same) {
+        pf_path.clear();
+        try {
+            pf = read_gap_parameters(fname);
+        } catch (const std::exception &e) {
+            return fail(GAPCU_EFILE, e.what());
+        }
+        if (have_stat && !key.empty()) {
+            pf_path = key;
+            pf_id.dev = st.st_dev; pf_id.ino = st.st_ino; pf_id.size = st.st_size;
+            pf_id.mt_s = st.st_mtim.tv_sec; pf_id.mt_ns = st.st_mtim.tv_nsec;
+        }
     }
     if (pf.nsparse > mm_ld || pf.nsparse > coeff_cap)
         return fail(GAPCU_ELIMIT, "The siez of sparse set large than nsparseX_max=" + std::to_string(mm_ld));
@@ -1210,7 +1283,7 @@ extern "C" int gapcu_read(const char *path, int *nsparsex, int *des_len, double 
     for (int k = 0; k < pf.des_len; k++) theta[k] = pf.theta[k];
     for (int s = 0; s < pf.nsparse; s++)
         for (int k = 0; k < pf.des_len; k++) mm[s + (size_t)mm_ld * k] = pf.mm[(size_t)s * pf.des_len + k];
-    if (invcmm) memset(invcmm, 0, sizeof(double) * (size_t)invcmm_ld * invcmm_ld);
+    if (invcmm) zero_fill(invcmm, sizeof(double) * (size_t)invcmm_ld * invcmm_ld);
     for (int s = 0; s < pf.nsparse; s++) coeff[s] = pf.coeff[s];
     return 0;
 }

@@ -67,6 +67,41 @@ def test_gapcu_read_matches_oracle_reader(lib, shipped_pot):
     assert rc == -4 and b"nsparseX_max" in lib.gapcu_last_error()
 
 
+def test_gapcu_read_zero_fill_of_invcmm(lib):
+    """FGAP_READ sets INVCMM = 0 (gap_calc.f90:361).  The library clears only pages that may hold
+    data (present or swapped according to /proc/self/pagemap) and leaves never-touched pages of a
+    fresh anonymous allocation alone -- they already read as zero.  Whatever the history of the
+    buffer, the caller must see zeros everywhere, and nothing outside the buffer may change."""
+    lib.gapcu_read.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                               C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    nsp, dl = C.c_int(), C.c_int()
+    theta = np.zeros(100); mm = np.zeros((4000, 100), order="F"); coeff = np.zeros(4000)
+    path = os.path.join(GOLDEN, "gap_parameters").encode()
+
+    def read_into(buf, ld):
+        assert lib.gapcu_read(path, C.byref(nsp), C.byref(dl), theta.ctypes.data, 100, mm.ctypes.data, 4000, 100,
+                              buf.ctypes.data, ld, coeff.ctypes.data, 4000) == 0
+
+    fresh = np.empty((4000, 4000), order="F")                 # 128 MB, pages never touched
+    read_into(fresh, 4000)
+    assert not fresh.any()
+    dirty = np.full((4000, 4000), 3.5, order="F")
+    read_into(dirty, 4000)
+    assert not dirty.any()
+    partly = np.empty((4000, 4000), order="F")
+    partly[17, 5] = 3.0; partly[3999, 3999] = -1.0; partly[0, 0] = 2.0; partly[:, 2000:2003] = 7.0
+    read_into(partly, 4000)
+    assert not partly.any()
+    # a window that starts and ends in the middle of pages of a dirty buffer: guard bytes stay
+    big = np.full(2000 * 2000 + 2000, 9.0)
+    win = big[777:777 + 2000 * 2000]
+    read_into(win, 2000)
+    assert not win.any() and (big[:777] == 9.0).all() and (big[777 + 2000 * 2000:] == 9.0).all()
+    small = np.full((50, 50), 1.0, order="F")                  # below the lazy threshold: plain memset
+    read_into(small, 50)
+    assert not small.any()
+
+
 def test_reader_round_trip_of_written_potential(lib, oracle, tmp_path):
     from structures import write_gap_parameters
     rng = np.random.default_rng(3)
