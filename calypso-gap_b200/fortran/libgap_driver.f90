@@ -44,6 +44,21 @@ module gapcu_c_api
             integer(c_int), intent(in) :: neighbor_count(*)
             real(c_double), intent(out) :: xx(*), dxdy(*), strs(*)
         end function
+        ! additive: independent structures over the devices of gapcu_set_devices (C-order arrays)
+        integer(c_int) function gapcu_calc_batch(nstruct, natoms, species, lat, pos, rcut, lgrad, &
+                                                 ene, force, stress) bind(C, name='gapcu_calc_batch')
+            import :: c_int, c_double
+            integer(c_int), value :: nstruct, lgrad
+            real(c_double), value :: rcut
+            integer(c_int), intent(in) :: natoms(*), species(*)
+            real(c_double), intent(in) :: lat(*), pos(*)
+            real(c_double), intent(out) :: ene(*), force(*), stress(*)
+        end function
+        integer(c_int) function gapcu_set_devices(n, devices) bind(C, name='gapcu_set_devices')
+            import :: c_int
+            integer(c_int), value :: n
+            integer(c_int), intent(in) :: devices(*)
+        end function
         subroutine gapcu_print_last_error() bind(C, name='gapcu_print_last_error')
         end subroutine
     end interface
@@ -145,3 +160,32 @@ SUBROUTINE write_array_2dim(n, m, a, name)
     enddo
     close(2244)
 END SUBROUTINE
+
+! Additive (not in the reference): a CALYPSO-style batch of independent structures in one call,
+! what gappy/tools/cgg2.py:111-115 does with one process per structure.  Fortran layouts:
+! NATOMS(NS); SPECIES, and the columns of POS3/FORCE3, concatenated over the structures (NTOT
+! atoms); LAT3(3,3,NS) with LAT3(:,c,s) = lattice vector c of structure s, POS3(3,NTOT),
+! FORCE3(3,NTOT), STRESS6(6,NS) -- i.e. the component index runs fastest, which is the C order
+! gapcu_calc_batch expects, so no copy is made.  NDEV > 0 selects devices DEVICES(1:NDEV) first.
+SUBROUTINE FGAP_CALC_BATCH(NS, NTOT, NATOMS, SPECIES, LAT3, POS3, Rcut, lgrad, ENE, FORCE3, STRESS6, NDEV, DEVICES)
+    use gapcu_c_api
+    implicit none
+    integer, intent(in) :: NS, NTOT, NDEV
+    integer, intent(in) :: NATOMS(NS), SPECIES(NTOT), DEVICES(*)
+    double precision, intent(in) :: LAT3(3,3,NS), POS3(3,NTOT), Rcut
+    logical, intent(in) :: lgrad
+    double precision, intent(out) :: ENE(NS), FORCE3(3,NTOT), STRESS6(6,NS)
+    integer(c_int) :: ig
+    ig = 0
+    if (lgrad) ig = 1
+    if (NDEV > 0) then
+        if (gapcu_set_devices(NDEV, DEVICES) /= 0) then
+            call gapcu_print_last_error()
+            stop
+        endif
+    endif
+    if (gapcu_calc_batch(NS, NATOMS, SPECIES, LAT3, POS3, Rcut, ig, ENE, FORCE3, STRESS6) /= 0) then
+        call gapcu_print_last_error()
+        stop
+    endif
+END SUBROUTINE FGAP_CALC_BATCH
