@@ -95,6 +95,7 @@ struct gapcu_ctx {
     int pipeline = 0;  // 0 auto, 1 split (K2 -> DMMA K3 -> K4), 2 fused single centre kernel
     int cluster = 0;   // CTAs per centre of the fused kernel: 0 auto, 1, 2 or 4
     bool direct_ok = false;   // every structure is small enough for k_neigh_direct (set_structures)
+    bool h2d_pending = false; // the pinned staging buffer feeds a copy nobody has waited for yet
     // ---- structures
     int nstruct = 0, ntot = 0, nbins = 0;
     double rcut = 0.0;
@@ -114,6 +115,8 @@ struct gapcu_ctx {
     // flags | out8 | force live in ONE allocation so that a call reads its results back with one copy
     DBuf<unsigned char> d_results;
     size_t res_o_out = 0, res_o_f = 0;   // byte offsets of out8 and force in d_results
+    // likewise structs | sid | pos | wgt ("inputs block"): one host-to-device copy per call
+    DBuf<unsigned char> d_inputs;
     DBuf<unsigned char> d_flush;
     // ---- spatial decomposition over ranks + NCCL (loaded lazily with dlopen)
     DomainDev dom = {0, {1, 1, 1}, {0, 0, 0}, {0.0, 0.0, 0.0}};
@@ -177,6 +180,30 @@ static cudaError_t ensure_results(gapcu_ctx *c, size_t nstruct, size_t NT) {
     return cudaSuccess;
 }
 
+// inputs block: same 256-byte aligned layout on the device as in the pinned staging buffer
+struct InputLayout { size_t o_structs, o_sid, o_pos, o_wgt, total; };
+static InputLayout input_layout(size_t nstruct, size_t NT) {
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    InputLayout L;
+    L.o_structs = 0;
+    L.o_sid = al(sizeof(StructDev) * nstruct);
+    L.o_pos = al(L.o_sid + sizeof(int) * NT);
+    L.o_wgt = al(L.o_pos + sizeof(double) * 3 * NT);
+    L.total = al(L.o_wgt + sizeof(double) * NT);
+    return L;
+}
+static cudaError_t ensure_inputs(gapcu_ctx *c, size_t nstruct, size_t NT) {
+    const InputLayout L = input_layout(nstruct, NT);
+    cudaError_t e = c->d_inputs.ensure(L.total);
+    if (e != cudaSuccess) return e;
+    c->d_structs.view = c->d_sid.view = c->d_pos.view = c->d_wgt.view = true;
+    c->d_structs.p = (StructDev *)(c->d_inputs.p + L.o_structs); c->d_structs.n = nstruct;
+    c->d_sid.p = (int *)(c->d_inputs.p + L.o_sid); c->d_sid.n = NT;
+    c->d_pos.p = (double *)(c->d_inputs.p + L.o_pos); c->d_pos.n = 3 * NT;
+    c->d_wgt.p = (double *)(c->d_inputs.p + L.o_wgt); c->d_wgt.n = NT;
+    return cudaSuccess;
+}
+
 // ---------------------------------------------------------------------------
 // context life cycle
 // ---------------------------------------------------------------------------
@@ -226,7 +253,7 @@ extern "C" void gapcu_ctx_destroy(gapcu_ctx *c) {
     c->d_bin_atoms.release(); c->d_nbr_cnt.release(); c->d_order.release(); c->d_abin.release(); c->d_sabin.release(); c->d_spos.release(); c->d_finpart.release(); c->d_pos.release(); c->d_wgt.release();
     c->d_G.release(); c->d_dEdG.release(); c->d_eatom.release(); c->d_fpair.release(); c->d_gself.release();
     c->d_vir.release(); c->d_force.release(); c->d_out8.release(); c->d_mindis.release(); c->d_keys.release();
-    c->d_stash.release(); c->d_epart.release(); c->d_accpart.release(); c->d_flags.release(); c->d_results.release(); c->d_flush.release(); c->d_role.release(); c->d_active.release();
+    c->d_stash.release(); c->d_epart.release(); c->d_accpart.release(); c->d_flags.release(); c->d_results.release(); c->d_inputs.release(); c->d_flush.release(); c->d_role.release(); c->d_active.release();
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->stage_ev_init) for (auto &e : c->stage_ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -393,11 +420,11 @@ static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, con
     c->direct_ok = direct && !getenv("GAPCU_NO_DIRECT");   // GAPCU_NO_DIRECT: always the cell list (A/B and tests)
     const size_t NT = (size_t)ntot;
     // ---- pack host staging: structs | sid | pos SoA | wgt
-    size_t b_structs = sizeof(StructDev) * nstruct, b_sid = sizeof(int) * NT, b_pos = sizeof(double) * 3 * NT,
-           b_wgt = sizeof(double) * NT;
-    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    size_t o_structs = 0, o_sid = al(o_structs + b_structs), o_pos = al(o_sid + b_sid), o_wgt = al(o_pos + b_pos),
-           total = al(o_wgt + b_wgt);
+    size_t b_structs = sizeof(StructDev) * nstruct, b_wgt = sizeof(double) * NT;
+    const InputLayout IL = input_layout((size_t)nstruct, NT);
+    const size_t o_structs = IL.o_structs, o_sid = IL.o_sid, o_pos = IL.o_pos, o_wgt = IL.o_wgt, total = IL.total;
+    // the staging buffer may still feed the previous call's copy if the caller never waited for it
+    if (c->h2d_pending) { CU(cudaStreamSynchronize(c->stream)); c->h2d_pending = false; }
     if (c->pin(total)) return fail(GAPCU_ECUDA, "cudaMallocHost failed");
     char *hp = (char *)c->h_pin;
     memcpy(hp + o_structs, c->h_structs.data(), b_structs);
@@ -427,15 +454,13 @@ static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, con
         memset(h_wgt, 0, b_wgt);
     }
     // ---- device buffers
-    CU(c->d_structs.ensure(nstruct)); CU(c->d_sid.ensure(NT)); CU(c->d_pos.ensure(3 * NT)); CU(c->d_wgt.ensure(NT));
+    CU(ensure_inputs(c, (size_t)nstruct, NT));
     CU(c->d_abin.ensure(NT)); CU(c->d_sabin.ensure(NT)); CU(c->d_spos.ensure(3 * NT)); CU(c->d_arank.ensure(NT)); CU(c->d_bin_count.ensure(c->nbins + 1));
     CU(c->d_bin_start.ensure(c->nbins + 2)); CU(c->d_bin_atoms.ensure(NT)); CU(c->d_nbr_cnt.ensure(NT)); CU(c->d_order.ensure(NT));
     CU(ensure_results(c, (size_t)nstruct, NT));
     CU(c->d_mindis.ensure(NT)); CU(c->d_role.ensure(NT)); CU(c->d_active.ensure(NT));
-    CU(cudaMemcpyAsync(c->d_structs.p, hp + o_structs, b_structs, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->d_sid.p, h_sid, b_sid, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->d_pos.p, h_pos, b_pos, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->d_wgt.p, h_wgt, b_wgt, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_inputs.p, hp, total, cudaMemcpyHostToDevice, c->stream));   // structs | sid | pos | wgt in one copy
+    c->h2d_pending = true;
     // ---- neighbour capacity estimate (grown on demand)
     int est = (int)(4.18879 * rcut * rcut * rcut * max_density * 1.25) + 32;
     est = std::min(1024, std::max(64, round_up(est, 32)));
@@ -554,6 +579,7 @@ static int run_neighbors(gapcu_ctx *c, bool with_keys, bool with_min, bool with_
 static int read_flags(gapcu_ctx *c) {
     CU(cudaMemcpyAsync(&c->h_flags, c->d_flags.p, sizeof(DevFlags), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    c->h2d_pending = false;
     return 0;
 }
 
@@ -770,6 +796,7 @@ extern "C" int gapcu_ctx_fetch(gapcu_ctx *c, double *ene, double *force, double 
         if (c->pin(c->res_o_f + b_f)) return fail(GAPCU_ECUDA, "cudaMallocHost failed");
         CU(cudaMemcpyAsync(c->h_pin, c->d_results.p, bytes, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
+        c->h2d_pending = false;
         c->h_flags = *(const DevFlags *)c->h_pin;
         h_out = (double *)((char *)c->h_pin + c->res_o_out); h_f = (double *)((char *)c->h_pin + c->res_o_f);
         if (c->h_flags.too_many)
@@ -1063,6 +1090,7 @@ extern "C" int gapcu_calc(int na, const int *species, const double *lat, const d
     for (int attempt = 0;; attempt++) {
         CU(cudaMemcpyAsync(c->h_pin, c->d_results.p, c->res_o_f + b_f, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
+        c->h2d_pending = false;
         c->h_flags = *h_fl;
         if (c->h_flags.too_many)
             return fail(GAPCU_ENEIGH, "Atoms neighbor: " + std::to_string(c->h_flags.maxcount) + " large than max_neighbor 1000");
@@ -1348,7 +1376,7 @@ extern "C" int gapcu_car2acsf_table(int na, int max_neighbor, int nf, const doub
     DBuf<double> d_table;
     std::vector<int> h_sid(NA, 0);
     std::vector<unsigned char> h_role(NA, 2);
-    CU(c->d_structs.ensure(1)); CU(c->d_sid.ensure(NA)); CU(c->d_pos.ensure(3 * NA)); CU(c->d_wgt.ensure(NA));
+    CU(ensure_inputs(c, 1, NA));
     CU(c->d_nbr_cnt.ensure(NA)); CU(ensure_results(c, 1, NA)); CU(c->d_role.ensure(NA)); CU(c->d_order.ensure(NA));
     CU(d_table.ensure(NA * max_neighbor * 6));
     if ((rc = ensure_work_buffers(c))) { d_table.release(); return rc; }
