@@ -924,14 +924,34 @@ template <int MODE, int PCAP, int CS>
 int launch_centre(cudaStream_t st, const CentreArgs &a) {
     const size_t sm = (size_t)a.lay.total;
     if (sm > 227 * 1024) return -1;
-    if (cudaFuncSetAttribute((const void *)k_centre<MODE, PCAP, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
-        return -2;
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    // attribute and occupancy queries cost microseconds each and sit on the critical path of a small
+    // call (the kernels before this one are short): remembered per (instance, device, footprint)
+    static int c_dev = -1, c_sms = 0, c_fit = 0;
+    static size_t c_sm = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != c_dev || sm != c_sm) {
+        if (cudaFuncSetAttribute((const void *)k_centre<MODE, PCAP, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess)
+            return -2;
+        cudaDeviceGetAttribute(&c_sms, cudaDevAttrMultiProcessorCount, dev);
+        c_fit = 0;
+        if (CS == 1) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c_fit, k_centre<MODE, PCAP, CS>, CT, sm) != cudaSuccess || c_fit < 1) c_fit = 1;
+            c_fit *= c_sms;   // resident CTAs of the device
+        } else {
+            cudaLaunchConfig_t q;
+            memset(&q, 0, sizeof q);
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = CS; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            q.gridDim = dim3(CS * c_sms, 1, 1); q.blockDim = dim3(CT, 1, 1); q.dynamicSmemBytes = sm; q.stream = st;
+            q.attrs = qa; q.numAttrs = 1;
+            if (cudaOccupancyMaxActiveClusters(&c_fit, k_centre<MODE, PCAP, CS>, &q) != cudaSuccess || c_fit < 1) return -3;   // resident clusters
+        }
+        c_dev = dev; c_sm = sm;
+    }
     if (CS == 1) {
-        int per_sm = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_centre<MODE, PCAP, CS>, CT, sm) != cudaSuccess || per_sm < 1) per_sm = 1;
-        const int grid = a.ntot < sms * per_sm ? a.ntot : sms * per_sm;
+        const int grid = a.ntot < c_fit ? a.ntot : c_fit;
         k_centre<MODE, PCAP, CS><<<grid, CT, sm, st>>>(a);
         return 0;
     }
@@ -941,12 +961,9 @@ int launch_centre(cudaStream_t st, const CentreArgs &a) {
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.gridDim = dim3(CS * sms, 1, 1); cfg.blockDim = dim3(CT, 1, 1); cfg.dynamicSmemBytes = sm; cfg.stream = st;
+    const int clusters = a.ntot < c_fit ? a.ntot : c_fit;
+    cfg.gridDim = dim3(CS * clusters, 1, 1); cfg.blockDim = dim3(CT, 1, 1); cfg.dynamicSmemBytes = sm; cfg.stream = st;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    int ncl = 0;
-    if (cudaOccupancyMaxActiveClusters(&ncl, k_centre<MODE, PCAP, CS>, &cfg) != cudaSuccess || ncl < 1) return -3;
-    const int clusters = a.ntot < ncl ? a.ntot : ncl;
-    cfg.gridDim = dim3(CS * clusters, 1, 1);
     return cudaLaunchKernelEx(&cfg, k_centre<MODE, PCAP, CS>, a) == cudaSuccess ? 0 : -4;
 }
 
