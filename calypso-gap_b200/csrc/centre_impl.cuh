@@ -980,8 +980,10 @@ int launch_centre_p1024(cudaStream_t st, const CentreArgs &a, int mode);
     int launch_centre_p##PC(cudaStream_t st, const CentreArgs &a, int mode) {             \
         if (mode == MODE_FWD) return launch_centre<MODE_FWD, PC, 1>(st, a);               \
         if (mode == MODE_BWD) return launch_centre<MODE_BWD, PC, 1>(st, a);               \
-        if (a.cs == 2) return launch_centre<MODE_FUSED, PC, 2>(st, a);                    \
-        if (a.cs == 4) return launch_centre<MODE_FUSED, PC, 4>(st, a);                    \
+        /* a cluster launch the device cannot place falls back to one CTA per centre */   \
+        if (a.cs == 4 && launch_centre<MODE_FUSED, PC, 4>(st, a) == 0) return 0;          \
+        if (a.cs == 2 && launch_centre<MODE_FUSED, PC, 2>(st, a) == 0) return 0;          \
+        if (a.cs > 1) cudaGetLastError();                                                 \
         return launch_centre<MODE_FUSED, PC, 1>(st, a);                                   \
     }                                                                                     \
     }
