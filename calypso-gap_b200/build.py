@@ -19,11 +19,11 @@ OBJ = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
-CU_SOURCES = ["neigh.cu", "centre.cu", "centre_p128.cu", "centre_p256.cu", "centre_p512.cu", "centre_p1024.cu", "gpr.cu", "gather.cu", "variance.cu",
+CU_SOURCES = ["neigh.cu", "centre.cu", "centre_p128.cu", "centre_p256.cu", "centre_p512.cu", "centre_p1024.cu", "gpr.cu", "gather.cu", "halo.cu", "variance.cu",
               "microbench.cu", "context.cu"]
 CPP_SOURCES = ["potential.cpp"]
 C_SOURCES = ["fortran_shim.c"]
-HEADERS = ["device_types.cuh", "centre_impl.cuh", "fastmath.cuh", "geom.cuh", "launch.cuh", "potential.hpp", os.path.join("..", "..", "include", "gapcu.h")]
+HEADERS = ["domain_host.inc", "device_types.cuh", "centre_impl.cuh", "fastmath.cuh", "geom.cuh", "launch.cuh", "potential.hpp", os.path.join("..", "..", "include", "gapcu.h")]
 
 
 def _newer(target, deps):

@@ -951,7 +951,8 @@ int launch_centre(cudaStream_t st, const CentreArgs &a) {
         c_dev = dev; c_sm = sm;
     }
     if (CS == 1) {
-        const int grid = a.ntot < c_fit ? a.ntot : c_fit;
+        const int nmax = a.ncentres_max > 0 ? a.ncentres_max : a.ntot;
+        const int grid = nmax < c_fit ? nmax : c_fit;
         k_centre<MODE, PCAP, CS><<<grid, CT, sm, st>>>(a);
         return 0;
     }
@@ -961,7 +962,8 @@ int launch_centre(cudaStream_t st, const CentreArgs &a) {
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    const int clusters = a.ntot < c_fit ? a.ntot : c_fit;
+    const int nmax = a.ncentres_max > 0 ? a.ncentres_max : a.ntot;
+    const int clusters = nmax < c_fit ? nmax : c_fit;
     cfg.gridDim = dim3(CS * clusters, 1, 1); cfg.blockDim = dim3(CT, 1, 1); cfg.dynamicSmemBytes = sm; cfg.stream = st;
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, k_centre<MODE, PCAP, CS>, a) == cudaSuccess ? 0 : -4;

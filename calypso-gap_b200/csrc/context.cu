@@ -32,6 +32,8 @@
 
 using namespace gapcu;
 
+struct gapcu_ctx;
+static void domain_destroy(gapcu_ctx *c);   // domain_host.inc
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 extern "C" const char *gapcu_last_error(void) { return g_err.c_str(); }
@@ -98,17 +100,23 @@ struct gapcu_ctx {
     bool h2d_pending = false; // the pinned staging buffer feeds a copy nobody has waited for yet
     // ---- structures
     int nstruct = 0, ntot = 0, nbins = 0;
+    int n_centres = 0;            // atoms evaluated as centres: all of them, or this rank's owned atoms (then ntot = owned + ghost capacity)
     double rcut = 0.0;
     std::vector<StructDev> h_structs;
     std::vector<int> h_natoms;
     DBuf<StructDev> d_structs;
-    DBuf<int> d_sid, d_arank, d_bin_count, d_bin_start, d_bin_atoms, d_nbr_cnt, d_order;
+    DBuf<int> d_sid, d_arank, d_bin_count, d_bin_start, d_bin_atoms, d_nbr_cnt, d_skin_cnt, d_order;
     DBuf<int4> d_abin, d_sabin;   // per atom / in bin order: (bin | atom, wrap offsets)
     DBuf<double> d_spos;          // coordinates in bin order
     DBuf<double> d_finpart;       // per (structure, chunk) partial sums of E and the strs contraction
     int max_natoms = 0;           // largest structure of the batch
     DBuf<double> d_pos, d_wgt, d_G, d_dEdG, d_eatom, d_fpair, d_gself, d_vir, d_force, d_out8, d_mindis, d_epart, d_accpart;
-    DBuf<uint64_t> d_keys;
+    DBuf<uint64_t> d_keys, d_skin_keys;   // exact lists (dis <= rcut) and candidate lists (dis <= rcut + skin)
+    DBuf<double> d_pos_build;             // positions the skin lists were built from (Verlet reuse)
+    double skin_user = 0.0;               // gapcu_ctx_set_skin; the effective skin never drops below SKIN_FLOOR
+    bool lists_valid = false;             // skin lists + pos_build describe the resident structures
+    bool reuse_next = false;              // the next compute may re-filter instead of rebuilding
+    bool last_reuse = false;              // how the pass in flight was run (a stale flag then means: rebuild)
     DBuf<uint32_t> d_stash;
     int sm_count = 0;
     DBuf<DevFlags> d_flags;
@@ -118,12 +126,11 @@ struct gapcu_ctx {
     // likewise structs | sid | pos | wgt ("inputs block"): one host-to-device copy per call
     DBuf<unsigned char> d_inputs;
     DBuf<unsigned char> d_flush;
-    // ---- spatial decomposition over ranks + NCCL (loaded lazily with dlopen)
+    // ---- spatial decomposition over ranks (domain_host.inc) + NCCL (loaded lazily with dlopen)
     DomainDev dom = {0, {1, 1, 1}, {0, 0, 0}, {0.0, 0.0, 0.0}};
-    DBuf<unsigned char> d_role;
-    DBuf<int> d_active;
+    struct DomainState *ds = nullptr;
     void *nccl_comm = nullptr;
-    int nccl_ranks = 1;
+    int nccl_ranks = 1, nccl_rank = 0;
     int cap = 0, pcap = 0, last_ntot = -1;
     bool pcap_known = false;
     int last_lgrad = 1;
@@ -137,6 +144,7 @@ struct gapcu_ctx {
     cudaEvent_t stage_ev[GAPCU_NSTAGE + 1];
     bool stage_ev_init = false;
 
+    double skin() const { return std::max(skin_user, 1e-9 * std::max(1.0, rcut)); }   // SKIN_FLOOR: see neigh.cu header
     PlanDev plan_dev() const {
         PlanDev p;
         p.itab = d_itab.p; p.dtab = d_dtab.p;
@@ -253,7 +261,9 @@ extern "C" void gapcu_ctx_destroy(gapcu_ctx *c) {
     c->d_bin_atoms.release(); c->d_nbr_cnt.release(); c->d_order.release(); c->d_abin.release(); c->d_sabin.release(); c->d_spos.release(); c->d_finpart.release(); c->d_pos.release(); c->d_wgt.release();
     c->d_G.release(); c->d_dEdG.release(); c->d_eatom.release(); c->d_fpair.release(); c->d_gself.release();
     c->d_vir.release(); c->d_force.release(); c->d_out8.release(); c->d_mindis.release(); c->d_keys.release();
-    c->d_stash.release(); c->d_epart.release(); c->d_accpart.release(); c->d_flags.release(); c->d_results.release(); c->d_inputs.release(); c->d_flush.release(); c->d_role.release(); c->d_active.release();
+    c->d_stash.release(); c->d_epart.release(); c->d_accpart.release(); c->d_flags.release(); c->d_results.release(); c->d_inputs.release(); c->d_flush.release();
+    c->d_skin_keys.release(); c->d_skin_cnt.release(); c->d_pos_build.release();
+    domain_destroy(c);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->stage_ev_init) for (auto &e : c->stage_ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -364,6 +374,53 @@ extern "C" int gapcu_ctx_set_pipeline(gapcu_ctx *c, int mode) {
 // ---------------------------------------------------------------------------
 // structures
 // ---------------------------------------------------------------------------
+static int lookup_weight(const gapcu_ctx *c, int species, double *w) {
+    // gap_calc.f90:75-83; a species missing from the file is an error here
+    int f = -1;
+    for (int q = 0; q < (int)c->z.size(); q++) if (species == c->z[q]) f = q;  // last match wins, as in the reference loop
+    if (f < 0) return fail(GAPCU_ESPECIES, "species " + std::to_string(species) + " is not in gap_parameters");
+    *w = c->w[f];
+    return 0;
+}
+
+// cell record of one periodic structure: lattice, image window (reference), cell-list grid for the
+// candidate radius rskin, bin count kept proportional to the atom count
+static int fill_struct(StructDev &sd, const double *lat9, double rcut, double rskin, int natoms, bool *direct) {
+    CellInfo ci = make_cell(lat9, rcut, rskin);
+    if (!(ci.volume > 0.0)) return fail(GAPCU_EARG, "singular lattice");
+    for (int d = 0; d < 3; d++)
+        if (ci.nabc[d] > 500) return fail(GAPCU_ENEIGH, "cell far smaller than rcut: neighbour list would exceed max_neighbor");
+    long cells = (long)ci.nbin[0] * ci.nbin[1] * ci.nbin[2];
+    const long lim = std::max(8l, 2l * natoms);
+    while (cells > lim) {
+        int d = 0;
+        for (int q = 1; q < 3; q++) if (ci.nbin[q] > ci.nbin[d]) d = q;
+        if (ci.nbin[d] <= 1) break;
+        ci.nbin[d]--;
+        cells = (long)ci.nbin[0] * ci.nbin[1] * ci.nbin[2];
+    }
+    memset(&sd, 0, sizeof sd);
+    memcpy(sd.lat, ci.lat, sizeof sd.lat);
+    memcpy(sd.inv, ci.inv, sizeof sd.inv);
+    sd.volume = ci.volume;
+    for (int d = 0; d < 3; d++)
+        sd.spacing[d] = 1.0 / std::sqrt(ci.inv[d] * ci.inv[d] + ci.inv[3 + d] * ci.inv[3 + d] + ci.inv[6 + d] * ci.inv[6 + d]);
+    for (int d = 0; d < 3; d++) {
+        sd.nabc[d] = ci.nabc[d];
+        sd.nbin[d] = ci.nbin[d];
+        // layers of bins scanned either side (potential.cpp:make_cell; the bin count may have been reduced above)
+        const double w = sd.spacing[d] / ci.nbin[d], full = rskin * (1.0 + 1e-9);
+        sd.mscan[d] = w >= full ? 1 : w >= 0.5 * full ? 2 : ci.nabc[d] + 1;
+        sd.org[d] = 0.0; sd.wid[d] = 1.0;
+    }
+    sd.open = 0;
+    sd.natoms = natoms; sd.nbins = (int)cells;
+    if (direct && (long)natoms * (2 * ci.nabc[0] + 1) * (2 * ci.nabc[1] + 1) * (2 * ci.nabc[2] + 1) > neighbor_direct_max_candidates()) *direct = false;
+    return 0;
+}
+
+static int set_structures_domain(gapcu_ctx *c, int natoms, const int *species, const double *lat_c, const double *pos, bool pos_soa, double rcut);
+
 // pos_soa: pos is [3][ntot_of_that_structure] per structure (Fortran pos(NA,3)); else C order [ntot][3].
 // need_weights = false for the bond-length path (no potential involved).
 static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, const int *species, const double *lat_c,
@@ -378,45 +435,28 @@ static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, con
         ntot += natoms[s];
     }
     if (ntot > (1l << 30)) return fail(GAPCU_ELIMIT, "too many atoms");
+    c->lists_valid = false; c->reuse_next = false;
+    if (c->dom.enabled && need_weights) {
+        if (nstruct != 1) return fail(GAPCU_EARG, "spatial decomposition works on a single structure");
+        c->rcut = rcut;
+        return set_structures_domain(c, natoms[0], species, lat_c, pos, pos_soa, rcut);
+    }
+    c->rcut = rcut;
+    const double rskin = rcut + c->skin();
     c->h_structs.resize(nstruct);
     c->h_natoms.assign(natoms, natoms + nstruct);
     int boff = 0, aoff = 0;
     double max_density = 0.0;
     bool direct = true;   // all structures small enough for the direct neighbour kernel
     for (int s = 0; s < nstruct; s++) {
-        CellInfo ci = make_cell(lat_c + 9 * (size_t)s, rcut);
-        if (!(ci.volume > 0.0)) return fail(GAPCU_EARG, "singular lattice");
-        for (int d = 0; d < 3; d++)
-            if (ci.nabc[d] > 500) return fail(GAPCU_ENEIGH, "cell far smaller than rcut: neighbour list would exceed max_neighbor");
-        // keep the bin count proportional to the atom count
-        long cells = (long)ci.nbin[0] * ci.nbin[1] * ci.nbin[2];
-        const long lim = std::max(8l, 2l * natoms[s]);
-        while (cells > lim) {
-            int d = 0;
-            for (int q = 1; q < 3; q++) if (ci.nbin[q] > ci.nbin[d]) d = q;
-            if (ci.nbin[d] <= 1) break;
-            ci.nbin[d]--;
-            cells = (long)ci.nbin[0] * ci.nbin[1] * ci.nbin[2];
-        }
         StructDev &sd = c->h_structs[s];
-        memcpy(sd.lat, ci.lat, sizeof sd.lat);
-        memcpy(sd.inv, ci.inv, sizeof sd.inv);
-        sd.volume = ci.volume;
-        for (int d = 0; d < 3; d++)
-            sd.spacing[d] = 1.0 / std::sqrt(ci.inv[d] * ci.inv[d] + ci.inv[3 + d] * ci.inv[3 + d] + ci.inv[6 + d] * ci.inv[6 + d]);
-        for (int d = 0; d < 3; d++) {
-            sd.nabc[d] = ci.nabc[d];
-            sd.nbin[d] = ci.nbin[d];
-            // layers of bins scanned either side (potential.cpp:make_cell; the bin count may have been reduced above)
-            const double w = sd.spacing[d] / ci.nbin[d], full = rcut * (1.0 + 1e-9);
-            sd.mscan[d] = w >= full ? 1 : w >= 0.5 * full ? 2 : ci.nabc[d] + 1;
-        }
-        sd.atom_off = aoff; sd.natoms = natoms[s]; sd.bin_off = boff; sd.nbins = (int)cells;
-        if ((long)natoms[s] * (2 * ci.nabc[0] + 1) * (2 * ci.nabc[1] + 1) * (2 * ci.nabc[2] + 1) > neighbor_direct_max_candidates()) direct = false;
-        aoff += natoms[s]; boff += (int)cells;
-        max_density = std::max(max_density, natoms[s] / ci.volume);
+        int rc = fill_struct(sd, lat_c + 9 * (size_t)s, rcut, rskin, natoms[s], &direct);
+        if (rc) return rc;
+        sd.atom_off = aoff; sd.bin_off = boff;
+        aoff += natoms[s]; boff += sd.nbins;
+        max_density = std::max(max_density, natoms[s] / sd.volume);
     }
-    c->nstruct = nstruct; c->ntot = (int)ntot; c->nbins = boff; c->rcut = rcut;
+    c->nstruct = nstruct; c->ntot = (int)ntot; c->n_centres = (int)ntot; c->nbins = boff;
     c->direct_ok = direct && !getenv("GAPCU_NO_DIRECT");   // GAPCU_NO_DIRECT: always the cell list (A/B and tests)
     const size_t NT = (size_t)ntot;
     // ---- pack host staging: structs | sid | pos SoA | wgt
@@ -442,27 +482,20 @@ static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, con
         a += n;
     }
     if (need_weights) {
-        // gap_calc.f90:75-83; a species missing from the file is an error here
-        const int ns = (int)c->z.size();
-        for (size_t t = 0; t < NT; t++) {
-            int f = -1;
-            for (int q = 0; q < ns; q++) if (species[t] == c->z[q]) f = q;  // last match wins, as in the reference loop
-            if (f < 0) return fail(GAPCU_ESPECIES, "species " + std::to_string(species[t]) + " is not in gap_parameters");
-            h_wgt[t] = c->w[f];
-        }
+        for (size_t t = 0; t < NT; t++) { int rc = lookup_weight(c, species[t], &h_wgt[t]); if (rc) return rc; }
     } else {
         memset(h_wgt, 0, b_wgt);
     }
     // ---- device buffers
     CU(ensure_inputs(c, (size_t)nstruct, NT));
-    CU(c->d_abin.ensure(NT)); CU(c->d_sabin.ensure(NT)); CU(c->d_spos.ensure(3 * NT)); CU(c->d_arank.ensure(NT)); CU(c->d_bin_count.ensure(c->nbins + 1));
-    CU(c->d_bin_start.ensure(c->nbins + 2)); CU(c->d_bin_atoms.ensure(NT)); CU(c->d_nbr_cnt.ensure(NT)); CU(c->d_order.ensure(NT));
+    CU(c->d_abin.ensure(NT)); CU(c->d_sabin.ensure(NT)); CU(c->d_spos.ensure(3 * NT)); CU(c->d_arank.ensure(NT)); CU(c->d_bin_count.ensure(2 * (size_t)c->nbins + 2));
+    CU(c->d_bin_start.ensure(c->nbins + 2)); CU(c->d_bin_atoms.ensure(NT)); CU(c->d_nbr_cnt.ensure(NT)); CU(c->d_skin_cnt.ensure(NT)); CU(c->d_order.ensure(NT));
     CU(ensure_results(c, (size_t)nstruct, NT));
-    CU(c->d_mindis.ensure(NT)); CU(c->d_role.ensure(NT)); CU(c->d_active.ensure(NT));
+    CU(c->d_mindis.ensure(NT));
     CU(cudaMemcpyAsync(c->d_inputs.p, hp, total, cudaMemcpyHostToDevice, c->stream));   // structs | sid | pos | wgt in one copy
     c->h2d_pending = true;
     // ---- neighbour capacity estimate (grown on demand)
-    int est = (int)(4.18879 * rcut * rcut * rcut * max_density * 1.25) + 32;
+    int est = (int)(4.18879 * rskin * rskin * rskin * max_density * 1.25) + 32;
     est = std::min(1024, std::max(64, round_up(est, 32)));
     if (c->cap < est) { c->cap = est; c->pcap_known = false; }
     if (c->last_ntot != c->ntot) { c->pcap_known = false; c->last_ntot = c->ntot; }
@@ -476,6 +509,14 @@ extern "C" int gapcu_ctx_set_structures(gapcu_ctx *c, int nstruct, const int *na
     return set_structures_impl(c, nstruct, natoms, species, lat, pos, false, rcut, true);
 }
 
+extern "C" int gapcu_ctx_set_skin(gapcu_ctx *c, double skin) {
+    if (!c || !(skin >= 0.0)) return fail(GAPCU_EARG, "skin must be >= 0");
+    c->skin_user = skin;
+    c->lists_valid = false;
+    c->pcap_known = false;
+    return 0;
+}
+
 // ---------------------------------------------------------------------------
 // NCCL, resolved at run time (the library has no link-time dependency on it)
 // ---------------------------------------------------------------------------
@@ -484,11 +525,16 @@ struct NcclId { char internal[128]; };
 struct NcclApi {
     int (*GetUniqueId)(NcclId *) = nullptr;
     int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
-    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     int (*CommDestroy)(void *) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     bool ok = false;
 } g_nccl;
+constexpr int NCCL_INT8 = 0, NCCL_INT32 = 2, NCCL_FLOAT64 = 8;
 
 int load_nccl() {
     if (g_nccl.ok) return 0;
@@ -497,20 +543,23 @@ int load_nccl() {
     if (!h) return fail(GAPCU_ECUDA, std::string("cannot load NCCL: ") + dlerror());
     g_nccl.GetUniqueId = (int (*)(NcclId *))dlsym(h, "ncclGetUniqueId");
     g_nccl.CommInitRank = (int (*)(void **, int, NcclId, int))dlsym(h, "ncclCommInitRank");
-    g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(h, "ncclAllGather");
+    g_nccl.Send = (int (*)(const void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclSend");
+    g_nccl.Recv = (int (*)(void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclRecv");
+    g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
     g_nccl.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
     g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) return fail(GAPCU_ECUDA, "NCCL symbols missing");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart ||
+        !g_nccl.GroupEnd)
+        return fail(GAPCU_ECUDA, "NCCL symbols missing");
     g_nccl.ok = true;
     return 0;
 }
-}  // namespace
-
-static int nccl_allreduce_sum(gapcu_ctx *c, double *buf, size_t count) {
-    const int r = g_nccl.AllReduce(buf, buf, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl_comm, c->stream);
-    if (r) return fail(GAPCU_ECUDA, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
-    return 0;
+int nccl_fail(const char *what, int r) {
+    return fail(GAPCU_ECUDA, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
 }
+}  // namespace
 
 extern "C" int gapcu_nccl_unique_id(char *out128) {
     int rc = load_nccl();
@@ -531,21 +580,10 @@ extern "C" int gapcu_ctx_nccl_init(gapcu_ctx *c, int nranks, int rank, const cha
     memcpy(id.internal, id128, 128);
     void *comm = nullptr;
     const int r = g_nccl.CommInitRank(&comm, nranks, id, rank);
-    if (r) return fail(GAPCU_ECUDA, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "error"));
+    if (r) return nccl_fail("ncclCommInitRank", r);
     c->nccl_comm = comm;
     c->nccl_ranks = nranks;
-    return 0;
-}
-
-extern "C" int gapcu_ctx_set_domain(gapcu_ctx *c, int g0, int g1, int g2, int m0, int m1, int m2) {
-    if (!c) return fail(GAPCU_EARG, "null context");
-    if (g0 < 1 || g1 < 1 || g2 < 1) return fail(GAPCU_EARG, "bad domain grid");
-    if (g0 * g1 * g2 == 1) { c->dom.enabled = 0; return 0; }
-    if (m0 < 0 || m0 >= g0 || m1 < 0 || m1 >= g1 || m2 < 0 || m2 >= g2) return fail(GAPCU_EARG, "brick outside the grid");
-    c->dom.enabled = 1;
-    c->dom.grid[0] = g0; c->dom.grid[1] = g1; c->dom.grid[2] = g2;
-    c->dom.mine[0] = m0; c->dom.mine[1] = m1; c->dom.mine[2] = m2;
-    c->pcap_known = false;
+    c->nccl_rank = rank;
     return 0;
 }
 
@@ -553,10 +591,10 @@ extern "C" int gapcu_ctx_set_domain(gapcu_ctx *c, int g0, int g1, int g2, int m0
 // compute
 // ---------------------------------------------------------------------------
 static int ensure_work_buffers(gapcu_ctx *c) {
-    const size_t NT = (size_t)c->ntot;
-    CU(c->d_keys.ensure(NT * c->cap));
-    CU(c->d_G.ensure(NT * c->D)); CU(c->d_dEdG.ensure(NT * c->D)); CU(c->d_eatom.ensure(NT));
-    CU(c->d_fpair.ensure(NT * c->cap * 3)); CU(c->d_gself.ensure(NT * 3)); CU(c->d_vir.ensure(NT * 6));
+    const size_t NT = (size_t)c->ntot, NC = (size_t)c->n_centres;
+    CU(c->d_keys.ensure(NT * c->cap)); CU(c->d_skin_keys.ensure(NT * c->cap));
+    CU(c->d_G.ensure(NC * c->D)); CU(c->d_dEdG.ensure(NC * c->D)); CU(c->d_eatom.ensure(NC));
+    CU(c->d_fpair.ensure(NC * c->cap * 3)); CU(c->d_gself.ensure(NC * 3)); CU(c->d_vir.ensure(NC * 6));
     c->max_natoms = 0;
     for (const StructDev &sd : c->h_structs) c->max_natoms = std::max(c->max_natoms, sd.natoms);
     CU(c->d_finpart.ensure((size_t)std::max(1, c->nstruct) * finalize_chunks(c->max_natoms) * 8));
@@ -566,12 +604,11 @@ static int ensure_work_buffers(gapcu_ctx *c) {
 // small undecomposed cells take the direct neighbour kernel, which also orders the centres
 static bool neighbors_direct(const gapcu_ctx *c) { return c->direct_ok && !c->dom.enabled; }
 
+static NeighborBuild neighbor_args(gapcu_ctx *c, bool with_keys, bool with_min, bool with_order);
+
 static int run_neighbors(gapcu_ctx *c, bool with_keys, bool with_min, bool with_order = false) {
-    launch_neighbor_build(c->stream, c->d_structs.p, c->d_sid.p, c->d_pos.p, c->ntot, c->nbins, c->rcut, c->cap,
-                          c->d_abin.p, c->d_arank.p, c->d_bin_count.p, c->d_bin_start.p, c->d_bin_atoms.p, c->d_sabin.p, c->d_spos.p,
-                          with_keys ? c->d_keys.p : nullptr, c->d_nbr_cnt.p, with_min ? c->d_mindis.p : nullptr,
-                          c->d_flags.p, c->dom, c->d_role.p, c->d_active.p, with_order ? c->d_order.p : nullptr,
-                          neighbors_direct(c), &c->launches);
+    const NeighborBuild b = neighbor_args(c, with_keys, with_min, with_order);
+    launch_neighbor_build(c->stream, b, &c->launches);
     CU(cudaGetLastError());
     return 0;
 }
@@ -593,7 +630,7 @@ static int make_centre_args(gapcu_ctx *c, int lgrad, int pcap, CentreArgs *out, 
     a.cls = c->class_tab();
     a.structs = c->d_structs.p; a.sid = c->d_sid.p; a.pos = c->d_pos.p; a.wgt = c->d_wgt.p;
     a.nbr_keys = c->d_keys.p; a.nbr_cnt = c->d_nbr_cnt.p; a.order = c->d_order.p; a.n_centres = &c->d_flags.p->n_centres; a.exp2_table = c->d_exp2.p;
-    a.ntot = c->ntot; a.cap = c->cap; a.pcap = pcap; a.lgrad = lgrad;
+    a.ntot = c->ntot; a.ncentres_max = c->n_centres; a.cap = c->cap; a.pcap = pcap; a.lgrad = lgrad;
     { static int var = -1; if (var < 0) { const char *e = getenv("GAPCU_VARIANT"); var = e ? atoi(e) : 0; } a.variant = var; }
     a.G = c->d_G.p; a.dEdG = c->d_dEdG.p; a.dEdG_out = c->d_dEdG.p; a.eatom = c->d_eatom.p;
     a.fpair = c->d_fpair.p; a.gself = c->d_gself.p; a.vir = c->d_vir.p;
@@ -616,7 +653,7 @@ static int make_centre_args(gapcu_ctx *c, int lgrad, int pcap, CentreArgs *out, 
         bool ok = false;
         for (int t = 0; t < 3 && !ok; t++)
             for (int pass = 0; pass < 2 && !ok; pass++) {
-                if (pass == 1 && t < 2) continue;          // the atomics fallback only as a last resort
+                if (pass == 1 && t < 2) continue;          // the shared accumulator set only as a last resort
                 a.npa = pass == 0 ? centre_warps() : 1;
                 for (a.lcap = want; a.lcap >= std::min(want, lmin[t]); a.lcap -= 512)
                     if (centre_smem_bytes(a, mode) <= targets[t]) { ok = true; break; }
@@ -636,42 +673,12 @@ static int make_centre_args(gapcu_ctx *c, int lgrad, int pcap, CentreArgs *out, 
     return 0;
 }
 
-// enqueue one full pass; ev (optional) = GAPCU_NSTAGE+1 events recorded at stage boundaries
-static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
-    if (!c->have_sf || !c->have_gpr) return fail(GAPCU_EARG, "no potential loaded");
-    if (c->D != c->plan.D) return fail(GAPCU_EARG, "des_len of the GPR data does not match 2*nsf of the SF table");
-    if (c->ntot <= 0) return fail(GAPCU_EARG, "no structures set");
-    int rc = ensure_work_buffers(c);
-    if (rc) return rc;
-    if (c->dom.enabled) {
-        if (c->nstruct != 1) return fail(GAPCU_EARG, "spatial decomposition works on a single structure");
-        const StructDev &sd = c->h_structs[0];
-        for (int d = 0; d < 3; d++) {
-            const double len = std::sqrt(sd.inv[d] * sd.inv[d] + sd.inv[3 + d] * sd.inv[3 + d] + sd.inv[6 + d] * sd.inv[6 + d]);
-            c->dom.margin[d] = c->rcut * len;   // rcut / interplanar spacing
-        }
-    }
-    CU(cudaMemsetAsync(c->d_flags.p, 0, sizeof(DevFlags), c->stream));
-    if (ev) CU(cudaEventRecord(ev[0], c->stream));
-    if ((rc = run_neighbors(c, true, false, true))) return rc;
-    if (!c->pcap_known) {
-        // first pass for this kind of input: learn the largest neighbour count
-        for (int attempt = 0; attempt < 4; attempt++) {
-            if ((rc = read_flags(c))) return rc;
-            if (c->h_flags.too_many)
-                return fail(GAPCU_ENEIGH, "Atoms neighbor: " + std::to_string(c->h_flags.maxcount) +
-                                              " large than max_neighbor 1000");
-            if (!c->h_flags.overflow) break;
-            c->cap = std::min(1024, round_up(c->h_flags.maxcount + 16, 32));
-            if ((rc = ensure_work_buffers(c))) return rc;
-            CU(cudaMemsetAsync(c->d_flags.p, 0, sizeof(DevFlags), c->stream));
-            if ((rc = run_neighbors(c, true, false, true))) return rc;
-        }
-        c->pcap = std::min(c->cap, std::max(32, round_up(c->h_flags.maxcount + 8, 32)));
-        c->pcap_known = true;
-    }
-    if (!neighbors_direct(c))
-        launch_order(c->stream, c->d_nbr_cnt.p, c->ntot, c->d_order.p, c->d_role.p, c->d_flags.p, &c->launches);
+// order -> centre kernel tiers -> (split pipeline: GPR, backward) -> force gather.  The neighbour
+// lists of the context's atoms are in place; ev (optional) records stage boundaries 1..5.
+static int run_centres_and_gather(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
+    int rc;
+    if (!neighbors_direct(c) || c->last_reuse)
+        launch_order(c->stream, c->d_nbr_cnt.p, c->n_centres, c->d_order.p, c->d_flags.p, &c->launches);
     CU(cudaGetLastError());
     if (ev) CU(cudaEventRecord(ev[1], c->stream));
     // Capacity tiers: `order` lists the centres by descending neighbour count, so the centres
@@ -699,8 +706,8 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
                 if (forced == 1 || forced == 2 || forced == 4) cs = forced;
                 // no tier can hold more centres than there are atoms.  Measured on B200 (tools/cluster_probe.py):
                 // the split pays while the CTAs of a launch do not have to share SMs more than two at a time
-                else if (c->ntot * 4 <= c->sm_count) cs = 4;
-                else if (c->ntot <= c->sm_count && c->ntot * 2 <= slots) cs = 2;
+                else if (c->n_centres * 4 <= c->sm_count) cs = 4;
+                else if (c->n_centres <= c->sm_count && c->n_centres * 2 <= slots) cs = 2;
             }
             if ((rc = make_centre_args(c, lgrad, cap == top ? c->pcap : cap, &t.a, &fused, cs))) return rc;
             t.a.q_begin = cap == top ? nullptr : &F->n_gt[idx];
@@ -708,7 +715,7 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
             tiers.push_back(t);
             // a launch with at most one centre per SM gains nothing from the leaner instances: the top
             // one serves every centre and the (mostly empty) lower tiers are not launched
-            if (cap == top && top <= 256 && c->ntot <= c->sm_count) { tiers.back().a.q_end = &F->n_centres; break; }
+            if (cap == top && top <= 256 && c->n_centres <= c->sm_count) { tiers.back().a.q_end = &F->n_centres; break; }
         }
         for (Tier &t : tiers)   // a later tier may have grown (moved) the shared list-parking buffer
             if (t.a.list_scratch) t.a.list_scratch = c->d_stash.p;
@@ -729,10 +736,10 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
         GprDev g;
         g.M = c->M; g.Mp = c->Mp; g.D = c->D; g.Dp = c->Dp; g.Mt = c->d_Mt.p; g.MtT = c->d_MtT.p; g.mn = c->d_mn.p;
         g.coeff = c->d_coeff.p; g.cmean = c->d_cmean.p; g.itheta = c->d_itheta.p;
-        const int max_slices = gpr_max_slices(c->ntot, c->Mp);
-        CU(c->d_epart.ensure((size_t)max_slices * c->ntot));
-        CU(c->d_accpart.ensure((size_t)max_slices * c->ntot * c->Dp));
-        if (launch_gpr(c->stream, g, c->d_G.p, c->ntot, c->d_eatom.p, c->d_dEdG.p, c->d_epart.p, c->d_accpart.p,
+        const int max_slices = gpr_max_slices(c->n_centres, c->Mp);
+        CU(c->d_epart.ensure((size_t)max_slices * c->n_centres));
+        CU(c->d_accpart.ensure((size_t)max_slices * c->n_centres * c->Dp));
+        if (launch_gpr(c->stream, g, c->d_G.p, c->n_centres, c->d_eatom.p, c->d_dEdG.p, c->d_epart.p, c->d_accpart.p,
                        max_slices, c->d_exp2.p, &c->launches))
             return fail(GAPCU_ELIMIT, "unsupported descriptor length for the GPR kernel");
         CU(cudaGetLastError());
@@ -744,16 +751,81 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
             }
         if (ev) CU(cudaEventRecord(ev[4], c->stream));
     }
-    launch_gather(c->stream, c->d_structs.p, c->nstruct, c->d_sid.p, c->ntot, c->cap, c->d_keys.p, c->d_nbr_cnt.p,
-                  c->d_fpair.p, c->d_gself.p, c->d_vir.p, c->d_eatom.p, lgrad, c->d_force.p, c->d_out8.p, c->d_role.p,
-                  c->dom.enabled ? c->d_active.p : nullptr, c->d_flags.p, c->d_finpart.p, c->max_natoms, &c->launches);
-    CU(cudaGetLastError());
-    if (c->dom.enabled && c->nccl_comm) {
-        // ghost-force return and the (E, stress) partial sums: one sum over ranks each
-        int rc2 = nccl_allreduce_sum(c, c->d_force.p, 3 * (size_t)c->ntot);
-        if (!rc2) rc2 = nccl_allreduce_sum(c, c->d_out8.p, 8 * (size_t)c->nstruct);
-        if (rc2) return rc2;
+    return 0;
+}
+
+static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev, bool reuse);
+#include "domain_host.inc"
+
+static NeighborBuild neighbor_args(gapcu_ctx *c, bool with_keys, bool with_min, bool with_order) {
+    NeighborBuild b;
+    memset(&b, 0, sizeof b);
+    b.structs = c->d_structs.p; b.sid = c->d_sid.p; b.pos = c->d_pos.p; b.ntot = c->ntot; b.nbins_total = c->nbins;
+    b.rcut = c->rcut; b.rskin = with_keys ? c->rcut + c->skin() : c->rcut; b.cap = c->cap;
+    b.abin = c->d_abin.p; b.arank = c->d_arank.p; b.bin_count = c->d_bin_count.p; b.bin_start = c->d_bin_start.p;
+    b.bin_atoms = c->d_bin_atoms.p; b.sabin = c->d_sabin.p; b.spos = c->d_spos.p;
+    b.skin_keys = with_keys ? c->d_skin_keys.p : nullptr; b.skin_cnt = c->d_skin_cnt.p;
+    b.nbr_keys = with_keys ? c->d_keys.p : nullptr; b.nbr_cnt = c->d_nbr_cnt.p;
+    b.min_dis = with_min ? c->d_mindis.p : nullptr;
+    b.flags = c->d_flags.p;
+    b.order = with_order ? c->d_order.p : nullptr;
+    b.direct = neighbors_direct(c);
+    b.n_own = c->n_centres;
+    if (c->dom.enabled && c->ds) { b.sft = c->ds->d_sft.p; b.nloc = &c->d_flags.p->n_loc; }
+    return b;
+}
+
+// enqueue one full pass; ev (optional) = GAPCU_NSTAGE+1 events recorded at stage boundaries.
+// reuse: keep the skin lists, only re-filter them against the current positions (Verlet reuse).
+static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev, bool reuse) {
+    if (!c->have_sf || !c->have_gpr) return fail(GAPCU_EARG, "no potential loaded");
+    if (c->D != c->plan.D) return fail(GAPCU_EARG, "des_len of the GPR data does not match 2*nsf of the SF table");
+    if (c->ntot <= 0) return fail(GAPCU_EARG, "no structures set");
+    if (c->dom.enabled) return domain_enqueue_pass(c, lgrad, ev, reuse);
+    reuse = reuse && c->lists_valid;
+    int rc = ensure_work_buffers(c);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(c->d_flags.p, 0, sizeof(DevFlags), c->stream));
+    if (ev) CU(cudaEventRecord(ev[0], c->stream));
+    c->last_reuse = reuse;
+    if (reuse) {
+        launch_refilter(c->stream, neighbor_args(c, true, false, false), c->d_pos_build.p, c->skin(), &c->launches);
+        CU(cudaGetLastError());
+    } else {
+        if ((rc = run_neighbors(c, true, false, true))) return rc;
+        if (!c->pcap_known) {
+            // first pass for this kind of input: learn the largest list lengths
+            for (int attempt = 0; attempt < 4; attempt++) {
+                if ((rc = read_flags(c))) return rc;
+                if (c->h_flags.too_many)
+                    return fail(GAPCU_ENEIGH, "Atoms neighbor: " + std::to_string(c->h_flags.maxcount) +
+                                                  " large than max_neighbor 1000");
+                if (!c->h_flags.overflow) break;
+                if (c->h_flags.maxskin > 1024) return fail(GAPCU_ELIMIT, "more than 1024 atoms within rcut + skin: reduce the skin");
+                c->cap = std::min(1024, round_up(c->h_flags.maxskin + 16, 32));
+                if ((rc = ensure_work_buffers(c))) return rc;
+                CU(cudaMemsetAsync(c->d_flags.p, 0, sizeof(DevFlags), c->stream));
+                if ((rc = run_neighbors(c, true, false, true))) return rc;
+            }
+            c->pcap = std::min(c->cap, std::max(32, round_up(c->h_flags.maxcount + 8, 32)));
+            c->pcap_known = true;
+        }
+        if (c->skin_user > 0.0) {   // a caller that set a skin will come back with moved positions
+            CU(c->d_pos_build.ensure(3 * (size_t)c->ntot));
+            CU(cudaMemcpyAsync(c->d_pos_build.p, c->d_pos.p, sizeof(double) * 3 * (size_t)c->ntot, cudaMemcpyDeviceToDevice, c->stream));
+            c->lists_valid = true;
+        }
     }
+    if ((rc = run_centres_and_gather(c, lgrad, ev))) return rc;
+    GatherArgs g;
+    memset(&g, 0, sizeof g);
+    g.structs = c->d_structs.p; g.nstruct = c->nstruct; g.sid = c->d_sid.p; g.ntot = c->ntot; g.cap = c->cap;
+    g.skin_keys = c->d_skin_keys.p; g.skin_cnt = c->d_skin_cnt.p; g.nbr_keys = c->d_keys.p; g.nbr_cnt = c->d_nbr_cnt.p;
+    g.fpair = c->d_fpair.p; g.gself = c->d_gself.p; g.vir = c->d_vir.p; g.eatom = c->d_eatom.p; g.lgrad = lgrad;
+    g.force_soa = c->d_force.p; g.out8 = c->d_out8.p; g.partial = c->d_finpart.p; g.max_natoms = c->max_natoms;
+    g.n_own = c->ntot;
+    launch_gather(c->stream, g, &c->launches);
+    CU(cudaGetLastError());
     if (ev) CU(cudaEventRecord(ev[5], c->stream));
     c->last_lgrad = lgrad;
     c->computed = true;
@@ -762,51 +834,102 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
 
 extern "C" int gapcu_ctx_compute(gapcu_ctx *c, int lgrad) {
     if (!c) return fail(GAPCU_EARG, "null context");
+    if (c->dom.enabled && c->ds && c->ds->group) return fail(GAPCU_EARG, "this context belongs to a group: use gapcu_group_compute");
     DeviceGuard dg_(c->device);
-    return enqueue_pass(c, lgrad, nullptr);
+    const bool reuse = c->reuse_next;
+    c->reuse_next = false;
+    return enqueue_pass(c, lgrad, nullptr, reuse);
 }
 
-// wait for the pass; if a list overflowed (neighbour count grew since the
-// capacity was learned) enlarge and run again.
+// New positions for the resident structures (same atoms, same cells): an MD or relaxation step.
+// pos: C order [ntot][3] (decomposed runs: this rank's owned atoms in the order of gapcu_ctx_owned).
+// reuse_lists != 0 and a skin > 0 set with gapcu_ctx_set_skin: the next compute keeps the skin lists and
+// only re-filters them (rebuilding on its own when an atom has moved more than skin/2).
+extern "C" int gapcu_ctx_update_positions(gapcu_ctx *c, const double *pos, int reuse_lists) {
+    if (!c || !pos) return fail(GAPCU_EARG, "null argument");
+    if (c->ntot <= 0) return fail(GAPCU_EARG, "no structures set");
+    DeviceGuard dg_(c->device);
+    if (c->dom.enabled) return domain_update_positions(c, pos, reuse_lists);
+    const size_t NT = (size_t)c->ntot;
+    if (c->h2d_pending) { CU(cudaStreamSynchronize(c->stream)); c->h2d_pending = false; }
+    if (c->pin(sizeof(double) * 3 * NT)) return fail(GAPCU_ECUDA, "cudaMallocHost failed");
+    double *hp = (double *)c->h_pin;
+    for (size_t t = 0; t < NT; t++) { hp[t] = pos[3 * t]; hp[NT + t] = pos[3 * t + 1]; hp[2 * NT + t] = pos[3 * t + 2]; }
+    CU(cudaMemcpyAsync(c->d_pos.p, hp, sizeof(double) * 3 * NT, cudaMemcpyHostToDevice, c->stream));
+    c->h2d_pending = true;
+    c->reuse_next = reuse_lists && c->skin_user > 0.0 && c->lists_valid;
+    c->computed = false;
+    return 0;
+}
+
+// After the results block came back: decide what the flags ask for.  Returns 0 = results are good,
+// 1 = the pass was re-enqueued (read again), < 0 = error.  In a decomposed run the flags are the
+// maxima over all ranks (halo.cu:k_halo_combine), so every rank takes the same branch here and the
+// re-run's collectives pair up.
+static int react_to_flags(gapcu_ctx *c, int attempt) {
+    const DevFlags &f = c->h_flags;
+    if (f.too_many)
+        return fail(GAPCU_ENEIGH, "Atoms neighbor: " + std::to_string(f.maxcount) + " large than max_neighbor 1000");
+    if (f.halo_far)
+        return fail(GAPCU_EDOMAIN, "an owned atom left its brick by more than the drift allowance: set the structure again to re-partition");
+    bool rerun = false, reuse = false;
+    if (f.overflow) {
+        if (f.maxskin > 1024) return fail(GAPCU_ELIMIT, "more than 1024 atoms within rcut + skin: reduce the skin");
+        c->cap = std::max(c->cap, std::min(1024, round_up(f.maxskin + 16, 32)));
+        c->pcap_known = false; c->lists_valid = false;
+        rerun = true;
+    }
+    if (f.halo_overflow && c->ds) { domain_forget_caps(c); c->lists_valid = false; rerun = true; }
+    if (f.stale) { c->lists_valid = false; rerun = true; }
+    if (c->dom.enabled && !c->pcap_known && !rerun) {
+        // first decomposed pass ran with the list capacity as kernel capacity: remember the real one
+        c->pcap = std::min(c->cap, std::max(32, round_up(f.maxcount + 8, 32)));
+        c->pcap_known = true;
+    }
+    if (!rerun) return 0;
+    if (attempt >= 3) return fail(GAPCU_ECUDA, "capacities did not converge");
+    int rc = enqueue_pass(c, c->last_lgrad, nullptr, reuse);
+    return rc ? rc : 1;
+}
+
+// wait for the pass; if a flag asks for it (a list outgrew its capacity, the skin lists went stale)
+// enlarge / rebuild and run again.
 static int finish_pass(gapcu_ctx *c) {
-    for (int attempt = 0; attempt < 4; attempt++) {
+    for (int attempt = 0;; attempt++) {
         int rc = read_flags(c);
         if (rc) return rc;
-        if (c->h_flags.too_many)
-            return fail(GAPCU_ENEIGH, "Atoms neighbor: " + std::to_string(c->h_flags.maxcount) + " large than max_neighbor 1000");
-        if (!c->h_flags.overflow) return 0;
-        c->cap = std::max(c->cap, std::min(1024, round_up(c->h_flags.maxcount + 16, 32)));
-        c->pcap_known = false;
-        if ((rc = enqueue_pass(c, c->last_lgrad, nullptr))) return rc;
+        rc = react_to_flags(c, attempt);
+        if (rc <= 0) return rc;
     }
-    return fail(GAPCU_ECUDA, "neighbour capacity did not converge");
 }
 
 extern "C" int gapcu_ctx_fetch(gapcu_ctx *c, double *ene, double *force, double *stress) {
     if (!c) return fail(GAPCU_EARG, "null context");
     if (!c->computed) return fail(GAPCU_EARG, "nothing computed");
     DeviceGuard dg_(c->device);
-    // flags, per-structure outputs and forces come back in one copy; if a neighbour list overflowed
-    // (the count grew since the capacity was learned) the pass is re-run with a larger capacity
-    const size_t NT = (size_t)c->ntot;
+    // flags, per-structure outputs and forces come back in one copy; if a flag asks for another pass
+    // (capacity outgrown, stale skin lists) it is run and read again
+    const size_t NT = (size_t)c->ntot, NF = (size_t)c->n_centres;   // NF: atoms whose forces this context returns
     const size_t b_f = sizeof(double) * 3 * NT;
     double *h_out = nullptr, *h_f = nullptr;
     for (int attempt = 0;; attempt++) {
         const size_t bytes = force ? c->res_o_f + b_f : c->res_o_f;
         if (c->pin(c->res_o_f + b_f)) return fail(GAPCU_ECUDA, "cudaMallocHost failed");
-        CU(cudaMemcpyAsync(c->h_pin, c->d_results.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+        if (force && NF < NT) {
+            // decomposed run: the owned atoms are the first NF of NT local points in each SoA row
+            CU(cudaMemcpyAsync(c->h_pin, c->d_results.p, c->res_o_f, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaMemcpy2DAsync((char *)c->h_pin + c->res_o_f, sizeof(double) * NF, c->d_force.p, sizeof(double) * NT,
+                                 sizeof(double) * NF, 3, cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            CU(cudaMemcpyAsync(c->h_pin, c->d_results.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+        }
         CU(cudaStreamSynchronize(c->stream));
         c->h2d_pending = false;
         c->h_flags = *(const DevFlags *)c->h_pin;
         h_out = (double *)((char *)c->h_pin + c->res_o_out); h_f = (double *)((char *)c->h_pin + c->res_o_f);
-        if (c->h_flags.too_many)
-            return fail(GAPCU_ENEIGH, "Atoms neighbor: " + std::to_string(c->h_flags.maxcount) + " large than max_neighbor 1000");
-        if (!c->h_flags.overflow) break;
-        if (attempt >= 3) return fail(GAPCU_ECUDA, "neighbour capacity did not converge");
-        c->cap = std::max(c->cap, std::min(1024, round_up(c->h_flags.maxcount + 16, 32)));
-        c->pcap_known = false;
-        int rc = enqueue_pass(c, c->last_lgrad, nullptr);
-        if (rc) return rc;
+        const int rc = react_to_flags(c, attempt);
+        if (rc < 0) return rc;
+        if (rc == 0) break;
     }
     if (c->h_flags.close_pairs)
         fprintf(stdout, " Warning: The distance of two atoms is very small (%d pairs below 0.5)\n", c->h_flags.close_pairs);
@@ -814,9 +937,11 @@ extern "C" int gapcu_ctx_fetch(gapcu_ctx *c, double *ene, double *force, double 
         if (ene) ene[s] = h_out[8 * s];
         if (stress) for (int q = 0; q < 6; q++) stress[6 * s + q] = h_out[8 * s + 1 + q];
     }
-    if (force)
-        for (size_t t = 0; t < NT; t++)
-            for (int d = 0; d < 3; d++) force[3 * t + d] = h_f[d * NT + t];
+    if (force) {
+        const size_t ld = NF < NT ? NF : NT;
+        for (size_t t = 0; t < NF; t++)
+            for (int d = 0; d < 3; d++) force[3 * t + d] = h_f[d * ld + t];
+    }
     return 0;
 }
 
@@ -941,8 +1066,12 @@ extern "C" int gapcu_ctx_time_compute(gapcu_ctx *c, int lgrad, int steps, long l
         c->stage_ev_init = true;
     }
     if (l2_flush_bytes > 0) CU(c->d_flush.ensure((size_t)l2_flush_bytes));
+    // after gapcu_ctx_update_positions(.., reuse_lists = 1) the passes of this call re-filter the kept
+    // skin lists; otherwise every pass rebuilds the neighbour lists (and, decomposed, the halo lists)
+    const bool reuse = c->reuse_next;
+    c->reuse_next = false;
     // make sure capacities are settled before timing
-    int rc = enqueue_pass(c, lgrad, nullptr);
+    int rc = enqueue_pass(c, lgrad, nullptr, reuse);
     if (rc) return rc;
     if ((rc = finish_pass(c))) return rc;
     std::vector<cudaEvent_t> ev(2 * (size_t)steps);
@@ -951,7 +1080,7 @@ extern "C" int gapcu_ctx_time_compute(gapcu_ctx *c, int lgrad, int steps, long l
     for (int s = 0; s < steps; s++) {
         if (l2_flush_bytes > 0) CU(cudaMemsetAsync(c->d_flush.p, s & 0xff, (size_t)l2_flush_bytes, c->stream));
         CU(cudaEventRecord(ev[2 * s], c->stream));
-        if ((rc = enqueue_pass(c, lgrad, nullptr))) return rc;
+        if ((rc = enqueue_pass(c, lgrad, nullptr, reuse))) return rc;
         CU(cudaEventRecord(ev[2 * s + 1], c->stream));
     }
     CU(cudaStreamSynchronize(c->stream));
@@ -969,7 +1098,7 @@ extern "C" int gapcu_ctx_time_compute(gapcu_ctx *c, int lgrad, int steps, long l
         for (int q = 0; q < GAPCU_NSTAGE; q++) stage_ms[q] = 0.0;
         for (int s = 0; s < steps; s++) {
             if (l2_flush_bytes > 0) CU(cudaMemsetAsync(c->d_flush.p, s & 0xff, (size_t)l2_flush_bytes, c->stream));
-            if ((rc = enqueue_pass(c, lgrad, c->stage_ev))) return rc;
+            if ((rc = enqueue_pass(c, lgrad, c->stage_ev, reuse))) return rc;
             CU(cudaStreamSynchronize(c->stream));
             for (int q = 0; q < 5; q++) {
                 float ms = 0.f;
@@ -1080,7 +1209,7 @@ extern "C" int gapcu_calc(int na, const int *species, const double *lat, const d
     stamp(1);
     if ((rc = set_structures_impl(c, 1, &na, species, lat_c, pos, true, rcut, true))) return rc;
     stamp(2);
-    if ((rc = enqueue_pass(c, lgrad ? 1 : 0, nullptr))) return rc;
+    if ((rc = enqueue_pass(c, lgrad ? 1 : 0, nullptr, false))) return rc;
     stamp(3);
     // results: flags | out8 | force SoA (= Fortran FORCE(NA,3)) in one batch, one synchronisation
     size_t b_f = sizeof(double) * 3 * (size_t)na;
@@ -1092,14 +1221,10 @@ extern "C" int gapcu_calc(int na, const int *species, const double *lat, const d
         CU(cudaStreamSynchronize(c->stream));
         c->h2d_pending = false;
         c->h_flags = *h_fl;
-        if (c->h_flags.too_many)
-            return fail(GAPCU_ENEIGH, "Atoms neighbor: " + std::to_string(c->h_flags.maxcount) + " large than max_neighbor 1000");
-        if (!c->h_flags.overflow) break;
-        if (attempt >= 3) return fail(GAPCU_ECUDA, "neighbour capacity did not converge");
-        // the neighbour count outgrew the learned capacity: enlarge and run again
-        c->cap = std::max(c->cap, std::min(1024, round_up(c->h_flags.maxcount + 16, 32)));
-        c->pcap_known = false;
-        if ((rc = enqueue_pass(c, lgrad ? 1 : 0, nullptr))) return rc;
+        // a list outgrew the learned capacity: react_to_flags enlarges and runs the pass again
+        rc = react_to_flags(c, attempt);
+        if (rc < 0) return rc;
+        if (rc == 0) break;
     }
     if (c->h_flags.close_pairs)
         fprintf(stdout, " Warning: The distance of two atoms is very small (%d pairs below 0.5)\n", c->h_flags.close_pairs);
@@ -1367,7 +1492,7 @@ extern "C" int gapcu_car2acsf_table(int na, int max_neighbor, int nf, const doub
     sd.lat[0] = sd.lat[4] = sd.lat[8] = 1.0; sd.inv[0] = sd.inv[4] = sd.inv[8] = 1.0; sd.volume = 1.0;
     sd.natoms = na; sd.nbins = 1; sd.nbin[0] = sd.nbin[1] = sd.nbin[2] = 1;
     c->h_natoms.assign(1, na);
-    c->nstruct = 1; c->ntot = na; c->nbins = 1; c->computed = false; c->pcap_known = false; c->last_ntot = -1;
+    c->nstruct = 1; c->ntot = na; c->n_centres = na; c->nbins = 1; c->computed = false; c->pcap_known = false; c->last_ntot = -1; c->lists_valid = false;
     c->cap = std::max(32, round_up(maxcnt, 32)); c->pcap = c->cap;
     if (!c->have_gpr || c->D != D) {  // the GPR part is irrelevant here; give the kernels a consistent dummy
         std::vector<double> th(D, 1.0), m1(D, 0.0), c1(1, 0.0);
@@ -1375,9 +1500,8 @@ extern "C" int gapcu_car2acsf_table(int na, int max_neighbor, int nf, const doub
     }
     DBuf<double> d_table;
     std::vector<int> h_sid(NA, 0);
-    std::vector<unsigned char> h_role(NA, 2);
     CU(ensure_inputs(c, 1, NA));
-    CU(c->d_nbr_cnt.ensure(NA)); CU(ensure_results(c, 1, NA)); CU(c->d_role.ensure(NA)); CU(c->d_order.ensure(NA));
+    CU(c->d_nbr_cnt.ensure(NA)); CU(ensure_results(c, 1, NA)); CU(c->d_order.ensure(NA));
     CU(d_table.ensure(NA * max_neighbor * 6));
     if ((rc = ensure_work_buffers(c))) { d_table.release(); return rc; }
     auto bail = [&](int code) { d_table.release(); return code; };
@@ -1385,7 +1509,6 @@ extern "C" int gapcu_car2acsf_table(int na, int max_neighbor, int nf, const doub
         cudaMemcpy(c->d_sid.p, h_sid.data(), sizeof(int) * NA, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(c->d_pos.p, pos, sizeof(double) * 3 * NA, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(c->d_nbr_cnt.p, neighbor_count, sizeof(int) * NA, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(c->d_role.p, h_role.data(), NA, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(d_table.p, neighbor, sizeof(double) * NA * max_neighbor * 6, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemset(c->d_wgt.p, 0, sizeof(double) * NA) != cudaSuccess)
         return bail(fail(GAPCU_ECUDA, "upload failed"));

@@ -14,18 +14,22 @@ struct StructDev {
     int nbin[3];
     int mscan[3];
     int atom_off, natoms, bin_off, nbins;
+    // binned region in fractional coordinates: the whole periodic cell (org = 0, wid = 1, open = 0) or,
+    // for one rank of a decomposed run, its brick plus the ghost shell, not periodic (open = 1)
+    double org[3], wid[3];
+    int open, pad_;
 };
 
 // Spatial decomposition of ONE large structure over ranks: the cell is cut
 // into grid[0] x grid[1] x grid[2] bricks in fractional coordinates; a rank OWNS the atoms of
-// its brick (it evaluates them as centres) and additionally lists the GHOST atoms within rcut
-// of the brick (it needs their neighbour lists to hand back the forces its centres exert on
-// them).  role: 0 = not involved, 1 = ghost, 2 = owned.  Disabled: every atom is owned.
+// its brick (it evaluates them as centres) and receives, from the owners, the GHOST images within
+// rcut + skin of the brick (halo.cu).  margin = (rcut + skin) / interplanar spacing: the shell
+// thickness in fractional units.
 struct DomainDev {
     int enabled;
     int grid[3];
     int mine[3];
-    double margin[3];   // rcut / interplanar spacing: ghost shell thickness in fractional units
+    double margin[3];
 };
 
 // Neighbour key: canonical (reference) order (j, n1, n2, n3) is plain integer order.
@@ -56,6 +60,13 @@ struct DevFlags {
     // exit and the sum of the CTAs' busy times (load-balance diagnostics)
     unsigned long long t_start_min, t_exit_min, t_exit_max, t_busy_sum, n_ctas;
     int ticket;          // CTAs of k_neigh_direct that are done (the last one orders the centres)
+    int maxskin;         // largest skin-list length seen (the lists' capacity must hold it)
+    int stale;           // an atom moved more than skin/2 since the skin lists were built: rebuild
+    // decomposed runs (halo.cu)
+    int halo_overflow;   // a send list or the local point array outgrew its capacity
+    int halo_count[27];  // records this rank sends in each direction (index 13 = centre, unused)
+    int n_ghost, n_loc;  // ghosts received, owned + ghosts
+    int halo_far;        // an owned atom drifted further from its brick than the exchange pattern covers
 };
 
 constexpr int MAXC_DEV = 16;  // distinct cutoffs (classes) supported
@@ -105,7 +116,8 @@ struct CentreArgs {
     const int *q_begin, *q_end;
     int queue_slot;
     const double *exp2_table;   // [32] 2^(j/32)
-    int ntot, cap, pcap;        // pcap: shared-memory neighbour capacity (>= max count)
+    int ntot, cap, pcap;        // ntot: stride of the SoA arrays; pcap: shared-memory neighbour capacity (>= max count)
+    int ncentres_max;           // upper bound of the centres this launch serves (sizes the persistent grid)
     int lcap;                   // triplet-list capacity per chunk
     uint32_t *list_scratch;     // [ctas][list_scratch_chunks][lcap+32+512] sorted lists kept from forward to backward
     int list_scratch_chunks;

@@ -2,12 +2,13 @@
 //
 // The reference sums  force(i) = - sum_n sum_k dedg(n,k) * dxdy(k,n,i,:)  over ALL
 // centres n through the dense dxdy array (gap_calc.f90:177-185).  Here every
-// centre n left dE_n/dx_slot for each of its neighbour slots (desc.cu); atom i
-// walks its OWN neighbour list and, for each entry (n, shift), finds the mirror
-// entry (i, -shift) in n's sorted list by binary search and reads that gradient:
-// a segmented, atomic-free gather in a fixed order.  The only atomics are one
-// add per atom into the zeroed output and the "orphan" path: a pair kept in one
-// direction only (distance within one ulp of rcut) is pushed by its producer.
+// centre n left dE_n/dx_slot for each of its neighbour slots (centre_impl.cuh); atom i
+// walks its own SKIN list (every image within rcut + skin, neigh.cu) and, for each
+// candidate (n, shift), looks for the mirror entry (i, -shift) in n's sorted EXACT list
+// by binary search; if n lists i, that slot's gradient is added.  Walking the superset
+// makes the gather complete even when the two directed distances of a pair straddle rcut
+// by an ulp (n lists i although i does not list n): no push path, no atomics, one plain
+// store per force component, every sum in a fixed order -> bit-reproducible.
 #include <cstdint>
 
 #include "device_types.cuh"
@@ -23,57 +24,46 @@ constexpr int GT = 128;  // threads per atom in k_gather: one mirror lookup per 
 struct FinArgs {
     const double *eatom, *vir;
     double *partial, *out8;
-    int lgrad, nchunk, nstruct;
+    int lgrad, nchunk, nstruct, n_own, raw;
 };
-__device__ void finalize_partial(const StructDev *structs, const FinArgs &f, const unsigned char *role, int chunk, int st);
+__device__ void finalize_partial(const StructDev *structs, const FinArgs &f, int chunk, int st);
 
 // Grid: nchunk * nstruct CTAs that reduce E and the strs contraction per structure (first, so
 // that they do not form a tail), then ntot CTAs that gather the forces (one atom each).  Both
 // parts read only what the centre kernel wrote, so they share one launch (a separate launch
 // costs ~7 us on small inputs).
 __global__ void __launch_bounds__(GT)
-k_gather(const StructDev *structs, const int *sid, int ntot, int cap, const uint64_t *nbr_keys,
-         const int *nbr_cnt, const double *fpair, const double *gself, double *force,
-         const unsigned char *role, const int *active, const DevFlags *flags, const int nfin, const FinArgs fin) {
+k_gather(const GatherArgs g, const int nfin, const FinArgs fin) {
     __shared__ double red[GT / 32][3];
     if ((int)blockIdx.x < nfin) {
-        finalize_partial(structs, fin, role, blockIdx.x % fin.nchunk, blockIdx.x / fin.nchunk);
+        finalize_partial(g.structs, fin, blockIdx.x % fin.nchunk, blockIdx.x / fin.nchunk);
         return;
     }
-    const int slot_i = blockIdx.x - nfin;
+    const int i = blockIdx.x - nfin;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (slot_i >= (active ? flags->n_active : ntot)) return;
-    const int i = active ? active[slot_i] : slot_i;
-    const bool i_owned = !role || role[i] == 2;
-    const StructDev &sd = structs[sid[i]];
+    if (g.nloc && i >= *g.nloc) return;
+    const int ntot = g.ntot, cap = g.cap;
+    const bool i_owned = i < g.n_own;
+    const StructDev &sd = g.structs[g.sid[i]];
     const int il = i - sd.atom_off;
-    const int P = min(nbr_cnt[i], cap);
+    const int P = min(g.skin_cnt[i], cap);
     double gx = 0.0, gy = 0.0, gz = 0.0;
     for (int s = tid; s < P; s += GT) {
         int jl, n1, n2, n3;
-        nbr_unkey(nbr_keys[(size_t)i * cap + s], jl, n1, n2, n3);
+        nbr_unkey(g.skin_keys[(size_t)i * cap + s], jl, n1, n2, n3);
         const int nb = sd.atom_off + jl;
-        const bool nb_owned = !role || role[nb] == 2;      // only this rank's centres have gradients here
-        if (!nb_owned && !i_owned) continue;
+        if (nb >= g.n_own) continue;      // a ghost is nobody's centre here: its owner's rank returns that part
         const uint64_t want = nbr_key(il, -n1, -n2, -n3);
-        const uint64_t *lst = nbr_keys + (size_t)nb * cap;
-        const int cnt_nb = min(nbr_cnt[nb], cap);
+        const uint64_t *lst = g.nbr_keys + (size_t)nb * cap;
+        const int cnt_nb = min(g.nbr_cnt[nb], cap);
         int lo = 0, hi = cnt_nb;
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
             if (lst[mid] < want) lo = mid + 1; else hi = mid;
         }
         if (lo < cnt_nb && lst[lo] == want) {
-            if (nb_owned) {
-                const double *fp = fpair + ((size_t)nb * cap + lo) * 3;
-                gx += fp[0]; gy += fp[1]; gz += fp[2];
-            }
-        } else if (i_owned) {
-            // nb does not list me, so nobody will gather what I exert on nb: push it
-            const double *fp = fpair + ((size_t)i * cap + s) * 3;
-            atomicAdd(&force[nb], -fp[0]);
-            atomicAdd(&force[ntot + nb], -fp[1]);
-            atomicAdd(&force[2 * ntot + nb], -fp[2]);
+            const double *fp = g.fpair + ((size_t)nb * cap + lo) * 3;
+            gx += fp[0]; gy += fp[1]; gz += fp[2];
         }
     }
 #pragma unroll
@@ -88,8 +78,8 @@ k_gather(const StructDev *structs, const int *sid, int ntot, int cap, const uint
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < GT / 32; w++) v += red[w][tid];
-        const double self = i_owned ? gself[(size_t)i * 3 + tid] : 0.0;
-        atomicAdd(&force[(size_t)tid * ntot + i], -(self + v));
+        if (i_owned) g.force_soa[(size_t)tid * ntot + i] = -(g.gself[(size_t)i * 3 + tid] + v);
+        else g.ghost_grad[(size_t)g.gslot[i - g.n_own] * 3 + tid] = v;
     }
 }
 
@@ -112,7 +102,7 @@ __device__ __forceinline__ void write_out8(const double *s, const StructDev &sd,
     o[7] = 0.0;        // variance (gap_calc.f90:206)
 }
 
-__device__ void finalize_partial(const StructDev *structs, const FinArgs &f, const unsigned char *role, const int chunk, const int st) {
+__device__ void finalize_partial(const StructDev *structs, const FinArgs &f, const int chunk, const int st) {
     __shared__ double red[GT / 32][7];
     __shared__ double tot[8];
     const StructDev &sd = structs[st];
@@ -120,11 +110,10 @@ __device__ void finalize_partial(const StructDev *structs, const FinArgs &f, con
     double *partial = f.partial, *out8 = f.out8;
     const int lgrad = f.lgrad, nchunk = f.nchunk;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int t0 = chunk * FIN_CHUNK, t1 = min(sd.natoms, t0 + FIN_CHUNK);
+    const int t0 = chunk * FIN_CHUNK, t1 = min(min(sd.natoms, f.n_own), t0 + FIN_CHUNK);   // decomposed run: this rank's centres only
     double v[7] = {0, 0, 0, 0, 0, 0, 0};
     for (int t = t0 + tid; t < t1; t += GT) {
         const int i = sd.atom_off + t;
-        if (role && role[i] != 2) continue;   // decomposed run: partial sums over this rank's centres
         v[0] += eatom[i];
         if (lgrad)
 #pragma unroll
@@ -146,16 +135,19 @@ __device__ void finalize_partial(const StructDev *structs, const FinArgs &f, con
     }
     if (nchunk == 1) {   // small structures: this CTA already holds the totals, no second launch
         __syncthreads();
-        if (tid == 0) write_out8(tot, sd, out8 + (size_t)st * 8);
+        if (tid == 0) {
+            if (f.raw) { for (int q = 0; q < 7; q++) out8[(size_t)st * 8 + q] = tot[q]; out8[(size_t)st * 8 + 7] = 0.0; }
+            else write_out8(tot, sd, out8 + (size_t)st * 8);
+        }
     }
 }
 
 __global__ void __launch_bounds__(32)
-k_finalize(const StructDev *structs, const double *partial, int nchunk, double *out8) {
+k_finalize(const StructDev *structs, const double *partial, int nchunk, double *out8, int n_own, int raw) {
     __shared__ double s[8];
     const StructDev &sd = structs[blockIdx.x];
     const int lane = threadIdx.x;
-    const int used = (sd.natoms + FIN_CHUNK - 1) / FIN_CHUNK;   // chunks of this structure (the others were not written)
+    const int used = (min(sd.natoms, n_own) + FIN_CHUNK - 1) / FIN_CHUNK;   // chunks of this structure that hold atoms
     if (lane < 7) {
         const double *p = partial + (size_t)blockIdx.x * nchunk * 8 + lane;
         double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
@@ -165,7 +157,10 @@ k_finalize(const StructDev *structs, const double *partial, int nchunk, double *
         s[lane] = (x0 + x1) + (x2 + x3);
     }
     __syncwarp();
-    if (lane == 0) write_out8(s, sd, out8 + (size_t)blockIdx.x * 8);
+    if (lane == 0) {
+        if (raw) { for (int q = 0; q < 7; q++) out8[(size_t)blockIdx.x * 8 + q] = s[q]; out8[(size_t)blockIdx.x * 8 + 7] = 0.0; }
+        else write_out8(s, sd, out8 + (size_t)blockIdx.x * 8);
+    }
 }
 
 // dE/dG := unit vector e_k for every atom (CAR2ACSF export: one backward pass per descriptor)
@@ -180,19 +175,15 @@ void launch_onehot(cudaStream_t st, double *dEdG, int ntot, int D, int k) {
 
 int finalize_chunks(int max_natoms) { return max_natoms > 0 ? (max_natoms + FIN_CHUNK - 1) / FIN_CHUNK : 1; }
 
-void launch_gather(cudaStream_t st, const StructDev *structs, int nstruct, const int *sid, int ntot, int cap,
-                   const uint64_t *nbr_keys, const int *nbr_cnt, const double *fpair, const double *gself,
-                   const double *vir, const double *eatom, int lgrad, double *force_soa, double *out8,
-                   const unsigned char *role, const int *active, const DevFlags *flags, double *partial, int max_natoms,
-                   long *launches) {
-    cudaMemsetAsync(force_soa, 0, sizeof(double) * 3 * (size_t)ntot, st);
-    const int nchunk = finalize_chunks(max_natoms);
+void launch_gather(cudaStream_t st, const GatherArgs &g, long *launches) {
+    const int nchunk = finalize_chunks(g.max_natoms);
     FinArgs fin;
-    fin.eatom = eatom; fin.vir = vir; fin.partial = partial; fin.out8 = out8; fin.lgrad = lgrad; fin.nchunk = nchunk; fin.nstruct = nstruct;
-    const int ngather = lgrad ? ntot : 0;   // without gradients only the reduction CTAs run
-    k_gather<<<nchunk * nstruct + ngather, GT, 0, st>>>(structs, sid, ntot, cap, nbr_keys, nbr_cnt, fpair, gself, force_soa, role,
-                                                         active, flags, nchunk * nstruct, fin);
-    if (nchunk > 1) k_finalize<<<nstruct, 32, 0, st>>>(structs, partial, nchunk, out8);
+    fin.eatom = g.eatom; fin.vir = g.vir; fin.partial = g.partial; fin.out8 = g.out8; fin.lgrad = g.lgrad; fin.nchunk = nchunk;
+    fin.nstruct = g.nstruct; fin.n_own = g.n_own; fin.raw = g.decomposed;
+    const int ngather = g.lgrad ? g.ntot : 0;   // without gradients only the reduction CTAs run
+    if (!g.lgrad) cudaMemsetAsync(g.force_soa, 0, sizeof(double) * 3 * (size_t)g.ntot, st);
+    k_gather<<<nchunk * g.nstruct + ngather, GT, 0, st>>>(g, nchunk * g.nstruct, fin);
+    if (nchunk > 1) k_finalize<<<g.nstruct, 32, 0, st>>>(g.structs, g.partial, nchunk, g.out8, g.n_own, g.decomposed);
     if (launches) *launches += nchunk > 1 ? 2 : 1;
 }
 

@@ -11,17 +11,35 @@ namespace gapcu {
 constexpr int MAX_NEIGHBOR_REF_DEV = 1000;  // gap_calc.f90:68
 
 // neigh.cu
-void launch_neighbor_build(cudaStream_t st, const StructDev *structs, const int *sid, const double *pos,
-                           int ntot, int nbins_total, double rcut, int cap, int4 *abin, int *arank,
-                           int *bin_count, int *bin_start, int *bin_atoms, int4 *sabin, double *spos, uint64_t *nbr_keys,
-                           int *nbr_cnt, double *min_dis, DevFlags *flags, const DomainDev &dom, unsigned char *role,
-                           int *active, int *order, bool direct, long *launches);
-// direct = true: every structure has natoms * (image window) <= neighbor_direct_max_candidates() and the
-// cell is not decomposed; then one kernel builds the lists AND fills `order` (no launch_order needed)
+struct NeighborBuild {
+    const StructDev *structs;
+    const int *sid;
+    const double *pos;        // [3][ntot] SoA
+    int ntot, nbins_total;
+    double rcut, rskin;       // rskin = rcut + skin: radius of the candidate (skin) lists
+    int cap;                  // row length of skin_keys / nbr_keys
+    // cell list scratch
+    int4 *abin; int *arank; int *bin_count /* [2][nbins_total] */; int *bin_start; int *bin_atoms; int4 *sabin; double *spos;
+    // outputs
+    uint64_t *skin_keys; int *skin_cnt;   // candidates within rskin, reference order (null: not kept)
+    uint64_t *nbr_keys; int *nbr_cnt;     // the reference's lists (dis <= rcut); nbr_keys null: counts / min distance only
+    double *min_dis;
+    DevFlags *flags;
+    int *order;               // direct kernel only: centres by descending count
+    bool direct;              // every structure is small: one kernel runs the reference's double loop
+    // decomposed runs: local points = owned [0, n_own) then ghosts, *nloc in all, image shifts in sft
+    const int4 *sft;          // null: periodic structures
+    const int *nloc;
+    int n_own;                // = ntot when not decomposed
+};
+void launch_neighbor_build(cudaStream_t st, const NeighborBuild &b, long *launches);
+// exact lists from kept skin lists and moved positions; flags->stale when an atom moved > skin/2
+void launch_refilter(cudaStream_t st, const NeighborBuild &b, const double *pos_build, double skin, long *launches);
+// direct = true needs natoms * (image window) <= neighbor_direct_max_candidates() for every structure and
+// no decomposition; that kernel also fills `order` (no launch_order needed)
 int neighbor_direct_max_candidates();
 
-void launch_order(cudaStream_t st, const int *nbr_cnt, int ntot, int *order, const unsigned char *role,
-                  DevFlags *flags, long *launches);
+void launch_order(cudaStream_t st, const int *nbr_cnt, int n_centres, int *order, DevFlags *flags, long *launches);
 
 // centre.cu  (mode: 0 forward, 1 backward, 2 fused forward + GPR + backward)
 size_t centre_smem_bytes(const CentreArgs &a, int mode);
@@ -50,12 +68,58 @@ void launch_gpr_prepare(cudaStream_t st, int M, int D, const double *mm_c_order,
                         double *coeff_p, double *cmean, double *itheta);
 
 // gather.cu
-void launch_gather(cudaStream_t st, const StructDev *structs, int nstruct, const int *sid, int ntot, int cap,
-                   const uint64_t *nbr_keys, const int *nbr_cnt, const double *fpair, const double *gself,
-                   const double *vir, const double *eatom, int lgrad, double *force_soa, double *out8,
-                   const unsigned char *role, const int *active, const DevFlags *flags, double *partial, int max_natoms,
-                   long *launches);
+struct GatherArgs {
+    const StructDev *structs;
+    int nstruct;
+    const int *sid;
+    int ntot, cap;
+    const uint64_t *skin_keys; const int *skin_cnt;   // walked by the gathering atom
+    const uint64_t *nbr_keys; const int *nbr_cnt;     // searched for the mirror entry
+    const double *fpair, *gself, *vir, *eatom;
+    int lgrad;
+    double *force_soa;        // [3][ntot] forces of the (owned) atoms
+    double *out8;             // [nstruct][8]
+    double *partial;          // [nstruct][finalize_chunks][8]
+    int max_natoms;
+    // decomposed runs: atoms >= n_own are ghosts; their sums go to ghost_grad[(i - n_own)][3] (gradient,
+    // not force) and travel back to the owners; E and the strs sums cover the owned atoms only and are
+    // NOT converted to stress here (raw partial sums in out8, combined over ranks by halo.cu)
+    const int *nloc;
+    int n_own;
+    double *ghost_grad;       // [padded ghost slots][3]
+    const int *gslot;         // ghost (local index - n_own) -> padded slot
+    int decomposed;
+};
+void launch_gather(cudaStream_t st, const GatherArgs &g, long *launches);
 int finalize_chunks(int max_natoms);   // partial needs nstruct * finalize_chunks(max_natoms) * 8 doubles
+
+// halo.cu (decomposed runs)
+constexpr int HALO_HDR = 16;      // bytes: record count of the message, padding
+constexpr int HALO_REC = 48;      // bytes per ghost record: x y z w (doubles), gid s1 s2 s3 (ints)
+constexpr int HALO_RECLEN = 48;   // doubles per rank in the all-gathered record (E, strs sums, flags, counts)
+struct HaloGeom {
+    double inv[9];
+    int grid[3], mine[3];
+    double nu[3];       // (rcut + skin + drift) / brick width: shell thickness in brick units
+    double drift[3];    // how far (brick units) an owned atom may sit outside its brick
+    int wrap[3][3];     // floor((mine + delta) / grid) for delta = -1, 0, +1: cell crossings towards that neighbour
+};
+struct HaloBufs {
+    unsigned char *send, *recv;   // per direction: header + cap[d] records at byte offset off[d]
+    const double *rgrad;          // [sum cap][3] gradients returned by the ranks that hold my atoms as ghosts
+    int cap[27];
+    size_t off[27];
+};
+void launch_halo_select(cudaStream_t st, const HaloGeom &G, const double *pos, int stride, int n_own, int4 *sft, uint32_t *mask,
+                        int *tile_cnt, int *tile_base, const HaloBufs &B, DevFlags *flags, long *launches);
+void launch_halo_fill(cudaStream_t st, const HaloGeom &G, const double *pos, const double *wgt, const int4 *sft, int stride,
+                      int n_own, const uint32_t *mask, const int *tile_base, const HaloBufs &B, const DevFlags *flags, long *launches);
+void launch_halo_unpack(cudaStream_t st, const HaloBufs &B, int n_own, int stride, double *pos, double *wgt, int4 *sft, int *gslot,
+                        DevFlags *flags, long *launches);
+void launch_halo_add(cudaStream_t st, int n_own, int stride, const uint32_t *mask, const int *tile_base, const HaloBufs &B,
+                     double *force, long *launches);
+void launch_halo_rec(cudaStream_t st, const double *out8_raw, const DevFlags *flags, double *rec, long *launches);
+void launch_halo_combine(cudaStream_t st, const double *rec_all, int nranks, double volume, double *out8, DevFlags *flags, long *launches);
 
 void launch_onehot(cudaStream_t st, double *dEdG, int ntot, int D, int k);
 

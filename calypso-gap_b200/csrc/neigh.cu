@@ -10,6 +10,16 @@
 //     atoms the caller did not wrap into the cell lose the same neighbours.
 // The cell list only proposes candidates.  Each list is sorted into the
 // reference order (j, n1, n2, n3), which also makes the result deterministic.
+//
+// Two lists per atom.  The SKIN list holds every image within rcut + skin, sorted; the
+// EXACT list is its subset with dis <= rcut (the reference's set), produced by re-testing the
+// skin entries in order (refilter).  A molecular-dynamics caller keeps the skin list over
+// several steps (gapcu_ctx_update_positions): each step only re-filters it with the reference
+// arithmetic on the new positions, so the sets stay bit-exact, and the list is rebuilt when an
+// atom has moved more than skin/2 since it was built.  The skin is never zero (the host adds
+// a floor of ~1e-9 A): a pair whose two directed distances straddle rcut by an ulp is then
+// still a candidate of BOTH atoms, which is what lets the force gather (gather.cu) find every
+// contribution by walking the skin list, without a push path and without atomics.
 #include <cstdint>
 
 #include "device_types.cuh"
@@ -29,45 +39,35 @@ __device__ __forceinline__ int floordiv_i(int a, int b) {
 }
 
 // fractional coordinates -> wrap offsets and bin; counts atoms per bin.
-__global__ void k_bin(const StructDev *structs, const int *sid, const double *pos, int ntot,
-                      int4 *abin, int *arank, int *bin_count, DomainDev dom, unsigned char *role, int *active,
-                      DevFlags *flags) {
+// Periodic structures: wrap offset = floor(f).  Open regions (decomposed runs): the point's image
+// shift is given (sft.yzw), its "wrap offset" is minus that shift, and the bin is taken relative to
+// the region's origin; owned points [0, n_own) and ghosts are counted separately so that the owned
+// records come first inside every cell (bin_count: [2][nbins_total]).
+__global__ void k_bin(const StructDev *structs, const int *sid, const double *pos, int ntot, const int *nloc, int n_own,
+                      const int4 *sft, int4 *abin, int *arank, int *bin_count, int nbins_total) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ntot) return;
+    if (i >= (nloc ? *nloc : ntot)) return;
     const StructDev &s = structs[sid[i]];
     double x = pos[i], y = pos[ntot + i], z = pos[2 * ntot + i];
     int b[3], w[3];
-    int rl = 2;
+    int sh[3] = {0, 0, 0};
+    if (s.open) { const int4 q = sft[i]; sh[0] = q.y; sh[1] = q.z; sh[2] = q.w; }
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         double f = x * s.inv[c] + y * s.inv[3 + c] + z * s.inv[6 + c];
-        double fl = floor(f);
-        w[c] = (int)fl;
-        const double fw = f - fl;
-        int bc = (int)(fw * s.nbin[c]);
+        double fw;
+        if (s.open) { w[c] = -sh[c]; fw = (f + (double)sh[c] - s.org[c]) / s.wid[c]; }
+        else { const double fl = floor(f); w[c] = (int)fl; fw = f - fl; }
+        int bc = (int)floor(fw * s.nbin[c]);
         bc = min(max(bc, 0), s.nbin[c] - 1);
         b[c] = bc;
-        if (dom.enabled && dom.grid[c] > 1) {
-            const int g = dom.grid[c];
-            const int mybrick = min(max((int)(fw * g), 0), g - 1);
-            if (mybrick != dom.mine[c]) {
-                // periodic distance (fractional) from fw to the brick [lo, hi]
-                const double lo = (double)dom.mine[c] / g, hi = (double)(dom.mine[c] + 1) / g;
-                double dlo = lo - fw, dhi = fw - hi;
-                dlo -= floor(dlo); dhi -= floor(dhi);          // into [0,1)
-                const double dist = fmin(dlo, dhi);
-                rl = min(rl, dist <= dom.margin[c] * (1.0 + 1e-9) + 1e-12 ? 1 : 0);
-            }
-        }
     }
-    if (role) role[i] = (unsigned char)rl;
-    if (active && rl >= 1) active[atomicAdd(&flags->n_active, 1)] = i;
     int id = (b[0] * s.nbin[1] + b[1]) * s.nbin[2] + b[2];
     abin[i] = make_int4(id, w[0], w[1], w[2]);
-    arank[i] = atomicAdd(&bin_count[s.bin_off + id], 1);
+    arank[i] = atomicAdd(&bin_count[(i >= n_own ? nbins_total : 0) + s.bin_off + id], 1);
 }
 
-// exclusive scan of bin_count -> bin_start[nb+1]; single CTA.
+// exclusive scan of the per-cell totals (owned + ghost) -> bin_start[nb+1]; single CTA.
 __global__ void k_scan_bins(const int *bin_count, int *bin_start, int nb) {
     __shared__ int warp_sums[32];
     __shared__ int carry;
@@ -76,7 +76,7 @@ __global__ void k_scan_bins(const int *bin_count, int *bin_start, int nb) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int base = 0; base < nb; base += blockDim.x) {
         int i = base + threadIdx.x;
-        int v = (i < nb) ? bin_count[i] : 0;
+        int v = (i < nb) ? bin_count[i] + bin_count[nb + i] : 0;
         int x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -108,24 +108,25 @@ __global__ void k_scan_bins(const int *bin_count, int *bin_start, int nb) {
 // index + wrap offsets, spos: coordinates), so that k_neigh reads the candidates of a cell as
 // contiguous, independent loads instead of a chain bin_atoms -> abin -> pos.
 __global__ void k_fill_bins(const StructDev *structs, const int *sid, const double *pos, const int4 *abin, const int *arank,
-                            const int *bin_start, int ntot, int *bin_atoms, int4 *sabin, double *spos) {
+                            const int *bin_start, const int *bin_count, int nbins_total, int ntot, const int *nloc, int n_own,
+                            int *bin_atoms, int4 *sabin, double *spos) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ntot) return;
+    if (i >= (nloc ? *nloc : ntot)) return;
     const StructDev &s = structs[sid[i]];
     const int4 b = abin[i];
-    const int slot = bin_start[s.bin_off + b.x] + arank[i];
+    const int slot = bin_start[s.bin_off + b.x] + (i >= n_own ? bin_count[s.bin_off + b.x] : 0) + arank[i];
     bin_atoms[slot] = i;
     sabin[slot] = make_int4(i, b.y, b.z, b.w);
     spos[slot] = pos[i]; spos[ntot + slot] = pos[ntot + i]; spos[2 * ntot + slot] = pos[2 * ntot + i];
 }
 
 // Small batches: bin, scan and fill in ONE single-CTA kernel (shared-memory counters) instead
-// of a memset and three launches; same outputs as k_bin / k_scan_bins / k_fill_bins.
+// of a memset and three launches; same outputs as k_bin / k_scan_bins / k_fill_bins (periodic
+// structures only).
 constexpr int SMALL_NBINS = 4096;
 __global__ void __launch_bounds__(1024)
 k_bin_small(const StructDev *structs, const int *sid, const double *pos, int ntot, int nbins_total, int4 *abin,
-            int *bin_start, int *bin_atoms, int4 *sabin, double *spos, DomainDev dom, unsigned char *role, int *active,
-            DevFlags *flags) {
+            int *bin_start, int *bin_atoms, int4 *sabin, double *spos) {
     __shared__ int cnt[SMALL_NBINS + 1];
     __shared__ int wsum[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -134,7 +135,7 @@ k_bin_small(const StructDev *structs, const int *sid, const double *pos, int nto
     for (int i = tid; i < ntot; i += 1024) {
         const StructDev &s = structs[sid[i]];
         const double x = pos[i], y = pos[ntot + i], z = pos[2 * ntot + i];
-        int b[3], w[3], rl = 2;
+        int b[3], w[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const double f = x * s.inv[c] + y * s.inv[3 + c] + z * s.inv[6 + c];
@@ -142,20 +143,9 @@ k_bin_small(const StructDev *structs, const int *sid, const double *pos, int nto
             w[c] = (int)fl;
             const double fw = f - fl;
             b[c] = min(max((int)(fw * s.nbin[c]), 0), s.nbin[c] - 1);
-            if (dom.enabled && dom.grid[c] > 1) {
-                const int g = dom.grid[c];
-                if (min(max((int)(fw * g), 0), g - 1) != dom.mine[c]) {
-                    const double lo = (double)dom.mine[c] / g, hi = (double)(dom.mine[c] + 1) / g;
-                    double dlo = lo - fw, dhi = fw - hi;
-                    dlo -= floor(dlo); dhi -= floor(dhi);
-                    rl = min(rl, fmin(dlo, dhi) <= dom.margin[c] * (1.0 + 1e-9) + 1e-12 ? 1 : 0);
-                }
-            }
         }
         const int id = (b[0] * s.nbin[1] + b[1]) * s.nbin[2] + b[2];
         abin[i] = make_int4(id, w[0], w[1], w[2]);
-        if (role) role[i] = (unsigned char)rl;
-        if (active && rl >= 1) active[atomicAdd(&flags->n_active, 1)] = i;
         atomicAdd(&cnt[s.bin_off + id], 1);
     }
     __syncthreads();
@@ -193,27 +183,94 @@ k_bin_small(const StructDev *structs, const int *sid, const double *pos, int nto
     }
 }
 
+
+// Exact list of centre i from its sorted candidate list `cand` (shared or global memory): the
+// entries with dis <= rcut (gap_calc.f90:101, reference arithmetic), in order.  All NT threads of
+// the CTA call it; wsum: NT/32 + 1 ints of shared memory.  Returns the count (every thread).
+template <int NT>
+__device__ int refilter_list(const uint64_t *cand, int ncand, int i, const double *pos, int ntot, const double *lat,
+                             int aoff, double xi, double yi, double zi, double rcut, uint64_t *out, int *wsum,
+                             int &nclose_out) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int outn = 0, nclose = 0;
+    for (int base = 0; base < ncand; base += NT) {
+        const int t = base + tid;
+        bool keep = false;
+        uint64_t key = 0;
+        if (t < ncand) {
+            key = cand[t];
+            int jl, n1, n2, n3;
+            nbr_unkey(key, jl, n1, n2, n3);
+            double ox, oy, oz;
+            const double dis = image_distance(pos, ntot, aoff + jl, lat, n1, n2, n3, xi, yi, zi, ox, oy, oz);
+            keep = !(dis > rcut);
+            nclose += keep && dis < 0.5;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        __syncthreads();                 // wsum of the previous round is consumed
+        if (lane == 0) wsum[wid] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; w++) { const int c = wsum[w]; if (w < wid) before += c; total += c; }
+        if (keep) out[outn + before + __popc(m & ((1u << lane) - 1u))] = key;
+        outn += total;
+    }
+    nclose_out = nclose;
+    return outn;
+}
+
 // One CTA per centre atom: gather candidates from the surrounding bins, apply the
-// reference test, sort into reference order, store keys (+ optional min distance).
-__global__ void __launch_bounds__(NB_THREADS, 8)
-k_neigh(const StructDev *structs, const int *sid, const double *pos, const int4 *abin,
-        const int *bin_start, const int4 *sabin, const double *spos, int ntot, double rcut, int cap,
-        uint64_t *nbr_keys, int *nbr_cnt, double *min_dis, DevFlags *flags, const int *active) {
+// reference test against rcut + skin, sort into reference order, store the skin list, then
+// re-filter it against rcut into the exact list (+ optional min distance).
+// Decomposed runs: the atoms are this rank's LOCAL points -- owned atoms
+// [0, n_own) followed by the ghost images received from the neighbour ranks, *nloc in all -- in
+// an open (non-periodic) region of fractional space; the "wrap offsets" of a point are minus
+// its image shift, so the shift arithmetic below is the same.  A ghost centre only lists OWNED
+// candidates (the first bin_nown[cell] records of a cell): its list exists to collect the forces
+// this rank's centres exert on it (gather.cu), not to evaluate it.
+struct NeighArgs {
+    const StructDev *structs;
+    const int *sid;
+    const double *pos;
+    const int4 *abin;
+    const int *bin_start;
+    const int *bin_nown;    // decomposed: owned records per cell (they come first); else null
+    const int4 *sabin;
+    const double *spos;
+    int ntot;               // stride of the SoA arrays
+    const int *nloc;        // decomposed: device count of local points; else null (= ntot)
+    int n_own;              // decomposed: centres >= n_own are ghosts; else ntot
+    double rcut, rskin;
+    int cap;
+    uint64_t *skin_keys;    // [ntot][cap] or null (bond-length query)
+    int *skin_cnt;
+    uint64_t *nbr_keys;     // [ntot][cap]
+    int *nbr_cnt;
+    double *min_dis;
+    DevFlags *flags;
+};
+
+__global__ void __launch_bounds__(NB_THREADS, 8) k_neigh(const NeighArgs A) {
     __shared__ uint64_t keys[NB_MAXLIST];
-    __shared__ int nkeys, nclose;
+    __shared__ int nkeys;
     __shared__ double lat[9];
     __shared__ double wmin[NB_THREADS / 32];
+    __shared__ int wsum[NB_THREADS / 32 + 1];
     __shared__ int c_start[NB_CELLS], c_off[NB_CELLS + 1];
     __shared__ int4 c_shift[NB_CELLS];
-    if (active && (int)blockIdx.x >= flags->n_active) return;
-    const int i = active ? active[blockIdx.x] : blockIdx.x;
+    const int i = blockIdx.x;
+    if (A.nloc && i >= *A.nloc) return;
+    const bool ghost = i >= A.n_own;
+    const int ntot = A.ntot;
+    const double *pos = A.pos;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const StructDev &s = structs[sid[i]];
+    const StructDev &s = A.structs[A.sid[i]];
     if (tid < 9) lat[tid] = s.lat[tid];
-    if (tid == 0) { nkeys = 0; nclose = 0; }
+    if (tid == 0) nkeys = 0;
     __syncthreads();
     const double xi = pos[i], yi = pos[ntot + i], zi = pos[2 * ntot + i];
-    const int4 bi = abin[i];
+    const int4 bi = A.abin[i];
     const int nb0 = s.nbin[0], nb1 = s.nbin[1], nb2 = s.nbin[2];
     const int b0 = bi.x / (nb1 * nb2), b1 = (bi.x / nb2) % nb1, b2 = bi.x % nb2;
     const int m0 = s.mscan[0], m1 = s.mscan[1], m2 = s.mscan[2];
@@ -221,25 +278,28 @@ k_neigh(const StructDev *structs, const int *sid, const double *pos, const int4 
     const int w1 = 2 * m1 + 1, w2 = 2 * m2 + 1;
     const int nscan = (2 * m0 + 1) * w1 * w2;
     const int aoff = s.atom_off;
-    // wrapped fractional coordinates of the centre: a whole cell is skipped when the slab gap to it
-    // along any lattice direction already exceeds rcut (prunes corner bins and far images)
-    double fw[3];
+    const bool open = s.open != 0;
+    const double rskin = A.rskin;
+    // position of the centre in bin units along each lattice direction: a whole cell is skipped when
+    // the slab gap to it along any direction already exceeds the search radius (prunes corner bins
+    // and far images).  Periodic cells: org = 0, wid = 1 and the wrap offset is floor(f).
+    const int wo[3] = {bi.y, bi.z, bi.w};
+    const int nbv[3] = {nb0, nb1, nb2};
+    double fb[3], bw[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         const double f = xi * s.inv[c] + yi * s.inv[3 + c] + zi * s.inv[6 + c];
-        fw[c] = f - floor(f);
+        fb[c] = (f - (double)wo[c] - s.org[c]) * ((double)nbv[c] / s.wid[c]);
+        bw[c] = s.spacing[c] * s.wid[c] / nbv[c];   // bin width in length units
     }
-    // bin width in length units along each direction
-    const double bw0 = s.spacing[0] / nb0, bw1 = s.spacing[1] / nb1, bw2 = s.spacing[2] / nb2;
-    const double fb0 = fw[0] * nb0, fb1 = fw[1] * nb1, fb2 = fw[2] * nb2;   // centre in bin units
-    const double rprune = rcut * (1.0 + 1e-9) + 1e-9;
+    const double fb0 = fb[0], fb1 = fb[1], fb2 = fb[2], bw0 = bw[0], bw1 = bw[1], bw2 = bw[2];
+    const double rprune = rskin * (1.0 + 1e-9) + 1e-9;
     const bool prune = nscan > 27;
     double dmin = 1e300;
+    int nclose = 0;
     // Cells are handled NB_CELLS at a time: their (start, count, shift) are fetched by one
     // thread each, the counts are scanned, and then the candidates of all those cells form ONE
-    // flat index space dealt over the threads.  Every thread so has several independent
-    // chains of dependent loads in flight (bin_atoms -> abin/pos) instead of walking cell by
-    // cell, which is what this latency-bound kernel needs.
+    // flat index space dealt over the threads.
     for (int c0 = 0; c0 < nscan; c0 += NB_CELLS) {
         const int nc = min(NB_CELLS, nscan - c0);
         __syncthreads();
@@ -249,18 +309,24 @@ k_neigh(const StructDev *structs, const int *sid, const double *pos, const int4 
                 const int cell = c0 + t;
                 const int d0 = cell / (w1 * w2) - m0, d1 = (cell / w2) % w1 - m1, d2 = cell % w2 - m2;
                 const int t0 = b0 + d0, t1 = b1 + d1, t2 = b2 + d2;
-                const int s0 = floordiv_i(t0, nb0), s1 = floordiv_i(t1, nb1), s2 = floordiv_i(t2, nb2);
-                const int id = ((t0 - s0 * nb0) * nb1 + (t1 - s1 * nb1)) * nb2 + (t2 - s2 * nb2);
-                double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-                if (prune) {   // slab gaps (negative: inside); only worth it when many image cells are scanned
-                    g0 = fmax((double)t0 - fb0, fb0 - (double)(t0 + 1)) * bw0;
-                    g1 = fmax((double)t1 - fb1, fb1 - (double)(t1 + 1)) * bw1;
-                    g2 = fmax((double)t2 - fb2, fb2 - (double)(t2 + 1)) * bw2;
+                int s0 = 0, s1 = 0, s2 = 0;
+                bool inside = true;
+                if (open) inside = t0 >= 0 && t0 < nb0 && t1 >= 0 && t1 < nb1 && t2 >= 0 && t2 < nb2;
+                else { s0 = floordiv_i(t0, nb0); s1 = floordiv_i(t1, nb1); s2 = floordiv_i(t2, nb2); }
+                if (inside) {
+                    const int id = ((t0 - s0 * nb0) * nb1 + (t1 - s1 * nb1)) * nb2 + (t2 - s2 * nb2);
+                    double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+                    if (prune) {   // slab gaps (negative: inside); only worth it when many image cells are scanned
+                        g0 = fmax((double)t0 - fb0, fb0 - (double)(t0 + 1)) * bw0;
+                        g1 = fmax((double)t1 - fb1, fb1 - (double)(t1 + 1)) * bw1;
+                        g2 = fmax((double)t2 - fb2, fb2 - (double)(t2 + 1)) * bw2;
+                    }
+                    const int start = A.bin_start[s.bin_off + id];
+                    if (!(g0 > rprune || g1 > rprune || g2 > rprune))
+                        cnt = ghost ? A.bin_nown[s.bin_off + id] : A.bin_start[s.bin_off + id + 1] - start;
+                    c_start[t] = start;
+                    c_shift[t] = make_int4(s0, s1, s2, 0);
                 }
-                const int start = bin_start[s.bin_off + id];
-                cnt = (g0 > rprune || g1 > rprune || g2 > rprune) ? 0 : bin_start[s.bin_off + id + 1] - start;
-                c_start[t] = start;
-                c_shift[t] = make_int4(s0, s1, s2, 0);
             }
             c_off[t] = cnt;
         }
@@ -285,8 +351,8 @@ k_neigh(const StructDev *structs, const int *sid, const double *pos, const int4 
         struct Cand { int4 bj; double x, y, z; };
         auto load = [&](int slot) {
             Cand r;
-            r.bj = sabin[slot];                          // (atom, wrap offsets) and coordinates in bin order:
-            r.x = spos[slot]; r.y = spos[ntot + slot]; r.z = spos[2 * ntot + slot];   // independent loads
+            r.bj = A.sabin[slot];                          // (atom, wrap offsets) and coordinates in bin order:
+            r.x = A.spos[slot]; r.y = A.spos[ntot + slot]; r.z = A.spos[2 * ntot + slot];   // independent loads
             return r;
         };
         const int per = (total + NB_THREADS - 1) / NB_THREADS;
@@ -319,15 +385,14 @@ k_neigh(const StructDev *structs, const int *sid, const double *pos, const int4 
                 if (abs(n1) > na0 || abs(n2) > na1 || abs(n3) > na2) continue;
                 double ox, oy, oz;
                 const double dis = image_distance_xyz(cur.x, cur.y, cur.z, lat, n1, n2, n3, xi, yi, zi, ox, oy, oz);
-                if (dis > rcut) continue;
-                if (dis < 0.5) atomicAdd(&nclose, 1);
-                dmin = fmin(dmin, dis);
-                const int p = atomicAdd(&nkeys, 1);
+                if (dis > rskin) continue;
+                if (!(dis > A.rcut)) { dmin = fmin(dmin, dis); nclose += dis < 0.5; }
+                const int p = atomicAdd(&nkeys, 1);   // order of arrival is irrelevant: the list is sorted below
                 if (p < NB_MAXLIST) keys[p] = nbr_key(j - aoff, n1, n2, n3);
             }
         }
     }
-    if (min_dis) {
+    if (A.min_dis) {
 #pragma unroll
         for (int o = 16; o; o >>= 1) dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
         if (lane == 0) wmin[wid] = dmin;
@@ -335,18 +400,16 @@ k_neigh(const StructDev *structs, const int *sid, const double *pos, const int4 
     __syncthreads();
     const int count = nkeys;
     if (tid == 0) {
-        nbr_cnt[i] = count;
-        atomicMax(&flags->maxcount, count);
-        if (count > MAX_NEIGHBOR_REF_DEV) atomicExch(&flags->too_many, 1);
-        if (count > cap) atomicExch(&flags->overflow, 1);
-        if (nclose) atomicAdd(&flags->close_pairs, nclose);
-        if (min_dis) {
+        if (A.skin_cnt) A.skin_cnt[i] = count;
+        atomicMax(&A.flags->maxskin, count);
+        if (count > A.cap || count > NB_MAXLIST) { atomicExch(&A.flags->overflow, 1); A.nbr_cnt[i] = 0; }
+        if (A.min_dis) {
             double m = wmin[0];
             for (int w = 1; w < NB_THREADS / 32; w++) m = fmin(m, wmin[w]);
-            min_dis[i] = m;
+            A.min_dis[i] = m;
         }
     }
-    if (count > cap || count > NB_MAXLIST || nbr_keys == nullptr) return;
+    if (count > A.cap || count > NB_MAXLIST) return;
     // bitonic sort of the keys (padded to a power of two with +inf keys)
     int n2 = 1;
     while (n2 < count) n2 <<= 1;
@@ -368,38 +431,96 @@ k_neigh(const StructDev *structs, const int *sid, const double *pos, const int4 
                 const bool keep_min = ((tid & jj) == 0) == ((tid & k) == 0);
                 key = keep_min ? (key < other ? key : other) : (key < other ? other : key);
             }
-        if (tid < count) nbr_keys[(size_t)i * cap + tid] = key;
+        __syncthreads();
+        keys[tid] = key;
+    } else {
+        for (int p = count + tid; p < n2; p += NB_THREADS) keys[p] = ~0ull;
+        __syncthreads();
+        for (int k = 2; k <= n2; k <<= 1)
+            for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                for (int t = tid; t < n2; t += NB_THREADS) {
+                    int p = t ^ jj;
+                    if (p > t) {
+                        uint64_t a = keys[t], b = keys[p];
+                        bool up = ((t & k) == 0);
+                        if ((a > b) == up) { keys[t] = b; keys[p] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+    }
+    __syncthreads();
+    if (A.skin_keys) for (int p = tid; p < count; p += NB_THREADS) A.skin_keys[(size_t)i * A.cap + p] = keys[p];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) nclose += __shfl_xor_sync(0xffffffffu, nclose, o);
+    if (lane == 0 && nclose && !ghost) atomicAdd(&A.flags->close_pairs, nclose);
+    if (A.nbr_keys == nullptr) {   // bond-length query: counts and flags only
+        if (tid == 0) { atomicMax(&A.flags->maxcount, count); }
         return;
     }
-    for (int p = count + tid; p < n2; p += NB_THREADS) keys[p] = ~0ull;
-    __syncthreads();
-    for (int k = 2; k <= n2; k <<= 1)
-        for (int jj = k >> 1; jj > 0; jj >>= 1) {
-            for (int t = tid; t < n2; t += NB_THREADS) {
-                int p = t ^ jj;
-                if (p > t) {
-                    uint64_t a = keys[t], b = keys[p];
-                    bool up = ((t & k) == 0);
-                    if ((a > b) == up) { keys[t] = b; keys[p] = a; }
-                }
-            }
-            __syncthreads();
+    int nclose2;
+    const int exact = refilter_list<NB_THREADS>(keys, count, i, pos, ntot, lat, aoff, xi, yi, zi, A.rcut,
+                                                A.nbr_keys + (size_t)i * A.cap, wsum, nclose2);
+    if (tid == 0) {
+        A.nbr_cnt[i] = exact;
+        if (!ghost) {
+            atomicMax(&A.flags->maxcount, exact);
+            if (exact > MAX_NEIGHBOR_REF_DEV) atomicExch(&A.flags->too_many, 1);
         }
-    for (int p = tid; p < count; p += NB_THREADS) nbr_keys[(size_t)i * cap + p] = keys[p];
+    }
+}
+
+// Verlet reuse (gapcu_ctx_update_positions): the skin list is kept, only the exact list is
+// re-derived from the new positions.  Thread 0 also checks how far the centre has moved since the
+// skin list was built: beyond skin/2 a pair could have entered rcut without being listed, and the
+// host rebuilds (flags->stale).
+__global__ void __launch_bounds__(NB_THREADS, 8)
+k_refilter(const StructDev *structs, const int *sid, const double *pos, const double *pos_build, int ntot, const int *nloc,
+           int n_own, double rcut, double half_skin2, int cap, const uint64_t *skin_keys, const int *skin_cnt,
+           uint64_t *nbr_keys, int *nbr_cnt, DevFlags *flags) {
+    __shared__ double lat[9];
+    __shared__ int wsum[NB_THREADS / 32 + 1];
+    const int i = blockIdx.x;
+    if (nloc && i >= *nloc) return;
+    const bool ghost = i >= n_own;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const StructDev &s = structs[sid[i]];
+    if (tid < 9) lat[tid] = s.lat[tid];
+    __syncthreads();
+    const double xi = pos[i], yi = pos[ntot + i], zi = pos[2 * ntot + i];
+    if (tid == 0 && !ghost) {
+        const double dx = xi - pos_build[i], dy = yi - pos_build[ntot + i], dz = zi - pos_build[2 * ntot + i];
+        if (dx * dx + dy * dy + dz * dz > half_skin2) atomicExch(&flags->stale, 1);
+    }
+    const int ncand = min(skin_cnt[i], cap);
+    int nclose = 0;
+    const int exact = refilter_list<NB_THREADS>(skin_keys + (size_t)i * cap, ncand, i, pos, ntot, lat, s.atom_off, xi, yi, zi,
+                                                rcut, nbr_keys + (size_t)i * cap, wsum, nclose);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) nclose += __shfl_xor_sync(0xffffffffu, nclose, o);
+    if (lane == 0 && nclose && !ghost) atomicAdd(&flags->close_pairs, nclose);
+    if (tid == 0) {
+        nbr_cnt[i] = exact;
+        if (!ghost) {
+            atomicMax(&flags->maxcount, exact);
+            if (exact > MAX_NEIGHBOR_REF_DEV) atomicExch(&flags->too_many, 1);
+        }
+        atomicMax(&flags->maxskin, ncand);
+    }
 }
 
 // Centres ordered by descending neighbour count (counting sort; single CTA).  The order
-// only schedules the persistent centre kernel; results do not depend on it.
+// only schedules the persistent centre kernel; results do not depend on it.  The centres are the
+// atoms [0, n) (decomposed runs: this rank's owned atoms).
 // The body works for any CTA size NT that divides 1024: thread t owns the NT-th part of the 1024
 // keys.  hist: NB_MAXLIST + 2 ints, wsum: 32 ints of shared memory.
 template <int NT>
-__device__ void order_body(const int *nbr_cnt, int ntot, int *order, const unsigned char *role, DevFlags *flags, int *hist, int *wsum) {
+__device__ void order_body(const int *nbr_cnt, int n, int *order, DevFlags *flags, int *hist, int *wsum) {
     constexpr int PER = 1024 / NT;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int t = tid; t < NB_MAXLIST + 2; t += NT) hist[t] = 0;
     __syncthreads();
-    for (int i = tid; i < ntot; i += NT)
-        if (!role || role[i] == 2) atomicAdd(&hist[NB_MAXLIST - min(max(nbr_cnt[i], 1), NB_MAXLIST)], 1);
+    for (int i = tid; i < n; i += NT) atomicAdd(&hist[NB_MAXLIST - min(max(nbr_cnt[i], 1), NB_MAXLIST)], 1);
     __syncthreads();
     // exclusive scan of the 1024 keys (PER consecutive keys per thread), key 0 = largest count
     int loc[PER], v = 0;
@@ -428,21 +549,21 @@ __device__ void order_body(const int *nbr_cnt, int ntot, int *order, const unsig
         if (key == NB_MAXLIST - 512) flags->n_gt[2] = excl;
         if (key == 0) flags->n_gt[3] = 0;
         excl += loc[k];
-        if (key == NB_MAXLIST - 1) flags->n_centres = excl;   // total number of owned atoms
+        if (key == NB_MAXLIST - 1) flags->n_centres = excl;   // total number of centres
     }
     __syncthreads();
-    for (int i = tid; i < ntot; i += NT) {
-        if (role && role[i] != 2) continue;
+    // NOTE the places inside one key come from atomics: the order of equal-count centres varies from
+    // run to run, which only changes which CTA evaluates which centre
+    for (int i = tid; i < n; i += NT) {
         const int key = NB_MAXLIST - min(max(nbr_cnt[i], 1), NB_MAXLIST);   // 0..1023 (0 and 1 neighbours share a key)
         order[atomicAdd(&hist[key], 1)] = i;
     }
 }
 
-__global__ void __launch_bounds__(1024) k_order_by_count(const int *nbr_cnt, int ntot, int *order,
-                                                        const unsigned char *role, DevFlags *flags) {
+__global__ void __launch_bounds__(1024) k_order_by_count(const int *nbr_cnt, int n, int *order, DevFlags *flags) {
     __shared__ int hist[NB_MAXLIST + 2];
     __shared__ int wsum[32];
-    order_body<1024>(nbr_cnt, ntot, order, role, flags, hist, wsum);
+    order_body<1024>(nbr_cnt, n, order, flags, hist, wsum);
 }
 
 // Small cells (an MD cell of tens of atoms): the reference's own double loop, one CTA per centre.
@@ -454,10 +575,11 @@ __global__ void __launch_bounds__(1024) k_order_by_count(const int *nbr_cnt, int
 // for the centre kernel (a handful of atoms: an own launch would cost more than the work).
 constexpr int DIRECT_MAX_CANDIDATES = 32 * NB_THREADS;
 __global__ void __launch_bounds__(NB_THREADS)
-k_neigh_direct(const StructDev *structs, const int *sid, const double *pos, int ntot, double rcut, int cap,
-               uint64_t *nbr_keys, int *nbr_cnt, double *min_dis, DevFlags *flags, int *order, unsigned char *role) {
+k_neigh_direct(const StructDev *structs, const int *sid, const double *pos, int ntot, double rcut, double rskin, int cap,
+               uint64_t *skin_keys, int *skin_cnt, uint64_t *nbr_keys, int *nbr_cnt, double *min_dis, DevFlags *flags,
+               int *order) {
     __shared__ double lat[9];
-    __shared__ int wcnt[NB_THREADS / 32], wclose[NB_THREADS / 32];
+    __shared__ int wcnt[NB_THREADS / 32], wskin[NB_THREADS / 32], wclose[NB_THREADS / 32];
     __shared__ double wmin[NB_THREADS / 32];
     __shared__ int hist[NB_MAXLIST + 2 + 32];
     __shared__ int s_last;
@@ -473,7 +595,7 @@ k_neigh_direct(const StructDev *structs, const int *sid, const double *pos, int 
     const int total = s.natoms * W;
     const int per = (total + NB_THREADS - 1) / NB_THREADS;   // <= 32 (host checks DIRECT_MAX_CANDIDATES)
     const int c0 = tid * per, c1 = min(total, c0 + per);
-    unsigned mask = 0;
+    unsigned mask = 0, smask = 0;   // exact (dis <= rcut) and skin (dis <= rskin) survivors of this thread's run
     int nclose = 0;
     double dmin = 1e300;
     if (c0 < c1) {
@@ -484,6 +606,7 @@ k_neigh_direct(const StructDev *structs, const int *sid, const double *pos, int 
             if (!(jl == il && n1 == 0 && n2 == 0 && n3 == 0)) {
                 double ox, oy, oz;
                 const double dis = image_distance_xyz(xj, yj, zj, lat, n1, n2, n3, xi, yi, zi, ox, oy, oz);
+                if (!(dis > rskin)) smask |= 1u << (c - c0);
                 if (!(dis > rcut)) {
                     mask |= 1u << (c - c0);
                     nclose += dis < 0.5;
@@ -496,39 +619,48 @@ k_neigh_direct(const StructDev *structs, const int *sid, const double *pos, int 
             }
         }
     }
-    // block-wide exclusive prefix sum of the kept counts
-    const int mine = __popc(mask);
-    int x = mine;
+    // block-wide exclusive prefix sums of the kept counts (exact and skin)
+    const int mine = __popc(mask), smine = __popc(smask);
+    int x = mine, y = smine;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, x, o), v = __shfl_up_sync(0xffffffffu, y, o);
+        if (lane >= o) { x += u; y += v; }
+    }
     int ncl = nclose;
 #pragma unroll
     for (int o = 16; o; o >>= 1) { ncl += __shfl_xor_sync(0xffffffffu, ncl, o); dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o)); }
-    if (lane == 31) wcnt[wid] = x;
+    if (lane == 31) { wcnt[wid] = x; wskin[wid] = y; }
     if (lane == 0) { wclose[wid] = ncl; wmin[wid] = dmin; }
     __syncthreads();
-    int base = x - mine, count = 0;
+    int base = x - mine, count = 0, sbase = y - smine, scount = 0;
 #pragma unroll
-    for (int w = 0; w < NB_THREADS / 32; w++) { if (w < wid) base += wcnt[w]; count += wcnt[w]; }
+    for (int w = 0; w < NB_THREADS / 32; w++) {
+        if (w < wid) { base += wcnt[w]; sbase += wskin[w]; }
+        count += wcnt[w]; scount += wskin[w];
+    }
     if (tid == 0) {
         nbr_cnt[i] = count;
-        if (role) role[i] = 2;
+        if (skin_cnt) skin_cnt[i] = scount;
         atomicMax(&flags->maxcount, count);
+        atomicMax(&flags->maxskin, scount);
         if (count > MAX_NEIGHBOR_REF_DEV) atomicExch(&flags->too_many, 1);
-        if (count > cap) atomicExch(&flags->overflow, 1);
+        if (scount > cap) atomicExch(&flags->overflow, 1);
         int nc = 0;
         double m = wmin[0];
         for (int w = 0; w < NB_THREADS / 32; w++) { nc += wclose[w]; m = fmin(m, wmin[w]); }
         if (nc) atomicAdd(&flags->close_pairs, nc);
         if (min_dis) min_dis[i] = m;
     }
-    if (nbr_keys != nullptr && count <= cap) {
-        uint64_t *dst = nbr_keys + (size_t)i * cap + base;
-        for (unsigned m = mask; m; m &= m - 1) {
-            const int c = c0 + __ffs(m) - 1;
+    if (nbr_keys != nullptr && scount <= cap) {
+        uint64_t *dst = nbr_keys + (size_t)i * cap + base, *sdst = skin_keys + (size_t)i * cap + sbase;
+        for (unsigned m = smask; m; m &= m - 1) {
+            const int bit = __ffs(m) - 1, c = c0 + bit;
             const int jl = c / W, w = c - jl * W;
             const int n1 = w / w12 - na0, r = w % w12, n2 = r / w2 - na1, n3 = r % w2 - na2;
-            *dst++ = nbr_key(jl, n1, n2, n3);
+            const uint64_t key = nbr_key(jl, n1, n2, n3);
+            *sdst++ = key;
+            if ((mask >> bit) & 1u) *dst++ = key;
         }
     }
     if (!order) return;
@@ -538,43 +670,52 @@ k_neigh_direct(const StructDev *structs, const int *sid, const double *pos, int 
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    order_body<NB_THREADS>(nbr_cnt, ntot, order, role, flags, hist, hist + NB_MAXLIST + 2);
+    order_body<NB_THREADS>(nbr_cnt, ntot, order, flags, hist, hist + NB_MAXLIST + 2);
 }
 
-void launch_order(cudaStream_t st, const int *nbr_cnt, int ntot, int *order, const unsigned char *role,
-                  DevFlags *flags, long *launches) {
-    k_order_by_count<<<1, 1024, 0, st>>>(nbr_cnt, ntot, order, role, flags);
+void launch_order(cudaStream_t st, const int *nbr_cnt, int n_centres, int *order, DevFlags *flags, long *launches) {
+    k_order_by_count<<<1, 1024, 0, st>>>(nbr_cnt, n_centres, order, flags);
     if (launches) *launches += 1;
 }
 
 // ---- host launchers ------------------------------------------------------
 int neighbor_direct_max_candidates() { return DIRECT_MAX_CANDIDATES; }
 
-void launch_neighbor_build(cudaStream_t st, const StructDev *structs, const int *sid, const double *pos,
-                           int ntot, int nbins_total, double rcut, int cap, int4 *abin, int *arank,
-                           int *bin_count, int *bin_start, int *bin_atoms, int4 *sabin, double *spos, uint64_t *nbr_keys,
-                           int *nbr_cnt, double *min_dis, DevFlags *flags, const DomainDev &dom, unsigned char *role,
-                           int *active, int *order, bool direct, long *launches) {
-    if (direct) {
+void launch_neighbor_build(cudaStream_t st, const NeighborBuild &b, long *launches) {
+    const int ntot = b.ntot;
+    if (b.direct) {
         // small cells: one launch does what binning, cell scan, sort and centre ordering do otherwise
-        k_neigh_direct<<<ntot, NB_THREADS, 0, st>>>(structs, sid, pos, ntot, rcut, cap, nbr_keys, nbr_cnt, min_dis, flags, order, role);
+        k_neigh_direct<<<ntot, NB_THREADS, 0, st>>>(b.structs, b.sid, b.pos, ntot, b.rcut, b.rskin, b.cap, b.skin_keys, b.skin_cnt,
+                                                    b.nbr_keys, b.nbr_cnt, b.min_dis, b.flags, b.order);
         if (launches) *launches += 1;
         return;
     }
-    if (ntot <= 8192 && nbins_total <= SMALL_NBINS) {
-        k_bin_small<<<1, 1024, 0, st>>>(structs, sid, pos, ntot, nbins_total, abin, bin_start, bin_atoms, sabin, spos, dom,
-                                        role, dom.enabled ? active : nullptr, flags);
-        if (launches) *launches -= 2;   // one launch instead of three
+    if (!b.sft && ntot <= 8192 && b.nbins_total <= SMALL_NBINS) {
+        k_bin_small<<<1, 1024, 0, st>>>(b.structs, b.sid, b.pos, ntot, b.nbins_total, b.abin, b.bin_start, b.bin_atoms, b.sabin, b.spos);
+        if (launches) *launches += 1;
     } else {
-        cudaMemsetAsync(bin_count, 0, sizeof(int) * (size_t)nbins_total, st);
+        cudaMemsetAsync(b.bin_count, 0, sizeof(int) * 2 * (size_t)b.nbins_total, st);
         int tb = 256, gb = (ntot + tb - 1) / tb;
-        k_bin<<<gb, tb, 0, st>>>(structs, sid, pos, ntot, abin, arank, bin_count, dom, role, dom.enabled ? active : nullptr, flags);
-        k_scan_bins<<<1, 1024, 0, st>>>(bin_count, bin_start, nbins_total);
-        k_fill_bins<<<gb, tb, 0, st>>>(structs, sid, pos, abin, arank, bin_start, ntot, bin_atoms, sabin, spos);
+        k_bin<<<gb, tb, 0, st>>>(b.structs, b.sid, b.pos, ntot, b.nloc, b.n_own, b.sft, b.abin, b.arank, b.bin_count, b.nbins_total);
+        k_scan_bins<<<1, 1024, 0, st>>>(b.bin_count, b.bin_start, b.nbins_total);
+        k_fill_bins<<<gb, tb, 0, st>>>(b.structs, b.sid, b.pos, b.abin, b.arank, b.bin_start, b.bin_count, b.nbins_total, ntot, b.nloc,
+                                       b.n_own, b.bin_atoms, b.sabin, b.spos);
+        if (launches) *launches += 3;
     }
-    k_neigh<<<ntot, NB_THREADS, 0, st>>>(structs, sid, pos, abin, bin_start, sabin, spos, ntot, rcut, cap,
-                                          nbr_keys, nbr_cnt, min_dis, flags, dom.enabled ? active : nullptr);
-    if (launches) *launches += 4;
+    NeighArgs A;
+    A.structs = b.structs; A.sid = b.sid; A.pos = b.pos; A.abin = b.abin; A.bin_start = b.bin_start;
+    A.bin_nown = b.sft ? b.bin_count : nullptr;
+    A.sabin = b.sabin; A.spos = b.spos; A.ntot = ntot; A.nloc = b.nloc; A.n_own = b.n_own;
+    A.rcut = b.rcut; A.rskin = b.rskin; A.cap = b.cap; A.skin_keys = b.skin_keys; A.skin_cnt = b.skin_cnt;
+    A.nbr_keys = b.nbr_keys; A.nbr_cnt = b.nbr_cnt; A.min_dis = b.min_dis; A.flags = b.flags;
+    k_neigh<<<ntot, NB_THREADS, 0, st>>>(A);
+    if (launches) *launches += 1;
+}
+
+void launch_refilter(cudaStream_t st, const NeighborBuild &b, const double *pos_build, double skin, long *launches) {
+    k_refilter<<<b.ntot, NB_THREADS, 0, st>>>(b.structs, b.sid, b.pos, pos_build, b.ntot, b.nloc, b.n_own, b.rcut,
+                                               0.25 * skin * skin, b.cap, b.skin_keys, b.skin_cnt, b.nbr_keys, b.nbr_cnt, b.flags);
+    if (launches) *launches += 1;
 }
 
 }  // namespace gapcu

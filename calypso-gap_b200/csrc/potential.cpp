@@ -181,7 +181,8 @@ inline void cross3(const double a[3], const double b[3], double c[3]) {
 }
 }  // namespace
 
-CellInfo make_cell(const double *L, double rcut) {
+CellInfo make_cell(const double *L, double rcut, double rbin) {
+    if (!(rbin >= rcut)) rbin = rcut;   // the cell list serves the candidate radius rcut + skin; the image window stays the reference's
     CellInfo ci;
     std::memcpy(ci.lat, L, sizeof ci.lat);
     // --- image window exactly as gap_calc.f90:85-88 / :240-257 -------------
@@ -215,7 +216,7 @@ CellInfo make_cell(const double *L, double rcut) {
         // least (d-1) bin widths apart along this direction, so d <= 2 covers rcut; the 5x5x5 block of
         // half-size bins holds ~3.7 rcut-spheres of candidates instead of the ~6.4 of 3x3x3 full-size ones
         // (k_neigh tests every candidate with the reference's arithmetic, so candidates are its cost).
-        const double half = 0.5 * rcut * (1.0 + 1e-9), full = rcut * (1.0 + 1e-9);
+        const double half = 0.5 * rbin * (1.0 + 1e-9), full = rbin * (1.0 + 1e-9);
         int nb = (int)std::floor(spacing / half);
         if (nb < 1) nb = 1;
         if (nb > 1024) nb = 1024;

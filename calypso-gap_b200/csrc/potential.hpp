@@ -69,6 +69,6 @@ struct CellInfo {
     int mscan[3];      // bins scanned either side of the centre's bin
     double volume;     // abs(det(lat))  (gap_calc.f90:201)
 };
-CellInfo make_cell(const double *lat_c_order, double rcut);
+CellInfo make_cell(const double *lat_c_order, double rcut, double rbin = 0.0);   // rbin: radius the cell list must cover (>= rcut)
 
 }  // namespace gapcu

@@ -26,7 +26,10 @@ SYMBOLS = [
     "gapcu_set_devices", "gapcu_calc_batch",
     "gapcu_device_count", "gapcu_ctx_create", "gapcu_ctx_destroy", "gapcu_ctx_load_potential",
     "gapcu_ctx_set_potential", "gapcu_ctx_set_pipeline", "gapcu_ctx_set_cluster", "gapcu_nccl_unique_id", "gapcu_ctx_nccl_init",
-    "gapcu_ctx_set_domain", "gapcu_ctx_set_structures", "gapcu_ctx_compute", "gapcu_ctx_fetch",
+    "gapcu_ctx_set_domain", "gapcu_ctx_set_drift", "gapcu_ctx_owned", "gapcu_ctx_set_skin", "gapcu_ctx_update_positions",
+    "gapcu_group_create", "gapcu_group_destroy", "gapcu_group_size", "gapcu_group_ctx", "gapcu_group_load_potential",
+    "gapcu_group_set_skin", "gapcu_group_set_structure", "gapcu_group_update_positions", "gapcu_group_compute", "gapcu_group_fetch",
+    "gapcu_ctx_set_structures", "gapcu_ctx_compute", "gapcu_ctx_fetch",
     "gapcu_ctx_fetch_descriptors", "gapcu_ctx_variance", "gapcu_ctx_fetch_neighbors", "gapcu_ctx_time_compute", "gapcu_stage_name",
     "gapcu_ctx_work_counters", "gapcu_ctx_balance", "gapcu_fp64_peaks",
 ]
@@ -60,6 +63,22 @@ def lib():
         L.gapcu_nccl_unique_id.argtypes = [C.c_char_p]
         L.gapcu_ctx_nccl_init.argtypes = [_vp, C.c_int, C.c_int, C.c_char_p]
         L.gapcu_ctx_set_domain.argtypes = [_vp] + [C.c_int] * 6
+        L.gapcu_ctx_set_drift.argtypes = [_vp, C.c_double]
+        L.gapcu_ctx_set_skin.argtypes = [_vp, C.c_double]
+        L.gapcu_ctx_owned.argtypes = [_vp, C.POINTER(C.c_int), _vp]
+        L.gapcu_ctx_update_positions.argtypes = [_vp, _vp, C.c_int]
+        L.gapcu_group_create.restype = _vp
+        L.gapcu_group_create.argtypes = [C.c_int, _ip]
+        L.gapcu_group_destroy.argtypes = [_vp]
+        L.gapcu_group_size.argtypes = [_vp]
+        L.gapcu_group_ctx.restype = _vp
+        L.gapcu_group_ctx.argtypes = [_vp, C.c_int]
+        L.gapcu_group_load_potential.argtypes = [_vp, C.c_char_p]
+        L.gapcu_group_set_skin.argtypes = [_vp, C.c_double]
+        L.gapcu_group_set_structure.argtypes = [_vp, C.c_int, _ip, _dp, _dp, C.c_double, _vp]
+        L.gapcu_group_update_positions.argtypes = [_vp, _dp, C.c_int]
+        L.gapcu_group_compute.argtypes = [_vp, C.c_int]
+        L.gapcu_group_fetch.argtypes = [_vp, _vp, _vp, _vp]
         L.gapcu_ctx_fetch.argtypes = [_vp, _vp, _vp, _vp]
         L.gapcu_ctx_fetch_descriptors.argtypes = [_vp, _vp, _vp, _vp]
         L.gapcu_ctx_fetch_neighbors.argtypes = [_vp, C.c_int, _ip, _ip, _ip, _dp]
@@ -88,8 +107,9 @@ def device_count():
 class Context:
     """One GPU, one stream, one potential, one resident batch of structures."""
 
-    def __init__(self, device=0):
-        h = lib().gapcu_ctx_create(int(device))
+    def __init__(self, device=0, handle=None):
+        self.borrowed = handle is not None      # a group's context: the group destroys it
+        h = handle if self.borrowed else lib().gapcu_ctx_create(int(device))
         if not h:
             raise GapcuError(-6, lib().gapcu_last_error().decode(errors="replace"))
         self.h = _vp(h)
@@ -97,9 +117,9 @@ class Context:
         self.des_len = None
 
     def close(self):
-        if self.h:
+        if self.h and not self.borrowed:
             lib().gapcu_ctx_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -148,8 +168,32 @@ class Context:
     def compute(self, lgrad=True):
         _check(lib().gapcu_ctx_compute(self.h, int(bool(lgrad))))
 
+    def set_skin(self, skin):
+        """Verlet skin in Angstrom: candidate lists hold rcut + skin, see update_positions."""
+        _check(lib().gapcu_ctx_set_skin(self.h, float(skin)))
+
+    def set_drift(self, drift):
+        _check(lib().gapcu_ctx_set_drift(self.h, float(drift)))
+
+    def owned(self):
+        """Indices (into the structure last set) of the atoms fetch() returns forces for."""
+        n = C.c_int()
+        _check(lib().gapcu_ctx_owned(self.h, C.byref(n), None))
+        ids = np.zeros(n.value, np.int32)
+        _check(lib().gapcu_ctx_owned(self.h, C.byref(n), ids.ctypes.data))
+        return ids
+
+    def update_positions(self, pos, reuse_lists=True):
+        """Moved positions of the resident atoms ([n, 3]; decomposed runs: the owned atoms in the
+        order of owned()).  reuse_lists: re-filter the kept skin lists instead of rebuilding."""
+        pos = np.ascontiguousarray(pos, np.float64)
+        _check(lib().gapcu_ctx_update_positions(self.h, pos.ctypes.data, int(bool(reuse_lists))))
+
     def fetch(self):
-        ns, nt = len(self.natoms), int(self.natoms.sum())
+        ns = len(self.natoms)
+        n = C.c_int()
+        _check(lib().gapcu_ctx_owned(self.h, C.byref(n), None))
+        nt = n.value
         ene = np.zeros(ns); force = np.zeros((nt, 3)); stress = np.zeros((ns, 6))
         _check(lib().gapcu_ctx_fetch(self.h, ene.ctypes.data, force.ctypes.data, stress.ctypes.data))
         return ene, force, stress
@@ -208,6 +252,65 @@ class Context:
         a = C.c_double(); b = C.c_double()
         _check(lib().gapcu_fp64_peaks(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+
+class Group:
+    """One structure cut into bricks, one context per brick, all in this process (devices may
+    repeat: several bricks on one GPU).  Arrays are those of the whole structure."""
+
+    def __init__(self, devices):
+        d = np.ascontiguousarray(list(devices), np.int32)
+        h = lib().gapcu_group_create(len(d), d)
+        if not h:
+            raise GapcuError(-6, lib().gapcu_last_error().decode(errors="replace"))
+        self.h = _vp(h)
+        self.n = len(d)
+        self.na = None
+
+    def close(self):
+        if self.h:
+            lib().gapcu_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def ctx(self, rank):
+        return Context(handle=lib().gapcu_group_ctx(self.h, int(rank)))
+
+    def load_potential(self, path):
+        _check(lib().gapcu_group_load_potential(self.h, os.fsencode(path)))
+
+    def set_skin(self, skin):
+        _check(lib().gapcu_group_set_skin(self.h, float(skin)))
+
+    def set_structure(self, species, lat, pos, rcut=6.0, grid=None):
+        species = np.ascontiguousarray(species, np.int32)
+        lat = np.ascontiguousarray(lat, np.float64); pos = np.ascontiguousarray(pos, np.float64)
+        g = None if grid is None else np.ascontiguousarray(grid, np.int32)
+        _check(lib().gapcu_group_set_structure(self.h, len(pos), species, lat, pos, float(rcut),
+                                               None if g is None else g.ctypes.data))
+        self.na = len(pos)
+
+    def update_positions(self, pos, reuse_lists=True):
+        _check(lib().gapcu_group_update_positions(self.h, np.ascontiguousarray(pos, np.float64), int(bool(reuse_lists))))
+
+    def compute(self, lgrad=True):
+        _check(lib().gapcu_group_compute(self.h, int(bool(lgrad))))
+
+    def fetch(self):
+        ene = np.zeros(1); force = np.zeros((self.na, 3)); stress = np.zeros(6)
+        _check(lib().gapcu_group_fetch(self.h, ene.ctypes.data, force.ctypes.data, stress.ctypes.data))
+        return float(ene[0]), force, stress
+
+    def evaluate(self, species, lat, pos, rcut=6.0, lgrad=True, grid=None):
+        self.set_structure(species, lat, pos, rcut, grid)
+        self.compute(lgrad)
+        e, f, s = self.fetch()
+        return {"energy": e, "forces": f, "stress": s}
 
 
 def set_devices(devices):

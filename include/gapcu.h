@@ -41,6 +41,7 @@ extern "C" {
 #define GAPCU_ECUDA -5      /* CUDA runtime error                                             */
 #define GAPCU_ENODEV -6     /* no CUDA device                                                 */
 #define GAPCU_EARG -7       /* invalid argument                                               */
+#define GAPCU_EDOMAIN -8    /* decomposed run: an atom left its brick, the caller must re-partition */
 
 const char *gapcu_last_error(void);
 
@@ -124,16 +125,58 @@ int gapcu_ctx_set_pipeline(gapcu_ctx *ctx, int mode);
 int gapcu_ctx_set_cluster(gapcu_ctx *ctx, int ctas_per_centre);
 
 /* Spatial decomposition of ONE large structure over the ranks of a node (SURVEY.md 8(e),
- * BASELINE config 4).  Every rank holds all positions; the cell is cut into g0 x g1 x g2
- * bricks in fractional coordinates; this rank evaluates the centres of brick (m0,m1,m2),
- * lists the ghost atoms within rcut of it, and the forces its centres exert on ghosts are
- * returned by one NCCL sum over ranks (as are E and the stress partial sums).  After
- * gapcu_ctx_fetch every rank holds the full result.  g0*g1*g2 == 1 switches it off.
+ * BASELINE config 4).  The cell is cut into g0 x g1 x g2 bricks in fractional coordinates; rank
+ * (m0*g1 + m1)*g2 + m2 evaluates the atoms of brick (m0,m1,m2).  gapcu_ctx_set_structures is given
+ * the WHOLE structure on every rank (what FGAP_CALC's caller holds) and keeps only the atoms of its
+ * brick; before every neighbour build the ranks exchange the ghost images within rcut + skin + drift
+ * of each brick (grouped ncclSend/ncclRecv, 26 directions) and after the force gather the gradients
+ * a rank's centres put on ghosts return to the owners; E, the stress sums and the status flags are
+ * combined with one all-gather of a 48-double record.  gapcu_ctx_fetch then returns E and stress of
+ * the whole structure and the forces of THIS RANK'S atoms, force[n_owned][3] in the order of
+ * gapcu_ctx_owned.  g0*g1*g2 == 1 switches the decomposition off.
+ * Every brick must be at least rcut + skin + 2*drift thick (GAPCU_EARG otherwise).  After
+ * gapcu_ctx_update_positions an atom may have left its brick: up to `drift` Angstrom (default 0.25,
+ * gapcu_ctx_set_drift) that is absorbed by the ghost shell; beyond, fetch returns GAPCU_EDOMAIN and
+ * the caller sets the structure again, which re-partitions.
  * NCCL is loaded with dlopen at the first call; the unique id made by rank 0 with
- * gapcu_nccl_unique_id (128 bytes) must be sent to the other ranks by the caller. */
+ * gapcu_nccl_unique_id (128 bytes) must be sent to the other ranks by the caller.  compute and
+ * fetch are collective: every rank calls them, and a re-run (a capacity outgrown, stale skin lists)
+ * is decided from flags merged over all ranks, so all ranks re-run together. */
 int gapcu_nccl_unique_id(char *out128);
 int gapcu_ctx_nccl_init(gapcu_ctx *ctx, int nranks, int rank, const char *id128);
 int gapcu_ctx_set_domain(gapcu_ctx *ctx, int g0, int g1, int g2, int m0, int m1, int m2);
+int gapcu_ctx_set_drift(gapcu_ctx *ctx, double drift_angstrom);
+/* atoms this context returns forces for: all of them, or the owned atoms of a decomposed run
+ * (ids = indices into the structure given to gapcu_ctx_set_structures; ids may be NULL) */
+int gapcu_ctx_owned(gapcu_ctx *ctx, int *n_owned, int *ids);
+
+/* The same decomposition inside ONE process: nranks contexts on the listed devices (a device may
+ * appear several times: several bricks on one GPU), ghost records and gradients moved by
+ * device-to-device copies ordered with events instead of NCCL.  All arrays are those of the whole
+ * structure (C order); grid3 = NULL picks the brick grid with the smallest ghost shell. */
+typedef struct gapcu_group gapcu_group;
+gapcu_group *gapcu_group_create(int nranks, const int *devices);
+void gapcu_group_destroy(gapcu_group *g);
+int gapcu_group_size(gapcu_group *g);
+gapcu_ctx *gapcu_group_ctx(gapcu_group *g, int rank);
+int gapcu_group_load_potential(gapcu_group *g, const char *path);
+int gapcu_group_set_skin(gapcu_group *g, double skin);
+int gapcu_group_set_structure(gapcu_group *g, int na, const int *species, const double *lat, const double *pos,
+                              double rcut, const int *grid3);
+int gapcu_group_update_positions(gapcu_group *g, const double *pos, int reuse_lists);
+int gapcu_group_compute(gapcu_group *g, int lgrad);
+int gapcu_group_fetch(gapcu_group *g, double *ene, double *force, double *stress);
+
+/* Verlet-skin reuse of the neighbour lists across MD / relaxation steps (the
+ * reference rebuilds its table on every call, gap_calc.f90:89-120).  With a skin > 0 the candidate
+ * lists hold every image within rcut + skin; gapcu_ctx_update_positions(pos, reuse_lists = 1) uploads
+ * moved positions of the SAME atoms and the next compute only re-tests the candidates against rcut
+ * with the reference's arithmetic, so the neighbour sets stay exactly the reference's.  When an atom
+ * has moved more than skin/2 since the lists were built the library rebuilds them by itself (at
+ * fetch).  pos: [ntot][3], C order (decomposed runs: the owned atoms, [n_owned][3]).  reuse_lists = 0
+ * rebuilds everything from the new positions. */
+int gapcu_ctx_set_skin(gapcu_ctx *ctx, double skin_angstrom);
+int gapcu_ctx_update_positions(gapcu_ctx *ctx, const double *pos, int reuse_lists);
 
 /* A batch of nstruct independent periodic structures (C order this time:
  * natoms[nstruct]; species[sum natoms]; lat[nstruct][3][3] rows = lattice
