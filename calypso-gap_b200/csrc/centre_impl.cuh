@@ -637,8 +637,16 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
     bool list_ready = false, list_stashed = false;
     if (FWD) {
         const bool stash = FUSED && nchunk > 1 && a.list_scratch && nchunk <= a.list_scratch_chunks;
+        int trip_base = 0;
         for (int ch = 0; ch < nchunk; ch++) {
             build_list(Qlo + ch * qchunk, min(Qhi, Qlo + (ch + 1) * qchunk), true);
+            if (a.trip_out) {
+                // debug export (gapcu_ctx_debug_triplets): the kept pairs exactly as the passes below consume them
+                const int n = ctl->nkept;
+                for (int t = tid; t < n; t += CT)
+                    if (trip_base + t < a.trip_cap) a.trip_out[(size_t)i * a.trip_cap + trip_base + t] = s_S[t];
+                trip_base += n;
+            }
             if (stash) {
                 // keep the sorted list of this chunk (L2 resident) for the backward pass
                 uint32_t *dst = a.list_scratch + ((size_t)blockIdx.x * a.list_scratch_chunks + ch) * (size_t)(lcap + 32 + 512);
@@ -650,6 +658,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             forward_list();
             __syncthreads();
         }
+        if (a.trip_out && tid == 0) a.trip_cnt[i] = trip_base;
         list_ready = (nchunk == 1);
         list_stashed = stash;
         __syncthreads();

@@ -117,6 +117,7 @@ struct gapcu_ctx {
     bool lists_valid = false;             // skin lists + pos_build describe the resident structures
     bool reuse_next = false;              // the next compute may re-filter instead of rebuilding
     bool last_reuse = false;              // how the pass in flight was run (a stale flag then means: rebuild)
+    uint32_t *dbg_trip = nullptr; int *dbg_trip_cnt = nullptr; int dbg_trip_cap = 0;   // gapcu_ctx_debug_triplets
     DBuf<uint32_t> d_stash;
     int sm_count = 0;
     DBuf<DevFlags> d_flags;
@@ -637,6 +638,7 @@ static int make_centre_args(gapcu_ctx *c, int lgrad, int pcap, CentreArgs *out, 
     a.gpr_M = c->M; a.gpr_Mp = c->Mp; a.gpr_Dp = c->Dp; a.gpr_Mt = c->d_Mt.p; a.gpr_MtT = c->d_MtT.p;
     a.gpr_coeff = c->d_coeff.p; a.gpr_cmean = c->d_cmean.p; a.gpr_itheta = c->d_itheta.p;
     a.flags = c->d_flags.p;
+    a.trip_out = c->dbg_trip; a.trip_cnt = c->dbg_trip_cnt; a.trip_cap = c->dbg_trip_cap;
     // The in-CTA GPR re-reads the sparse set once per atom: worth it while that set is
     // small (it stays in L1/L2 and a separate GEMM launch would be latency bound);
     // large sets go through the tiled DMMA kernel.
@@ -1023,6 +1025,36 @@ extern "C" int gapcu_ctx_fetch_neighbors(gapcu_ctx *c, int cap, int *count, int 
         }
     }
     return mx;
+}
+
+// Debug export of the neighbour PAIRS the angular functions are summed over (the reference's
+// "k_neighbor > j_neighbor" loops with their three cutoff tests, wacsf.f90:177-244): for every atom the
+// kept pairs exactly as the centre kernel's passes consume them, items[atom][k] = slot_j | slot_k << 10 |
+// nclasses << 20 (slots index the atom's neighbour list in reference order; the pair belongs to the
+// cutoff classes 0 .. nclasses-1, classes = distinct SF cutoffs in descending order).  Runs one pass of
+// the split pipeline.  count[ntot], items[ntot][cap]; returns the largest count.
+extern "C" int gapcu_ctx_debug_triplets(gapcu_ctx *c, int cap, int *count, unsigned *items) {
+    if (!c || cap <= 0 || !count || !items) return fail(GAPCU_EARG, "bad arguments");
+    if (c->ntot <= 0 || c->dom.enabled) return fail(GAPCU_EARG, "set an undecomposed structure first");
+    DeviceGuard dg_(c->device);
+    const size_t NT = (size_t)c->ntot;
+    DBuf<uint32_t> d_items; DBuf<int> d_cnt;
+    auto bail = [&](int r) { d_items.release(); d_cnt.release(); c->dbg_trip = nullptr; c->dbg_trip_cnt = nullptr; c->dbg_trip_cap = 0; return r; };
+    if (d_items.ensure(NT * cap) != cudaSuccess || d_cnt.ensure(NT) != cudaSuccess) return bail(fail(GAPCU_ECUDA, "out of device memory"));
+    if (cudaMemsetAsync(d_cnt.p, 0, sizeof(int) * NT, c->stream) != cudaSuccess) return bail(fail(GAPCU_ECUDA, "memset failed"));
+    const int pipe = c->pipeline, clus = c->cluster;
+    c->pipeline = 1; c->cluster = 1;
+    c->dbg_trip = d_items.p; c->dbg_trip_cnt = d_cnt.p; c->dbg_trip_cap = cap;
+    int rc = enqueue_pass(c, 1, nullptr, false);
+    if (!rc) rc = finish_pass(c);
+    c->pipeline = pipe; c->cluster = clus;
+    if (rc) return bail(rc);
+    if (cudaMemcpy(count, d_cnt.p, sizeof(int) * NT, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(items, d_items.p, sizeof(uint32_t) * NT * cap, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return bail(fail(GAPCU_ECUDA, "download failed"));
+    int mx = 0;
+    for (size_t i = 0; i < NT; i++) mx = std::max(mx, count[i]);
+    return bail(mx);
 }
 
 extern "C" int gapcu_ctx_balance(gapcu_ctx *c, double *out4) {

@@ -140,6 +140,10 @@ struct CentreArgs {
     const double *gpr_cmean;    // [Dp]
     const double *gpr_itheta;   // [Dp]
     DevFlags *flags;
+    // debug export of the kept neighbour pairs (triplets i-j-k) per centre: items = slot_j | slot_k << 10 | nclasses << 20
+    uint32_t *trip_out;         // [ntot][trip_cap] or null
+    int *trip_cnt;              // [ntot]
+    int trip_cap;
 };
 
 }  // namespace gapcu

@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(NB_THREADS, 8) k_neigh(const NeighArgs A) {
     const double rprune = rskin * (1.0 + 1e-9) + 1e-9;
     const bool prune = nscan > 27;
     double dmin = 1e300;
-    int nclose = 0;
+    int nclose = 0, nexact = 0;
     // Cells are handled NB_CELLS at a time: their (start, count, shift) are fetched by one
     // thread each, the counts are scanned, and then the candidates of all those cells form ONE
     // flat index space dealt over the threads.
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(NB_THREADS, 8) k_neigh(const NeighArgs A) {
                 double ox, oy, oz;
                 const double dis = image_distance_xyz(cur.x, cur.y, cur.z, lat, n1, n2, n3, xi, yi, zi, ox, oy, oz);
                 if (dis > rskin) continue;
-                if (!(dis > A.rcut)) { dmin = fmin(dmin, dis); nclose += dis < 0.5; }
+                if (!(dis > A.rcut)) { dmin = fmin(dmin, dis); nclose += dis < 0.5; nexact++; }
                 const int p = atomicAdd(&nkeys, 1);   // order of arrival is irrelevant: the list is sorted below
                 if (p < NB_MAXLIST) keys[p] = nbr_key(j - aoff, n1, n2, n3);
             }
@@ -409,7 +409,21 @@ __global__ void __launch_bounds__(NB_THREADS, 8) k_neigh(const NeighArgs A) {
             A.min_dis[i] = m;
         }
     }
-    if (count > A.cap || count > NB_MAXLIST) return;
+    if (count > A.cap || count > NB_MAXLIST) {
+        // the list does not fit (the host enlarges it and runs again); the reference's own limit is still
+        // reported from the number of neighbours within rcut (gap_calc.f90:107-111)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) nexact += __shfl_xor_sync(0xffffffffu, nexact, o);
+        if (lane == 0) wsum[wid] = nexact;
+        __syncthreads();
+        if (tid == 0 && !ghost) {
+            int tot = 0;
+            for (int w = 0; w < NB_THREADS / 32; w++) tot += wsum[w];
+            atomicMax(&A.flags->maxcount, tot);
+            if (tot > MAX_NEIGHBOR_REF_DEV) atomicExch(&A.flags->too_many, 1);
+        }
+        return;
+    }
     // bitonic sort of the keys (padded to a power of two with +inf keys)
     int n2 = 1;
     while (n2 < count) n2 <<= 1;

@@ -30,7 +30,7 @@ SYMBOLS = [
     "gapcu_group_create", "gapcu_group_destroy", "gapcu_group_size", "gapcu_group_ctx", "gapcu_group_load_potential",
     "gapcu_group_set_skin", "gapcu_group_set_structure", "gapcu_group_update_positions", "gapcu_group_compute", "gapcu_group_fetch",
     "gapcu_ctx_set_structures", "gapcu_ctx_compute", "gapcu_ctx_fetch",
-    "gapcu_ctx_fetch_descriptors", "gapcu_ctx_variance", "gapcu_ctx_fetch_neighbors", "gapcu_ctx_time_compute", "gapcu_stage_name",
+    "gapcu_ctx_fetch_descriptors", "gapcu_ctx_variance", "gapcu_ctx_fetch_neighbors", "gapcu_ctx_debug_triplets", "gapcu_ctx_time_compute", "gapcu_stage_name",
     "gapcu_ctx_work_counters", "gapcu_ctx_balance", "gapcu_fp64_peaks",
 ]
 FORTRAN_SYMBOLS = ["fgap_calc_", "fgap_read_", "fget_bond_", "car2acsf_", "write_array_2dim_"]
@@ -227,6 +227,20 @@ class Context:
         shift = np.zeros((nt, cap, 3), np.int32); dis = np.zeros((nt, cap))
         _check(lib().gapcu_ctx_fetch_neighbors(self.h, cap, count, idx, shift, dis))
         return count, idx, shift, dis
+
+    def triplets(self, cap=8192):
+        """Kept neighbour pairs per atom as the kernel sums them: list of (slot_j, slot_k, nclasses) arrays."""
+        nt = int(self.natoms.sum())
+        count = np.zeros(nt, np.int32); items = np.zeros((nt, cap), np.uint32)
+        lib().gapcu_ctx_debug_triplets.argtypes = [_vp, C.c_int, _ip, _vp]
+        mx = _check(lib().gapcu_ctx_debug_triplets(self.h, cap, count, items.ctypes.data))
+        if mx > cap:
+            raise ValueError("triplet capacity %d too small (need %d)" % (cap, mx))
+        out = []
+        for i in range(nt):
+            it = items[i, :count[i]]
+            out.append(np.stack([it & 1023, (it >> 10) & 1023, it >> 20], 1).astype(np.int32))
+        return out
 
     def time_compute(self, steps, lgrad=True, l2_flush_bytes=0, stages=True):
         ms = C.c_double(); launches = C.c_long()

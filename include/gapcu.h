@@ -202,6 +202,14 @@ int gapcu_ctx_variance(gapcu_ctx *ctx, const double *qmm, double *variance, doub
  * dis[ntot][cap].  Returns the largest count, or a negative code. */
 int gapcu_ctx_fetch_neighbors(gapcu_ctx *ctx, int cap, int *count, int *idx, int *shift, double *dis);
 
+/* Debug: the neighbour pairs (triplets centre-j-k) the angular symmetry functions are summed over,
+ * as the kernel keeps them after the reference's three cutoff tests (wacsf.f90:177-244, "k_neighbor >
+ * j_neighbor", "rjk .gt. cutoff").  items[atom][k] = slot_j | slot_k << 10 | nclasses << 20 with
+ * slot_j < slot_k positions in the atom's neighbour list (reference order) and the pair a member of
+ * the cutoff classes 0..nclasses-1 (distinct SF cutoffs, descending).  count[ntot], items[ntot][cap].
+ * Returns the largest count (entries beyond cap are dropped) or a negative code. */
+int gapcu_ctx_debug_triplets(gapcu_ctx *ctx, int cap, int *count, unsigned *items);
+
 /* Device-side timing of `steps` back-to-back gapcu_ctx_compute passes with CUDA
  * events on the context's stream (inputs resident).  If l2_flush_bytes > 0 a
  * buffer of that size is overwritten between passes, outside the timed events.

@@ -407,6 +407,35 @@ static void radial_dense(const gapo_params *p, int ii, int shifted, const double
 }
 
 /* types 2 (lambda=+1) and 4 (lambda=-1): wacsf.f90:169-432, 534-791 */
+/* Export of the triplet set of one centre for one cutoff (tests: triplet-set exactness): the
+ * (js, ks) slot pairs the loops of wacsf.f90:177-244 keep -- "k_neighbor > j_neighbor" in list order,
+ * "rij .gt. cutoff" / "rik .gt. cutoff" / "rjk .gt. cutoff" cycle -- with the reference's arithmetic.
+ * pairs: [cap][2]; returns the number of kept pairs (all of them are counted, the first cap stored),
+ * or -1 when the neighbour table overflows. */
+int gapo_triplets(int na, const double *lat, const double *pos, double rcut, int centre, double cutoff, int cap, int *pairs) {
+    nbtab t;
+    if (nbtab_build(&t, na, lat, pos, NULL, rcut, MAX_NEIGHBOR_REF, centre, centre + 1)) { nbtab_free(&t); return -1; }
+    int cnt = t.count[0], n = 0;
+    for (int js = 0; js < cnt; js++) {
+        double rij = t.dis[js];
+        if (rij > cutoff) continue;
+        const double *xj = t.xyz + 3 * js;
+        for (int ks = js + 1; ks < cnt; ks++) {
+            double rik = t.dis[ks];
+            if (rik > cutoff) continue;
+            const double *xk = t.xyz + 3 * ks;
+            double rjk = (xj[0] - xk[0]) * (xj[0] - xk[0]) + (xj[1] - xk[1]) * (xj[1] - xk[1]) +
+                         (xj[2] - xk[2]) * (xj[2] - xk[2]);
+            rjk = sqrt(rjk);
+            if (rjk > cutoff) continue;
+            if (n < cap) { pairs[2 * n] = js; pairs[2 * n + 1] = ks; }
+            n++;
+        }
+    }
+    nbtab_free(&t);
+    return n;
+}
+
 static void angular_dense(const gapo_params *p, int ii, double lambda, const double *pos, const nbtab *nb,
                           int c0, int c1, int lgrad, dense_out *o, double *ntrip_out) {
     const int nnn = p->nsf;
@@ -899,9 +928,30 @@ static void sparse_backward(const gapo_params *p, const double *posi, const nben
  * candidate pair-SF tests, kept triplet-SF evals, 0...}.  Same return codes as
  * gapo_calc_dense; max_nb is the neighbour capacity per atom (reference: 1000).
  */
+static int calc_sparse_range(const gapo_params *p, int na, const int *species, const double *lat, const double *pos,
+                             double rcut, int lgrad, int max_nb, int c0, int c1, double *ene, double *force, double *stress,
+                             double *xx_out, double *dedg_out, double *eatom_out, double *stats);
+
 int gapo_calc_sparse(const gapo_params *p, int na, const int *species, const double *lat, const double *pos,
                      double rcut, int lgrad, int max_nb, double *ene, double *force, double *stress,
                      double *xx_out, double *dedg_out, double *eatom_out, double *stats) {
+    return calc_sparse_range(p, na, species, lat, pos, rcut, lgrad, max_nb, 0, na, ene, force, stress, xx_out, dedg_out,
+                             eatom_out, stats);
+}
+
+/* Centres [c0, c1) only: their energies, the forces they exert and their share of the stress (a
+ * bounded sample of a structure too large to finish on the CPU in benchmark time: bench.py's
+ * cpu_baseline on the 100k-atom cell).  Descriptor outputs are indexed by the full atom index. */
+int gapo_calc_sparse_centres(const gapo_params *p, int na, const int *species, const double *lat, const double *pos,
+                             double rcut, int lgrad, int max_nb, int c0, int c1, double *ene, double *force, double *stress) {
+    if (c0 < 0) c0 = 0;
+    if (c1 > na || c1 <= 0) c1 = na;
+    return calc_sparse_range(p, na, species, lat, pos, rcut, lgrad, max_nb, c0, c1, ene, force, stress, NULL, NULL, NULL, NULL);
+}
+
+static int calc_sparse_range(const gapo_params *p, int na, const int *species, const double *lat, const double *pos,
+                             double rcut, int lgrad, int max_nb, int c0, int c1, double *ene, double *force, double *stress,
+                             double *xx_out, double *dedg_out, double *eatom_out, double *stats) {
     const int D = p->des_len;
     if (D != 2 * p->nsf) return -3;
     double *weights = (double *)malloc(sizeof(double) * (size_t)na + 8);
@@ -917,7 +967,7 @@ int gapo_calc_sparse(const gapo_params *p, int na, const int *species, const dou
     double vir[9] = {0}, e = 0.0, wc[4] = {0, 0, 0, 0};
     for (int i = 0; i < 3 * na; i++) force[i] = 0.0;
     int ret = 0;
-    for (int i = 0; i < na; i++) {
+    for (int i = c0; i < c1; i++) {
         int cnt = sparse_neighbors(&g, na, lat, pos, weights, rcut, nabc, i, nb, max_nb);
         if (cnt < 0) { ret = -1; break; }
         wc[0] += cnt;

@@ -64,6 +64,8 @@ class Oracle:
             f = getattr(L, name)
             f.restype = C.c_int
             f.argtypes = [C.c_int, _dp, _dp, C.c_double, C.c_int, _ip, _ip, _ip, _dp]
+        L.gapo_triplets.restype = C.c_int
+        L.gapo_triplets.argtypes = [C.c_int, _dp, _dp, C.c_double, C.c_int, C.c_double, C.c_int, _ip]
         L.gapo_get_bond.restype = C.c_double
         L.gapo_get_bond.argtypes = [C.c_int, _dp, _dp, C.c_double]
         L.gapo_calc_dense.restype = C.c_int
@@ -72,6 +74,9 @@ class Oracle:
         L.gapo_calc_sparse.restype = C.c_int
         L.gapo_calc_sparse.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp, C.c_double, C.c_int, C.c_int,
                                        C.POINTER(C.c_double), _dp, _dp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gapo_calc_sparse_centres.restype = C.c_int
+        L.gapo_calc_sparse_centres.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               C.POINTER(C.c_double), _dp, _dp]
         L.gapo_car2acsf_dense.restype = C.c_int
         L.gapo_car2acsf_dense.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp, C.c_double, C.c_int, _dp, _dp, _dp]
 
@@ -110,6 +115,16 @@ class Oracle:
         if mx < 0:
             raise RuntimeError("neighbour overflow (> %d)" % cap)
         return count, idx, shift, dis
+
+    def triplets(self, lat, pos, rcut, centre, cutoff, cap=8192):
+        """(slot_j, slot_k) pairs of `centre` that the angular loops keep for a function with this cutoff
+        (wacsf.f90:177-244), slots = positions in the reference-order neighbour list.  Returns [n, 2]."""
+        lat = np.ascontiguousarray(lat, np.float64); pos = np.ascontiguousarray(pos, np.float64)
+        pairs = np.zeros((cap, 2), np.int32)
+        n = self.lib.gapo_triplets(pos.shape[0], lat, pos, float(rcut), int(centre), float(cutoff), cap, pairs)
+        if n < 0 or n > cap:
+            raise RuntimeError("triplet export overflow (%d)" % n)
+        return pairs[:n].copy()
 
     def get_bond(self, lat, pos, rcut):
         lat = np.ascontiguousarray(lat, np.float64); pos = np.ascontiguousarray(pos, np.float64)
@@ -175,6 +190,17 @@ class Potential:
     def calc_sparse(self, species, lat, pos, rcut=6.0, lgrad=True, max_nb=1000, desc=False, stats=False):
         """Same arithmetic in O(N) memory (validated against calc_dense)."""
         return self._calc(False, species, lat, pos, rcut, lgrad, max_nb, desc, stats)
+
+    def calc_sparse_centres(self, species, lat, pos, rcut, lgrad, c0, c1, max_nb=1000):
+        """Centres [c0, c1) of a large structure only (bench.py's bounded CPU sample)."""
+        species = np.ascontiguousarray(species, np.int32)
+        lat = np.ascontiguousarray(lat, np.float64); pos = np.ascontiguousarray(pos, np.float64)
+        ene = C.c_double(); force = np.zeros((pos.shape[0], 3)); stress = np.zeros(6)
+        rc = self.o.lib.gapo_calc_sparse_centres(self.h, pos.shape[0], species, lat, pos, float(rcut), int(bool(lgrad)), int(max_nb),
+                                                 int(c0), int(c1), C.byref(ene), force, stress)
+        if rc:
+            raise RuntimeError(_ERR.get(rc, "oracle error %d" % rc))
+        return {"energy": ene.value, "forces": force, "stress": stress}
 
     def variance(self, xx, qmm, delta=1.0):
         """The predictive variance the reference carries commented out (gap_calc.f90:205-210):
