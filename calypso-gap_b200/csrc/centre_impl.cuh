@@ -124,28 +124,22 @@ __device__ __forceinline__ void tri_decode(int q, int &a, int &b) {
     a = q - bb * (bb - 1) / 2;
 }
 
-// add a 3-vector to a [3][PCAP] accumulator at index idx.  Private (per warp) set: lanes
-// that hit the same idx take turns in lane order (deterministic, no atomics).  Shared set
-// (very long neighbour lists only): shared-memory atomics.
+// add a 3-vector to a [3][PCAP] accumulator at index idx: lanes of the calling warp that hit the same
+// idx take turns in lane order (deterministic, no atomics).  The set is either private to the warp or,
+// for very long neighbour lists, shared by the CTA -- then the caller lets one warp at a time in.
 template <int PCAP>
 __device__ __forceinline__ void scatter3(double *pa, int idx, double v0, double v1, double v2,
-                                         unsigned amask, unsigned ltmask, bool priv) {
-    if (priv) {
-        const unsigned peers = __match_any_sync(amask, idx);
-        const int rank = __popc(peers & ltmask);
-        const int maxr = __reduce_max_sync(amask, rank);
-        for (int r = 0; r <= maxr; r++) {
-            if (rank == r) {
-                pa[idx] += v0;
-                pa[PCAP + idx] += v1;
-                pa[2 * PCAP + idx] += v2;
-            }
-            __syncwarp(amask);
+                                         unsigned amask, unsigned ltmask) {
+    const unsigned peers = __match_any_sync(amask, idx);
+    const int rank = __popc(peers & ltmask);
+    const int maxr = __reduce_max_sync(amask, rank);
+    for (int r = 0; r <= maxr; r++) {
+        if (rank == r) {
+            pa[idx] += v0;
+            pa[PCAP + idx] += v1;
+            pa[2 * PCAP + idx] += v2;
         }
-    } else {
-        atomicAdd(&pa[idx], v0);
-        atomicAdd(&pa[PCAP + idx], v1);
-        atomicAdd(&pa[2 * PCAP + idx], v2);
+        __syncwarp(amask);
     }
 }
 
@@ -552,16 +546,23 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         // every warp gets a similar mix (fixed assignment: keeps the summation order reproducible)
         for (int round = 0; round * NW < TB; round++) {
             const int g = round * NW + ((round & 1) ? NW - 1 - wid : wid);
-            if (g >= TB) continue;
+            // shared accumulator set (very long lists, no room for private sets): the warps of a round add
+            // their batches one after the other in warp order, so block barriers sit inside this loop and
+            // every warp has to reach them -- a warp without a batch only skips the arithmetic
+            bool act = false;
+            unsigned am = 0;
+            int ra = 0, rb = 0;
+            double v0 = 0, v1 = 0, v2 = 0, w0 = 0, w1 = 0, w2 = 0;
+            if (g < TB) {
             __syncwarp();   // orders this batch's accumulator reads after the previous batch's writes for lanes that sat that one out
             while (o + 1 < ncls && g >= ctl->obp[o + 1]) o++;
             const int v = ncls - o, q = g - ctl->obp[o], Qb = ctl->obq[o], n = ctl->ocnt[o];
             const int idx = lane * Qb + q;  // lanes far apart in the list -> mostly distinct rows
-            const bool act = idx < n;
-            const unsigned am = __ballot_sync(0xffffffffu, act);
-            if (!act) continue;
+            act = idx < n;
+            am = __ballot_sync(0xffffffffu, act);
+            if (act) {
             const uint32_t it = s_S[ctl->obase[o] + idx];
-            const int ra = it & 1023, rb = (it >> 10) & 1023;
+            ra = it & 1023; rb = (it >> 10) & 1023;
             const double2 axy = NB2(ra, 0), azr = NB2(ra, 1), aiw = NB2(ra, 2);
             const double2 bxy = NB2(rb, 0), bzr = NB2(rb, 1), biw = NB2(rb, 2);
             const double rja = azr.y, rkb = bzr.y, ira = aiw.x, irb = biw.x;
@@ -618,8 +619,24 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             const double gij = cij * ira, gik = cik * irb, gjk = cjk * irjk;
             const double dxa = axy.x - xi, dya = axy.y - yi, dza = azr.x - zi, dxb = bxy.x - xi, dyb = bxy.y - yi, dzb = bzr.x - zi;
             const double ga = gij + gjk, gb = gik + gjk;
-            scatter3<PCAP>(pa, ra, fma(ga, dxa, -gjk * dxb), fma(ga, dya, -gjk * dyb), fma(ga, dza, -gjk * dzb), am, ltmask, priv);
-            scatter3<PCAP>(pa, rb, fma(gb, dxb, -gjk * dxa), fma(gb, dyb, -gjk * dya), fma(gb, dzb, -gjk * dza), am, ltmask, priv);
+            v0 = fma(ga, dxa, -gjk * dxb); v1 = fma(ga, dya, -gjk * dyb); v2 = fma(ga, dza, -gjk * dzb);
+            w0 = fma(gb, dxb, -gjk * dxa); w1 = fma(gb, dyb, -gjk * dya); w2 = fma(gb, dzb, -gjk * dza);
+            }
+            }
+            if (priv) {
+                if (act) {
+                    scatter3<PCAP>(pa, ra, v0, v1, v2, am, ltmask);
+                    scatter3<PCAP>(pa, rb, w0, w1, w2, am, ltmask);
+                }
+            } else {
+                for (int w = 0; w < NW; w++) {
+                    if (w == wid && act) {
+                        scatter3<PCAP>(pa, ra, v0, v1, v2, am, ltmask);
+                        scatter3<PCAP>(pa, rb, w0, w1, w2, am, ltmask);
+                    }
+                    __syncthreads();
+                }
+            }
         }
         __syncthreads();
         if (priv) {
@@ -934,9 +951,10 @@ int launch_centre(cudaStream_t st, const CentreArgs &a) {
     const size_t sm = (size_t)a.lay.total;
     if (sm > 227 * 1024) return -1;
     // attribute and occupancy queries cost microseconds each and sit on the critical path of a small
-    // call (the kernels before this one are short): remembered per (instance, device, footprint)
-    static int c_dev = -1, c_sms = 0, c_fit = 0;
-    static size_t c_sm = 0;
+    // call (the kernels before this one are short): remembered per (instance, device, footprint) and per
+    // host thread -- contexts driven from different threads (one per GPU) never share or race on it
+    static thread_local int c_dev = -1, c_sms = 0, c_fit = 0;
+    static thread_local size_t c_sm = 0;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev != c_dev || sm != c_sm) {

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -1382,53 +1383,39 @@ extern "C" int gapcu_calc_batch(int nstruct, const int *natoms, const int *speci
 
 // Zero-fill of a large caller buffer (FGAP_READ's INVCMM = 0 on 4000 x 4000 doubles, gap_calc.f90:361,
 // which the reference's ASE calculator pays on every MD step because it builds a fresh Calculator
-// per step, gappy/ASE/gap_calc.py:41).  The f2py wrapper hands over a freshly allocated array: 128 MB
-// of an anonymous private mapping whose pages were never touched and therefore read as zero.
-// Writing zeros into them costs ~35 ms of page faults; instead the kernel's page map is consulted
-// and only pages that are present or swapped (i.e. that may hold data) are cleared.  Anything that
-// is not provably a private anonymous mapping, and any failure on the way, falls back to memset.
+// per step, gappy/ASE/gap_calc.py:41).  Writing 128 MB of zeros costs ~35 ms of page faults and
+// bandwidth.  For whole pages of a PRIVATE ANONYMOUS mapping (what a large malloc / numpy allocation
+// is) Linux documents a cheaper way to the same contents: madvise(MADV_DONTNEED) drops the pages and
+// "subsequent accesses ... will result in zero-fill-on-demand pages" -- independent of whether the
+// pages were present, swapped or never touched, so no page-map inspection is involved.  The range is
+// checked against /proc/self/maps first (writable, private, no backing file); anything else, any
+// failure, and the partial pages at both ends are cleared with memset.  GAPCU_ZERO=memset forces memset.
 static void zero_fill(void *ptr, size_t bytes) {
     const size_t PAGE = (size_t)sysconf(_SC_PAGESIZE);
-    if (bytes < (8u << 20) || PAGE == 0) { memset(ptr, 0, bytes); return; }
+    static const bool force_memset = [] { const char *e = getenv("GAPCU_ZERO"); return e && !strcmp(e, "memset"); }();
+    if (bytes < (8u << 20) || PAGE == 0 || force_memset) { memset(ptr, 0, bytes); return; }
     const uintptr_t a0 = (uintptr_t)ptr, a1 = a0 + bytes;
     const uintptr_t p0 = (a0 + PAGE - 1) / PAGE * PAGE, p1 = a1 / PAGE * PAGE;   // whole pages inside
-    // the range must be covered by writable, private mappings without a backing file (inode 0);
-    // numpy's madvise(MADV_HUGEPAGE) on the aligned interior splits an allocation into several
     bool anon = false;
     if (FILE *mf = fopen("/proc/self/maps", "r")) {
         char line[512];
         uintptr_t cur = a0;
         while (fgets(line, sizeof line, mf)) {
             unsigned long lo = 0, hi = 0, inode = 0;
-            char perms[8] = {0};
-            if (sscanf(line, "%lx-%lx %7s %*x %*s %lu", &lo, &hi, perms, &inode) != 4) continue;
+            char perms[8] = {0}, path[256] = {0};
+            const int got = sscanf(line, "%lx-%lx %7s %*x %*s %lu %255s", &lo, &hi, perms, &inode, path);
+            if (got < 4) continue;
             if (hi <= cur) continue;
-            if (lo > cur || inode != 0 || perms[1] != 'w' || perms[3] != 'p') break;   // hole or not anonymous
+            // a hole, a file mapping, a shared mapping or a special region ([stack], hugetlb, ...): not provably anonymous
+            if (lo > cur || inode != 0 || perms[1] != 'w' || perms[3] != 'p' || (got >= 5 && path[0] && strcmp(path, "[heap]") != 0)) break;
             cur = hi;
             if (cur >= a1) { anon = true; break; }
         }
         fclose(mf);
     }
-    int fd = anon ? open("/proc/self/pagemap", O_RDONLY) : -1;
-    if (fd < 0 || p1 <= p0) { if (fd >= 0) close(fd); memset(ptr, 0, bytes); return; }
+    if (!anon || p1 <= p0 || madvise((void *)p0, p1 - p0, MADV_DONTNEED) != 0) { memset(ptr, 0, bytes); return; }
     memset(ptr, 0, p0 - a0);
     memset((void *)p1, 0, a1 - p1);
-    std::vector<uint64_t> ent(8192);
-    bool ok = true;
-    for (uintptr_t pg = p0; pg < p1 && ok;) {
-        const size_t n = std::min<size_t>(ent.size(), (p1 - pg) / PAGE);
-        const ssize_t got = pread(fd, ent.data(), n * 8, (off_t)(pg / PAGE * 8));
-        if (got != (ssize_t)(n * 8)) { ok = false; memset((void *)pg, 0, p1 - pg); break; }
-        for (size_t k = 0; k < n;) {
-            if (!(ent[k] >> 62)) { k++; continue; }          // bit 63 present, bit 62 swapped: neither -> still zero
-            size_t e = k + 1;
-            while (e < n && (ent[e] >> 62)) e++;
-            memset((void *)(pg + k * PAGE), 0, (e - k) * PAGE);
-            k = e;
-        }
-        pg += n * PAGE;
-    }
-    close(fd);
 }
 
 extern "C" int gapcu_read(const char *path, int *nsparsex, int *des_len, double *theta, int theta_cap, double *mm,

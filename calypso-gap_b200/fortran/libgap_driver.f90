@@ -4,6 +4,12 @@
 ! of gappy/libgap/{gap_calc,wacsf,get_bond}.f90 (gappy/setup.py:38-41) and link
 ! libgapcu.so; f2py derives the same Python signatures as from the reference.
 !
+! Errors: the message is printed the way the reference prints before it stops.  Where the reference
+! itself STOPs (gap_parameters missing / malformed / beyond nsf_max, nsparseX_max: gap_calc.f90:323-341;
+! more than 1000 neighbours: gap_calc.f90:107-111) this is a plain STOP (exit status 0); every other
+! failure (CUDA error, no device, bad arguments, unknown species) is ERROR STOP 1 so that the shell or
+! the scheduler sees a failed run (gapcu_stop below; same rule as csrc/fortran_shim.c).
+!
 ! This image has no Fortran compiler, so the file is exercised only by reading;
 ! csrc/fortran_shim.c defines the same five external symbols (gfortran mangling,
 ! all arguments by reference) and is what the tests link.  Keep the two in step.
@@ -64,11 +70,23 @@ module gapcu_c_api
     end interface
 end module gapcu_c_api
 
+! code: the GAPCU_E* value returned by the C ABI (include/gapcu.h); -1 = EFILE, -2 = ENEIGH, -4 = ELIMIT
+SUBROUTINE gapcu_stop(code, limit_is_reference_stop)
+    use gapcu_c_api
+    implicit none
+    integer, intent(in) :: code
+    logical, intent(in) :: limit_is_reference_stop
+    call gapcu_print_last_error()
+    if (code == -1 .or. code == -2 .or. (limit_is_reference_stop .and. code == -4)) stop
+    error stop 1
+END SUBROUTINE gapcu_stop
+
 ! gappy/libgap/gap_calc.f90:1-5
 SUBROUTINE FGAP_CALC(NA, SPECIES, LAT, POS, ENE, FORCE, STRESS, VARIANCE, nsparseX, des_len, &
                      theta, MM, qmm, coeff, Rcut, lgrad)
     use gapcu_c_api
     implicit none
+    integer :: gapcu_rc
     integer, intent(in) :: NA
     integer, intent(in), dimension(NA) :: SPECIES
     double precision, intent(in), dimension(3,3) :: LAT
@@ -86,49 +104,46 @@ SUBROUTINE FGAP_CALC(NA, SPECIES, LAT, POS, ENE, FORCE, STRESS, VARIANCE, nspars
     integer :: ig
     ig = 0
     if (lgrad) ig = 1
-    if (gapcu_calc(NA, SPECIES, LAT, POS, nsparseX, des_len, THETA, MM, QMM, COEFF, Rcut, ig, &
-                   ENE, FORCE, STRESS, VARIANCE) /= 0) then
-        call gapcu_print_last_error()
-        stop
-    endif
+    gapcu_rc = gapcu_calc(NA, SPECIES, LAT, POS, nsparseX, des_len, THETA, MM, QMM, COEFF, Rcut, ig, &
+                   ENE, FORCE, STRESS, VARIANCE)
+    if (gapcu_rc /= 0) call gapcu_stop(gapcu_rc, .false.)
 END SUBROUTINE FGAP_CALC
 
 ! gappy/libgap/gap_calc.f90:303-314
 SUBROUTINE FGAP_READ(nsparseX, des_len, theta, MM, invcmm, coeff)
     use gapcu_c_api
     implicit none
+    integer :: gapcu_rc
     integer, parameter :: nsf_max = 100
     integer, parameter :: nsparseX_max = 4000
     integer, intent(out) :: nsparseX, des_len
     double precision, intent(out) :: theta(nsf_max), MM(nsparseX_max, nsf_max)
     double precision, intent(out) :: invcmm(nsparseX_max, nsparseX_max), coeff(nsparseX_max)
-    if (gapcu_read('gap_parameters'//c_null_char, nsparseX, des_len, theta, nsf_max, MM, nsparseX_max, nsf_max, &
-                   invcmm, nsparseX_max, coeff, nsparseX_max) /= 0) then
-        call gapcu_print_last_error()
-        stop
-    endif
+    gapcu_rc = gapcu_read('gap_parameters'//c_null_char, nsparseX, des_len, theta, nsf_max, MM, nsparseX_max, nsf_max, &
+                   invcmm, nsparseX_max, coeff, nsparseX_max)
+    if (gapcu_rc /= 0) call gapcu_stop(gapcu_rc, .true.)
 END SUBROUTINE FGAP_READ
 
 ! gappy/libgap/get_bond.f90:4-12
 SUBROUTINE FGET_BOND(na, lat, elements, pos, rcut, min_bond)
     use gapcu_c_api
     implicit none
+    integer :: gapcu_rc
     INTEGER, intent(in) :: na
     REAL(8), intent(in), dimension(3,3) :: lat
     INTEGER, intent(in), dimension(na) :: elements
     REAL(8), intent(in), dimension(na,3) :: pos
     REAL(8), intent(in) :: rcut
     REAL(8), intent(out) :: min_bond
-    if (gapcu_bond(na, lat, elements, pos, rcut, min_bond) /= 0) then
-        call gapcu_print_last_error()
-        stop
-    endif
+    gapcu_rc = gapcu_bond(na, lat, elements, pos, rcut, min_bond)
+    if (gapcu_rc /= 0) call gapcu_stop(gapcu_rc, .false.)
 END SUBROUTINE FGET_BOND
 
 ! gappy/libgap/wacsf.f90:2-12
 SUBROUTINE CAR2ACSF(NA, max_neighbor, nf, pos, neighbor, neighbor_count, xx, dxdy, strs, lgrad)
     use gapcu_c_api
     implicit none
+    integer :: gapcu_rc
     INTEGER, intent(in) :: NA, max_neighbor, NF
     REAL(8), intent(in), dimension(NA,3) :: pos
     REAL(8), intent(in), dimension(NA,max_neighbor,6) :: neighbor
@@ -140,10 +155,8 @@ SUBROUTINE CAR2ACSF(NA, max_neighbor, nf, pos, neighbor, neighbor_count, xx, dxd
     integer :: ig
     ig = 0
     if (lgrad) ig = 1
-    if (gapcu_car2acsf_table(NA, max_neighbor, nf, pos, neighbor, neighbor_count, ig, xx, dxdy, strs) /= 0) then
-        call gapcu_print_last_error()
-        stop
-    endif
+    gapcu_rc = gapcu_car2acsf_table(NA, max_neighbor, nf, pos, neighbor, neighbor_count, ig, xx, dxdy, strs)
+    if (gapcu_rc /= 0) call gapcu_stop(gapcu_rc, .false.)
 END SUBROUTINE CAR2ACSF
 
 ! gappy/libgap/wacsf.f90:798-810 (debug dump; every call site in the reference is commented out)
@@ -170,6 +183,7 @@ END SUBROUTINE
 SUBROUTINE FGAP_CALC_BATCH(NS, NTOT, NATOMS, SPECIES, LAT3, POS3, Rcut, lgrad, ENE, FORCE3, STRESS6, NDEV, DEVICES)
     use gapcu_c_api
     implicit none
+    integer :: gapcu_rc
     integer, intent(in) :: NS, NTOT, NDEV
     integer, intent(in) :: NATOMS(NS), SPECIES(NTOT), DEVICES(*)
     double precision, intent(in) :: LAT3(3,3,NS), POS3(3,NTOT), Rcut
@@ -179,13 +193,9 @@ SUBROUTINE FGAP_CALC_BATCH(NS, NTOT, NATOMS, SPECIES, LAT3, POS3, Rcut, lgrad, E
     ig = 0
     if (lgrad) ig = 1
     if (NDEV > 0) then
-        if (gapcu_set_devices(NDEV, DEVICES) /= 0) then
-            call gapcu_print_last_error()
-            stop
-        endif
+        gapcu_rc = gapcu_set_devices(NDEV, DEVICES)
+        if (gapcu_rc /= 0) call gapcu_stop(gapcu_rc, .false.)
     endif
-    if (gapcu_calc_batch(NS, NATOMS, SPECIES, LAT3, POS3, Rcut, ig, ENE, FORCE3, STRESS6) /= 0) then
-        call gapcu_print_last_error()
-        stop
-    endif
+    gapcu_rc = gapcu_calc_batch(NS, NATOMS, SPECIES, LAT3, POS3, Rcut, ig, ENE, FORCE3, STRESS6)
+    if (gapcu_rc /= 0) call gapcu_stop(gapcu_rc, .false.)
 END SUBROUTINE FGAP_CALC_BATCH
