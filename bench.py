@@ -471,18 +471,16 @@ def extra_c5(args, gapcu, _ctx):
             "stage_ms_per_step": {k: v / steps for k, v in st.items()}}
 
 
-def _c3_make(i):
-    from structures import random_candidate
-    return random_candidate(3000 + i)
-
-
 def extra_c3(args, gapcu, _ctx):
     """BASELINE config 3 as written: 4,096 random candidates (32-128 atoms) through gapcu_calc_batch over
     every visible device, host arrays in and out; the first structures are checked against the oracle."""
-    from multiprocessing import Pool
+    import pickle
     n = args.c3_structs
-    with Pool(min(os.cpu_count() or 1, 64)) as pool:
-        structs = pool.map(_c3_make, range(n), chunksize=8)
+    out = os.path.join("/tmp", "gapcu_bench_c3_%d.pkl" % n)
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_c3.py"), str(n), out])   # child process: no fork from the CUDA process
+    with open(out, "rb") as fh:
+        structs = pickle.load(fh)
+    os.remove(out)
     cells, poss, zs = [s[0] for s in structs], [s[1] for s in structs], [s[2] for s in structs]
     natoms = sum(len(p) for p in poss)
     ndev = gapcu.device_count()

@@ -14,7 +14,7 @@ static SmemLayout make_layout(const CentreArgs &a, int mode) {
     int o = hot_bytes(pt, a.plan.ncls);   // Hot<PCAP>: neighbour records, gradient accumulator, class counts, fc tables
     auto take = [&](long bytes) { int r = o; o += (int)((bytes + 15) & ~15l); return r; };
     take(0);
-    const bool bwd = mode != MODE_FWD, fwd = mode != MODE_BWD, fused = mode == MODE_FUSED;
+    const bool bwd = mode != MODE_FWD, fwd = mode != MODE_BWD, fused = mode >= MODE_FUSED;
     L.t32 = take(8 * 32);
     L.t2 = take(8 * MAXC_DEV);
     L.galpha = take(8 * (a.plan.n_grp + 1));
@@ -70,7 +70,8 @@ int launch_backward(cudaStream_t st, const CentreArgs &a, long *launches) {
 }
 int launch_fused(cudaStream_t st, const CentreArgs &a, long *launches) {
     if (launches) *launches += 1;
-    return launch_mode(st, a, MODE_FUSED);
+    const bool se = a.share_exp && a.estash && a.cs == 1 && centre_pcap_template(a.pcap) <= 256;
+    return launch_mode(st, a, se ? MODE_FUSED_SE : MODE_FUSED);
 }
 
 }  // namespace gapcu

@@ -64,7 +64,12 @@ constexpr int CT = 256;  // threads per centre CTA (measured: 384 threads x 2 CT
 constexpr int NW = CT / 32;
 constexpr int MAXG = 4;  // alpha groups of one class handled per forward pass (register accumulators)
 
-enum { MODE_FWD = 0, MODE_BWD = 1, MODE_FUSED = 2 };
+// MODE_FUSED_SE: the fused kernel for potentials whose angular cutoff classes all carry the same one or two
+// exponents alpha (the shipped table: 0.01 and 0.1 for every cutoff).  exp(-alpha s) of a triplet then does
+// not depend on the class: it is evaluated ONCE, in the forward pass of the first angular class, parked in
+// an L2-resident per-CTA buffer, and read back by the other classes' forward passes and by the backward
+// pass (which otherwise repeats every exponential of the forward pass).
+enum { MODE_FWD = 0, MODE_BWD = 1, MODE_FUSED = 2, MODE_FUSED_SE = 3 };
 
 // Byte offsets of the per-neighbour arrays at the start of the dynamic shared memory.
 template <int PCAP>
@@ -151,7 +156,7 @@ __device__ __forceinline__ double dist2_fma(double dx, double dy, double dz) { r
 
 template <int MODE, int PCAP, int CS>
 __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i, const bool first) {
-    constexpr bool FWD = MODE != MODE_BWD, BWD = MODE != MODE_FWD, FUSED = MODE == MODE_FUSED;
+    constexpr bool FWD = MODE != MODE_BWD, BWD = MODE != MODE_FWD, FUSED = MODE >= MODE_FUSED, SE = MODE == MODE_FUSED_SE;
     // rank of this CTA among the CS CTAs that share centre i; lead = the one that writes the outputs
     const int crank = CS > 1 ? (int)cg::this_cluster().block_rank() : 0;
     const bool lead = crank == 0;
@@ -292,6 +297,9 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
     const int nchunk = (angmask && Q > 0) ? (Q + lcap - 1) / lcap : 0;
     const int qchunk = nchunk ? ((Q + nchunk - 1) / nchunk + 31) & ~31 : 0;
     unsigned long long wk_trip = 0, wk_tc = 0, wk_tsf = 0;
+    // parked exponentials: one double2 per kept pair, chunk after chunk of this centre's list
+    constexpr bool se = SE;
+    double2 *est = SE ? a.estash + (size_t)blockIdx.x * a.estash_stride : nullptr;
 
     auto build_list = [&](int q0, int q1, bool count_work) {
         const int n = q1 - q0;
@@ -458,16 +466,30 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                     acc[1][0] += pe1; acc[1][1] = fma(pe1, x.cosv, acc[1][1]); acc[1][2] += pw1; acc[1][3] = fma(pw1, x.cosv, acc[1][3]);
                 };
                 int t = myrank;
+                const bool reuse = se && c != a.c_first;   // this class reads the exponentials the first angular class parked
                 for (; t + CT < n_c; t += 2 * CT) {
                     const Item x = prep(t), y = prep(t + CT);
-                    const double ex0 = exp_neg(-al0 * x.ssum, s_t32), ey0 = exp_neg(-al0 * y.ssum, s_t32);
-                    const double ex1 = exp_neg(-al1 * x.ssum, s_t32), ey1 = exp_neg(-al1 * y.ssum, s_t32);
+                    double ex0, ey0, ex1, ey1;
+                    if (reuse) {
+                        const double2 sx = __ldcg(est + t), sy = __ldcg(est + t + CT);
+                        ex0 = sx.x; ex1 = sx.y; ey0 = sy.x; ey1 = sy.y;
+                    } else {
+                        ex0 = exp_neg(-al0 * x.ssum, s_t32); ey0 = exp_neg(-al0 * y.ssum, s_t32);
+                        ex1 = exp_neg(-al1 * x.ssum, s_t32); ey1 = exp_neg(-al1 * y.ssum, s_t32);
+                        if (se) { __stcg(est + t, make_double2(ex0, ex1)); __stcg(est + t + CT, make_double2(ey0, ey1)); }
+                    }
                     add(x, ex0, ex1);
                     add(y, ey0, ey1);
                 }
                 if (t < n_c) {
                     const Item x = prep(t);
-                    add(x, exp_neg(-al0 * x.ssum, s_t32), exp_neg(-al1 * x.ssum, s_t32));
+                    double ex0, ex1;
+                    if (reuse) { const double2 sx = __ldcg(est + t); ex0 = sx.x; ex1 = sx.y; }
+                    else {
+                        ex0 = exp_neg(-al0 * x.ssum, s_t32); ex1 = exp_neg(-al1 * x.ssum, s_t32);
+                        if (se) __stcg(est + t, make_double2(ex0, ex1));
+                    }
+                    add(x, ex0, ex1);
                 }
                 if (__any_sync(0xffffffffu, myrank < n_c)) {
 #pragma unroll
@@ -484,9 +506,11 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                         }
                     }
                 }
+                if (se && c == a.c_first) __syncthreads();   // the parked values are read by other threads from here on
                 continue;
             }
-            for (int gb = g0; gb < g1; gb += MAXG) {
+            // (the parked-exponentials variant is only dispatched for <= 2 exponents per class: dead code there)
+            for (int gb = g0; !SE && gb < g1; gb += MAXG) {
                 const int ng = min(MAXG, g1 - gb);
                 double acc[MAXG][4];
 #pragma unroll
@@ -561,7 +585,10 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             act = idx < n;
             am = __ballot_sync(0xffffffffu, act);
             if (act) {
-            const uint32_t it = s_S[ctl->obase[o] + idx];
+            const int li = ctl->obase[o] + idx;
+            const uint32_t it = s_S[li];
+            double2 pk = make_double2(0.0, 0.0);
+            if (se) pk = __ldcg(est + li);      // requested before the geometry below needs it
             ra = it & 1023; rb = (it >> 10) & 1023;
             const double2 axy = NB2(ra, 0), azr = NB2(ra, 1), aiw = NB2(ra, 2);
             const double2 bxy = NB2(rb, 0), bzr = NB2(rb, 1), biw = NB2(rb, 2);
@@ -592,7 +619,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 int gg = g0;
                 for (; gg + 1 < g1; gg += 2) {
                     const double al0 = s_galpha[gg], al1 = s_galpha[gg + 1];
-                    const double e0 = exp_neg(-al0 * ssum, s_t32), e1 = exp_neg(-al1 * ssum, s_t32);
+                    const double e0 = se ? pk.x : exp_neg(-al0 * ssum, s_t32), e1 = se ? pk.y : exp_neg(-al1 * ssum, s_t32);
                     const double4 gd0 = *(const double4 *)(s_gd + 4 * gg), gd1 = *(const double4 *)(s_gd + 4 * gg + 4);
                     const double t00 = e0 * fma(ww, gd0.y, gd0.x), t01 = e0 * fma(ww, gd0.w, gd0.z);
                     const double t10 = e1 * fma(ww, gd1.y, gd1.x), t11 = e1 * fma(ww, gd1.w, gd1.z);
@@ -602,7 +629,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 }
                 if (gg < g1) {
                     const double al = s_galpha[gg];
-                    const double e = exp_neg(-al * ssum, s_t32);
+                    const double e = se ? pk.x : exp_neg(-al * ssum, s_t32);
                     const double4 gd = *(const double4 *)(s_gd + 4 * gg);   // DU, DW, DUL, DWL
                     const double t0 = e * fma(ww, gd.y, gd.x), t1 = e * fma(ww, gd.w, gd.z);
                     T0 += t0;
@@ -656,6 +683,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         const bool stash = FUSED && nchunk > 1 && a.list_scratch && nchunk <= a.list_scratch_chunks;
         int trip_base = 0;
         for (int ch = 0; ch < nchunk; ch++) {
+            if (SE) est = a.estash + (size_t)blockIdx.x * a.estash_stride + (size_t)ch * (lcap + 32);
             build_list(Qlo + ch * qchunk, min(Qhi, Qlo + (ch + 1) * qchunk), true);
             if (a.trip_out) {
                 // debug export (gapcu_ctx_debug_triplets): the kept pairs exactly as the passes below consume them
@@ -846,6 +874,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         }
         __syncthreads();
         for (int ch = 0; ch < nchunk; ch++) {
+            if (SE) est = a.estash + (size_t)blockIdx.x * a.estash_stride + (size_t)ch * (lcap + 32);
             if (list_stashed) {
                 const uint32_t *src = a.list_scratch + ((size_t)blockIdx.x * a.list_scratch_chunks + ch) * (size_t)(lcap + 32 + 512);
                 int *cs = (int *)ctl;
@@ -1004,7 +1033,12 @@ int launch_centre_p1024(cudaStream_t st, const CentreArgs &a, int mode);
 
 // the split pipeline (forward / backward launches) always runs one CTA per centre; the fused
 // kernel also exists with 2 and 4 CTAs per centre (a.cs, chosen by the host for small launches)
-#define GAPCU_CENTRE_INSTANCE(PC)                                                         \
+template <int PC, bool ON>
+int launch_centre_se(cudaStream_t st, const CentreArgs &a) {
+    if constexpr (ON) return launch_centre<MODE_FUSED_SE, PC, 1>(st, a);
+    else return launch_centre<MODE_FUSED, PC, 1>(st, a);
+}
+#define GAPCU_CENTRE_INSTANCE_(PC, SE_ON)                                                \
     namespace gapcu {                                                                     \
     int launch_centre_p##PC(cudaStream_t st, const CentreArgs &a, int mode) {             \
         if (mode == MODE_FWD) return launch_centre<MODE_FWD, PC, 1>(st, a);               \
@@ -1013,8 +1047,12 @@ int launch_centre_p1024(cudaStream_t st, const CentreArgs &a, int mode);
         if (a.cs == 4 && launch_centre<MODE_FUSED, PC, 4>(st, a) == 0) return 0;          \
         if (a.cs == 2 && launch_centre<MODE_FUSED, PC, 2>(st, a) == 0) return 0;          \
         if (a.cs > 1) cudaGetLastError();                                                 \
+        if (mode == MODE_FUSED_SE) return launch_centre_se<PC, SE_ON>(st, a);             \
         return launch_centre<MODE_FUSED, PC, 1>(st, a);                                   \
     }                                                                                     \
     }
+// instances with / without the parked-exponentials variant (only the two small capacity tiers carry it)
+#define GAPCU_CENTRE_INSTANCE(PC) GAPCU_CENTRE_INSTANCE_(PC, false)
+#define GAPCU_CENTRE_INSTANCE_SE(PC) GAPCU_CENTRE_INSTANCE_(PC, true)
 
 }  // namespace gapcu

@@ -106,6 +106,7 @@ struct gapcu_ctx {
     std::vector<StructDev> h_structs;
     std::vector<int> h_natoms;
     DBuf<StructDev> d_structs;
+    DBuf<int> d_hist, d_scan_sums;   // scratch of the multi-CTA centre ordering / cell scan
     DBuf<int> d_sid, d_arank, d_bin_count, d_bin_start, d_bin_atoms, d_nbr_cnt, d_skin_cnt, d_order;
     DBuf<int4> d_abin, d_sabin;   // per atom / in bin order: (bin | atom, wrap offsets)
     DBuf<double> d_spos;          // coordinates in bin order
@@ -120,6 +121,7 @@ struct gapcu_ctx {
     bool last_reuse = false;              // how the pass in flight was run (a stale flag then means: rebuild)
     uint32_t *dbg_trip = nullptr; int *dbg_trip_cnt = nullptr; int dbg_trip_cap = 0;   // gapcu_ctx_debug_triplets
     DBuf<uint32_t> d_stash;
+    DBuf<double2> d_estash;       // parked exponentials of the fused kernel, per persistent CTA
     int sm_count = 0;
     DBuf<DevFlags> d_flags;
     // flags | out8 | force live in ONE allocation so that a call reads its results back with one copy
@@ -264,7 +266,7 @@ extern "C" void gapcu_ctx_destroy(gapcu_ctx *c) {
     c->d_G.release(); c->d_dEdG.release(); c->d_eatom.release(); c->d_fpair.release(); c->d_gself.release();
     c->d_vir.release(); c->d_force.release(); c->d_out8.release(); c->d_mindis.release(); c->d_keys.release();
     c->d_stash.release(); c->d_epart.release(); c->d_accpart.release(); c->d_flags.release(); c->d_results.release(); c->d_inputs.release(); c->d_flush.release();
-    c->d_skin_keys.release(); c->d_skin_cnt.release(); c->d_pos_build.release();
+    c->d_skin_keys.release(); c->d_skin_cnt.release(); c->d_pos_build.release(); c->d_hist.release(); c->d_scan_sums.release(); c->d_estash.release();
     domain_destroy(c);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->stage_ev_init) for (auto &e : c->stage_ev) cudaEventDestroy(e);
@@ -493,7 +495,7 @@ static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, con
     CU(c->d_abin.ensure(NT)); CU(c->d_sabin.ensure(NT)); CU(c->d_spos.ensure(3 * NT)); CU(c->d_arank.ensure(NT)); CU(c->d_bin_count.ensure(2 * (size_t)c->nbins + 2));
     CU(c->d_bin_start.ensure(c->nbins + 2)); CU(c->d_bin_atoms.ensure(NT)); CU(c->d_nbr_cnt.ensure(NT)); CU(c->d_skin_cnt.ensure(NT)); CU(c->d_order.ensure(NT));
     CU(ensure_results(c, (size_t)nstruct, NT));
-    CU(c->d_mindis.ensure(NT));
+    CU(c->d_mindis.ensure(NT)); CU(c->d_scan_sums.ensure((size_t)c->nbins / 4096 + 4));
     CU(cudaMemcpyAsync(c->d_inputs.p, hp, total, cudaMemcpyHostToDevice, c->stream));   // structs | sid | pos | wgt in one copy
     c->h2d_pending = true;
     // ---- neighbour capacity estimate (grown on demand)
@@ -594,6 +596,7 @@ extern "C" int gapcu_ctx_nccl_init(gapcu_ctx *c, int nranks, int rank, const cha
 // ---------------------------------------------------------------------------
 static int ensure_work_buffers(gapcu_ctx *c) {
     const size_t NT = (size_t)c->ntot, NC = (size_t)c->n_centres;
+    CU(c->d_hist.ensure(1024 + 2)); CU(c->d_scan_sums.ensure((size_t)c->nbins / 4096 + 4));
     CU(c->d_keys.ensure(NT * c->cap)); CU(c->d_skin_keys.ensure(NT * c->cap));
     CU(c->d_G.ensure(NC * c->D)); CU(c->d_dEdG.ensure(NC * c->D)); CU(c->d_eatom.ensure(NC));
     CU(c->d_fpair.ensure(NC * c->cap * 3)); CU(c->d_gself.ensure(NC * 3)); CU(c->d_vir.ensure(NC * 6));
@@ -640,6 +643,21 @@ static int make_centre_args(gapcu_ctx *c, int lgrad, int pcap, CentreArgs *out, 
     a.gpr_coeff = c->d_coeff.p; a.gpr_cmean = c->d_cmean.p; a.gpr_itheta = c->d_itheta.p;
     a.flags = c->d_flags.p;
     a.trip_out = c->dbg_trip; a.trip_cnt = c->dbg_trip_cnt; a.trip_cap = c->dbg_trip_cap;
+    {   // parked exponentials (centre_impl.cuh MODE_FUSED_SE): every angular class carries the same 1 or 2 alphas
+        const SfPlan &pl = c->plan;
+        int first = -1, ng0 = 0;
+        bool same = true;
+        for (int k = 0; k < pl.ncls && same; k++) {
+            const int g0 = pl.grp_begin[k], g1 = pl.grp_begin[k + 1];
+            if (g1 == g0) continue;
+            if (first < 0) { first = k; ng0 = g1 - g0; same = ng0 <= 2; continue; }
+            same = (g1 - g0) == ng0;
+            for (int g = 0; g < ng0 && same; g++) same = pl.grp_alpha[g0 + g] == pl.grp_alpha[pl.grp_begin[first] + g];
+        }
+        static const bool off = getenv("GAPCU_NO_SHARE_EXP") != nullptr;   // A/B switch
+        a.share_exp = (first >= 0 && same && !off) ? 1 : 0;
+        a.c_first = first < 0 ? 0 : first;
+    }
     // The in-CTA GPR re-reads the sparse set once per atom: worth it while that set is
     // small (it stays in L1/L2 and a separate GEMM launch would be latency bound);
     // large sets go through the tiled DMMA kernel.
@@ -670,6 +688,12 @@ static int make_centre_args(gapcu_ctx *c, int lgrad, int pcap, CentreArgs *out, 
             CU(c->d_stash.ensure(centre_stash_words(a, chunks, ctas)));
             a.list_scratch = c->d_stash.p; a.list_scratch_chunks = chunks;
         }
+        if (fused && a.share_exp && pcap <= 256) {
+            if (!c->sm_count) cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
+            a.estash_stride = std::max(1, chunks) * (a.lcap + 32);     // every chunk of a centre's list has its own slice
+            CU(c->d_estash.ensure((size_t)c->sm_count * 4 * a.estash_stride));
+            a.estash = c->d_estash.p;
+        }
     }
     *out = a;
     *fused_out = fused;
@@ -681,7 +705,7 @@ static int make_centre_args(gapcu_ctx *c, int lgrad, int pcap, CentreArgs *out, 
 static int run_centres_and_gather(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
     int rc;
     if (!neighbors_direct(c) || c->last_reuse)
-        launch_order(c->stream, c->d_nbr_cnt.p, c->n_centres, c->d_order.p, c->d_flags.p, &c->launches);
+        launch_order(c->stream, c->d_nbr_cnt.p, c->n_centres, c->d_order.p, c->d_flags.p, c->d_hist.p, &c->launches);
     CU(cudaGetLastError());
     if (ev) CU(cudaEventRecord(ev[1], c->stream));
     // Capacity tiers: `order` lists the centres by descending neighbour count, so the centres
@@ -720,8 +744,10 @@ static int run_centres_and_gather(gapcu_ctx *c, int lgrad, cudaEvent_t *ev) {
             // one serves every centre and the (mostly empty) lower tiers are not launched
             if (cap == top && top <= 256 && c->n_centres <= c->sm_count) { tiers.back().a.q_end = &F->n_centres; break; }
         }
-        for (Tier &t : tiers)   // a later tier may have grown (moved) the shared list-parking buffer
+        for (Tier &t : tiers) {  // a later tier may have grown (moved) the shared parking buffers
             if (t.a.list_scratch) t.a.list_scratch = c->d_stash.p;
+            if (t.a.estash) t.a.estash = c->d_estash.p;
+        }
     }
     const char *too_big = "centre kernel needs more shared memory than an SM has";
     if (fused) {
@@ -765,6 +791,7 @@ static NeighborBuild neighbor_args(gapcu_ctx *c, bool with_keys, bool with_min, 
     memset(&b, 0, sizeof b);
     b.structs = c->d_structs.p; b.sid = c->d_sid.p; b.pos = c->d_pos.p; b.ntot = c->ntot; b.nbins_total = c->nbins;
     b.rcut = c->rcut; b.rskin = with_keys ? c->rcut + c->skin() : c->rcut; b.cap = c->cap;
+    b.arank_scratch = c->d_scan_sums.p;
     b.abin = c->d_abin.p; b.arank = c->d_arank.p; b.bin_count = c->d_bin_count.p; b.bin_start = c->d_bin_start.p;
     b.bin_atoms = c->d_bin_atoms.p; b.sabin = c->d_sabin.p; b.spos = c->d_spos.p;
     b.skin_keys = with_keys ? c->d_skin_keys.p : nullptr; b.skin_cnt = c->d_skin_cnt.p;

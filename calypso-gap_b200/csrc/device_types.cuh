@@ -140,6 +140,11 @@ struct CentreArgs {
     const double *gpr_cmean;    // [Dp]
     const double *gpr_itheta;   // [Dp]
     DevFlags *flags;
+    // MODE_FUSED_SE: parked exponentials, [persistent CTAs][estash_stride] double2 (L2 resident)
+    double2 *estash;
+    int estash_stride;
+    int share_exp;              // every angular class carries the same one or two alphas
+    int c_first;                // first class with angular functions
     // debug export of the kept neighbour pairs (triplets i-j-k) per centre: items = slot_j | slot_k << 10 | nclasses << 20
     uint32_t *trip_out;         // [ntot][trip_cap] or null
     int *trip_cnt;              // [ntot]

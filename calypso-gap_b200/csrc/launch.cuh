@@ -19,6 +19,7 @@ struct NeighborBuild {
     double rcut, rskin;       // rskin = rcut + skin: radius of the candidate (skin) lists
     int cap;                  // row length of skin_keys / nbr_keys
     // cell list scratch
+    int *arank_scratch;       // ints for the multi-CTA cell scan: nbins_total / 4096 + 2
     int4 *abin; int *arank; int *bin_count /* [2][nbins_total] */; int *bin_start; int *bin_atoms; int4 *sabin; double *spos;
     // outputs
     uint64_t *skin_keys; int *skin_cnt;   // candidates within rskin, reference order (null: not kept)
@@ -39,7 +40,8 @@ void launch_refilter(cudaStream_t st, const NeighborBuild &b, const double *pos_
 // no decomposition; that kernel also fills `order` (no launch_order needed)
 int neighbor_direct_max_candidates();
 
-void launch_order(cudaStream_t st, const int *nbr_cnt, int n_centres, int *order, DevFlags *flags, long *launches);
+// hist: NB_MAXLIST + 2 ints of device scratch (null: always the single-CTA kernel)
+void launch_order(cudaStream_t st, const int *nbr_cnt, int n_centres, int *order, DevFlags *flags, int *hist, long *launches);
 
 // centre.cu  (mode: 0 forward, 1 backward, 2 fused forward + GPR + backward)
 size_t centre_smem_bytes(const CentreArgs &a, int mode);

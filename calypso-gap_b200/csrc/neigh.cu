@@ -104,6 +104,68 @@ __global__ void k_scan_bins(const int *bin_count, int *bin_start, int nb) {
     if (threadIdx.x == 0) bin_start[nb] = carry;
 }
 
+// The same scan for many cells, in three launches.  sums: one int per CTA (+1).
+constexpr int SCAN_PER_CTA = 4096;
+__global__ void __launch_bounds__(1024) k_scan_bins_part(const int *bin_count, int *bin_start, int nb, int *sums) {
+    __shared__ int wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int i0 = blockIdx.x * SCAN_PER_CTA + tid * 4;
+    int v[4], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const int i = i0 + k; v[k] = i < nb ? bin_count[i] + bin_count[nb + i] : 0; tot += v[k]; }
+    int x = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wsum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int s = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+        wsum[lane] = s;
+    }
+    __syncthreads();
+    int run = (wid ? wsum[wid - 1] : 0) + x - tot;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { if (i0 + k < nb) bin_start[i0 + k] = run; run += v[k]; }
+    if (tid == 1023) sums[blockIdx.x] = run;
+}
+__global__ void __launch_bounds__(1024) k_scan_bins_top(int *sums, int n, int *bin_start, int nb) {
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        const int v = i < n ? sums[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) wsum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int s = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+            wsum[lane] = s;
+        }
+        __syncthreads();
+        const int excl = carry + (wid ? wsum[wid - 1] : 0) + x - v;
+        if (i < n) sums[i] = excl;
+        __syncthreads();
+        if (tid == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) bin_start[nb] = carry;
+}
+__global__ void __launch_bounds__(1024) k_scan_bins_add(int *bin_start, int nb, const int *sums) {
+    const int off = sums[blockIdx.x];
+    const int i0 = blockIdx.x * SCAN_PER_CTA + threadIdx.x * 4;
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (i0 + k < nb) bin_start[i0 + k] += off;
+}
+
 // Besides the permutation bin_atoms, the atoms' records are copied into bin order (sabin: atom
 // index + wrap offsets, spos: coordinates), so that k_neigh reads the candidates of a cell as
 // contiguous, independent loads instead of a chain bin_atoms -> abin -> pos.
@@ -687,9 +749,78 @@ k_neigh_direct(const StructDev *structs, const int *sid, const double *pos, int 
     order_body<NB_THREADS>(nbr_cnt, ntot, order, flags, hist, hist + NB_MAXLIST + 2);
 }
 
-void launch_order(cudaStream_t st, const int *nbr_cnt, int n_centres, int *order, DevFlags *flags, long *launches) {
-    k_order_by_count<<<1, 1024, 0, st>>>(nbr_cnt, n_centres, order, flags);
-    if (launches) *launches += 1;
+// The same ordering for many centres (a 10^5-atom cell): a single CTA would walk the counts alone for
+// ~0.1 ms.  Histogram with per-CTA shared-memory counters flushed by global atomics, the 1024-key scan
+// in one small CTA, then a grid-wide scatter.  hist: NB_MAXLIST + 2 ints of global memory.
+constexpr int ORD_PER_CTA = 4096;
+__global__ void __launch_bounds__(256) k_order_hist(const int *nbr_cnt, int n, int *hist) {
+    __shared__ int h[NB_MAXLIST];
+    for (int t = threadIdx.x; t < NB_MAXLIST; t += 256) h[t] = 0;
+    __syncthreads();
+    const int i0 = blockIdx.x * ORD_PER_CTA, i1 = min(n, i0 + ORD_PER_CTA);
+    for (int i = i0 + threadIdx.x; i < i1; i += 256) atomicAdd(&h[NB_MAXLIST - min(max(nbr_cnt[i], 1), NB_MAXLIST)], 1);
+    __syncthreads();
+    for (int t = threadIdx.x; t < NB_MAXLIST; t += 256) if (h[t]) atomicAdd(&hist[t], h[t]);
+}
+__global__ void __launch_bounds__(1024) k_order_scan(int *hist, DevFlags *flags) {
+    __shared__ int wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int v = hist[tid];
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wsum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int s = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+        wsum[lane] = s;
+    }
+    __syncthreads();
+    const int excl = (wid ? wsum[wid - 1] : 0) + x - v;
+    hist[tid] = excl;
+    if (tid == NB_MAXLIST - 128) flags->n_gt[0] = excl;
+    if (tid == NB_MAXLIST - 256) flags->n_gt[1] = excl;
+    if (tid == NB_MAXLIST - 512) flags->n_gt[2] = excl;
+    if (tid == 0) flags->n_gt[3] = 0;
+    if (tid == NB_MAXLIST - 1) flags->n_centres = excl + v;
+}
+__global__ void __launch_bounds__(256) k_order_scatter(const int *nbr_cnt, int n, int *hist, int *order) {
+    // places inside one key come from atomics: the order of equal-count centres varies from run to run,
+    // which only changes which CTA evaluates which centre.  Per-CTA shared counters keep the global
+    // atomics to one per (CTA, key present).
+    __shared__ int h[NB_MAXLIST], base[NB_MAXLIST];
+    for (int t = threadIdx.x; t < NB_MAXLIST; t += 256) h[t] = 0;
+    __syncthreads();
+    const int i0 = blockIdx.x * ORD_PER_CTA, i1 = min(n, i0 + ORD_PER_CTA);
+    int key[ORD_PER_CTA / 256], slot[ORD_PER_CTA / 256];
+#pragma unroll
+    for (int k = 0; k < ORD_PER_CTA / 256; k++) {
+        const int i = i0 + threadIdx.x + k * 256;
+        key[k] = -1;
+        if (i < i1) { key[k] = NB_MAXLIST - min(max(nbr_cnt[i], 1), NB_MAXLIST); slot[k] = atomicAdd(&h[key[k]], 1); }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < NB_MAXLIST; t += 256) if (h[t]) base[t] = atomicAdd(&hist[t], h[t]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < ORD_PER_CTA / 256; k++)
+        if (key[k] >= 0) order[base[key[k]] + slot[k]] = i0 + threadIdx.x + k * 256;
+}
+
+void launch_order(cudaStream_t st, const int *nbr_cnt, int n_centres, int *order, DevFlags *flags, int *hist, long *launches) {
+    if (n_centres <= 8192 || !hist) {
+        k_order_by_count<<<1, 1024, 0, st>>>(nbr_cnt, n_centres, order, flags);
+        if (launches) *launches += 1;
+        return;
+    }
+    const int g = (n_centres + ORD_PER_CTA - 1) / ORD_PER_CTA;
+    cudaMemsetAsync(hist, 0, sizeof(int) * NB_MAXLIST, st);
+    k_order_hist<<<g, 256, 0, st>>>(nbr_cnt, n_centres, hist);
+    k_order_scan<<<1, 1024, 0, st>>>(hist, flags);
+    k_order_scatter<<<g, 256, 0, st>>>(nbr_cnt, n_centres, hist, order);
+    if (launches) *launches += 3;
 }
 
 // ---- host launchers ------------------------------------------------------
@@ -711,7 +842,15 @@ void launch_neighbor_build(cudaStream_t st, const NeighborBuild &b, long *launch
         cudaMemsetAsync(b.bin_count, 0, sizeof(int) * 2 * (size_t)b.nbins_total, st);
         int tb = 256, gb = (ntot + tb - 1) / tb;
         k_bin<<<gb, tb, 0, st>>>(b.structs, b.sid, b.pos, ntot, b.nloc, b.n_own, b.sft, b.abin, b.arank, b.bin_count, b.nbins_total);
-        k_scan_bins<<<1, 1024, 0, st>>>(b.bin_count, b.bin_start, b.nbins_total);
+        if (b.nbins_total <= 8192) {
+            k_scan_bins<<<1, 1024, 0, st>>>(b.bin_count, b.bin_start, b.nbins_total);
+        } else {   // many cells: per-CTA scans, a scan of the CTA totals, then the offsets are added
+            const int gs = (b.nbins_total + SCAN_PER_CTA - 1) / SCAN_PER_CTA;
+            k_scan_bins_part<<<gs, 1024, 0, st>>>(b.bin_count, b.bin_start, b.nbins_total, b.arank_scratch);
+            k_scan_bins_top<<<1, 1024, 0, st>>>(b.arank_scratch, gs, b.bin_start, b.nbins_total);
+            k_scan_bins_add<<<gs, 1024, 0, st>>>(b.bin_start, b.nbins_total, b.arank_scratch);
+            if (launches) *launches += 2;
+        }
         k_fill_bins<<<gb, tb, 0, st>>>(b.structs, b.sid, b.pos, b.abin, b.arank, b.bin_start, b.bin_count, b.nbins_total, ntot, b.nloc,
                                        b.n_own, b.bin_atoms, b.sabin, b.spos);
         if (launches) *launches += 3;

@@ -101,9 +101,15 @@ def test_c3_full_batch_properties():
     per structure is too strong (capacity tiers differ), so: every structure's net force vanishes, energies are
     finite and extensive-looking, and evaluating a permuted batch permutes the results."""
     import gapcu
-    from multiprocessing import Pool
-    with Pool(min(os.cpu_count() or 1, 32)) as pool:
-        structs = pool.map(_make_c3, range(4096), chunksize=16)
+    import pickle
+    import subprocess
+    import sys
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:       # generated in a child process: no fork from the CUDA process
+        out = os.path.join(d, "c3.pkl")
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_c3.py"), "4096", out])
+        with open(out, "rb") as fh:
+            structs = pickle.load(fh)
     c = gapcu.Context(0)
     c.load_potential(POT_C2)
     zs, cells, poss = [s[2] for s in structs], [s[0] for s in structs], [s[1] for s in structs]
@@ -122,10 +128,6 @@ def test_c3_full_batch_properties():
     assert np.abs(e2 - e[perm]).max() <= 1e-12 * np.abs(e).max()
     assert np.abs(s2 - s[perm]).max() <= 1e-11 * np.abs(s).max()
     c.close()
-
-
-def _make_c3(i):
-    return random_candidate(3000 + i)
 
 
 @st.composite
