@@ -191,6 +191,17 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned ltmask = (1u << lane) - 1u;
+    // development aid: where a centre's time goes.  Compiled in only with -DGAPCU_PHASE_TIMING (the
+    // bookkeeping costs registers the production kernel does not have); then GAPCU_VARIANT & 16 switches it on.
+#ifdef GAPCU_PHASE_TIMING
+    const bool ptime = (a.variant & 16) && tid == 0;
+    long long pt_last = ptime ? clock64() : 0;
+    auto phase_end = [&](int ph) {
+        if (ptime) { const long long now = clock64(); atomicAdd(&a.flags->phase_cycles[ph], (unsigned long long)(now - pt_last)); pt_last = now; }
+    };
+#else
+    auto phase_end = [](int) {};
+#endif
     const int P = a.nbr_cnt[i];
     const StructDev &sd = a.structs[a.sid[i]];
     const int ntot = a.ntot;
@@ -254,6 +265,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         }
     }
     __syncthreads();
+    phase_end(0);
     // ---- 2: radial forward: one warp task per function, lanes over neighbours ----------
     if (FWD) {
         for (int q = wid + NW * crank; q < pl.n_rad; q += NW * CS) {   // the cluster's CTAs share the functions
@@ -284,6 +296,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         atomicAdd(&a.flags->work[8], pc * (pc - 1) / 2);
     }
 
+    phase_end(1);
     // ---- 3: triplet list builder (phase A + deterministic counting sort) ----------
     const uint32_t angmask = a.cls.angmask;
     // pair range of this CTA: the whole triangle, or one of CS contiguous parts of it
@@ -692,6 +705,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                     if (trip_base + t < a.trip_cap) a.trip_out[(size_t)i * a.trip_cap + trip_base + t] = s_S[t];
                 trip_base += n;
             }
+            phase_end(2);
             if (stash) {
                 // keep the sorted list of this chunk (L2 resident) for the backward pass
                 uint32_t *dst = a.list_scratch + ((size_t)blockIdx.x * a.list_scratch_chunks + ch) * (size_t)(lcap + 32 + 512);
@@ -702,6 +716,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             }
             forward_list();
             __syncthreads();
+            phase_end(3);
         }
         if (a.trip_out && tid == 0) a.trip_cnt[i] = trip_base;
         list_ready = (nchunk == 1);
@@ -821,6 +836,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         }
         __syncthreads();
     }
+    phase_end(4);
     if (BWD) {
         if (!a.lgrad) return;
         // per (class, alpha) group: sums of dE/dG over its functions
@@ -873,6 +889,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             }
         }
         __syncthreads();
+        phase_end(5);
         for (int ch = 0; ch < nchunk; ch++) {
             if (SE) est = a.estash + (size_t)blockIdx.x * a.estash_stride + (size_t)ch * (lcap + 32);
             if (list_stashed) {
@@ -888,6 +905,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             }
             backward_list();
         }
+        phase_end(6);
         // ---- epilogue: per neighbour gradient, centre gradient, strs contraction ----------
         if constexpr (CS > 1) {
             cg::this_cluster().sync();   // every CTA's accumulator is final; the lead adds them in rank order
@@ -923,6 +941,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             if (tid < 3) a.gself[(size_t)i * 3 + tid] = v;
             else a.vir[(size_t)i * 6 + (tid - 3)] = v;
         }
+        phase_end(7);
     }
 #undef NB2
 #undef FCD2

@@ -1105,6 +1105,7 @@ extern "C" int gapcu_ctx_work_counters(gapcu_ctx *c, double *out, int n) {
     int rc = read_flags(c);
     if (rc) return rc;
     for (int q = 0; q < n && q < 10; q++) out[q] = (double)c->h_flags.work[q];
+    for (int q = 10; q < n && q < 18; q++) out[q] = (double)c->h_flags.phase_cycles[q - 10];   // GAPCU_VARIANT & 16
     return 0;
 }
 

@@ -67,6 +67,9 @@ struct DevFlags {
     int halo_count[27];  // records this rank sends in each direction (index 13 = centre, unused)
     int n_ghost, n_loc;  // ghosts received, owned + ghosts
     int halo_far;        // an owned atom drifted further from its brick than the exchange pattern covers
+    // GAPCU_VARIANT & 16: cycles thread 0 of every centre CTA spent per phase of the centre kernel
+    // (0 stage, 1 radial fwd, 2 list build, 3 angular fwd, 4 reduce + GPR, 5 radial bwd, 6 angular bwd, 7 epilogue)
+    unsigned long long phase_cycles[8];
 };
 
 constexpr int MAXC_DEV = 16;  // distinct cutoffs (classes) supported
