@@ -107,6 +107,9 @@ struct gapcu_ctx {
     std::vector<int> h_natoms;
     DBuf<StructDev> d_structs;
     DBuf<int> d_hist, d_scan_sums;   // scratch of the multi-CTA centre ordering / cell scan
+    int *d_blk = nullptr;            // structure of every block of cells (in the inputs block)
+    int nblocks = 0;                 // blocks of cells for k_neigh_block; 0: some structure does not fit that form
+    bool k1_legacy = false;          // a block overflowed once: stay with k_neigh for this context
     DBuf<int> d_sid, d_arank, d_bin_count, d_bin_start, d_bin_atoms, d_nbr_cnt, d_skin_cnt, d_order;
     DBuf<int4> d_abin, d_sabin;   // per atom / in bin order: (bin | atom, wrap offsets)
     DBuf<double> d_spos;          // coordinates in bin order
@@ -193,19 +196,20 @@ static cudaError_t ensure_results(gapcu_ctx *c, size_t nstruct, size_t NT) {
 }
 
 // inputs block: same 256-byte aligned layout on the device as in the pinned staging buffer
-struct InputLayout { size_t o_structs, o_sid, o_pos, o_wgt, total; };
-static InputLayout input_layout(size_t nstruct, size_t NT) {
+struct InputLayout { size_t o_structs, o_sid, o_pos, o_wgt, o_blk, total; };
+static InputLayout input_layout(size_t nstruct, size_t NT, size_t nblocks = 0) {
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     InputLayout L;
     L.o_structs = 0;
     L.o_sid = al(sizeof(StructDev) * nstruct);
     L.o_pos = al(L.o_sid + sizeof(int) * NT);
     L.o_wgt = al(L.o_pos + sizeof(double) * 3 * NT);
-    L.total = al(L.o_wgt + sizeof(double) * NT);
+    L.o_blk = al(L.o_wgt + sizeof(double) * NT);
+    L.total = al(L.o_blk + sizeof(int) * nblocks);
     return L;
 }
-static cudaError_t ensure_inputs(gapcu_ctx *c, size_t nstruct, size_t NT) {
-    const InputLayout L = input_layout(nstruct, NT);
+static cudaError_t ensure_inputs(gapcu_ctx *c, size_t nstruct, size_t NT, size_t nblocks = 0) {
+    const InputLayout L = input_layout(nstruct, NT, nblocks);
     cudaError_t e = c->d_inputs.ensure(L.total);
     if (e != cudaSuccess) return e;
     c->d_structs.view = c->d_sid.view = c->d_pos.view = c->d_wgt.view = true;
@@ -213,6 +217,7 @@ static cudaError_t ensure_inputs(gapcu_ctx *c, size_t nstruct, size_t NT) {
     c->d_sid.p = (int *)(c->d_inputs.p + L.o_sid); c->d_sid.n = NT;
     c->d_pos.p = (double *)(c->d_inputs.p + L.o_pos); c->d_pos.n = 3 * NT;
     c->d_wgt.p = (double *)(c->d_inputs.p + L.o_wgt); c->d_wgt.n = NT;
+    c->d_blk = (int *)(c->d_inputs.p + L.o_blk);
     return cudaSuccess;
 }
 
@@ -423,6 +428,26 @@ static int fill_struct(StructDev &sd, const double *lat9, double rcut, double rs
     return 0;
 }
 
+// Blocks of cells for k_neigh_block: up to 2 x 2 x 2 bins, shrunk until the bins around a block (block
+// plus the scanned layers) number at most neighbor_block_max_bins() and are expected to hold well under
+// neighbor_block_max_candidates() atoms.  Returns the number of blocks, 0 when no block shape qualifies.
+static int plan_blocks(StructDev &sd, double atoms_in_region) {
+    int bs[3];
+    for (int d = 0; d < 3; d++) bs[d] = std::min(2, sd.nbin[d]);
+    const double per_bin = atoms_in_region / std::max(1, sd.nbin[0] * sd.nbin[1] * sd.nbin[2]);
+    for (;;) {
+        const long ncb = (long)(bs[0] + 2 * sd.mscan[0]) * (bs[1] + 2 * sd.mscan[1]) * (bs[2] + 2 * sd.mscan[2]);
+        if (ncb <= neighbor_block_max_bins() && ncb * per_bin <= 0.72 * neighbor_block_max_candidates()) break;
+        int d = -1;
+        for (int q = 0; q < 3; q++) if (bs[q] > 1 && (d < 0 || sd.mscan[q] < sd.mscan[d])) d = q;   // shrinking a thin-layer direction saves most
+        if (d < 0) return 0;
+        bs[d] = 1;
+    }
+    int n = 1;
+    for (int d = 0; d < 3; d++) { sd.bs[d] = bs[d]; sd.nblk[d] = (sd.nbin[d] + bs[d] - 1) / bs[d]; n *= sd.nblk[d]; }
+    return n;
+}
+
 static int set_structures_domain(gapcu_ctx *c, int natoms, const int *species, const double *lat_c, const double *pos, bool pos_soa, double rcut);
 
 // pos_soa: pos is [3][ntot_of_that_structure] per structure (Fortran pos(NA,3)); else C order [ntot][3].
@@ -452,6 +477,8 @@ static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, con
     int boff = 0, aoff = 0;
     double max_density = 0.0;
     bool direct = true;   // all structures small enough for the direct neighbour kernel
+    bool blocks_ok = true;   // every structure fits the block form of the list kernel
+    int nblk_total = 0;
     for (int s = 0; s < nstruct; s++) {
         StructDev &sd = c->h_structs[s];
         int rc = fill_struct(sd, lat_c + 9 * (size_t)s, rcut, rskin, natoms[s], &direct);
@@ -459,13 +486,19 @@ static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, con
         sd.atom_off = aoff; sd.bin_off = boff;
         aoff += natoms[s]; boff += sd.nbins;
         max_density = std::max(max_density, natoms[s] / sd.volume);
+        if (blocks_ok) {
+            const int nb = plan_blocks(sd, natoms[s]);
+            sd.blk_off = nblk_total;
+            if (nb == 0) blocks_ok = false; else nblk_total += nb;
+        }
     }
+    c->nblocks = blocks_ok ? nblk_total : 0;
     c->nstruct = nstruct; c->ntot = (int)ntot; c->n_centres = (int)ntot; c->nbins = boff;
     c->direct_ok = direct && !getenv("GAPCU_NO_DIRECT");   // GAPCU_NO_DIRECT: always the cell list (A/B and tests)
     const size_t NT = (size_t)ntot;
     // ---- pack host staging: structs | sid | pos SoA | wgt
     size_t b_structs = sizeof(StructDev) * nstruct, b_wgt = sizeof(double) * NT;
-    const InputLayout IL = input_layout((size_t)nstruct, NT);
+    const InputLayout IL = input_layout((size_t)nstruct, NT, (size_t)c->nblocks);
     const size_t o_structs = IL.o_structs, o_sid = IL.o_sid, o_pos = IL.o_pos, o_wgt = IL.o_wgt, total = IL.total;
     // the staging buffer may still feed the previous call's copy if the caller never waited for it
     if (c->h2d_pending) { CU(cudaStreamSynchronize(c->stream)); c->h2d_pending = false; }
@@ -485,13 +518,21 @@ static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, con
         }
         a += n;
     }
+    {   // structure of every block of cells
+        int *h_blk = (int *)(hp + IL.o_blk);
+        for (int s = 0; s < nstruct && c->nblocks; s++) {
+            const StructDev &sd = c->h_structs[s];
+            const int nb = sd.nblk[0] * sd.nblk[1] * sd.nblk[2];
+            for (int k = 0; k < nb; k++) h_blk[sd.blk_off + k] = s;
+        }
+    }
     if (need_weights) {
         for (size_t t = 0; t < NT; t++) { int rc = lookup_weight(c, species[t], &h_wgt[t]); if (rc) return rc; }
     } else {
         memset(h_wgt, 0, b_wgt);
     }
     // ---- device buffers
-    CU(ensure_inputs(c, (size_t)nstruct, NT));
+    CU(ensure_inputs(c, (size_t)nstruct, NT, (size_t)c->nblocks));
     CU(c->d_abin.ensure(NT)); CU(c->d_sabin.ensure(NT)); CU(c->d_spos.ensure(3 * NT)); CU(c->d_arank.ensure(NT)); CU(c->d_bin_count.ensure(2 * (size_t)c->nbins + 2));
     CU(c->d_bin_start.ensure(c->nbins + 2)); CU(c->d_bin_atoms.ensure(NT)); CU(c->d_nbr_cnt.ensure(NT)); CU(c->d_skin_cnt.ensure(NT)); CU(c->d_order.ensure(NT));
     CU(ensure_results(c, (size_t)nstruct, NT));
@@ -802,6 +843,15 @@ static NeighborBuild neighbor_args(gapcu_ctx *c, bool with_keys, bool with_min, 
     b.direct = neighbors_direct(c);
     b.n_own = c->n_centres;
     if (c->dom.enabled && c->ds) { b.sft = c->ds->d_sft.p; b.nloc = &c->d_flags.p->n_loc; }
+    static const bool legacy_env = getenv("GAPCU_K1_LEGACY") != nullptr;   // A/B switch: always one CTA per centre
+    b.nblocks = (c->k1_legacy || legacy_env) ? 0 : c->nblocks;
+    // the block form pays from a few blocks per SM on; below, one CTA per centre keeps more of the device busy
+    if (!c->sm_count) cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
+    if (b.nblocks < 2 * c->sm_count) b.nblocks = 0;
+    b.t2skin = sqrt_threshold(b.rskin); b.t2cut = sqrt_threshold(b.rcut);
+    b.t2close = std::nextafter(sqrt_threshold(0.5), 0.0);     // sqrt(x) < 0.5: one step below the largest x with sqrt(x) <= 0.5 ...
+    while (std::sqrt(b.t2close) >= 0.5) b.t2close = std::nextafter(b.t2close, 0.0);   // ... made exact
+    b.blk_struct = c->nstruct > 1 ? c->d_blk : nullptr;
     return b;
 }
 
@@ -830,9 +880,10 @@ static int enqueue_pass(gapcu_ctx *c, int lgrad, cudaEvent_t *ev, bool reuse) {
                 if (c->h_flags.too_many)
                     return fail(GAPCU_ENEIGH, "Atoms neighbor: " + std::to_string(c->h_flags.maxcount) +
                                                   " large than max_neighbor 1000");
-                if (!c->h_flags.overflow) break;
+                if (c->h_flags.blk_overflow) c->k1_legacy = true;
+                if (!c->h_flags.overflow && !c->h_flags.blk_overflow) break;
                 if (c->h_flags.maxskin > 1024) return fail(GAPCU_ELIMIT, "more than 1024 atoms within rcut + skin: reduce the skin");
-                c->cap = std::min(1024, round_up(c->h_flags.maxskin + 16, 32));
+                if (c->h_flags.overflow) c->cap = std::min(1024, round_up(c->h_flags.maxskin + 16, 32));
                 if ((rc = ensure_work_buffers(c))) return rc;
                 CU(cudaMemsetAsync(c->d_flags.p, 0, sizeof(DevFlags), c->stream));
                 if ((rc = run_neighbors(c, true, false, true))) return rc;
@@ -910,6 +961,7 @@ static int react_to_flags(gapcu_ctx *c, int attempt) {
         rerun = true;
     }
     if (f.halo_overflow && c->ds) { domain_forget_caps(c); c->lists_valid = false; rerun = true; }
+    if (f.blk_overflow) { c->k1_legacy = true; c->lists_valid = false; rerun = true; }
     if (f.stale) { c->lists_valid = false; rerun = true; }
     if (c->dom.enabled && !c->pcap_known && !rerun) {
         // first decomposed pass ran with the list capacity as kernel capacity: remember the real one

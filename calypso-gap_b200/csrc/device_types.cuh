@@ -17,7 +17,10 @@ struct StructDev {
     // binned region in fractional coordinates: the whole periodic cell (org = 0, wid = 1, open = 0) or,
     // for one rank of a decomposed run, its brick plus the ghost shell, not periodic (open = 1)
     double org[3], wid[3];
-    int open, pad_;
+    int open;
+    // blocks of cells for k_neigh_block: bs bins per block and direction, nblk blocks per direction,
+    // blk_off = blocks of the structures before this one
+    int bs[3], nblk[3], blk_off;
 };
 
 // Spatial decomposition of ONE large structure over ranks: the cell is cut
@@ -67,6 +70,7 @@ struct DevFlags {
     int halo_count[27];  // records this rank sends in each direction (index 13 = centre, unused)
     int n_ghost, n_loc;  // ghosts received, owned + ghosts
     int halo_far;        // an owned atom drifted further from its brick than the exchange pattern covers
+    int blk_overflow;    // a block of cells has more candidates than k_neigh_block holds: use k_neigh
     // GAPCU_VARIANT & 16: cycles thread 0 of every centre CTA spent per phase of the centre kernel
     // (0 stage, 1 radial fwd, 2 list build, 3 angular fwd, 4 reduce + GPR, 5 radial bwd, 6 angular bwd, 7 epilogue)
     unsigned long long phase_cycles[8];

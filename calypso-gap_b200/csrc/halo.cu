@@ -216,6 +216,7 @@ __global__ void k_halo_rec(const double *out8_raw, const DevFlags *flags, double
     if (t == 14) rec[14] = (double)flags->close_pairs;
     if (t == 15) rec[15] = (double)flags->n_loc;
     if (t >= 16 && t < 16 + 27) rec[t] = (double)flags->halo_count[t - 16];
+    if (t == 43) rec[43] = (double)flags->blk_overflow;
 }
 
 // all ranks' records -> E and stress (sums in rank order: every rank gets the same bits) and merged flags
@@ -235,7 +236,7 @@ __global__ void k_halo_combine(const double *rec_all, int nranks, double volume,
         out8[4] = -s[2] * f; out8[5] = -s[5] * f; out8[6] = -s[3] * f;   // xy yz xz  (gap_calc.f90:221-226)
         out8[7] = 0.0;
     }
-    if (t >= 7 && t < 16 + 27) {
+    if (t >= 7 && t < 16 + 28) {
         double mx = 0.0, sum = 0.0;
         for (int r = 0; r < nranks; r++) { const double v = rec_all[(size_t)r * HALO_RECLEN + t]; mx = fmax(mx, v); sum += v; }
         const int iv = (int)mx;
@@ -248,7 +249,8 @@ __global__ void k_halo_combine(const double *rec_all, int nranks, double volume,
         if (t == 13) flags->halo_far = iv;
         if (t == 14) flags->close_pairs = (int)sum;
         if (t == 15) flags->n_loc = iv;               // largest local point count of any rank
-        if (t >= 16) flags->halo_count[t - 16] = iv;  // largest send count per direction
+        if (t >= 16 && t < 43) flags->halo_count[t - 16] = iv;  // largest send count per direction
+        if (t == 43) flags->blk_overflow = iv;
     }
 }
 

@@ -32,7 +32,13 @@ struct NeighborBuild {
     const int4 *sft;          // null: periodic structures
     const int *nloc;
     int n_own;                // = ntot when not decomposed
+    // block form of the list kernel (k_neigh_block): blocks of cells in all structures (0: one CTA per centre, k_neigh)
+    int nblocks;
+    const int *blk_struct;    // structure of every block (null: one structure)
+    double t2skin, t2cut, t2close;   // max{x : sqrt_rn(x) <= rskin}, the same for rcut, max{x : sqrt_rn(x) < 0.5}
 };
+int neighbor_block_max_bins();        // candidate bins a block may have
+int neighbor_block_max_candidates();  // candidates a block may have (beyond: flags->blk_overflow, fall back to k_neigh)
 void launch_neighbor_build(cudaStream_t st, const NeighborBuild &b, long *launches);
 // exact lists from kept skin lists and moved positions; flags->stale when an atom moved > skin/2
 void launch_refilter(cudaStream_t st, const NeighborBuild &b, const double *pos_build, double skin, long *launches);

@@ -546,6 +546,252 @@ __global__ void __launch_bounds__(NB_THREADS, 8) k_neigh(const NeighArgs A) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K1, block form: one CTA per BLOCK of cells (up to 2 x 2 x 2 bins, ~20 centres) instead of one per centre.
+// The images in the bins around the block -- every candidate any centre of the block can have -- are
+// collected ONCE, as keys (j, cell shift - wrap offset of j), and sorted ONCE.  Adding a centre's own wrap
+// offset to the shift fields turns such a key into the centre's reference key (j, n1, n2, n3) without
+// changing the order, so a warp that walks the sorted candidates and appends the survivors with ballots
+// emits both lists of its centre already in reference order: no per-centre sort, no atomics, the
+// candidates' coordinates staged once in shared memory.  Same tests, same arithmetic as k_neigh (which
+// stays as the fallback for blocks with more candidates than fit and for exotic cell shapes).
+constexpr int KB_THREADS = 256, KB_WARPS = KB_THREADS / 32, KB_CAP = 1024, KB_BINS = 512, KB_GROUP = 128;
+struct NeighBlockArgs {
+    NeighArgs n;
+    const int *blk_struct;   // structure of every block (null: a single structure)
+    double t2skin, t2cut, t2close;   // squared-distance thresholds equivalent to dis <= rskin, dis <= rcut, dis < 0.5
+    float f2pre;             // single-precision pre-filter: (rskin + margin)^2
+};
+// dynamic shared memory of k_neigh_block
+struct KbSmem {
+    uint64_t ck[KB_CAP];                       // sorted candidate keys
+    double cx[KB_CAP], cy[KB_CAP], cz[KB_CAP]; // their raw coordinates (exact test)
+    float fx[KB_CAP], fy[KB_CAP], fz[KB_CAP];  // their image positions relative to the block, single precision (pre-filter)
+    int cb_start[KB_BINS], cb_off[KB_BINS + 1], cb_shift[KB_BINS];
+    unsigned short surv[KB_WARPS][KB_GROUP];   // per warp: candidates of the current group that pass the pre-filter
+    double lat[9], org[3];
+    int own_start[8], own_off[9];
+    int flags[6];
+};
+
+__global__ void __launch_bounds__(KB_THREADS) k_neigh_block(const NeighBlockArgs B) {
+    const NeighArgs &A = B.n;
+    extern __shared__ __align__(16) unsigned char kb_raw[];
+    KbSmem &S = *reinterpret_cast<KbSmem *>(kb_raw);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const StructDev &s = A.structs[B.blk_struct ? B.blk_struct[blockIdx.x] : 0];
+    const int lb = blockIdx.x - s.blk_off;
+    const int nb0 = s.nbin[0], nb1 = s.nbin[1], nb2 = s.nbin[2];
+    const int B0 = (lb / (s.nblk[1] * s.nblk[2])) * s.bs[0], B1 = ((lb / s.nblk[2]) % s.nblk[1]) * s.bs[1], B2 = (lb % s.nblk[2]) * s.bs[2];
+    const int e0 = min(B0 + s.bs[0], nb0), e1 = min(B1 + s.bs[1], nb1), e2 = min(B2 + s.bs[2], nb2);   // block = bins [B, e)
+    const int ntot = A.ntot;
+    const bool open = s.open != 0;
+    if (tid < 9) S.lat[tid] = s.lat[tid];
+    if (tid < 3) {
+        // a reference point near the block (its lower corner in the wrapped frame): single precision is only
+        // ever applied to differences from it, so the pre-filter's error stays ~1e-6 A
+        const double f0 = s.org[0] + s.wid[0] * B0 / nb0, f1 = s.org[1] + s.wid[1] * B1 / nb1, f2 = s.org[2] + s.wid[2] * B2 / nb2;
+        S.org[tid] = f0 * s.lat[tid] + f1 * s.lat[3 + tid] + f2 * s.lat[6 + tid];
+    }
+    if (tid < 6) S.flags[tid] = 0;
+    // ---- centres of the block
+    const int o1 = e1 - B1, o2 = e2 - B2, nown = (e0 - B0) * o1 * o2;
+    if (tid < 8) {
+        int cnt = 0;
+        if (tid < nown) {
+            const int id = ((B0 + tid / (o1 * o2)) * nb1 + (B1 + (tid / o2) % o1)) * nb2 + (B2 + tid % o2);
+            S.own_start[tid] = A.bin_start[s.bin_off + id];
+            cnt = A.bin_start[s.bin_off + id + 1] - S.own_start[tid];
+        }
+        S.own_off[tid] = cnt;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int k = 0; k < 8; k++) { const int v = S.own_off[k]; S.own_off[k] = run; run += v; }
+        S.own_off[8] = run;
+    }
+    __syncthreads();
+    const int ncentres = S.own_off[8];
+    if (ncentres == 0) return;
+    // ---- candidate bins: [B - m, e - 1 + m] per direction, wrapped (periodic) or clipped (open region)
+    const int m0 = s.mscan[0], m1 = s.mscan[1], m2 = s.mscan[2];
+    const int w0 = e0 - B0 + 2 * m0, w1 = e1 - B1 + 2 * m1, w2 = e2 - B2 + 2 * m2;
+    const int ncb = w0 * w1 * w2;      // host guarantees <= KB_BINS
+    for (int t = tid; t < KB_BINS; t += KB_THREADS) {
+        int cnt = 0;
+        if (t < ncb) {
+            const int t0 = B0 - m0 + t / (w1 * w2), t1 = B1 - m1 + (t / w2) % w1, t2 = B2 - m2 + t % w2;
+            int s0 = 0, s1 = 0, s2 = 0;
+            bool inside = true;
+            if (open) inside = t0 >= 0 && t0 < nb0 && t1 >= 0 && t1 < nb1 && t2 >= 0 && t2 < nb2;
+            else { s0 = floordiv_i(t0, nb0); s1 = floordiv_i(t1, nb1); s2 = floordiv_i(t2, nb2); }
+            if (inside) {
+                const int id = ((t0 - s0 * nb0) * nb1 + (t1 - s1 * nb1)) * nb2 + (t2 - s2 * nb2);
+                const int start = A.bin_start[s.bin_off + id];
+                cnt = A.bin_start[s.bin_off + id + 1] - start;
+                S.cb_start[t] = start;
+                S.cb_shift[t] = ((s0 + 512) << 20) | ((s1 + 512) << 10) | (s2 + 512);
+            }
+        }
+        S.cb_off[t] = cnt;
+    }
+    __syncthreads();
+    if (wid == 0) {  // exclusive scan of the bin counts by one warp
+        int run = 0;
+        for (int base = 0; base < KB_BINS; base += 32) {
+            const int v = S.cb_off[base + lane];
+            int x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            S.cb_off[base + lane] = run + x - v;
+            run += __shfl_sync(0xffffffffu, x, 31);
+        }
+        if (lane == 0) S.cb_off[KB_BINS] = run;
+    }
+    __syncthreads();
+    const int ncand = S.cb_off[KB_BINS];
+    if (ncand > KB_CAP) {       // too dense for this form: the host switches to k_neigh and runs again
+        if (tid == 0) atomicExch(&A.flags->blk_overflow, 1);
+        return;
+    }
+    // ---- candidate keys: (j, shift of the bin - wrap offset of j), then one sort for the whole block
+    for (int c = tid; c < ncand; c += KB_THREADS) {
+        int lo = 0, hi = ncb;    // bin of candidate c: last bin with cb_off <= c
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (S.cb_off[mid] <= c) lo = mid; else hi = mid; }
+        const int4 rec = A.sabin[S.cb_start[lo] + (c - S.cb_off[lo])];      // (atom, wrap offsets)
+        const int sh = S.cb_shift[lo];
+        const int c0 = ((sh >> 20) & 1023) - rec.y, c1 = ((sh >> 10) & 1023) - rec.z, c2 = (sh & 1023) - rec.w;   // still offset by +512
+        // a field outside 0..1023 cannot be a neighbour of anything inside the reference's image window
+        const bool ok = (unsigned)c0 < 1024u && (unsigned)c1 < 1024u && (unsigned)c2 < 1024u;
+        S.ck[c] = ok ? (((uint64_t)(uint32_t)rec.x << 32) | (uint64_t)((c0 << 20) | (c1 << 10) | c2)) : ~0ull;
+    }
+    int n2 = 32;
+    while (n2 < ncand) n2 <<= 1;
+    for (int c = ncand + tid; c < n2; c += KB_THREADS) S.ck[c] = ~0ull;
+    __syncthreads();
+    // bitonic sort, one compare-exchange per thread and trip (pair q -> elements t and t + jj, t = q with a 0 inserted at bit jj)
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            for (int q = tid; q < (n2 >> 1); q += KB_THREADS) {
+                const int t = ((q & ~(jj - 1)) << 1) | (q & (jj - 1));
+                const uint64_t a = S.ck[t], b = S.ck[t + jj];
+                if ((a > b) == ((t & k) == 0)) { S.ck[t] = b; S.ck[t + jj] = a; }
+            }
+            __syncthreads();
+        }
+    for (int c = tid; c < ncand; c += KB_THREADS) {
+        const uint64_t key = S.ck[c];
+        float gx = 1e30f, gy = 1e30f, gz = 1e30f;
+        if (key != ~0ull) {
+            const int j = (int)(key >> 32);
+            const uint32_t f = (uint32_t)key;
+            const double x = A.pos[j], y = A.pos[ntot + j], z = A.pos[2 * ntot + j];
+            S.cx[c] = x; S.cy[c] = y; S.cz[c] = z;
+            const double q1 = (double)((int)((f >> 20) & 1023) - 512), q2 = (double)((int)((f >> 10) & 1023) - 512), q3 = (double)((int)(f & 1023) - 512);
+            gx = (float)(x + q1 * S.lat[0] + q2 * S.lat[3] + q3 * S.lat[6] - S.org[0]);
+            gy = (float)(y + q1 * S.lat[1] + q2 * S.lat[4] + q3 * S.lat[7] - S.org[1]);
+            gz = (float)(z + q1 * S.lat[2] + q2 * S.lat[5] + q3 * S.lat[8] - S.org[2]);
+        }
+        S.fx[c] = gx; S.fy[c] = gy; S.fz[c] = gz;
+    }
+    __syncthreads();
+    // ---- every warp walks the sorted candidates for its centres: groups of 128 candidates pass a cheap
+    // single-precision pre-filter (a strict superset of dis <= rskin), the survivors are compacted in order
+    // and take the exact test with the reference's arithmetic
+    const int na0 = s.nabc[0], na1 = s.nabc[1], na2 = s.nabc[2];
+    const int aoff = s.atom_off, cap = A.cap;
+    const unsigned ltmask = (1u << lane) - 1u;
+    const double *lat = S.lat;
+    unsigned short *sv = S.surv[wid];
+    int w_maxskin = 0, w_maxcnt = 0, w_close = 0, w_many = 0, w_over = 0;
+    for (int kc = wid; kc < ncentres; kc += KB_WARPS) {
+        int ob = 0;
+        while (S.own_off[ob + 1] <= kc) ob++;
+        const int4 ci = A.sabin[S.own_start[ob] + (kc - S.own_off[ob])];
+        const int i = ci.x;
+        const bool ghost = i >= A.n_own;
+        const double xi = A.pos[i], yi = A.pos[ntot + i], zi = A.pos[2 * ntot + i];
+        // the centre in the same wrapped frame, relative to the block's reference point
+        const float hx = (float)(xi - ((double)ci.y * lat[0] + (double)ci.z * lat[3] + (double)ci.w * lat[6]) - S.org[0]);
+        const float hy = (float)(yi - ((double)ci.y * lat[1] + (double)ci.z * lat[4] + (double)ci.w * lat[7]) - S.org[1]);
+        const float hz = (float)(zi - ((double)ci.y * lat[2] + (double)ci.z * lat[5] + (double)ci.w * lat[8]) - S.org[2]);
+        uint64_t *skin = A.skin_keys ? A.skin_keys + (size_t)i * cap : nullptr;
+        uint64_t *exact = A.nbr_keys ? A.nbr_keys + (size_t)i * cap : nullptr;
+        int ns = 0, ne = 0, nclose = 0;
+        double d2min = 1e300;
+        for (int g0 = 0; g0 < ncand; g0 += KB_GROUP) {
+            int nsv = 0;
+#pragma unroll
+            for (int u = 0; u < KB_GROUP / 32; u++) {
+                const int c = g0 + u * 32 + lane;
+                bool pass = false;
+                if (c < ncand) {
+                    const float dx = S.fx[c] - hx, dy = S.fy[c] - hy, dz = S.fz[c] - hz;
+                    pass = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= B.f2pre;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, pass);
+                if (pass) sv[nsv + __popc(m & ltmask)] = (unsigned short)c;
+                nsv += __popc(m);
+            }
+            __syncwarp();
+            for (int base = 0; base < nsv; base += 32) {
+                bool ks = false, ke = false;
+                uint64_t key = 0;
+                if (base + lane < nsv) {
+                    const int c = sv[base + lane];
+                    const uint64_t k0 = S.ck[c];
+                    const int j = (int)(k0 >> 32);
+                    const uint32_t f = (uint32_t)k0;
+                    const int n1 = (int)((f >> 20) & 1023) - 512 + ci.y, n2s = (int)((f >> 10) & 1023) - 512 + ci.z, n3 = (int)(f & 1023) - 512 + ci.w;
+                    bool ok = !(j == i && n1 == 0 && n2s == 0 && n3 == 0) && abs(n1) <= na0 && abs(n2s) <= na1 && abs(n3) <= na2;
+                    if (ghost) ok = ok && j < A.n_own;
+                    if (ok) {
+                        const double d2 = image_dist2_xyz(S.cx[c], S.cy[c], S.cz[c], lat, n1, n2s, n3, xi, yi, zi);
+                        ks = d2 <= B.t2skin;
+                        ke = d2 <= B.t2cut;
+                        if (ke) { d2min = fmin(d2min, d2); nclose += d2 <= B.t2close; }
+                        key = nbr_key(j - aoff, n1, n2s, n3);
+                    }
+                }
+                const unsigned ms = __ballot_sync(0xffffffffu, ks), me = __ballot_sync(0xffffffffu, ke);
+                if (ks && skin) { const int p = ns + __popc(ms & ltmask); if (p < cap) skin[p] = key; }
+                if (ke && exact) { const int p = ne + __popc(me & ltmask); if (p < cap) exact[p] = key; }
+                ns += __popc(ms); ne += __popc(me);
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { nclose += __shfl_xor_sync(0xffffffffu, nclose, o); d2min = fmin(d2min, __shfl_xor_sync(0xffffffffu, d2min, o)); }
+        if (lane == 0) {
+            if (A.skin_cnt) A.skin_cnt[i] = ns;
+            A.nbr_cnt[i] = ns > cap ? 0 : ne;
+            if (A.min_dis) A.min_dis[i] = d2min < 1e299 ? __dsqrt_rn(d2min) : 1e300;   // sqrt is monotone: the root of the smallest d2
+        }
+        w_maxskin = max(w_maxskin, ns);
+        if (ns > cap) w_over = 1;
+        if (!ghost) {
+            w_maxcnt = max(w_maxcnt, ne);
+            w_close += nclose;
+            if (ne > MAX_NEIGHBOR_REF_DEV) w_many = 1;
+        }
+    }
+    if (lane == 0) {
+        atomicMax(&S.flags[0], w_maxskin); atomicMax(&S.flags[1], w_maxcnt);
+        if (w_many) S.flags[2] = 1;
+        if (w_over) S.flags[3] = 1;
+        if (w_close) atomicAdd(&S.flags[4], w_close);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        atomicMax(&A.flags->maxskin, S.flags[0]);
+        atomicMax(&A.flags->maxcount, S.flags[1]);
+        if (S.flags[2]) atomicExch(&A.flags->too_many, 1);
+        if (S.flags[3]) atomicExch(&A.flags->overflow, 1);
+        if (S.flags[4]) atomicAdd(&A.flags->close_pairs, S.flags[4]);
+    }
+}
+
 // Verlet reuse (gapcu_ctx_update_positions): the skin list is kept, only the exact list is
 // re-derived from the new positions.  Thread 0 also checks how far the centre has moved since the
 // skin list was built: beyond skin/2 a pair could have entered rcut without being listed, and the
@@ -861,9 +1107,28 @@ void launch_neighbor_build(cudaStream_t st, const NeighborBuild &b, long *launch
     A.sabin = b.sabin; A.spos = b.spos; A.ntot = ntot; A.nloc = b.nloc; A.n_own = b.n_own;
     A.rcut = b.rcut; A.rskin = b.rskin; A.cap = b.cap; A.skin_keys = b.skin_keys; A.skin_cnt = b.skin_cnt;
     A.nbr_keys = b.nbr_keys; A.nbr_cnt = b.nbr_cnt; A.min_dis = b.min_dis; A.flags = b.flags;
-    k_neigh<<<ntot, NB_THREADS, 0, st>>>(A);
+    if (b.nblocks > 0) {
+        NeighBlockArgs BA;
+        BA.n = A; BA.blk_struct = b.blk_struct;
+        BA.t2skin = b.t2skin; BA.t2cut = b.t2cut; BA.t2close = b.t2close;
+        const float pre = (float)(b.rskin * 1.0001 + 0.02);     // far above the single-precision error of the pre-filter (~1e-5 A)
+        BA.f2pre = pre * pre;
+        static thread_local int attr_dev = -1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev != attr_dev) {
+            cudaFuncSetAttribute((const void *)k_neigh_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KbSmem));
+            attr_dev = dev;
+        }
+        k_neigh_block<<<b.nblocks, KB_THREADS, sizeof(KbSmem), st>>>(BA);
+    } else {
+        k_neigh<<<ntot, NB_THREADS, 0, st>>>(A);
+    }
     if (launches) *launches += 1;
 }
+
+int neighbor_block_max_bins() { return KB_BINS; }
+int neighbor_block_max_candidates() { return KB_CAP; }
 
 void launch_refilter(cudaStream_t st, const NeighborBuild &b, const double *pos_build, double skin, long *launches) {
     k_refilter<<<b.ntot, NB_THREADS, 0, st>>>(b.structs, b.sid, b.pos, pos_build, b.ntot, b.nloc, b.n_own, b.rcut,
