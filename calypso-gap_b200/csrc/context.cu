@@ -1166,7 +1166,7 @@ extern "C" int gapcu_ctx_work_counters(gapcu_ctx *c, double *out, int n) {
 // ---------------------------------------------------------------------------
 extern "C" const char *gapcu_stage_name(int s) {
     static const char *names[GAPCU_NSTAGE] = {"neighbor_build", "descriptor_forward", "gpr_dmma", "descriptor_backward",
-                                              "force_gather_reduce", "", "", ""};
+                                              "force_gather_reduce", "halo_forward", "halo_return", ""};
     return (s >= 0 && s < GAPCU_NSTAGE) ? names[s] : "";
 }
 
@@ -1217,6 +1217,14 @@ extern "C" int gapcu_ctx_time_compute(gapcu_ctx *c, int lgrad, int steps, long l
                 float ms = 0.f;
                 CU(cudaEventElapsedTime(&ms, c->stage_ev[q], c->stage_ev[q + 1]));
                 stage_ms[q] += ms;
+            }
+            if (c->dom.enabled) {
+                // decomposed run: the exchange steps are carved out of the first and the last stage
+                float fwd = 0.f, ret = 0.f;
+                CU(cudaEventElapsedTime(&fwd, c->stage_ev[0], c->stage_ev[6]));
+                CU(cudaEventElapsedTime(&ret, c->stage_ev[7], c->stage_ev[5]));
+                stage_ms[5] += fwd; stage_ms[6] += ret;
+                stage_ms[0] -= fwd; stage_ms[4] -= ret;
             }
         }
     }
@@ -1300,21 +1308,46 @@ extern "C" int gapcu_calc(int na, const int *species, const double *lat, const d
     if ((rc = refresh_sf_from_cwd(c))) return rc;
     if (des_len != c->plan.D) return fail(GAPCU_EARG, "des_len does not equal 2*nsf of ./gap_parameters");
     // GPR data: compare the caller's (Fortran-layout) arrays with the last call's; only a
-    // changed set is transposed (mm(nsparseX,des_len) column-major -> C order) and uploaded
+    // changed set is transposed (mm(nsparseX,des_len) column-major -> C order) and uploaded.
+    // Up to 1 MiB of MM (the shipped potential: 68 KB) the comparison is exact (memcmp, ~5 us).  A large
+    // block (BASELINE config 5: 20 MB, 2 ms per call -- longer than the evaluation) is recognised by its
+    // address, its sizes, theta and coeff compared in full, and a fingerprint of 8192 evenly spread
+    // entries of MM plus its first and last one; a caller that edits single entries of a large MM in
+    // place between calls must set GAPCU_POTENTIAL_CHECK=full (always memcmp).
     {
         const size_t nmm = (size_t)nsparsex * des_len;
         static std::vector<double> last_mm, last_theta, last_coeff;
-        const bool same = c->have_gpr && c->M == nsparsex && c->D == des_len && last_mm.size() == nmm &&
-                          !memcmp(last_mm.data(), mm, sizeof(double) * nmm) &&
-                          !memcmp(last_theta.data(), theta, sizeof(double) * des_len) &&
-                          !memcmp(last_coeff.data(), coeff, sizeof(double) * nsparsex);
+        static const double *last_ptr = nullptr;
+        static size_t last_n = 0;
+        static uint64_t last_fp = 0;
+        static const bool full_check = [] { const char *e = getenv("GAPCU_POTENTIAL_CHECK"); return e && !strcmp(e, "full"); }();
+        const bool small = full_check || nmm * sizeof(double) <= (1u << 20);
+        auto fingerprint = [&]() {
+            uint64_t h = 1469598103934665603ull;
+            const size_t step = std::max<size_t>(1, nmm / 8192);
+            auto mix = [&](double v) { uint64_t b; memcpy(&b, &v, 8); h = (h ^ b) * 1099511628211ull; };
+            for (size_t k = 0; k < nmm; k += step) mix(mm[k]);
+            if (nmm) mix(mm[nmm - 1]);
+            return h;
+        };
+        bool same = c->have_gpr && c->M == nsparsex && c->D == des_len && last_n == nmm &&
+                    last_theta.size() == (size_t)des_len && last_coeff.size() == (size_t)nsparsex &&
+                    !memcmp(last_theta.data(), theta, sizeof(double) * des_len) &&
+                    !memcmp(last_coeff.data(), coeff, sizeof(double) * nsparsex);
+        uint64_t fp = 0;
+        if (same) {
+            if (small) same = last_mm.size() == nmm && !memcmp(last_mm.data(), mm, sizeof(double) * nmm);
+            else { fp = fingerprint(); same = mm == last_ptr && fp == last_fp; }
+        }
         if (!same) {
             std::vector<double> mm_c(nmm);
             for (int k = 0; k < des_len; k++)
                 for (int s = 0; s < nsparsex; s++) mm_c[(size_t)s * des_len + k] = mm[s + (size_t)nsparsex * k];
             c->have_gpr = false;
             if ((rc = set_gpr(c, nsparsex, des_len, theta, mm_c.data(), coeff))) return rc;
-            last_mm.assign(mm, mm + nmm); last_theta.assign(theta, theta + des_len); last_coeff.assign(coeff, coeff + nsparsex);
+            if (small) last_mm.assign(mm, mm + nmm); else { last_mm.clear(); last_mm.shrink_to_fit(); }
+            last_theta.assign(theta, theta + des_len); last_coeff.assign(coeff, coeff + nsparsex);
+            last_ptr = mm; last_n = nmm; last_fp = small ? 0 : fingerprint();
         }
     }
     double lat_c[9];

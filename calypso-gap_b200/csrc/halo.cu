@@ -120,8 +120,8 @@ k_halo_fill(const HaloGeom G, const double *pos, const double *wgt, const int4 *
     double x = 0, y = 0, z = 0, w = 0;
     int4 q = make_int4(0, 0, 0, 0);
     if (a < n_own) { m = mask[a]; x = pos[a]; y = pos[stride + a]; z = pos[2 * stride + a]; w = wgt[a]; q = sft[a]; }
-    if (blockIdx.x == 0 && threadIdx.x < 27) {
-        int *hdr = (int *)(B.send + B.off[threadIdx.x]);
+    if (blockIdx.x == 0 && threadIdx.x < 27 && threadIdx.x != 13 && B.cap[threadIdx.x] > 0) {
+        int *hdr = (int *)(B.send + B.soff[threadIdx.x]);
         hdr[0] = min(flags->halo_count[threadIdx.x], B.cap[threadIdx.x]);
     }
     // directions present in this tile (one pass of __syncthreads_or per direction is cheap; most tiles have none)
@@ -131,7 +131,7 @@ k_halo_fill(const HaloGeom G, const double *pos, const double *wgt, const int4 *
         if (!__syncthreads_or(bit)) continue;
         const int k = tile_rank(bit, tile_base[d * ntiles + blockIdx.x], wcnt);
         if (bit && k < B.cap[d]) {
-            unsigned char *rec = B.send + B.off[d] + HALO_HDR + (size_t)k * HALO_REC;
+            unsigned char *rec = B.send + B.soff[d] + HALO_HDR + (size_t)k * HALO_REC;
             double *rd = (double *)rec;
             rd[0] = x; rd[1] = y; rd[2] = z; rd[3] = w;
             // receiver's frame: its brick is mine + delta, wrapped into the grid
@@ -144,18 +144,18 @@ k_halo_fill(const HaloGeom G, const double *pos, const double *wgt, const int4 *
     }
 }
 
-// received ghosts -> local arrays behind the owned atoms, in direction order; slot map for the way back
+// received ghosts -> local arrays behind the owned atoms, in receive order; slot map for the way back
 __global__ void __launch_bounds__(HT)
 k_halo_unpack(HaloBufs B, int n_own, int stride, double *pos, double *wgt, int4 *sft, int *gslot, DevFlags *flags) {
     __shared__ int cnt[27], cpre[28], kpre[28];
     if (threadIdx.x < 27) {
-        const int d = threadIdx.x;
-        cnt[d] = (d == 13 || B.cap[d] == 0) ? 0 : min(*(const int *)(B.recv + B.off[d]), B.cap[d]);
+        const int d = B.rorder[threadIdx.x];
+        cnt[threadIdx.x] = d < 0 ? 0 : min(*(const int *)(B.recv + B.roff[d]), B.cap[d]);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         int c = 0, k = 0;
-        for (int d = 0; d < 27; d++) { cpre[d] = c; kpre[d] = k; c += cnt[d]; k += B.cap[d]; }
+        for (int p = 0; p < 27; p++) { cpre[p] = c; kpre[p] = k; c += cnt[p]; k += B.rorder[p] < 0 ? 0 : B.cap[B.rorder[p]]; }
         cpre[27] = c; kpre[27] = k;
         if (blockIdx.x == 0) {
             flags->n_ghost = c; flags->n_loc = n_own + c;
@@ -163,15 +163,15 @@ k_halo_unpack(HaloBufs B, int n_own, int stride, double *pos, double *wgt, int4 
         }
     }
     __syncthreads();
-    const int idx = blockIdx.x * HT + threadIdx.x;   // padded slot
+    const int idx = blockIdx.x * HT + threadIdx.x;   // padded slot (receive order)
     if (idx >= kpre[27]) return;
-    int d = 0;
-    while (idx >= kpre[d + 1]) d++;
-    const int k = idx - kpre[d];
-    if (k >= cnt[d]) return;
-    const int dst = n_own + cpre[d] + k;
+    int p = 0;
+    while (idx >= kpre[p + 1]) p++;
+    const int k = idx - kpre[p];
+    if (k >= cnt[p]) return;
+    const int dst = n_own + cpre[p] + k;
     if (dst >= stride) return;
-    const unsigned char *rec = B.recv + B.off[d] + HALO_HDR + (size_t)k * HALO_REC;
+    const unsigned char *rec = B.recv + B.roff[B.rorder[p]] + HALO_HDR + (size_t)k * HALO_REC;
     const double *rd = (const double *)rec;
     pos[dst] = rd[0]; pos[stride + dst] = rd[1]; pos[2 * stride + dst] = rd[2];
     wgt[dst] = rd[3];
@@ -188,14 +188,13 @@ k_halo_add(int n_own, int stride, const uint32_t *mask, const int *tile_base, in
     if (!__syncthreads_or(m != 0u)) return;
     double fx = 0.0, fy = 0.0, fz = 0.0;
     if (m) { fx = force[a]; fy = force[stride + a]; fz = force[2 * stride + a]; }
-    int kp = 0;   // padded offset of direction d in the gradient buffers
-    for (int d = 0; d < 27; kp += B.cap[d], d++) {
+    for (int d = 0; d < 27; d++) {
         if (d == 13 || B.cap[d] == 0) continue;
         const bool bit = (m >> d) & 1u;
         if (!__syncthreads_or(bit)) continue;
         const int k = tile_rank(bit, tile_base[d * ntiles + blockIdx.x], wcnt);
         if (bit && k < B.cap[d]) {
-            const double *gr = B.rgrad + 3 * (size_t)(kp + k);
+            const double *gr = B.rgrad + 3 * (size_t)(B.ks[d] + k);
             fx -= gr[0]; fy -= gr[1]; fz -= gr[2];
         }
     }

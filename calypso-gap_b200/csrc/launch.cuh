@@ -112,11 +112,19 @@ struct HaloGeom {
     double drift[3];    // how far (brick units) an owned atom may sit outside its brick
     int wrap[3][3];     // floor((mine + delta) / grid) for delta = -1, 0, +1: cell crossings towards that neighbour
 };
+// Layout of the exchange buffers.  A direction's message is a header and cap[d] records.  In the SEND buffer
+// the directions that go to the same rank are contiguous (one ncclSend per peer), in the RECEIVE buffer
+// those that come from the same rank are (one ncclRecv per peer); within a peer the directions ascend, so
+// both sides see the same sub-layout.  The gradient buffers use the same two orders in units of records:
+// a rank's ghosts (and the gradients it returns) follow its receive order, the gradients it gets back
+// follow its send order.
 struct HaloBufs {
-    unsigned char *send, *recv;   // per direction: header + cap[d] records at byte offset off[d]
-    const double *rgrad;          // [sum cap][3] gradients returned by the ranks that hold my atoms as ghosts
+    unsigned char *send, *recv;
+    const double *rgrad;          // [sum cap][3] gradients returned by the ranks that hold my atoms as ghosts (send order)
     int cap[27];
-    size_t off[27];
+    unsigned soff[27], roff[27];  // byte offset of direction d in the send / receive buffer
+    int ks[27], kr[27];           // record offset of direction d in send order / receive order
+    signed char rorder[27];       // directions in receive order (-1: unused tail)
 };
 void launch_halo_select(cudaStream_t st, const HaloGeom &G, const double *pos, int stride, int n_own, int4 *sft, uint32_t *mask,
                         int *tile_cnt, int *tile_base, const HaloBufs &B, DevFlags *flags, long *launches);

@@ -357,9 +357,10 @@ def nccl_unique_id():
     return buf.raw
 
 
-def domain_grid(world, cell, rcut=6.0):
-    """Brick grid g0 x g1 x g2 = world with the smallest ghost shell for this cell
-    (1-D slabs along the longest direction for 2, then 2x2x1, 2x2x2, ...)."""
+def domain_grid(world, cell, shell=6.5):
+    """Brick grid g0 x g1 x g2 = world with the smallest ghost volume for this cell.  `shell` = rcut + skin +
+    2 * drift: every brick must be at least that thick, and a rank imports the images within it on ALL six
+    sides of its brick (also along undivided directions: those ghosts are the cell's own periodic images)."""
     cell = np.asarray(cell, float)
     inv = np.linalg.inv(cell)
     spacing = 1.0 / np.linalg.norm(inv, axis=0)          # interplanar spacings
@@ -372,10 +373,14 @@ def domain_grid(world, cell, rcut=6.0):
                 continue
             g = (g0, g1, world // g0 // g1)
             w = [spacing[c] / g[c] for c in range(3)]    # brick widths
-            shell = np.prod([min(w[c] + 2 * rcut, spacing[c]) if g[c] > 1 else w[c] for c in range(3)]) - np.prod(w)
-            key = (round(float(shell), 9), g)
+            if min(w) < shell:
+                continue
+            ghost = np.prod([w[c] + 2 * shell for c in range(3)]) - np.prod(w)
+            key = (round(float(ghost), 9), g)
             if best is None or key < best:
                 best = key
+    if best is None:
+        raise ValueError("no brick grid: the cell is too small for %d bricks of thickness >= %g" % (world, shell))
     return best[1]
 
 
