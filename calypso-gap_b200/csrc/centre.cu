@@ -70,7 +70,9 @@ int launch_backward(cudaStream_t st, const CentreArgs &a, long *launches) {
 }
 int launch_fused(cudaStream_t st, const CentreArgs &a, long *launches) {
     if (launches) *launches += 1;
-    const bool se = a.share_exp && a.estash && a.cs == 1 && centre_pcap_template(a.pcap) <= 256;
+    // parked exponentials pay on large launches (+1 % at 27k centres); on a 1000-centre launch the extra L2
+    // round trips cost 4 %
+    const bool se = a.share_exp && a.estash && a.cs == 1 && centre_pcap_template(a.pcap) <= 256 && a.ncentres_max >= 4096;
     return launch_mode(st, a, se ? MODE_FUSED_SE : MODE_FUSED);
 }
 
