@@ -29,7 +29,7 @@
 
 namespace gapcu {
 
-constexpr int HT = 256;   // owned atoms per tile = threads per CTA
+constexpr int HT = 256;   // threads per CTA; a TILE of the ordered compaction is one warp = 32 consecutive owned atoms
 
 __device__ __forceinline__ int dir_index(int d0, int d1, int d2) { return (d0 + 1) * 9 + (d1 + 1) * 3 + (d2 + 1); }
 
@@ -71,10 +71,15 @@ k_halo_mask(const HaloGeom G, const double *pos, int stride, int n_own, int4 *sf
                 }
         mask[a] = m;
     }
+    // a tile is one warp's 32 atoms: per direction, the number of its atoms that go that way
+    const int lane = threadIdx.x & 31, tile = blockIdx.x * (HT / 32) + (threadIdx.x >> 5);
+    int mine = 0;
+#pragma unroll
     for (int d = 0; d < 27; d++) {
-        const int n = __syncthreads_count((m >> d) & 1u);
-        if (threadIdx.x == 0) tile_cnt[d * ntiles + blockIdx.x] = n;
+        const unsigned b = __ballot_sync(0xffffffffu, (m >> d) & 1u);
+        if (lane == d) mine = __popc(b);
     }
+    if (lane < 27 && tile < ntiles) tile_cnt[lane * ntiles + tile] = mine;
 }
 
 // one warp per direction: exclusive scan of the tile counts, total -> flags / header, capacity check
@@ -97,25 +102,18 @@ k_halo_scan(const int *tile_cnt, int *tile_base, int ntiles, HaloBufs B, DevFlag
     }
 }
 
-// position of this thread's atom in the send list of direction d (valid where its mask bit is set)
-__device__ __forceinline__ int tile_rank(bool bit, int tile_base, int *wcnt) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+// position of this lane's atom in the send list of direction d (valid where its mask bit is set)
+__device__ __forceinline__ int tile_rank(bool bit, int tile_base) {
     const unsigned b = __ballot_sync(0xffffffffu, bit);
-    __syncthreads();
-    if (lane == 0) wcnt[wid] = __popc(b);
-    __syncthreads();
-    int k = tile_base + __popc(b & ((1u << lane) - 1u));
-#pragma unroll
-    for (int w = 0; w < HT / 32; w++) if (w < wid) k += wcnt[w];
-    return k;
+    return tile_base + __popc(b & ((1u << (threadIdx.x & 31)) - 1u));
 }
 
 // ordered fill of the 26 send buffers: header (count), then records (x, y, z, w | gid, s1, s2, s3)
 __global__ void __launch_bounds__(HT)
 k_halo_fill(const HaloGeom G, const double *pos, const double *wgt, const int4 *sft, int stride, int n_own,
             const uint32_t *mask, const int *tile_base, int ntiles, HaloBufs B, const DevFlags *flags) {
-    __shared__ int wcnt[HT / 32];
     const int a = blockIdx.x * HT + threadIdx.x;
+    const int tile = blockIdx.x * (HT / 32) + (threadIdx.x >> 5);
     uint32_t m = 0;
     double x = 0, y = 0, z = 0, w = 0;
     int4 q = make_int4(0, 0, 0, 0);
@@ -124,12 +122,12 @@ k_halo_fill(const HaloGeom G, const double *pos, const double *wgt, const int4 *
         int *hdr = (int *)(B.send + B.soff[threadIdx.x]);
         hdr[0] = min(flags->halo_count[threadIdx.x], B.cap[threadIdx.x]);
     }
-    // directions present in this tile (one pass of __syncthreads_or per direction is cheap; most tiles have none)
-    for (int d = 0; d < 27; d++) {
-        if (d == 13 || B.cap[d] == 0) continue;
+    // only the directions some atom of this warp goes to
+    for (unsigned todo = __reduce_or_sync(0xffffffffu, m) & ~(1u << 13); todo; todo &= todo - 1) {
+        const int d = __ffs(todo) - 1;
+        if (B.cap[d] == 0) continue;
         const bool bit = (m >> d) & 1u;
-        if (!__syncthreads_or(bit)) continue;
-        const int k = tile_rank(bit, tile_base[d * ntiles + blockIdx.x], wcnt);
+        const int k = tile_rank(bit, tile_base[d * ntiles + tile]);
         if (bit && k < B.cap[d]) {
             unsigned char *rec = B.send + B.soff[d] + HALO_HDR + (size_t)k * HALO_REC;
             double *rd = (double *)rec;
@@ -182,17 +180,18 @@ k_halo_unpack(HaloBufs B, int n_own, int stride, double *pos, double *wgt, int4 
 // owners subtract the returned gradients from their forces, direction by direction (fixed order)
 __global__ void __launch_bounds__(HT)
 k_halo_add(int n_own, int stride, const uint32_t *mask, const int *tile_base, int ntiles, HaloBufs B, double *force) {
-    __shared__ int wcnt[HT / 32];
     const int a = blockIdx.x * HT + threadIdx.x;
+    const int tile = blockIdx.x * (HT / 32) + (threadIdx.x >> 5);
     const uint32_t m = a < n_own ? mask[a] : 0u;
-    if (!__syncthreads_or(m != 0u)) return;
+    unsigned todo = __reduce_or_sync(0xffffffffu, m) & ~(1u << 13);
+    if (!todo) return;
     double fx = 0.0, fy = 0.0, fz = 0.0;
     if (m) { fx = force[a]; fy = force[stride + a]; fz = force[2 * stride + a]; }
-    for (int d = 0; d < 27; d++) {
-        if (d == 13 || B.cap[d] == 0) continue;
+    for (; todo; todo &= todo - 1) {          // ascending directions: a fixed order of subtraction
+        const int d = __ffs(todo) - 1;
+        if (B.cap[d] == 0) continue;
         const bool bit = (m >> d) & 1u;
-        if (!__syncthreads_or(bit)) continue;
-        const int k = tile_rank(bit, tile_base[d * ntiles + blockIdx.x], wcnt);
+        const int k = tile_rank(bit, tile_base[d * ntiles + tile]);
         if (bit && k < B.cap[d]) {
             const double *gr = B.rgrad + 3 * (size_t)(B.ks[d] + k);
             fx -= gr[0]; fy -= gr[1]; fz -= gr[2];
@@ -255,16 +254,16 @@ __global__ void k_halo_combine(const double *rec_all, int nranks, double volume,
 
 void launch_halo_select(cudaStream_t st, const HaloGeom &G, const double *pos, int stride, int n_own, int4 *sft, uint32_t *mask,
                         int *tile_cnt, int *tile_base, const HaloBufs &B, DevFlags *flags, long *launches) {
-    const int ntiles = (n_own + HT - 1) / HT;
-    k_halo_mask<<<ntiles, HT, 0, st>>>(G, pos, stride, n_own, sft, mask, tile_cnt, ntiles, flags);
+    const int ntiles = (n_own + 31) / 32;
+    k_halo_mask<<<(n_own + HT - 1) / HT, HT, 0, st>>>(G, pos, stride, n_own, sft, mask, tile_cnt, ntiles, flags);
     k_halo_scan<<<27, 32, 0, st>>>(tile_cnt, tile_base, ntiles, B, flags);
     if (launches) *launches += 2;
 }
 
 void launch_halo_fill(cudaStream_t st, const HaloGeom &G, const double *pos, const double *wgt, const int4 *sft, int stride,
                       int n_own, const uint32_t *mask, const int *tile_base, const HaloBufs &B, const DevFlags *flags, long *launches) {
-    const int ntiles = (n_own + HT - 1) / HT;
-    k_halo_fill<<<ntiles, HT, 0, st>>>(G, pos, wgt, sft, stride, n_own, mask, tile_base, ntiles, B, flags);
+    const int ntiles = (n_own + 31) / 32;
+    k_halo_fill<<<(n_own + HT - 1) / HT, HT, 0, st>>>(G, pos, wgt, sft, stride, n_own, mask, tile_base, ntiles, B, flags);
     if (launches) *launches += 1;
 }
 
@@ -278,8 +277,8 @@ void launch_halo_unpack(cudaStream_t st, const HaloBufs &B, int n_own, int strid
 
 void launch_halo_add(cudaStream_t st, int n_own, int stride, const uint32_t *mask, const int *tile_base, const HaloBufs &B,
                      double *force, long *launches) {
-    const int ntiles = (n_own + HT - 1) / HT;
-    k_halo_add<<<ntiles, HT, 0, st>>>(n_own, stride, mask, tile_base, ntiles, B, force);
+    const int ntiles = (n_own + 31) / 32;
+    k_halo_add<<<(n_own + HT - 1) / HT, HT, 0, st>>>(n_own, stride, mask, tile_base, ntiles, B, force);
     if (launches) *launches += 1;
 }
 

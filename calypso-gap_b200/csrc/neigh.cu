@@ -998,7 +998,7 @@ k_neigh_direct(const StructDev *structs, const int *sid, const double *pos, int 
 // The same ordering for many centres (a 10^5-atom cell): a single CTA would walk the counts alone for
 // ~0.1 ms.  Histogram with per-CTA shared-memory counters flushed by global atomics, the 1024-key scan
 // in one small CTA, then a grid-wide scatter.  hist: NB_MAXLIST + 2 ints of global memory.
-constexpr int ORD_PER_CTA = 4096;
+constexpr int ORD_PER_CTA = 1024;
 __global__ void __launch_bounds__(256) k_order_hist(const int *nbr_cnt, int n, int *hist) {
     __shared__ int h[NB_MAXLIST];
     for (int t = threadIdx.x; t < NB_MAXLIST; t += 256) h[t] = 0;
@@ -1088,7 +1088,7 @@ void launch_neighbor_build(cudaStream_t st, const NeighborBuild &b, long *launch
         cudaMemsetAsync(b.bin_count, 0, sizeof(int) * 2 * (size_t)b.nbins_total, st);
         int tb = 256, gb = (ntot + tb - 1) / tb;
         k_bin<<<gb, tb, 0, st>>>(b.structs, b.sid, b.pos, ntot, b.nloc, b.n_own, b.sft, b.abin, b.arank, b.bin_count, b.nbins_total);
-        if (b.nbins_total <= 8192) {
+        if (b.nbins_total <= 16384) {
             k_scan_bins<<<1, 1024, 0, st>>>(b.bin_count, b.bin_start, b.nbins_total);
         } else {   // many cells: per-CTA scans, a scan of the CTA totals, then the offsets are added
             const int gs = (b.nbins_total + SCAN_PER_CTA - 1) / SCAN_PER_CTA;
