@@ -780,6 +780,14 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
                 const double *col = a.gpr_MtT + (size_t)k0 * Mp + j;
                 int k = k0;
+                for (; k + 7 < k1; k += 8, col += 8 * (size_t)Mp) {   // eight loads in flight: this loop waits on L2, not on arithmetic
+                    const double m0 = __ldg(col), m1 = __ldg(col + Mp), m2 = __ldg(col + 2 * (size_t)Mp), m3 = __ldg(col + 3 * (size_t)Mp);
+                    const double m4 = __ldg(col + 4 * (size_t)Mp), m5 = __ldg(col + 5 * (size_t)Mp), m6 = __ldg(col + 6 * (size_t)Mp), m7 = __ldg(col + 7 * (size_t)Mp);
+                    const double d0 = s_xs[k] - m0, d1 = s_xs[k + 1] - m1, d2 = s_xs[k + 2] - m2, d3 = s_xs[k + 3] - m3;
+                    const double d4 = s_xs[k + 4] - m4, d5 = s_xs[k + 5] - m5, d6 = s_xs[k + 6] - m6, d7 = s_xs[k + 7] - m7;
+                    s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
+                    s0 = fma(d4, d4, s0); s1 = fma(d5, d5, s1); s2 = fma(d6, d6, s2); s3 = fma(d7, d7, s3);
+                }
                 for (; k + 3 < k1; k += 4, col += 4 * (size_t)Mp) {   // four independent chains, loads issued together
                     const double m0 = __ldg(col), m1 = __ldg(col + Mp), m2 = __ldg(col + 2 * (size_t)Mp), m3 = __ldg(col + 3 * (size_t)Mp);
                     const double d0 = s_xs[k] - m0, d1 = s_xs[k + 1] - m1, d2 = s_xs[k + 2] - m2, d3 = s_xs[k + 3] - m3;
@@ -817,6 +825,14 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
                 const double *rp = a.gpr_Mt + k + (size_t)j0 * Dp;
                 int j = j0;
+                for (; j + 7 < j1; j += 8, rp += 8 * (size_t)Dp) {
+                    const double m0 = __ldg(rp), m1 = __ldg(rp + Dp), m2 = __ldg(rp + 2 * (size_t)Dp), m3 = __ldg(rp + 3 * (size_t)Dp);
+                    const double m4 = __ldg(rp + 4 * (size_t)Dp), m5 = __ldg(rp + 5 * (size_t)Dp), m6 = __ldg(rp + 6 * (size_t)Dp), m7 = __ldg(rp + 7 * (size_t)Dp);
+                    a0 = fma(s_W[j], xk - m0, a0); a1 = fma(s_W[j + 1], xk - m1, a1);
+                    a2 = fma(s_W[j + 2], xk - m2, a2); a3 = fma(s_W[j + 3], xk - m3, a3);
+                    a0 = fma(s_W[j + 4], xk - m4, a0); a1 = fma(s_W[j + 5], xk - m5, a1);
+                    a2 = fma(s_W[j + 6], xk - m6, a2); a3 = fma(s_W[j + 7], xk - m7, a3);
+                }
                 for (; j + 3 < j1; j += 4, rp += 4 * (size_t)Dp) {
                     const double m0 = __ldg(rp), m1 = __ldg(rp + Dp), m2 = __ldg(rp + 2 * (size_t)Dp), m3 = __ldg(rp + 3 * (size_t)Dp);
                     a0 = fma(s_W[j], xk - m0, a0); a1 = fma(s_W[j + 1], xk - m1, a1);

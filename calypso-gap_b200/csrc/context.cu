@@ -1290,11 +1290,74 @@ int refresh_sf_from_cwd(gapcu_ctx *c) {
 }
 }  // namespace
 
+// FGAP_CALC on several devices: with more than one device set (gapcu_set_devices) a large structure is cut
+// into one brick per device and evaluated by an in-process group (domain_host.inc) -- same arguments, same
+// results, the caller does not change.  Below GAPCU_GROUP_MIN_ATOMS atoms (default 20000) a single device is
+// faster and is used.
+namespace {
+gapcu_group *g_group = nullptr;
+std::vector<int> g_group_devs;
+FileId g_group_file;
+}  // namespace
+
+static int calc_on_group(int na, const int *species, const double *lat, const double *pos, int nsparsex, int des_len,
+                         const double *theta, const double *mm, const double *coeff, double rcut, int lgrad, double *ene,
+                         double *force, double *stress) {
+    if (!g_group || g_group_devs != g_devices) {
+        if (g_group) gapcu_group_destroy(g_group);
+        g_group = gapcu_group_create((int)g_devices.size(), g_devices.data());
+        if (!g_group) return GAPCU_ECUDA;
+        g_group_devs = g_devices;
+        g_group_file = FileId();
+    }
+    struct stat st;
+    if (stat("gap_parameters", &st) != 0) return fail(GAPCU_EFILE, "gap_parameters file does not exist!");
+    const bool same_file = st.st_dev == g_group_file.dev && st.st_ino == g_group_file.ino && st.st_size == g_group_file.size &&
+                           st.st_mtim.tv_sec == g_group_file.mt_s && st.st_mtim.tv_nsec == g_group_file.mt_ns;
+    int rc;
+    std::vector<double> mm_c;
+    for (gapcu_ctx *c : g_group->ctx) {
+        DeviceGuard dg_(c->device);
+        if (!same_file || !c->have_sf) {
+            PotentialFile pf;
+            try { pf = read_gap_parameters("gap_parameters"); } catch (const std::exception &e) { return fail(GAPCU_EFILE, e.what()); }
+            if ((rc = set_sf(c, pf.z, pf.w, pf.ntype, pf.alpha, pf.cutoff))) return rc;
+        }
+        if (des_len != c->plan.D) return fail(GAPCU_EARG, "des_len does not equal 2*nsf of ./gap_parameters");
+        if (mm_c.empty()) {
+            mm_c.resize((size_t)nsparsex * des_len);
+            for (int k = 0; k < des_len; k++)
+                for (int s = 0; s < nsparsex; s++) mm_c[(size_t)s * des_len + k] = mm[s + (size_t)nsparsex * k];
+        }
+        if ((rc = set_gpr(c, nsparsex, des_len, theta, mm_c.data(), coeff))) return rc;   // keeps the device copy when unchanged
+    }
+    g_group_file.dev = st.st_dev; g_group_file.ino = st.st_ino; g_group_file.size = st.st_size;
+    g_group_file.mt_s = st.st_mtim.tv_sec; g_group_file.mt_ns = st.st_mtim.tv_nsec;
+    double lat_c[9];
+    for (int r = 0; r < 3; r++) for (int col = 0; col < 3; col++) lat_c[r * 3 + col] = lat[r + 3 * col];
+    std::vector<double> pos_c(3 * (size_t)na), f_c(3 * (size_t)na);
+    for (int t = 0; t < na; t++) for (int d = 0; d < 3; d++) pos_c[3 * (size_t)t + d] = pos[t + (size_t)na * d];
+    if ((rc = gapcu_group_set_structure(g_group, na, species, lat_c, pos_c.data(), rcut, nullptr))) return rc;
+    if ((rc = gapcu_group_compute(g_group, lgrad ? 1 : 0))) return rc;
+    if ((rc = gapcu_group_fetch(g_group, ene, f_c.data(), stress))) return rc;
+    for (int t = 0; t < na; t++) for (int d = 0; d < 3; d++) force[t + (size_t)na * d] = f_c[3 * (size_t)t + d];
+    return 0;
+}
+
 extern "C" int gapcu_calc(int na, const int *species, const double *lat, const double *pos, int nsparsex, int des_len,
                           const double *theta, const double *mm, const double *qmm, const double *coeff, double rcut,
                           int lgrad, double *ene, double *force, double *stress, double *variance) {
     (void)qmm;
     std::lock_guard<std::mutex> lk(g_mu);
+    if (g_devices.size() > 1 && na > 0) {
+        const char *e_min = getenv("GAPCU_GROUP_MIN_ATOMS");
+        const int min_atoms = e_min ? atoi(e_min) : 20000;
+        if (na >= min_atoms) {
+            const int rc = calc_on_group(na, species, lat, pos, nsparsex, des_len, theta, mm, coeff, rcut, lgrad, ene, force, stress);
+            // a cell too small to cut (GAPCU_EARG from the brick planner) falls through to one device
+            if (rc != GAPCU_EARG) { if (!rc && variance) *variance = 0.0; return rc; }
+        }
+    }
     // GAPCU_TRACE=1: host-side time stamps of this call's phases on stderr (development aid)
     static const bool trace = getenv("GAPCU_TRACE") != nullptr;
     std::chrono::steady_clock::time_point tp[6];
@@ -1396,14 +1459,14 @@ extern "C" int gapcu_set_devices(int n, const int *devices) {
     std::vector<int> want(devices, devices + n);
     for (size_t k = 0; k < want.size(); k++) {
         if (want[k] < 0 || want[k] >= have) return fail(GAPCU_EARG, "device " + std::to_string(want[k]) + " does not exist");
-        for (size_t q = 0; q < k; q++)
-            if (want[q] == want[k]) return fail(GAPCU_EARG, "device " + std::to_string(want[k]) + " listed twice");
+        // a device may be listed several times: that many contexts (batch shards / bricks) share it
     }
     g_devices = want;
     // contexts on devices that are no longer wanted go away; the others keep their state
     if (g_ctx && g_ctx->device != default_device()) { gapcu_ctx_destroy(g_ctx); g_ctx = nullptr; g_file = FileId(); }
     for (BatchSlot &b : g_batch) if (b.ctx) gapcu_ctx_destroy(b.ctx);
     g_batch.clear();
+    if (g_group) { gapcu_group_destroy(g_group); g_group = nullptr; g_group_devs.clear(); }
     return 0;
 }
 

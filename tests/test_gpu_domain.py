@@ -152,3 +152,35 @@ def test_atom_beyond_the_drift_allowance_is_reported():
     r = g.evaluate(z, cell, p, 6.0, True, (2, 1, 1))
     assert np.isfinite(r["energy"])
     g.close()
+
+
+def test_fgap_calc_on_several_devices_is_a_brick_group(single, monkeypatch):
+    """The drop-in call itself: with more than one device set, FGAP_CALC's C entry point cuts a large
+    structure into bricks (here two contexts on the one GPU) and must return what a single device returns,
+    in the Fortran layouts."""
+    import gapcu
+    from oracle import Oracle
+    pot = Oracle("parity").read(POT_C2)
+    monkeypatch.chdir(os.path.join(ROOT, "bench_data"))
+    link = os.path.join(ROOT, "bench_data", "gap_parameters")
+    made = not os.path.lexists(link)
+    if made:
+        os.symlink("gap_parameters_c2", link)
+    try:
+        cell, pos, z = cubic_supercell(12, 10, 8, seed=4500)
+        want = single.evaluate(z, cell, pos, 6.0, True)
+        monkeypatch.setenv("GAPCU_GROUP_MIN_ATOMS", "500")
+        gapcu.set_devices([0, 0])
+        e, f, s, v = gapcu.fortran_calc(z, cell, pos, pot.theta, pot.mm, pot.coeff, 6.0, True)
+        _close({"energy": e, "forces": f, "stress": s}, want)
+        assert v == 0.0
+        # a cell too small to cut falls back to one device
+        cell2, pos2, z2 = cubic_supercell(5, 5, 5, seed=4501)
+        e2, f2, s2, _ = gapcu.fortran_calc(z2, cell2, pos2, pot.theta, pot.mm, pot.coeff, 6.0, True)
+        monkeypatch.setenv("GAPCU_GROUP_MIN_ATOMS", "100")
+        e3, f3, s3, _ = gapcu.fortran_calc(z2, cell2, pos2, pot.theta, pot.mm, pot.coeff, 6.0, True)
+        assert abs(e3 - e2) <= 1e-12 * abs(e2) and np.abs(f3 - f2).max() <= 1e-9
+    finally:
+        gapcu.set_devices([])
+        if made:
+            os.remove(link)

@@ -595,8 +595,9 @@ def test_calc_batch_dropin_entry_point(shipped_pot, golden_frames, bc_structure,
             assert np.array_equal(e0, e) and all(not fk.any() for fk in f0)
         with pytest.raises(gapcu.GapcuError):
             gapcu.set_devices([gapcu.device_count()])
-        with pytest.raises(gapcu.GapcuError):
-            gapcu.set_devices([0, 0])
+        gapcu.set_devices([0, 0])                    # allowed: two contexts share the device
+        e2, f2, s2 = gapcu.calc_batch([t[0] for t in structs], [t[1] for t in structs], [t[2] for t in structs], 6.0, True)
+        assert np.abs(e2 - e).max() <= 1e-13 * np.abs(e).max()
     finally:
         gapcu.set_devices([])
 
