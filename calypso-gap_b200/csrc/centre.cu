@@ -26,7 +26,7 @@ static SmemLayout make_layout(const CentreArgs &a, int mode) {
     L.S = take(4 * (a.lcap + 32));
     // scratch region, three lives: [U | gw] while lists are built and the forward runs,
     // [part | xs | W] during the in-CTA GPR, [private accumulators] during the backward
-    const long scr_u = ((4l * (a.lcap + NW * 32 + 32) + 15) & ~15l);
+    const long scr_u = ((4l * (a.lcap + NW * 64 + 32) + 15) & ~15l);   // per-warp parts: a fair share + up to 63 entries
     const long scr_fwd = scr_u + (fwd ? 8l * NW * D : 0);
     const long gpr_part = 8l * NW * (a.gpr_Mp > D ? a.gpr_Mp : D);
     const long scr_gpr = fused ? gpr_part + 8l * (D + a.gpr_Mp + 8) : 0;

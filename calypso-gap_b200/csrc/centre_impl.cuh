@@ -77,9 +77,10 @@ struct Hot {
     static constexpr int NB = 0;                 // [PCAP] records of 6 doubles: x y z r 1/r w
     static constexpr int ACC = NB + 48 * PCAP;   // [3][PCAP] dE_i/dx of every neighbour slot
     static constexpr int NC = ACC + 24 * PCAP;   // [PCAP] bytes: number of classes the neighbour belongs to
-    static constexpr int FCD = NC + PCAP;        // [ncls][PCAP] (fc, fc') pairs
+    static constexpr int PERM = NC + PCAP;       // [PCAP] bytes: list slot of the neighbour staged at this place (sorted staging)
+    static constexpr int FCD = PERM + PCAP;      // [ncls][PCAP] (fc, fc') pairs
 };
-inline int hot_bytes(int pcap_t, int ncls) { return 48 * pcap_t + 24 * pcap_t + pcap_t + 16 * ncls * pcap_t; }
+inline int hot_bytes(int pcap_t, int ncls) { return 48 * pcap_t + 24 * pcap_t + 2 * pcap_t + 16 * ncls * pcap_t; }
 
 // control block in shared memory
 struct Ctl {
@@ -93,6 +94,7 @@ struct Ctl {
     int obq[MAXC_DEV + 1];      // batches of order slot o
     int obp[MAXC_DEV + 2];      // first batch of order slot o
     int TB, nkept;
+    int pc[MAXC_DEV + 1];       // neighbours that belong to class c (sorted staging: the places 0 .. pc[c]-1)
 };
 static_assert(sizeof(Ctl) <= 4 * 512, "Ctl does not fit its slot");
 
@@ -155,7 +157,7 @@ extern __shared__ __align__(16) unsigned char smem[];   // dynamic shared memory
 __device__ __forceinline__ double dist2_fma(double dx, double dy, double dz) { return fma(dz, dz, fma(dy, dy, dx * dx)); }
 
 template <int MODE, int PCAP, int CS>
-__device__ __forceinline__ void process_centre(const CentreArgs &a, const int i, const bool first) {
+__device__ __forceinline__ void process_centre(const CentreArgs &a, const int i, const bool first, unsigned long long *s_work) {
     constexpr bool FWD = MODE != MODE_BWD, BWD = MODE != MODE_FWD, FUSED = MODE >= MODE_FUSED, SE = MODE == MODE_FUSED_SE;
     // rank of this CTA among the CS CTAs that share centre i; lead = the one that writes the outputs
     const int crank = CS > 1 ? (int)cg::this_cluster().block_rank() : 0;
@@ -166,6 +168,16 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
 #define FCD2(c, s) (*(double2 *)(smem + H::FCD + ((c) * PCAP + (s)) * 16))
 #define FCV(c, s) (*(double *)(smem + H::FCD + ((c) * PCAP + (s)) * 16))
 #define NCB(s) (smem[H::NC + (s)])
+#define PERM(s) (smem[H::PERM + (s)])
+    // Tiers whose lists fit one neighbour per thread stage the neighbours ORDERED by the number of classes
+    // they belong to (descending; ties in list order): the neighbours of class c are then the places
+    // 0 .. pc[c]-1, and a pair (a < b) can only belong to the classes of b -- for two thirds of the pairs that
+    // is the widest class alone, one threshold test.  PERM maps a place back to the list slot the outputs
+    // (fpair) are indexed by.
+#ifndef GAPCU_SORTED
+#define GAPCU_SORTED 1
+#endif
+    constexpr bool SORTED = PCAP <= CT && GAPCU_SORTED;
     double *const s_acc = (double *)(smem + H::ACC);   // [3][PCAP]
     const PlanDev &pl = a.plan;
     const int ncls = pl.ncls, D = pl.D, nsf = pl.nsf;
@@ -208,7 +220,15 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
     const int *g_iplus = pl.itab + pl.o_grp_iplus, *g_iminus = pl.itab + pl.o_grp_iminus;
 
     // ---- 0: tables (centre independent: loaded once per persistent CTA) ----------------
+    __shared__ int s_nrad[MAXC_DEV], s_nf[MAXC_DEV];   // per class: radial functions, angular functions (work counters)
     if (first) {
+        if (tid < MAXC_DEV) {
+            int nr = 0, nf = 0;
+            for (int q = 0; q < pl.n_rad; q++) nr += pl.itab[pl.o_rad_cls + q] == tid;
+            if (tid < ncls)
+                for (int g = GRP_BEGIN(a, tid); g < GRP_BEGIN(a, tid + 1); g++) nf += (g_iplus[g] >= 0) + (g_iminus[g] >= 0);
+            s_nrad[tid] = nr; s_nf[tid] = nf;
+        }
         if (tid < 32) s_t32[tid] = a.exp2_table[tid];
         if (tid < MAXC_DEV) s_t2[tid] = tid < ncls ? a.cls.t2[tid] : -1.0;
         for (int t = tid; t < pl.n_grp; t += CT) s_galpha[t] = pl.dtab[pl.o_grp_alpha + t];
@@ -228,11 +248,9 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
     __syncthreads();
 
     const double xi = a.pos[i], yi = a.pos[ntot + i], zi = a.pos[2 * ntot + i];
-    unsigned long long wk_pc = 0, wk_rad = 0;
 
     // ---- 1: stage neighbours (a: geometry per neighbour, b: fc/fc' per (neighbour, class)) ----
-    for (int s = tid; s < P; s += CT) {
-        double ox, oy, oz, dis, wj;
+    auto neighbour_record = [&](int s, double &ox, double &oy, double &oz, double &dis, double &wj) {
         if (a.nbr_table) {
             // CAR2ACSF: image position, distance and weight as the caller tabulated them (wacsf.f90:80-84)
             const size_t NA = (size_t)ntot, ld = (size_t)a.table_ld;
@@ -245,58 +263,122 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             dis = image_distance(a.pos, ntot, j, s_lat, n1, n2, n3, xi, yi, zi, ox, oy, oz);
             wj = a.wgt[j];
         }
-        NB2(s, 0) = make_double2(ox, oy);
-        NB2(s, 1) = make_double2(oz, dis);
-        NB2(s, 2) = make_double2(1.0 / dis, wj);
         int nc = 0;
         while (nc < ncls && !(dis > a.cls.rc[nc])) nc++;  // reference: "if (rij.gt.cutoff) cycle"
-        NCB(s) = (unsigned char)nc;
-        if (lead) wk_pc += nc;
-    }
-    __syncthreads();
-    const int P32 = (P + 31) & ~31;
-    for (int t = tid; t < ncls * P32; t += CT) {
-        const int c = t / P32, s = t - c * P32;
-        if (s < P && c < NCB(s)) {
-            const double pirc = a.cls.pirc[c];
-            double sn, cs;
-            sincos_0pi(NB2(s, 1).y * pirc, &sn, &cs);
-            FCD2(c, s) = make_double2(0.5 * (cs + 1.0), -0.5 * pirc * sn);
+        return nc;
+    };
+    if constexpr (SORTED) {
+        // one neighbour per thread; counting sort by class count (descending), list order within a count
+        const int s = tid;
+        double ox = 0.0, oy = 0.0, oz = 0.0, dis = 1.0, wj = 0.0;
+        int nc = -1;
+        if (s < P) nc = neighbour_record(s, ox, oy, oz, dis, wj);
+        unsigned mym = 0;
+        int cntv = 0;
+        for (int v = 0; v <= ncls; v++) {
+            const unsigned m = __ballot_sync(0xffffffffu, nc == v);
+            if (lane == v) cntv = __popc(m);
+            if (nc == v) mym = m;
+        }
+        if (lane <= ncls) ctl->hw[wid][lane] = cntv;
+        __syncthreads();
+        // lane v: neighbours with count v staged by the warps before this one / by all warps
+        int before = 0, all = 0;
+        if (lane <= ncls)
+            for (int w = 0; w < NW; w++) { const int h = ctl->hw[w][lane]; before += w < wid ? h : 0; all += h; }
+        int ge = all;   // -> neighbours with count >= lane
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_down_sync(0xffffffffu, ge, d); if (lane + d < 32) ge += y; }
+        const int place = __shfl_sync(0xffffffffu, ge - all + before, nc < 0 ? 0 : nc) + __popc(mym & ltmask);
+        if (s < P) {
+            NB2(place, 0) = make_double2(ox, oy);
+            NB2(place, 1) = make_double2(oz, dis);
+            NB2(place, 2) = make_double2(1.0 / dis, wj);
+            NCB(place) = (unsigned char)nc;
+            PERM(place) = (unsigned char)s;
+        }
+        if (wid == 0 && lane <= ncls) ctl->pc[lane] = ge - all;   // count > lane: members of class `lane`
+    } else {
+        for (int s = tid; s < P; s += CT) {
+            double ox, oy, oz, dis, wj;
+            const int nc = neighbour_record(s, ox, oy, oz, dis, wj);
+            NB2(s, 0) = make_double2(ox, oy);
+            NB2(s, 1) = make_double2(oz, dis);
+            NB2(s, 2) = make_double2(1.0 / dis, wj);
+            NCB(s) = (unsigned char)nc;
         }
     }
     __syncthreads();
-    phase_end(0);
+    if constexpr (!SORTED) {
+        // members of every class (work counters; the sorted staging has them from its counting sort)
+        for (int c = wid; c < ncls; c += NW) {
+            int n = 0;
+            for (int s = lane; s < P; s += 32) n += NCB(s) > c;
+            n = __reduce_add_sync(0xffffffffu, n);
+            if (lane == 0) ctl->pc[c] = n;
+        }
+    }
+    const int P32 = (P + 31) & ~31;
+    // fc / fc' of every (class, member) pair; threads t0, t0 + tstep, ... of the caller's group
+    auto fc_tables = [&](int t0, int tstep) {
+        for (int t = t0; t < ncls * P32; t += tstep) {
+            const int c = t / P32, s = t - c * P32;
+            if (s < P && c < NCB(s)) {
+                const double pirc = a.cls.pirc[c];
+                double sn, cs;
+                sincos_0pi(NB2(s, 1).y * pirc, &sn, &cs);
+                FCD2(c, s) = make_double2(0.5 * (cs + 1.0), -0.5 * pirc * sn);
+            }
+        }
+    };
     // ---- 2: radial forward: one warp task per function, lanes over neighbours ----------
-    if (FWD) {
-        for (int q = wid + NW * crank; q < pl.n_rad; q += NW * CS) {   // the cluster's CTAs share the functions
-            const int2 ri = s_radi[q];
-            const int c = ri.y & 0xffff;
-            const double prm = s_radp[q];
-            const bool t1 = (ri.y >> 16) == 1;
-            double gu = 0.0, gwt = 0.0;
+    auto radial_forward = [&]() {
+        // two functions per warp and pass (independent exponential chains, one transposed reduction for the four sums)
+        for (int q = wid + NW * crank; q < pl.n_rad; q += 2 * NW * CS) {   // the cluster's CTAs share the functions
+            const int q2 = q + NW * CS;
+            const bool two = q2 < pl.n_rad;
+            const int2 ri = s_radi[q], rj = s_radi[two ? q2 : q];
+            const int c = ri.y & 0xffff, c2 = two ? (rj.y & 0xffff) : ncls;   // ncls: no neighbour belongs to it
+            const double prm = s_radp[q], prm2 = s_radp[two ? q2 : q];
+            const bool t1 = (ri.y >> 16) == 1, t2nd = (rj.y >> 16) == 1;
+            double gu = 0.0, gwt = 0.0, hu = 0.0, hwt = 0.0;
             for (int s = lane; s < P; s += 32) {
-                if (c < NCB(s)) {
-                    const double dis = NB2(s, 1).y;
+                const int nc = NCB(s);
+                const double dis = NB2(s, 1).y, wj = NB2(s, 2).y;
+                if (c < nc) {
                     const double d = t1 ? dis : dis - prm;
                     const double g = exp_neg((t1 ? -prm : -4.0) * d * d, s_t32) * FCV(c, s);
                     gu += g;
-                    gwt = fma(g, NB2(s, 2).y, gwt);
-                    wk_rad++;
+                    gwt = fma(g, wj, gwt);
+                }
+                if (c2 < nc) {
+                    const double d = t2nd ? dis : dis - prm2;
+                    const double g = exp_neg((t2nd ? -prm2 : -4.0) * d * d, s_t32) * FCV(c2, s);
+                    hu += g;
+                    hwt = fma(g, wj, hwt);
                 }
             }
-            gu = warp_sum(gu); gwt = warp_sum(gwt);
-            if (lane == 0) { s_gw[wid * D + ri.x] += gu; s_gw[wid * D + ri.x + nsf] += gwt; }
+            const double tot = warp_sum4(gu, gwt, hu, hwt, lane);   // lanes 0, 8, 16, 24 hold the four sums
+            if ((lane & 7) == 0) {
+                const int which = lane >> 3;
+                if (which < 2) s_gw[wid * D + ri.x + (which ? nsf : 0)] += tot;
+                else if (two) s_gw[wid * D + rj.x + ((which & 1) ? nsf : 0)] += tot;
+            }
         }
-    }
-    __syncthreads();
-    if (FWD && lead && tid < ncls && GRP_BEGIN(a, tid + 1) > GRP_BEGIN(a, tid)) {
-        // sum_c Q_c of SURVEY.md 8(d): candidate pairs of every angular cutoff class
-        unsigned long long pc = 0;
-        for (int s = 0; s < P; s++) pc += (NCB(s) > tid);
-        atomicAdd(&a.flags->work[8], pc * (pc - 1) / 2);
-    }
+    };
+    // work counters of this centre: pairs per class, radial evaluations, candidate pairs
+    // of the angular classes -- all functions of the classes' member counts.  One warp.
+    auto count_centre = [&]() {
+        const int pcv = lane < ncls ? ctl->pc[lane] : 0;
+        const unsigned npc = __reduce_add_sync(0xffffffffu, (unsigned)pcv);
+        const unsigned nrd = __reduce_add_sync(0xffffffffu, (unsigned)(lane < ncls ? pcv * s_nrad[lane] : 0));
+        const unsigned ncq = __reduce_add_sync(0xffffffffu, (unsigned)((lane < ncls && s_nf[lane]) ? pcv * (pcv - 1) / 2 : 0));
+        if (lane == 0) {
+            s_work[0] += 1; s_work[1] += P; s_work[2] += npc; s_work[3] += (unsigned)(P * (P - 1) / 2);
+            s_work[7] += nrd; s_work[8] += ncq;
+        }
+    };
 
-    phase_end(1);
     // ---- 3: triplet list builder (phase A + deterministic counting sort) ----------
     const uint32_t angmask = a.cls.angmask;
     // pair range of this CTA: the whole triangle, or one of CS contiguous parts of it
@@ -309,12 +391,14 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
     const int Q = Qhi - Qlo;
     const int nchunk = (angmask && Q > 0) ? (Q + lcap - 1) / lcap : 0;
     const int qchunk = nchunk ? ((Q + nchunk - 1) / nchunk + 31) & ~31 : 0;
-    unsigned long long wk_trip = 0, wk_tc = 0, wk_tsf = 0;
     // parked exponentials: one double2 per kept pair, chunk after chunk of this centre's list
     constexpr bool se = SE;
     double2 *est = SE ? a.estash + (size_t)blockIdx.x * a.estash_stride : nullptr;
 
-    auto build_list = [&](int q0, int q1, bool count_work) {
+    // Part 1 (all warps): every pair of the flat triangular range [q0, q1) is tested once; survivors go to this
+    // warp's part of the scratch list with their bucket (= number of classes they belong to), the warp's
+    // bucket counts to ctl->hw.  Returns the warp's number of survivors.
+    auto list_pairs = [&](int q0, int q1) {
         const int n = q1 - q0;
         const int R = (((n + NW - 1) / NW) + 31) & ~31;  // per-warp contiguous sub-range
         const int wq0 = q0 + wid * R, wq1 = min(q1, wq0 + R);
@@ -329,28 +413,24 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         int ra = 0, rb = 1;
         if (wq0 + lane < wq1) tri_decode(wq0 + lane, ra, rb);
         for (int qb = wq0; qb < wq1; qb += 32) {
-            int bk = 0;
+            int bk = 0, lim = 0;
+            double rjk2 = 0.0;
             if (qb + lane < wq1) {
-                const int lim = min((int)NCB(ra), (int)NCB(rb));
+                // sorted staging: the place rb > ra belongs to no more classes than ra
+                lim = SORTED ? (int)NCB(rb) : min((int)NCB(ra), (int)NCB(rb));
                 const double2 axy = NB2(ra, 0), bxy = NB2(rb, 0);
                 const double az = NB2(ra, 1).x, bz = NB2(rb, 1).x;
-                const double rjk2 = pair_dist2(axy.x, axy.y, az, bxy.x, bxy.y, bz);
-                // thresholds descend: the classes with rjk2 <= t2[c] are a prefix.  Up to 8 classes:
-                // independent compares against constant-bank operands (no loads, no dependent
-                // chain); more: bisection over the shared-memory copy.
-                int lo = 0;
-                if (packed) {
-#pragma unroll
-                    for (int c = 0; c < 8; c++) lo += (rjk2 <= a.cls.t2[c]);   // absent classes hold -1
-                } else {
-#pragma unroll
-                    for (int step = MAXC_DEV / 2; step; step >>= 1)
-                        if (rjk2 <= s_t2[lo + step - 1]) lo += step;
-                    if (lo == MAXC_DEV - 1 && rjk2 <= s_t2[MAXC_DEV - 1]) lo = MAXC_DEV;
-                }
-                bk = min(lo, lim);
-                if (!((angmask >> bk) & 1u)) bk = 0;
+                rjk2 = pair_dist2(axy.x, axy.y, az, bxy.x, bxy.y, bz);
             }
+            // thresholds descend: the classes with rjk2 <= t2[c] are a prefix, and only the first `lim` of them
+            // matter.  A trip covers one or two rows rb, whose lim the sorted staging makes (nearly) equal and
+            // mostly 1: test as many thresholds as the trip's largest lim asks for
+            const int limmax = __reduce_max_sync(0xffffffffu, lim);
+            int lo = rjk2 <= a.cls.t2[0];
+#pragma unroll 1
+            for (int c = 1; c < limmax; c++) lo += rjk2 <= s_t2[c];
+            bk = min(lo, lim);
+            if (!((angmask >> bk) & 1u)) bk = 0;
             const unsigned m = __ballot_sync(0xffffffffu, bk > 0);
             if (bk > 0) seg[cnt + __popc(m & ltmask)] = (uint32_t)ra | ((uint32_t)rb << 10) | ((uint32_t)bk << 20);
             cnt += __popc(m);
@@ -378,44 +458,43 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             if (lane == 8) ctl->hw[wid][0] = 0;
         }
         if (lane == 0) ctl->cntw[wid] = cnt;
-        __syncthreads();
-        if (wid == 0) {
-            // lane o <-> bucket v = ncls - o (heavy buckets first); totals over warps, then an
-            // exclusive scan over the lanes gives every bucket its place in S
-            const int o = lane, v = ncls - lane;
-            int t = 0;
-            if (o < ncls)
-                for (int w = 0; w < NW; w++) { const int h = ctl->hw[w][v]; ctl->basew[w][v] = t; t += h; }
-            const int nb = (t + 31) >> 5;
-            int off = t, bp = nb;
+        return cnt;
+    };
+    // Part 2 (ONE warp, after a block barrier): places of the (warp, bucket) runs in the sorted list S
+    auto list_scan = [&](bool count_work) {
+        // lane o <-> bucket v = ncls - o (heavy buckets first); totals over warps, then an
+        // exclusive scan over the lanes gives every bucket its place in S
+        const int o = lane, v = ncls - lane;
+        int t = 0;
+        if (o < ncls)
+            for (int w = 0; w < NW; w++) { const int h = ctl->hw[w][v]; ctl->basew[w][v] = t; t += h; }
+        const int nb = (t + 31) >> 5;
+        int off = t, bp = nb;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int yo = __shfl_up_sync(0xffffffffu, off, d), yb = __shfl_up_sync(0xffffffffu, bp, d);
-                if (lane >= d) { off += yo; bp += yb; }
-            }
-            // off/bp are inclusive sums over order slots 0..o
-            if (o < ncls) {
-                ctl->tot[v] = t;
-                ctl->obase[o] = off - t; ctl->ocnt[o] = t; ctl->obq[o] = nb; ctl->obp[o] = bp - nb;
-                for (int w = 0; w < NW; w++) ctl->basew[w][v] += off - t;
-                ctl->npre[v - 1] = off;   // items with bucket > v-1, i.e. bucket >= v: slots 0..o
-            }
-            if (o == ncls - 1 || (ncls == 0 && o == 0)) { ctl->obp[ncls] = bp; ctl->TB = bp; ctl->nkept = off; }
-            __syncwarp();
-            if (count_work && lane == 0) {
-                wk_trip += ctl->nkept;
-                for (int c = 0; c < ncls; c++) {
-                    const int g0 = GRP_BEGIN(a, c), g1 = GRP_BEGIN(a, c + 1);
-                    if (g1 > g0) {
-                        int nf = 0;
-                        for (int g = g0; g < g1; g++) nf += (g_iplus[g] >= 0) + (g_iminus[g] >= 0);
-                        wk_tc += ctl->npre[c];
-                        wk_tsf += (unsigned long long)ctl->npre[c] * nf;
-                    }
-                }
-            }
+        for (int d = 1; d < 32; d <<= 1) {
+            const int yo = __shfl_up_sync(0xffffffffu, off, d), yb = __shfl_up_sync(0xffffffffu, bp, d);
+            if (lane >= d) { off += yo; bp += yb; }
         }
-        __syncthreads();
+        // off/bp are inclusive sums over order slots 0..o
+        if (o < ncls) {
+            ctl->tot[v] = t;
+            ctl->obase[o] = off - t; ctl->ocnt[o] = t; ctl->obq[o] = nb; ctl->obp[o] = bp - nb;
+            for (int w = 0; w < NW; w++) ctl->basew[w][v] += off - t;
+            ctl->npre[v - 1] = off;   // items with bucket > v-1, i.e. bucket >= v: slots 0..o
+        }
+        if (o == ncls - 1 || (ncls == 0 && o == 0)) { ctl->obp[ncls] = bp; ctl->TB = bp; ctl->nkept = off; }
+        __syncwarp();
+        if (count_work) {
+            const int tcv = (lane < ncls && s_nf[lane]) ? ctl->npre[lane] : 0;
+            const unsigned tc = __reduce_add_sync(0xffffffffu, (unsigned)tcv);
+            const unsigned tsf = __reduce_add_sync(0xffffffffu, (unsigned)(tcv * (lane < ncls ? s_nf[lane] : 0)));
+            if (lane == 0) { s_work[4] += (unsigned)ctl->nkept; s_work[5] += tc; s_work[6] += tsf; }
+        }
+    };
+    // Part 3 (all warps, after a block barrier): the warp's survivors move to their bucket's run in S
+    auto list_scatter = [&](int q0, int q1, int cnt) {
+        const int R = (((q1 - q0 + NW - 1) / NW) + 31) & ~31;
+        const uint32_t *seg = s_U + wid * R;
         for (int t0 = 0; t0 < cnt; t0 += 32) {
             const int t = t0 + lane;
             const bool act = t < cnt;
@@ -432,6 +511,14 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             }
             __syncwarp();
         }
+    };
+    // the three parts in sequence (list re-builds of the backward pass and of further chunks)
+    auto build_list = [&](int q0, int q1, bool count_work) {
+        const int cnt = list_pairs(q0, q1);
+        __syncthreads();
+        if (wid == 0) list_scan(count_work);
+        __syncthreads();
+        list_scatter(q0, q1, cnt);
         __syncthreads();
     };
 
@@ -577,12 +664,21 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             for (int t = lane; t < 3 * PCAP; t += 32) pa[t] = 0.0;
             __syncwarp();
         }
-        const int TB = ctl->TB;
-        int o = 0;
-        // batches are ordered heavy bucket first; deal them 0..NW-1, NW-1..0, 0..NW-1, ... so that
-        // every warp gets a similar mix (fixed assignment: keeps the summation order reproducible)
-        for (int round = 0; round * NW < TB; round++) {
-            const int g = round * NW + ((round & 1) ? NW - 1 - wid : wid);
+        // Batches of 32 triplets of one bucket (uniform class loop), heavy buckets first; batch number
+        // obp[o] + q goes to warp (obp[o] + q) mod NW: a fixed round robin over all buckets, so every warp
+        // gets its share of the expensive batches and the summation order is reproducible.  Everything
+        // that depends on the bucket only is fetched once per bucket.
+        // g2: every angular class carries the same two exponents (the shipped table) -- the exponentials of
+        // a triplet are then evaluated (or fetched, MODE_FUSED_SE) once, not once per class, and the sum over
+        // the groups is straight-line code.
+        const bool g2 = a.share_exp == 2;
+        const double al0 = s_galpha[GRP_BEGIN(a, a.c_first)], al1 = s_galpha[GRP_BEGIN(a, a.c_first) + (g2 ? 1 : 0)];
+        for (int o = 0; o < ncls; o++) {
+            const int v = ncls - o, Qb = ctl->obq[o], n = ctl->ocnt[o], base = ctl->obase[o];
+            if (n == 0) continue;
+            const int rot = (wid - ctl->obp[o]) & (NW - 1);
+            for (int qr = 0; qr < Qb; qr += NW) {
+            const int q = qr + rot;
             // shared accumulator set (very long lists, no room for private sets): the warps of a round add
             // their batches one after the other in warp order, so block barriers sit inside this loop and
             // every warp has to reach them -- a warp without a batch only skips the arithmetic
@@ -590,15 +686,13 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             unsigned am = 0;
             int ra = 0, rb = 0;
             double v0 = 0, v1 = 0, v2 = 0, w0 = 0, w1 = 0, w2 = 0;
-            if (g < TB) {
+            if (q < Qb) {
             __syncwarp();   // orders this batch's accumulator reads after the previous batch's writes for lanes that sat that one out
-            while (o + 1 < ncls && g >= ctl->obp[o + 1]) o++;
-            const int v = ncls - o, q = g - ctl->obp[o], Qb = ctl->obq[o], n = ctl->ocnt[o];
             const int idx = lane * Qb + q;  // lanes far apart in the list -> mostly distinct rows
             act = idx < n;
             am = __ballot_sync(0xffffffffu, act);
             if (act) {
-            const int li = ctl->obase[o] + idx;
+            const int li = base + idx;
             const uint32_t it = s_S[li];
             double2 pk = make_double2(0.0, 0.0);
             if (se) pk = __ldcg(est + li);      // requested before the geometry below needs it
@@ -615,7 +709,33 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             const double ww = aiw.y * biw.y;
             const double u1 = irb - cosv * ira, u2 = ira - cosv * irb, u3 = -rjk * ira * irb;
             double cij = 0.0, cik = 0.0, cjk = 0.0;
+            if (g2) {
+                const double e0 = se ? pk.x : exp_neg(-al0 * ssum, s_t32), e1 = se ? pk.y : exp_neg(-al1 * ssum, s_t32);
+                const double e0w = e0 * ww, e1w = e1 * ww;
 #pragma unroll 2
+                for (int c = 0; c < v; c++) {
+                    const int g0 = GRP_BEGIN(a, c);
+                    if (g0 == GRP_BEGIN(a, c + 1)) continue;
+                    const double pirc = a.cls.pirc[c];
+                    double sn, cs;
+                    sincos_0pi(rjk * pirc, &sn, &cs);
+                    const double fjk = 0.5 * (cs + 1.0), dfjk = -0.5 * pirc * sn;
+                    const double2 fda = FCD2(c, ra), fdb = FCD2(c, rb);
+                    const double fa = fda.x, fb = fdb.x, dfa = fda.y, dfb = fdb.y;
+                    const double fab = fa * fb, phi = fab * fjk;
+                    const double4 gd0 = *(const double4 *)(s_gd + 4 * g0), gd1 = *(const double4 *)(s_gd + 4 * g0 + 4);   // DU, DW, DUL, DWL
+                    const double t00 = fma(e0w, gd0.y, e0 * gd0.x), t01 = fma(e0w, gd0.w, e0 * gd0.z);
+                    const double t10 = fma(e1w, gd1.y, e1 * gd1.x), t11 = fma(e1w, gd1.w, e1 * gd1.z);
+                    const double T0 = t00 + t10, S1 = t01 + t11;
+                    const double S3 = fma(al0, fma(cosv, t01, t00), al1 * fma(cosv, t11, t10));
+                    const double S2 = fma(cosv, S1, T0);
+                    const double pS1 = phi * S1, pS3 = 2.0 * phi * S3;
+                    cij += pS1 * u1 - pS3 * rja + S2 * (dfa * fb * fjk);
+                    cik += pS1 * u2 - pS3 * rkb + S2 * (fa * dfb * fjk);
+                    cjk += pS1 * u3 - pS3 * rjk + S2 * (fab * dfjk);
+                }
+            } else {
+#pragma unroll 1
             for (int c = 0; c < v; c++) {
                 const int g0 = GRP_BEGIN(a, c), g1 = GRP_BEGIN(a, c + 1);
                 if (g0 == g1) continue;
@@ -631,14 +751,14 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 // two groups per trip: their exponentials are independent chains (ILP; measured -7 %)
                 int gg = g0;
                 for (; gg + 1 < g1; gg += 2) {
-                    const double al0 = s_galpha[gg], al1 = s_galpha[gg + 1];
-                    const double e0 = se ? pk.x : exp_neg(-al0 * ssum, s_t32), e1 = se ? pk.y : exp_neg(-al1 * ssum, s_t32);
+                    const double bl0 = s_galpha[gg], bl1 = s_galpha[gg + 1];
+                    const double e0 = se ? pk.x : exp_neg(-bl0 * ssum, s_t32), e1 = se ? pk.y : exp_neg(-bl1 * ssum, s_t32);
                     const double4 gd0 = *(const double4 *)(s_gd + 4 * gg), gd1 = *(const double4 *)(s_gd + 4 * gg + 4);
                     const double t00 = e0 * fma(ww, gd0.y, gd0.x), t01 = e0 * fma(ww, gd0.w, gd0.z);
                     const double t10 = e1 * fma(ww, gd1.y, gd1.x), t11 = e1 * fma(ww, gd1.w, gd1.z);
                     T0 += t00 + t10;
                     S1 += t01 + t11;
-                    S3 = fma(al0, fma(cosv, t01, t00), fma(al1, fma(cosv, t11, t10), S3));
+                    S3 = fma(bl0, fma(cosv, t01, t00), fma(bl1, fma(cosv, t11, t10), S3));
                 }
                 if (gg < g1) {
                     const double al = s_galpha[gg];
@@ -654,6 +774,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 cij += pS1 * u1 - pS3 * rja + S2 * (dfa * fb * fjk);
                 cik += pS1 * u2 - pS3 * rkb + S2 * (fa * dfb * fjk);
                 cjk += pS1 * u3 - pS3 * rjk + S2 * (fab * dfjk);
+            }
             }
             // dE/dx_j = (gij+gjk) d_j - gjk d_k ; dE/dx_k = (gik+gjk) d_k - gjk d_j
             const double gij = cij * ira, gik = cik * irb, gjk = cjk * irjk;
@@ -677,8 +798,10 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                     __syncthreads();
                 }
             }
+            }
         }
         __syncthreads();
+        phase_end(14);
         if (priv) {
             for (int t = tid; t < 3 * PCAP; t += CT) {
                 double v = 0.0;
@@ -692,17 +815,54 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
 
     // ---- drive the phases ---------------------------------------------------------------
     bool list_ready = false, list_stashed = false;
+    if (!FWD || nchunk == 0) {
+        fc_tables(tid, CT);
+        __syncthreads();
+    }
+    phase_end(0);
     if (FWD) {
         const bool stash = FUSED && nchunk > 1 && a.list_scratch && nchunk <= a.list_scratch_chunks;
         int trip_base = 0;
+        if (nchunk == 0) {
+            radial_forward();
+            if (lead && wid == 0) count_centre();
+            __syncthreads();
+        }
+        phase_end(1);
         for (int ch = 0; ch < nchunk; ch++) {
             if (SE) est = a.estash + (size_t)blockIdx.x * a.estash_stride + (size_t)ch * (lcap + 32);
-            build_list(Qlo + ch * qchunk, min(Qhi, Qlo + (ch + 1) * qchunk), true);
+            const int q0 = Qlo + ch * qchunk, q1 = min(Qhi, Qlo + (ch + 1) * qchunk);
+            // The pair tests need the staged records only.  While ONE warp then places the buckets (a short
+            // serial step), the other seven fill the fc tables; the list scatter and the radial functions
+            // (which need those tables) share the next slot: two block barriers and a serial section less
+            // than stage -> tables -> radial -> list.
+            const int cnt = list_pairs(q0, q1);
+            __syncthreads();
+            phase_end(8);
+            if (wid == 0) {
+                list_scan(true);
+                if (ch == 0 && lead) count_centre();
+            } else if (ch == 0) {
+                fc_tables(tid - 32, CT - 32);
+            }
+            __syncthreads();
+            phase_end(9);
+            list_scatter(q0, q1, cnt);
+            if (ch == 0) radial_forward();
+            __syncthreads();
+            phase_end(10);
             if (a.trip_out) {
                 // debug export (gapcu_ctx_debug_triplets): the kept pairs exactly as the passes below consume them
                 const int n = ctl->nkept;
                 for (int t = tid; t < n; t += CT)
-                    if (trip_base + t < a.trip_cap) a.trip_out[(size_t)i * a.trip_cap + trip_base + t] = s_S[t];
+                    if (trip_base + t < a.trip_cap) {
+                        uint32_t it = s_S[t];
+                        if constexpr (SORTED) {   // places -> list slots, smaller slot first
+                            const uint32_t sa = PERM(it & 1023), sb = PERM((it >> 10) & 1023);
+                            it = min(sa, sb) | (max(sa, sb) << 10) | (it & ~0xfffffu);
+                        }
+                        a.trip_out[(size_t)i * a.trip_cap + trip_base + t] = it;
+                    }
                 trip_base += n;
             }
             phase_end(2);
@@ -746,25 +906,11 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 if (lead && a.G) a.G[(size_t)i * D + k] = v;
             }
         }
-        // work counters
-        unsigned long long v0 = wk_pc, v1 = wk_rad;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); }
-        if (lane == 0) { atomicAdd(&a.flags->work[2], v0); atomicAdd(&a.flags->work[7], v1); }
-        if (tid == 0) {
-            if (lead) {
-                atomicAdd(&a.flags->work[0], 1ull);
-                atomicAdd(&a.flags->work[1], (unsigned long long)P);
-                atomicAdd(&a.flags->work[3], (unsigned long long)Qall);
-            }
-            atomicAdd(&a.flags->work[4], wk_trip);
-            atomicAdd(&a.flags->work[5], wk_tc);
-            atomicAdd(&a.flags->work[6], wk_tsf);
-        }
     }
     if (FUSED) {
         // ---- 5: sparse GPR of this atom (gap_calc.f90:143-166), difference form ----------
         __syncthreads();
+        phase_end(11);
         const int M = a.gpr_M, Mp = a.gpr_Mp, Dp = a.gpr_Dp;
         for (int k = tid; k < D; k += CT) s_xs[k] = (s_G[k] - a.gpr_cmean[k]) * a.gpr_itheta[k];
         __syncthreads();
@@ -780,13 +926,15 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
                 const double *col = a.gpr_MtT + (size_t)k0 * Mp + j;
                 int k = k0;
-                for (; k + 7 < k1; k += 8, col += 8 * (size_t)Mp) {   // eight loads in flight: this loop waits on L2, not on arithmetic
-                    const double m0 = __ldg(col), m1 = __ldg(col + Mp), m2 = __ldg(col + 2 * (size_t)Mp), m3 = __ldg(col + 3 * (size_t)Mp);
-                    const double m4 = __ldg(col + 4 * (size_t)Mp), m5 = __ldg(col + 5 * (size_t)Mp), m6 = __ldg(col + 6 * (size_t)Mp), m7 = __ldg(col + 7 * (size_t)Mp);
-                    const double d0 = s_xs[k] - m0, d1 = s_xs[k + 1] - m1, d2 = s_xs[k + 2] - m2, d3 = s_xs[k + 3] - m3;
-                    const double d4 = s_xs[k + 4] - m4, d5 = s_xs[k + 5] - m5, d6 = s_xs[k + 6] - m6, d7 = s_xs[k + 7] - m7;
-                    s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
-                    s0 = fma(d4, d4, s0); s1 = fma(d5, d5, s1); s2 = fma(d6, d6, s2); s3 = fma(d7, d7, s3);
+                for (; k + 15 < k1; k += 16, col += 16 * (size_t)Mp) {   // sixteen loads in flight: this loop waits on L2, not on arithmetic
+                    double m[16];
+#pragma unroll
+                    for (int u = 0; u < 16; u++) m[u] = __ldg(col + u * (size_t)Mp);
+#pragma unroll
+                    for (int u = 0; u < 16; u += 4) {
+                        const double d0 = s_xs[k + u] - m[u], d1 = s_xs[k + u + 1] - m[u + 1], d2 = s_xs[k + u + 2] - m[u + 2], d3 = s_xs[k + u + 3] - m[u + 3];
+                        s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
+                    }
                 }
                 for (; k + 3 < k1; k += 4, col += 4 * (size_t)Mp) {   // four independent chains, loads issued together
                     const double m0 = __ldg(col), m1 = __ldg(col + Mp), m2 = __ldg(col + 2 * (size_t)Mp), m3 = __ldg(col + 3 * (size_t)Mp);
@@ -798,6 +946,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             }
         }
         __syncthreads();
+        phase_end(12);
         double esum = 0.0;
         for (int j = tid; j < Mp; j += CT) {
             double sacc = 0.0;
@@ -825,13 +974,15 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
                 const double *rp = a.gpr_Mt + k + (size_t)j0 * Dp;
                 int j = j0;
-                for (; j + 7 < j1; j += 8, rp += 8 * (size_t)Dp) {
-                    const double m0 = __ldg(rp), m1 = __ldg(rp + Dp), m2 = __ldg(rp + 2 * (size_t)Dp), m3 = __ldg(rp + 3 * (size_t)Dp);
-                    const double m4 = __ldg(rp + 4 * (size_t)Dp), m5 = __ldg(rp + 5 * (size_t)Dp), m6 = __ldg(rp + 6 * (size_t)Dp), m7 = __ldg(rp + 7 * (size_t)Dp);
-                    a0 = fma(s_W[j], xk - m0, a0); a1 = fma(s_W[j + 1], xk - m1, a1);
-                    a2 = fma(s_W[j + 2], xk - m2, a2); a3 = fma(s_W[j + 3], xk - m3, a3);
-                    a0 = fma(s_W[j + 4], xk - m4, a0); a1 = fma(s_W[j + 5], xk - m5, a1);
-                    a2 = fma(s_W[j + 6], xk - m6, a2); a3 = fma(s_W[j + 7], xk - m7, a3);
+                for (; j + 15 < j1; j += 16, rp += 16 * (size_t)Dp) {
+                    double m[16];
+#pragma unroll
+                    for (int u = 0; u < 16; u++) m[u] = __ldg(rp + u * (size_t)Dp);
+#pragma unroll
+                    for (int u = 0; u < 16; u += 4) {
+                        a0 = fma(s_W[j + u], xk - m[u], a0); a1 = fma(s_W[j + u + 1], xk - m[u + 1], a1);
+                        a2 = fma(s_W[j + u + 2], xk - m[u + 2], a2); a3 = fma(s_W[j + u + 3], xk - m[u + 3], a3);
+                    }
                 }
                 for (; j + 3 < j1; j += 4, rp += 4 * (size_t)Dp) {
                     const double m0 = __ldg(rp), m1 = __ldg(rp + Dp), m2 = __ldg(rp + 2 * (size_t)Dp), m3 = __ldg(rp + 3 * (size_t)Dp);
@@ -939,7 +1090,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                     gx += ra[s]; gy += ra[PCAP + s]; gz += ra[2 * PCAP + s];
                 }
             }
-            double *fp = a.fpair + ((size_t)i * a.cap + s) * 3;
+            double *fp = a.fpair + ((size_t)i * a.cap + (SORTED ? (int)PERM(s) : s)) * 3;
             fp[0] = gx; fp[1] = gy; fp[2] = gz;
             acc9[0] -= gx; acc9[1] -= gy; acc9[2] -= gz;
             acc9[3] += dx * gx; acc9[4] += dx * gy; acc9[5] += dx * gz;
@@ -963,6 +1114,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
 #undef FCD2
 #undef FCV
 #undef NCB
+#undef PERM
 }
 
 // Persistent CTAs: as many as fit the device, each pulling centre atoms from a queue
@@ -971,6 +1123,10 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
 template <int MODE, int PCAP, int CS>
 __global__ void __launch_bounds__(CT, 3) k_centre(const CentreArgs a) {
     __shared__ int s_next;
+    // work counters (gapcu_ctx_work_counters) are summed per CTA and flushed once: 29 global atomics per
+    // centre on ten addresses were a serial point of their own
+    __shared__ unsigned long long s_work[10];
+    if (threadIdx.x < 10) s_work[threadIdx.x] = 0;
     bool first = true;
     unsigned long long t0 = 0;
     if (threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
@@ -995,9 +1151,11 @@ __global__ void __launch_bounds__(CT, 3) k_centre(const CentreArgs a) {
         }
         const int n = s_next;
         if (n >= q_end) break;
-        process_centre<MODE, PCAP, CS>(a, a.order ? a.order[n] : n, first);
+        process_centre<MODE, PCAP, CS>(a, a.order ? a.order[n] : n, first, s_work);
         first = false;
     }
+    __syncthreads();
+    if (threadIdx.x < 10 && s_work[threadIdx.x]) atomicAdd(&a.flags->work[threadIdx.x], s_work[threadIdx.x]);
     if (threadIdx.x == 0) {
         unsigned long long t1;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));

@@ -696,7 +696,7 @@ static int make_centre_args(gapcu_ctx *c, int lgrad, int pcap, CentreArgs *out, 
             for (int g = 0; g < ng0 && same; g++) same = pl.grp_alpha[g0 + g] == pl.grp_alpha[pl.grp_begin[first] + g];
         }
         static const bool off = getenv("GAPCU_NO_SHARE_EXP") != nullptr;   // A/B switch
-        a.share_exp = (first >= 0 && same && !off) ? 1 : 0;
+        a.share_exp = (first >= 0 && same && !off) ? ng0 : 0;   // 1 or 2: the number of shared exponents
         a.c_first = first < 0 ? 0 : first;
     }
     // The in-CTA GPR re-reads the sparse set once per atom: worth it while that set is
@@ -1157,7 +1157,7 @@ extern "C" int gapcu_ctx_work_counters(gapcu_ctx *c, double *out, int n) {
     int rc = read_flags(c);
     if (rc) return rc;
     for (int q = 0; q < n && q < 10; q++) out[q] = (double)c->h_flags.work[q];
-    for (int q = 10; q < n && q < 18; q++) out[q] = (double)c->h_flags.phase_cycles[q - 10];   // GAPCU_VARIANT & 16
+    for (int q = 10; q < n && q < 26; q++) out[q] = (double)c->h_flags.phase_cycles[q - 10];   // GAPCU_VARIANT & 16
     return 0;
 }
 

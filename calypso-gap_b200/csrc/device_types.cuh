@@ -73,7 +73,7 @@ struct DevFlags {
     int blk_overflow;    // a block of cells has more candidates than k_neigh_block holds: use k_neigh
     // GAPCU_VARIANT & 16: cycles thread 0 of every centre CTA spent per phase of the centre kernel
     // (0 stage, 1 radial fwd, 2 list build, 3 angular fwd, 4 reduce + GPR, 5 radial bwd, 6 angular bwd, 7 epilogue)
-    unsigned long long phase_cycles[8];
+    unsigned long long phase_cycles[16];   // 8..15: sub-phases (8 pair tests, 9 bucket scan, 10 list scatter, 11 descriptor sums, 12 GPR distances, 13 GPR gradient, 14 backward batches, 15 accumulator merge); their parents hold the rest
 };
 
 constexpr int MAXC_DEV = 16;  // distinct cutoffs (classes) supported
@@ -150,7 +150,7 @@ struct CentreArgs {
     // MODE_FUSED_SE: parked exponentials, [persistent CTAs][estash_stride] double2 (L2 resident)
     double2 *estash;
     int estash_stride;
-    int share_exp;              // every angular class carries the same one or two alphas
+    int share_exp;              // 1 or 2: every angular class carries the same one / two alphas; 0: not so
     int c_first;                // first class with angular functions
     // debug export of the kept neighbour pairs (triplets i-j-k) per centre: items = slot_j | slot_k << 10 | nclasses << 20
     uint32_t *trip_out;         // [ntot][trip_cap] or null

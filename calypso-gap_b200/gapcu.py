@@ -251,12 +251,13 @@ class Context:
         return ms.value, {n: v for n, v in zip(names, st) if n}, launches.value
 
     def work_counters(self):
-        out = np.zeros(18)
-        _check(lib().gapcu_ctx_work_counters(self.h, out, 18))
+        out = np.zeros(26)
+        _check(lib().gapcu_ctx_work_counters(self.h, out, 26))
         keys = ["atoms", "pairs", "pair_classes", "candidates", "triplets", "triplet_classes", "triplet_sf", "radial_sf", "class_candidates"]
         d = dict(zip(keys, out))
         if out[10:].any():      # GAPCU_VARIANT=16: cycles per phase of the centre kernel (thread 0 of every CTA)
-            d["phase_cycles"] = dict(zip(["stage", "radial_fwd", "list_build", "angular_fwd", "reduce_gpr", "radial_bwd", "angular_bwd", "epilogue"], out[10:]))
+            d["phase_cycles"] = dict(zip(["stage", "radial_fwd", "list_build", "angular_fwd", "reduce_gpr", "radial_bwd", "angular_bwd", "epilogue",
+                                         "list_pairs", "list_scan", "list_scatter", "desc_sums", "gpr_dist", "gpr_grad", "bwd_batches", "bwd_merge"], out[10:]))
         return d
 
     def balance(self):
