@@ -221,7 +221,9 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
 
     // ---- 0: tables (centre independent: loaded once per persistent CTA) ----------------
     __shared__ int s_nrad[MAXC_DEV], s_nf[MAXC_DEV];   // per class: radial functions, angular functions (work counters)
+    __shared__ SinCosEntry s_trig[SINCOS_TAB_N];       // (cos, sin)(k/16) for sincos_tab
     if (first) {
+        if (tid < 2 * SINCOS_TAB_N) ((double *)s_trig)[tid] = a.exp2_table[32 + tid];
         if (tid < MAXC_DEV) {
             int nr = 0, nf = 0;
             for (int q = 0; q < pl.n_rad; q++) nr += pl.itab[pl.o_rad_cls + q] == tid;
@@ -244,7 +246,9 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
     if (FWD) for (int t = tid; t < NW * D; t += CT) s_gw[t] = 0.0;
     if (MODE == MODE_BWD) for (int t = tid; t < D; t += CT) s_du[t] = a.dEdG[(size_t)i * D + t];
     __shared__ double s_lat[9];
+    __shared__ double s_ctr[3];   // the centre's position: read where needed, not carried in registers through the hot loops
     if (tid < 9) s_lat[tid] = sd.lat[tid];
+    if (tid < 3) s_ctr[tid] = a.pos[tid * ntot + i];
     __syncthreads();
 
     const double xi = a.pos[i], yi = a.pos[ntot + i], zi = a.pos[2 * ntot + i];
@@ -326,7 +330,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             if (s < P && c < NCB(s)) {
                 const double pirc = a.cls.pirc[c];
                 double sn, cs;
-                sincos_0pi(NB2(s, 1).y * pirc, &sn, &cs);
+                sincos_tab(NB2(s, 1).y * pirc, s_trig, &sn, &cs);
                 FCD2(c, s) = make_double2(0.5 * (cs + 1.0), -0.5 * pirc * sn);
             }
         }
@@ -546,9 +550,9 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 x.cosv = (ra2 + rb2 - rjk2) * 0.5 * aiw.x * biw.x;
                 x.ssum = ra2 + rb2 + rjk2;
                 x.ww = aiw.y * biw.y;
-                const double rjk = rjk2 * rsqrt_pos(fmax(rjk2, 1e-300));
+                const double rjk = rjk2 * rsqrt_pos(rjk2);   // two neighbours never coincide (the backward pass divides by rjk as the reference does)
                 double sn, cs;
-                sincos_0pi(rjk * pirc, &sn, &cs);
+                sincos_tab(rjk * pirc, s_trig, &sn, &cs);
                 x.phi = *(const double *)(fcc + ra * 16) * *(const double *)(fcc + rb * 16) * (0.5 * (cs + 1.0));
                 return x;
             };
@@ -674,11 +678,13 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         const bool g2 = a.share_exp == 2;
         const double al0 = s_galpha[GRP_BEGIN(a, a.c_first)], al1 = s_galpha[GRP_BEGIN(a, a.c_first) + (g2 ? 1 : 0)];
         for (int o = 0; o < ncls; o++) {
+            if (ctl->ocnt[o] == 0) continue;
+            for (int qr = 0; qr < ctl->obq[o]; qr += NW) {
+            // the bucket's constants are re-read from shared memory per batch: carried in registers across
+            // the batch they were spilled to local memory, whose loads miss the small L1 this kernel leaves
+            asm volatile("" ::: "memory");
             const int v = ncls - o, Qb = ctl->obq[o], n = ctl->ocnt[o], base = ctl->obase[o];
-            if (n == 0) continue;
-            const int rot = (wid - ctl->obp[o]) & (NW - 1);
-            for (int qr = 0; qr < Qb; qr += NW) {
-            const int q = qr + rot;
+            const int q = qr + ((wid - ctl->obp[o]) & (NW - 1));
             // shared accumulator set (very long lists, no room for private sets): the warps of a round add
             // their batches one after the other in warp order, so block barriers sit inside this loop and
             // every warp has to reach them -- a warp without a batch only skips the arithmetic
@@ -718,7 +724,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                     if (g0 == GRP_BEGIN(a, c + 1)) continue;
                     const double pirc = a.cls.pirc[c];
                     double sn, cs;
-                    sincos_0pi(rjk * pirc, &sn, &cs);
+                    sincos_tab(rjk * pirc, s_trig, &sn, &cs);
                     const double fjk = 0.5 * (cs + 1.0), dfjk = -0.5 * pirc * sn;
                     const double2 fda = FCD2(c, ra), fdb = FCD2(c, rb);
                     const double fa = fda.x, fb = fdb.x, dfa = fda.y, dfb = fdb.y;
@@ -741,7 +747,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 if (g0 == g1) continue;
                 const double pirc = a.cls.pirc[c];
                 double sn, cs;
-                sincos_0pi(rjk * pirc, &sn, &cs);
+                sincos_tab(rjk * pirc, s_trig, &sn, &cs);
                 const double fjk = 0.5 * (cs + 1.0), dfjk = -0.5 * pirc * sn;
                 const double2 fda = FCD2(c, ra), fdb = FCD2(c, rb);
                 const double fa = fda.x, fb = fdb.x, dfa = fda.y, dfb = fdb.y;
@@ -778,7 +784,12 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             }
             // dE/dx_j = (gij+gjk) d_j - gjk d_k ; dE/dx_k = (gik+gjk) d_k - gjk d_j
             const double gij = cij * ira, gik = cik * irb, gjk = cjk * irjk;
-            const double dxa = axy.x - xi, dya = axy.y - yi, dza = azr.x - zi, dxb = bxy.x - xi, dyb = bxy.y - yi, dzb = bzr.x - zi;
+            // coordinates again from shared memory: holding them across the class loop cost spills to local memory
+            asm volatile("" ::: "memory");
+            const double2 axy2 = NB2(ra, 0), bxy2 = NB2(rb, 0);
+            const double az2 = NB2(ra, 1).x, bz2 = NB2(rb, 1).x;
+            const double cx = s_ctr[0], cy = s_ctr[1], cz = s_ctr[2];
+            const double dxa = axy2.x - cx, dya = axy2.y - cy, dza = az2 - cz, dxb = bxy2.x - cx, dyb = bxy2.y - cy, dzb = bz2 - cz;
             const double ga = gij + gjk, gb = gik + gjk;
             v0 = fma(ga, dxa, -gjk * dxb); v1 = fma(ga, dya, -gjk * dyb); v2 = fma(ga, dza, -gjk * dzb);
             w0 = fma(gb, dxb, -gjk * dxa); w1 = fma(gb, dyb, -gjk * dya); w2 = fma(gb, dzb, -gjk * dza);
@@ -1045,9 +1056,9 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                     const int s2 = sb + tid;
                     const bool in = s2 < P;
                     const double g = in ? v * NB2(s2, 2).x : 0.0;     // (dE/dr) / r
-                    s_acc[s2] = in ? g * (NB2(s2, 0).x - xi) : 0.0;
-                    s_acc[PCAP + s2] = in ? g * (NB2(s2, 0).y - yi) : 0.0;
-                    s_acc[2 * PCAP + s2] = in ? g * (NB2(s2, 1).x - zi) : 0.0;
+                    s_acc[s2] = in ? g * (NB2(s2, 0).x - s_ctr[0]) : 0.0;
+                    s_acc[PCAP + s2] = in ? g * (NB2(s2, 0).y - s_ctr[1]) : 0.0;
+                    s_acc[2 * PCAP + s2] = in ? g * (NB2(s2, 1).x - s_ctr[2]) : 0.0;
                 }
                 __syncthreads();
             }
@@ -1080,7 +1091,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         }
         double acc9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // gself xyz, vir xx xy xz yy yz zz
         for (int s = tid; s < P; s += CT) {
-            const double dx = NB2(s, 0).x - xi, dy = NB2(s, 0).y - yi, dz = NB2(s, 1).x - zi;
+            const double dx = NB2(s, 0).x - s_ctr[0], dy = NB2(s, 0).y - s_ctr[1], dz = NB2(s, 1).x - s_ctr[2];
             double gx = s_acc[s], gy = s_acc[PCAP + s], gz = s_acc[2 * PCAP + s];
             if constexpr (CS > 1) {
                 cg::cluster_group cl = cg::this_cluster();

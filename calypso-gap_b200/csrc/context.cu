@@ -247,9 +247,11 @@ extern "C" gapcu_ctx *gapcu_ctx_create(int device) {
         return nullptr;
     }
     memset(&c->h_flags, 0, sizeof c->h_flags);
-    double t32[32];
+    // 2^(j/32) for exp_neg, then (cos, sin)(k/16) for sincos_tab (fastmath.cuh): one small device table
+    double t32[32 + 2 * SINCOS_TAB_N];
     fill_exp2_table(t32);
-    if (c->d_exp2.ensure(32) != cudaSuccess ||
+    fill_sincos_table((SinCosEntry *)(t32 + 32));
+    if (c->d_exp2.ensure(32 + 2 * SINCOS_TAB_N) != cudaSuccess ||
         cudaMemcpy(c->d_exp2.p, t32, sizeof t32, cudaMemcpyHostToDevice) != cudaSuccess) {
         fail(GAPCU_ECUDA, "cudaMalloc failed");
         delete c;
@@ -710,7 +712,7 @@ static int make_centre_args(gapcu_ctx *c, int lgrad, int pcap, CentreArgs *out, 
         const int q = pcap * (pcap - 1) / 2;
         const int want = std::min(8192, std::max(2048, round_up(q, 32)));
         const int mode = fused ? 2 : 1;
-        const size_t targets[3] = {(size_t)((a.variant & 8) ? 112 : 74) * 1024, 112 * 1024, 220 * 1024};   // 3, 2, 1 CTAs per SM
+        const size_t targets[3] = {(size_t)((a.variant & 8) ? 112 * 1024 : 75264), 112 * 1024, 220 * 1024};   // 3, 2, 1 CTAs per SM (the kernel's static tables take another 1.2 KB, the system 1 KB per CTA)
         const int lmin[3] = {3584, 3072, 1024};
         bool ok = false;
         for (int t = 0; t < 3 && !ok; t++)

@@ -122,7 +122,7 @@ struct CentreArgs {
     // capacity tier served by this launch: entries [*q_begin, *q_end) of `order` (null: 0 / all), own queue head
     const int *q_begin, *q_end;
     int queue_slot;
-    const double *exp2_table;   // [32] 2^(j/32)
+    const double *exp2_table;   // [32] 2^(j/32), then SINCOS_TAB_N x (cos, sin)(k/16)
     int ntot, cap, pcap;        // ntot: stride of the SoA arrays; pcap: shared-memory neighbour capacity (>= max count)
     int ncentres_max;           // upper bound of the centres this launch serves (sizes the persistent grid)
     int lcap;                   // triplet-list capacity per chunk

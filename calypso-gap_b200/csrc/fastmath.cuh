@@ -10,6 +10,9 @@
 //                   of a denormal or zero (one integer max on the exponent, no FP clamp)
 //   sincos_0pi(y)   0 <= y <= 3.3: no quadrant logic, both functions are polynomials in
 //                   t = y - pi/2 (sin y = cos t, cos y = -sin t)
+//   sincos_tab(y)   same range, through a 54-entry table of (cos, sin)(k/16) and the angle-addition
+//                   formulas with |delta| <= 1/32: 18 FP64 operations and 6 constants instead of 31
+//                   and 20 (the hot loops' version; the table is filled with sincos_0pi)
 #pragma once
 #include <math.h>
 #include <string.h>
@@ -47,7 +50,11 @@ static inline void fill_exp2_table(double *t) {
     /* 19-28: cos t = 1 - z/2 + z^2 (C2 + C3 z + ... + C11 z^9) */                                \
     0.041666666666666664, -0.001388888888888889, 2.48015873015873e-05, -2.755731922398589e-07,     \
     2.08767569878681e-09, -1.1470745597729725e-11, 4.779477332387385e-14, -1.5619206968586225e-16, \
-    4.110317623312165e-19, -8.896791392450574e-22
+    4.110317623312165e-19, -8.896791392450574e-22,                                                  \
+    /* 29-31: cos d - 1 = z (-1/2 + z (C2 + z (C3 + z C4))), z = d^2, |d| <= 1/32 (next term 2e-22) */ \
+    0.041666666666666664, -0.001388888888888889, 2.48015873015873e-05,                              \
+    /* 32-34: sin d = d + d z (S1 + z (S2 + z S3))          (next term 3e-18 relative) */          \
+    -0.16666666666666666, 0.008333333333333333, -0.0001984126984126984
 
 #if defined(__CUDACC__)
 __constant__ double gapcu_kc_dev[] = {GAPCU_KC_LIST};
@@ -112,6 +119,35 @@ GAPCU_HD void sincos_0pi(double y, double *sn, double *cs) {
     c = fma(z2, c, fma(z, -0.5, 1.0));                   // cos(t)
     *sn = c;
     *cs = -s;
+}
+
+// sin(y), cos(y) for 0 <= y <= 3.3 with a table T[k] = (cos(k/16), sin(k/16)), k = 0..53 (SINCOS_TAB_N
+// entries, filled by fill_sincos_table or, on the device, by the threads of a CTA with sincos_0pi):
+// k = nearest integer to 16 y, d = y - k/16 exactly (both have few enough bits), then
+// cos(x_k + d) = C_k cos d - S_k sin d, sin(x_k + d) = S_k cos d + C_k sin d with short Taylor sums.
+constexpr int SINCOS_TAB_N = 54;
+struct SinCosEntry { double c, s; };
+GAPCU_HD void sincos_tab(double y, const SinCosEntry *T, double *sn, double *cs) {
+    const double MAGIC = 6755399441055744.0;             // 1.5 * 2^52
+    const double kd = fma(y, 16.0, MAGIC);
+    long long kbits;
+    memcpy(&kbits, &kd, sizeof kbits);
+    const int k = (int)(unsigned int)kbits;
+    const double d = fma(kd - MAGIC, -0.0625, y);
+    const SinCosEntry e = T[k];
+    const double z = d * d;
+    double cm1 = fma(z, KC(31), KC(30));
+    cm1 = fma(cm1, z, KC(29));
+    cm1 = fma(cm1, z, -0.5);
+    cm1 *= z;                                             // cos d - 1
+    double sp = fma(z, KC(34), KC(33));
+    sp = fma(sp, z, KC(32));
+    const double sd = fma(sp, d * z, d);                  // sin d
+    *cs = fma(-e.s, sd, fma(e.c, cm1, e.c));
+    *sn = fma(e.c, sd, fma(e.s, cm1, e.s));
+}
+static inline void fill_sincos_table(SinCosEntry *T) {
+    for (int k = 0; k < SINCOS_TAB_N; k++) { T[k].c = cos(k / 16.0); T[k].s = sin(k / 16.0); }
 }
 
 #if defined(__CUDACC__)

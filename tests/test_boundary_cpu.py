@@ -169,17 +169,19 @@ def test_no_gpu_means_loud_failure():
 
 
 def test_fastmath_host_versions(tmp_path):
-    """csrc/fastmath.cuh compiles for the host too: exp_neg / sincos_0pi vs libm."""
+    """csrc/fastmath.cuh compiles for the host too: exp_neg / sincos_0pi / sincos_tab vs libm."""
     src = tmp_path / "fm.cpp"
     src.write_text('#include <cstdio>\n#include <cmath>\n#include "%s"\n'
                    'extern "C" double fm_exp(double x){ static double T[32]; static int i=0; if(!i){gapcu::fill_exp2_table(T);i=1;} return gapcu::exp_neg(x,T);}\n'
                    'extern "C" void fm_sc(double y,double*s,double*c){ gapcu::sincos_0pi(y,s,c);}\n'
+                   'extern "C" void fm_sct(double y,double*s,double*c){ static gapcu::SinCosEntry T[gapcu::SINCOS_TAB_N]; static int i=0; if(!i){gapcu::fill_sincos_table(T);i=1;} gapcu::sincos_tab(y,T,s,c);}\n'
                    % os.path.join(ROOT, "calypso-gap_b200", "csrc", "fastmath.cuh"))
     so = tmp_path / "fm.so"
     subprocess.check_call(["g++", "-O2", "-mfma", "-fPIC", "-shared", "-o", str(so), str(src)])
     L = C.CDLL(str(so))
     L.fm_exp.restype = C.c_double; L.fm_exp.argtypes = [C.c_double]
     L.fm_sc.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.fm_sct.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     rng = np.random.default_rng(0)
     xs = -np.concatenate([rng.uniform(0, 700, 20000), rng.uniform(0, 5, 20000), [0.0, 1e-300, 700.0]])
     got = np.array([L.fm_exp(x) for x in xs])
@@ -192,3 +194,5 @@ def test_fastmath_host_versions(tmp_path):
     for y in np.concatenate([rng.uniform(0, 3.3, 20000), [0.0, np.pi / 2, 3.141592654]]):
         L.fm_sc(y, C.byref(s), C.byref(c))
         assert abs(s.value - np.sin(y)) < 4e-16 and abs(c.value - np.cos(y)) < 4e-16   # absolute: what fc / fc' need
+        L.fm_sct(y, C.byref(s), C.byref(c))                                             # the table version of the hot loops
+        assert abs(s.value - np.sin(y)) < 3e-16 and abs(c.value - np.cos(y)) < 3e-16
