@@ -95,6 +95,7 @@ struct Ctl {
     int obp[MAXC_DEV + 2];      // first batch of order slot o
     int TB, nkept;
     int pc[MAXC_DEV + 1];       // neighbours that belong to class c (sorted staging: the places 0 .. pc[c]-1)
+    int estb;                   // MODE_FUSED_SE: first entry of this CTA's (and chunk's) slice of the parked exponentials
 };
 static_assert(sizeof(Ctl) <= 4 * 512, "Ctl does not fit its slot");
 
@@ -701,7 +702,8 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             const int li = base + idx;
             const uint32_t it = s_S[li];
             double2 pk = make_double2(0.0, 0.0);
-            if (se) pk = __ldcg(est + li);      // requested before the geometry below needs it
+            if (se) pk = __ldcg(a.estash + (size_t)(ctl->estb + li));   // requested before the geometry below needs it; the slice's
+                                                                       // start comes from shared memory (as a register it was spilled)
             ra = it & 1023; rb = (it >> 10) & 1023;
             const double2 axy = NB2(ra, 0), azr = NB2(ra, 1), aiw = NB2(ra, 2);
             const double2 bxy = NB2(rb, 0), bzr = NB2(rb, 1), biw = NB2(rb, 2);
@@ -841,7 +843,10 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         }
         phase_end(1);
         for (int ch = 0; ch < nchunk; ch++) {
-            if (SE) est = a.estash + (size_t)blockIdx.x * a.estash_stride + (size_t)ch * (lcap + 32);
+            if (SE) {
+                est = a.estash + (size_t)blockIdx.x * a.estash_stride + (size_t)ch * (lcap + 32);
+                if (tid == 0) ctl->estb = (int)(blockIdx.x * a.estash_stride + ch * (lcap + 32));   // read after the barriers below
+            }
             const int q0 = Qlo + ch * qchunk, q1 = min(Qhi, Qlo + (ch + 1) * qchunk);
             // The pair tests need the staged records only.  While ONE warp then places the buckets (a short
             // serial step), the other seven fill the fc tables; the list scatter and the radial functions
@@ -1069,7 +1074,10 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         __syncthreads();
         phase_end(5);
         for (int ch = 0; ch < nchunk; ch++) {
-            if (SE) est = a.estash + (size_t)blockIdx.x * a.estash_stride + (size_t)ch * (lcap + 32);
+            if (SE && nchunk > 1) {   // (one chunk: still set from the forward pass; several: barriers follow in both branches below)
+                est = a.estash + (size_t)blockIdx.x * a.estash_stride + (size_t)ch * (lcap + 32);
+                if (tid == 0) ctl->estb = (int)(blockIdx.x * a.estash_stride + ch * (lcap + 32));
+            }
             if (list_stashed) {
                 const uint32_t *src = a.list_scratch + ((size_t)blockIdx.x * a.list_scratch_chunks + ch) * (size_t)(lcap + 32 + 512);
                 int *cs = (int *)ctl;
