@@ -1,5 +1,7 @@
 // centre.cu -- host side of the per-centre wACSF kernel: shared-memory layout and dispatch to
 // the capacity-specialised instances (centre_impl.cuh, centre_p*.cu).
+#include <cstdlib>
+
 #include "centre_impl.cuh"
 
 namespace gapcu {
@@ -72,7 +74,8 @@ int launch_fused(cudaStream_t st, const CentreArgs &a, long *launches) {
     if (launches) *launches += 1;
     // parked exponentials pay on large launches (+1 % at 27k centres); on a 1000-centre launch the extra L2
     // round trips cost 4 %
-    const bool se = a.share_exp && a.estash && a.cs == 1 && centre_pcap_template(a.pcap) <= 256 && a.ncentres_max >= 4096;
+    static const int se_min = getenv("GAPCU_SE_MIN") ? atoi(getenv("GAPCU_SE_MIN")) : 4096;   // A/B switch
+    const bool se = a.share_exp && a.estash && a.cs == 1 && centre_pcap_template(a.pcap) <= 256 && a.ncentres_max >= se_min;
     return launch_mode(st, a, se ? MODE_FUSED_SE : MODE_FUSED);
 }
 

@@ -152,13 +152,16 @@ __device__ __forceinline__ void scatter3(double *pa, int idx, double v0, double 
 }
 
 extern __shared__ __align__(16) unsigned char smem[];   // dynamic shared memory: Hot<PCAP> arrays, then SmemLayout
+// work counters (gapcu_ctx_work_counters) of this CTA, flushed once at its exit: 29 global atomics per centre
+// on ten addresses were a serial point of their own.  File scope: a fixed address, no pointer to carry.
+__shared__ unsigned long long s_work[10];
 
 // squared distance with fused multiply-adds (value only; the kept/dropped decision of a pair
 // is always taken with pair_dist2, the reference's arithmetic)
 __device__ __forceinline__ double dist2_fma(double dx, double dy, double dz) { return fma(dz, dz, fma(dy, dy, dx * dx)); }
 
 template <int MODE, int PCAP, int CS>
-__device__ __forceinline__ void process_centre(const CentreArgs &a, const int i, const bool first, unsigned long long *s_work) {
+__device__ __forceinline__ void process_centre(const CentreArgs &a, const int i, const bool first) {
     constexpr bool FWD = MODE != MODE_BWD, BWD = MODE != MODE_FWD, FUSED = MODE >= MODE_FUSED, SE = MODE == MODE_FUSED_SE;
     // rank of this CTA among the CS CTAs that share centre i; lead = the one that writes the outputs
     const int crank = CS > 1 ? (int)cg::this_cluster().block_rank() : 0;
@@ -394,8 +397,9 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         Qlo = min(Qall, crank * qpart); Qhi = min(Qall, Qlo + qpart);
     }
     const int Q = Qhi - Qlo;
-    const int nchunk = (angmask && Q > 0) ? (Q + lcap - 1) / lcap : 0;
-    const int qchunk = nchunk ? ((Q + nchunk - 1) / nchunk + 31) & ~31 : 0;
+    // (one chunk is the rule: no integer divisions on that path)
+    const int nchunk = (angmask && Q > 0) ? (Q <= lcap ? 1 : (Q + lcap - 1) / lcap) : 0;
+    const int qchunk = nchunk <= 1 ? ((Q + 31) & ~31) : (((Q + nchunk - 1) / nchunk + 31) & ~31);
     // parked exponentials: one double2 per kept pair, chunk after chunk of this centre's list
     constexpr bool se = SE;
     double2 *est = SE ? a.estash + (size_t)blockIdx.x * a.estash_stride : nullptr;
@@ -930,6 +934,8 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         const int M = a.gpr_M, Mp = a.gpr_Mp, Dp = a.gpr_Dp;
         for (int k = tid; k < D; k += CT) s_xs[k] = (s_G[k] - a.gpr_cmean[k]) * a.gpr_itheta[k];
         __syncthreads();
+        // (the sparse set is read past L1 -- ld.global.cg: 2 x 72 KB per centre stream through an L1 of ~30 KB
+        // that the spilled registers and the neighbour records of the co-resident CTAs live in)
         // squared distances: thread (sparse point j, slab h of the descriptor components); as many
         // slabs as the CTA has threads for, so that a thread runs a long loop instead of a short one
         double *part = (double *)(smem + L.scratch);          // [slabs <= NW][Mp] partial sums (gw/U are dead by now)
@@ -945,7 +951,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 for (; k + 15 < k1; k += 16, col += 16 * (size_t)Mp) {   // sixteen loads in flight: this loop waits on L2, not on arithmetic
                     double m[16];
 #pragma unroll
-                    for (int u = 0; u < 16; u++) m[u] = __ldg(col + u * (size_t)Mp);
+                    for (int u = 0; u < 16; u++) m[u] = __ldcg(col + u * (size_t)Mp);
 #pragma unroll
                     for (int u = 0; u < 16; u += 4) {
                         const double d0 = s_xs[k + u] - m[u], d1 = s_xs[k + u + 1] - m[u + 1], d2 = s_xs[k + u + 2] - m[u + 2], d3 = s_xs[k + u + 3] - m[u + 3];
@@ -953,11 +959,11 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                     }
                 }
                 for (; k + 3 < k1; k += 4, col += 4 * (size_t)Mp) {   // four independent chains, loads issued together
-                    const double m0 = __ldg(col), m1 = __ldg(col + Mp), m2 = __ldg(col + 2 * (size_t)Mp), m3 = __ldg(col + 3 * (size_t)Mp);
+                    const double m0 = __ldcg(col), m1 = __ldcg(col + Mp), m2 = __ldcg(col + 2 * (size_t)Mp), m3 = __ldcg(col + 3 * (size_t)Mp);
                     const double d0 = s_xs[k] - m0, d1 = s_xs[k + 1] - m1, d2 = s_xs[k + 2] - m2, d3 = s_xs[k + 3] - m3;
                     s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
                 }
-                for (; k < k1; k++, col += Mp) { const double d0 = s_xs[k] - __ldg(col); s0 = fma(d0, d0, s0); }
+                for (; k < k1; k++, col += Mp) { const double d0 = s_xs[k] - __ldcg(col); s0 = fma(d0, d0, s0); }
                 part[h * Mp + j] = (s0 + s1) + (s2 + s3);
             }
         }
@@ -993,7 +999,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 for (; j + 15 < j1; j += 16, rp += 16 * (size_t)Dp) {
                     double m[16];
 #pragma unroll
-                    for (int u = 0; u < 16; u++) m[u] = __ldg(rp + u * (size_t)Dp);
+                    for (int u = 0; u < 16; u++) m[u] = __ldcg(rp + u * (size_t)Dp);
 #pragma unroll
                     for (int u = 0; u < 16; u += 4) {
                         a0 = fma(s_W[j + u], xk - m[u], a0); a1 = fma(s_W[j + u + 1], xk - m[u + 1], a1);
@@ -1001,11 +1007,11 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                     }
                 }
                 for (; j + 3 < j1; j += 4, rp += 4 * (size_t)Dp) {
-                    const double m0 = __ldg(rp), m1 = __ldg(rp + Dp), m2 = __ldg(rp + 2 * (size_t)Dp), m3 = __ldg(rp + 3 * (size_t)Dp);
+                    const double m0 = __ldcg(rp), m1 = __ldcg(rp + Dp), m2 = __ldcg(rp + 2 * (size_t)Dp), m3 = __ldcg(rp + 3 * (size_t)Dp);
                     a0 = fma(s_W[j], xk - m0, a0); a1 = fma(s_W[j + 1], xk - m1, a1);
                     a2 = fma(s_W[j + 2], xk - m2, a2); a3 = fma(s_W[j + 3], xk - m3, a3);
                 }
-                for (; j < j1; j++, rp += Dp) a0 = fma(s_W[j], xk - __ldg(rp), a0);
+                for (; j < j1; j++, rp += Dp) a0 = fma(s_W[j], xk - __ldcg(rp), a0);
                 part[h * D + k] = (a0 + a1) + (a2 + a3);   // part is reused with stride D
             }
         }
@@ -1142,9 +1148,6 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
 template <int MODE, int PCAP, int CS>
 __global__ void __launch_bounds__(CT, 3) k_centre(const CentreArgs a) {
     __shared__ int s_next;
-    // work counters (gapcu_ctx_work_counters) are summed per CTA and flushed once: 29 global atomics per
-    // centre on ten addresses were a serial point of their own
-    __shared__ unsigned long long s_work[10];
     if (threadIdx.x < 10) s_work[threadIdx.x] = 0;
     bool first = true;
     unsigned long long t0 = 0;
@@ -1170,7 +1173,7 @@ __global__ void __launch_bounds__(CT, 3) k_centre(const CentreArgs a) {
         }
         const int n = s_next;
         if (n >= q_end) break;
-        process_centre<MODE, PCAP, CS>(a, a.order ? a.order[n] : n, first, s_work);
+        process_centre<MODE, PCAP, CS>(a, a.order ? a.order[n] : n, first);
         first = false;
     }
     __syncthreads();
