@@ -243,7 +243,7 @@ def run_ours(args):
         def e2e_step():
             k[0] += 1
             return fc(ptrs[k[0] % nsets])
-        h2d = 24 * natoms + 8 * natoms + 4 * natoms + 400   # pos + species weights + structure ids + cell record
+        h2d = 24 * natoms + 400   # positions + cell record every step; species weights (8 B/atom) and structure ids (4 B/atom) only travel when they change, i.e. on the first call
         d2h = 24 * natoms + 512 + 256                        # one copy: flags/counters slot, (E, stress, variance) slot, forces
         api = "gapcu_calc (C ABI bound by FGAP_CALC), host buffers, ./gap_parameters side channel"
     else:

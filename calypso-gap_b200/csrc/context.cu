@@ -132,6 +132,12 @@ struct gapcu_ctx {
     size_t res_o_out = 0, res_o_f = 0;   // byte offsets of out8 and force in d_results
     // likewise structs | sid | pos | wgt ("inputs block"): one host-to-device copy per call
     DBuf<unsigned char> d_inputs;
+    // what the device copy of the inputs block still holds from the last set_structures (an MD or relaxation loop
+    // sends the same structure sizes and species every step: only cell records and positions travel then)
+    bool in_valid = false, in_wgt_ok = false;
+    std::vector<int> in_natoms, in_species;
+    size_t in_nblocks = 0;
+    unsigned long in_sf_version = 0, sf_version = 0;
     DBuf<unsigned char> d_flush;
     // ---- spatial decomposition over ranks (domain_host.inc) + NCCL (loaded lazily with dlopen)
     DomainDev dom = {0, {1, 1, 1}, {0, 0, 0}, {0.0, 0.0, 0.0}};
@@ -210,6 +216,7 @@ static InputLayout input_layout(size_t nstruct, size_t NT, size_t nblocks = 0) {
 }
 static cudaError_t ensure_inputs(gapcu_ctx *c, size_t nstruct, size_t NT, size_t nblocks = 0) {
     const InputLayout L = input_layout(nstruct, NT, nblocks);
+    c->in_valid = false;   // whoever lays the block out anew owns its contents (set_structures_impl re-validates)
     cudaError_t e = c->d_inputs.ensure(L.total);
     if (e != cudaSuccess) return e;
     c->d_structs.view = c->d_sid.view = c->d_pos.view = c->d_wgt.view = true;
@@ -294,7 +301,7 @@ static int set_sf(gapcu_ctx *c, const std::vector<int> &z, const std::vector<dou
     }
     if (c->plan.n_unknown)
         fprintf(stdout, " Unknown function type in gap_parameters (%d functions left at zero)\n", c->plan.n_unknown);
-    c->z = z; c->w = w;
+    c->z = z; c->w = w; c->sf_version++;
     // exponent arguments -alpha*(rij^2+rik^2+rjk^2), -alpha*r^2, -4 (r-rs)^2 must be <= 0 (exp_neg, fastmath.cuh;
     // arbitrarily negative ones are fine: the result saturates at ~2^-1021)
     for (size_t i = 0; i < ntype.size(); i++)
@@ -506,12 +513,21 @@ static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, con
     if (c->h2d_pending) { CU(cudaStreamSynchronize(c->stream)); c->h2d_pending = false; }
     if (c->pin(total)) return fail(GAPCU_ECUDA, "cudaMallocHost failed");
     char *hp = (char *)c->h_pin;
+    // ---- device buffers (first: the inputs block tells which of its parts are still good)
+    const bool was_valid = c->in_valid;
+    const unsigned char *old_block = c->d_inputs.p;
+    CU(ensure_inputs(c, (size_t)nstruct, NT, (size_t)c->nblocks));
+    const bool block_kept = was_valid && c->d_inputs.p == old_block && c->in_nblocks == (size_t)c->nblocks &&
+                            c->in_natoms.size() == (size_t)nstruct && !memcmp(c->in_natoms.data(), natoms, sizeof(int) * nstruct);
+    const bool keep_sid = block_kept;   // structure ids and block owners depend on the atom counts (and block plan) only
+    const bool keep_wgt = block_kept && need_weights && c->in_wgt_ok && c->in_sf_version == c->sf_version &&
+                          c->in_species.size() == NT && !memcmp(c->in_species.data(), species, sizeof(int) * NT);
     memcpy(hp + o_structs, c->h_structs.data(), b_structs);
     int *h_sid = (int *)(hp + o_sid);
     double *h_pos = (double *)(hp + o_pos), *h_wgt = (double *)(hp + o_wgt);
     for (int s = 0, a = 0; s < nstruct; s++) {
         const int n = natoms[s];
-        for (int t = 0; t < n; t++) h_sid[a + t] = s;
+        if (!keep_sid) for (int t = 0; t < n; t++) h_sid[a + t] = s;
         if (pos_soa) {
             for (int d = 0; d < 3; d++) memcpy(h_pos + d * NT + a, pos + 3 * (size_t)a + (size_t)d * n, sizeof(double) * n);
         } else {
@@ -520,7 +536,7 @@ static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, con
         }
         a += n;
     }
-    {   // structure of every block of cells
+    if (!keep_sid) {   // structure of every block of cells
         int *h_blk = (int *)(hp + IL.o_blk);
         for (int s = 0; s < nstruct && c->nblocks; s++) {
             const StructDev &sd = c->h_structs[s];
@@ -528,19 +544,38 @@ static int set_structures_impl(gapcu_ctx *c, int nstruct, const int *natoms, con
             for (int k = 0; k < nb; k++) h_blk[sd.blk_off + k] = s;
         }
     }
-    if (need_weights) {
-        for (size_t t = 0; t < NT; t++) { int rc = lookup_weight(c, species[t], &h_wgt[t]); if (rc) return rc; }
-    } else {
-        memset(h_wgt, 0, b_wgt);
+    if (!keep_wgt) {
+        if (need_weights) {
+            for (size_t t = 0; t < NT; t++) { int rc = lookup_weight(c, species[t], &h_wgt[t]); if (rc) return rc; }
+        } else {
+            memset(h_wgt, 0, b_wgt);
+        }
     }
-    // ---- device buffers
-    CU(ensure_inputs(c, (size_t)nstruct, NT, (size_t)c->nblocks));
     CU(c->d_abin.ensure(NT)); CU(c->d_sabin.ensure(NT)); CU(c->d_spos.ensure(3 * NT)); CU(c->d_arank.ensure(NT)); CU(c->d_bin_count.ensure(2 * (size_t)c->nbins + 2));
     CU(c->d_bin_start.ensure(c->nbins + 2)); CU(c->d_bin_atoms.ensure(NT)); CU(c->d_nbr_cnt.ensure(NT)); CU(c->d_skin_cnt.ensure(NT)); CU(c->d_order.ensure(NT));
     CU(ensure_results(c, (size_t)nstruct, NT));
     CU(c->d_mindis.ensure(NT)); CU(c->d_scan_sums.ensure((size_t)c->nbins / 4096 + 4));
-    CU(cudaMemcpyAsync(c->d_inputs.p, hp, total, cudaMemcpyHostToDevice, c->stream));   // structs | sid | pos | wgt in one copy
+    if (!keep_sid && !keep_wgt) {
+        CU(cudaMemcpyAsync(c->d_inputs.p, hp, total, cudaMemcpyHostToDevice, c->stream));   // structs | sid | pos | wgt | blk in one copy
+    } else {
+        // only what changed travels: cell records and positions, and whichever of the other parts is stale
+        CU(cudaMemcpyAsync(c->d_inputs.p + o_structs, hp + o_structs, b_structs, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_inputs.p + o_pos, hp + o_pos, sizeof(double) * 3 * NT, cudaMemcpyHostToDevice, c->stream));
+        if (!keep_sid) {
+            CU(cudaMemcpyAsync(c->d_inputs.p + o_sid, hp + o_sid, sizeof(int) * NT, cudaMemcpyHostToDevice, c->stream));
+            if (c->nblocks) CU(cudaMemcpyAsync(c->d_inputs.p + IL.o_blk, hp + IL.o_blk, sizeof(int) * (size_t)c->nblocks, cudaMemcpyHostToDevice, c->stream));
+        }
+        if (!keep_wgt) CU(cudaMemcpyAsync(c->d_inputs.p + o_wgt, hp + o_wgt, b_wgt, cudaMemcpyHostToDevice, c->stream));
+    }
     c->h2d_pending = true;
+    c->in_valid = true;
+    c->in_natoms.assign(natoms, natoms + nstruct); c->in_nblocks = (size_t)c->nblocks;
+    if (need_weights) {
+        if (!keep_wgt) c->in_species.assign(species, species + NT);
+        c->in_wgt_ok = true; c->in_sf_version = c->sf_version;
+    } else {
+        c->in_wgt_ok = false;
+    }
     // ---- neighbour capacity estimate (grown on demand)
     int est = (int)(4.18879 * rskin * rskin * rskin * max_density * 1.25) + 32;
     est = std::min(1024, std::max(64, round_up(est, 32)));
