@@ -99,6 +99,10 @@ struct Ctl {
 };
 static_assert(sizeof(Ctl) <= 4 * 512, "Ctl does not fit its slot");
 
+__device__ __forceinline__ void st_shared_u32(unsigned addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -419,6 +423,9 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             if (lane <= ncls) ctl->hw[wid][lane] = 0;
             __syncwarp();
         }
+        const bool allang = (angmask >> 1) & 1u;   // every bucket >= 1 is wanted (bits above a set bit are set)
+        const unsigned seg_sa = (unsigned)__cvta_generic_to_shared(seg);
+        int n1 = 0;                                // bucket-1 survivors of the trips that can hold nothing else
         int ra = 0, rb = 1;
         if (wq0 + lane < wq1) tri_decode(wq0 + lane, ra, rb);
         for (int qb = wq0; qb < wq1; qb += 32) {
@@ -439,11 +446,14 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
 #pragma unroll 1
             for (int c = 1; c < limmax; c++) lo += rjk2 <= s_t2[c];
             bk = min(lo, lim);
-            if (!((angmask >> bk) & 1u)) bk = 0;
+            if (!allang && !((angmask >> bk) & 1u)) bk = 0;
             const unsigned m = __ballot_sync(0xffffffffu, bk > 0);
-            if (bk > 0) seg[cnt + __popc(m & ltmask)] = (uint32_t)ra | ((uint32_t)rb << 10) | ((uint32_t)bk << 20);
+            // (plain 32-bit shared address: the generic pointer form re-derived the window base on every trip)
+            if (bk > 0) st_shared_u32(seg_sa + 4u * (unsigned)(cnt + __popc(m & ltmask)), (uint32_t)ra | ((uint32_t)rb << 10) | ((uint32_t)bk << 20));
             cnt += __popc(m);
-            if (packed) {
+            if (limmax <= 1) {
+                n1 += __popc(m);                 // only bucket 1 can occur in this trip: no per-lane bookkeeping
+            } else if (packed) {
                 hist += (unsigned long long)(bk > 0) << (((bk - 1) & 7) * 8);
             } else if (bk > 0) {
                 const unsigned peers = __match_any_sync(m, bk);
@@ -462,9 +472,11 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             const uint32_t o1 = __reduce_add_sync(0xffffffffu, (hi32 >> 8) & 0x00ff00ffu);   // buckets 6, 8
             if (lane < 8) {
                 const uint32_t w = (lane & 4) ? ((lane & 1) ? o1 : e1) : ((lane & 1) ? o0 : e0);
-                ctl->hw[wid][lane + 1] = (lane & 2) ? (w >> 16) : (w & 0xffffu);
+                ctl->hw[wid][lane + 1] = ((lane & 2) ? (w >> 16) : (w & 0xffffu)) + (lane == 0 ? n1 : 0);
             }
             if (lane == 8) ctl->hw[wid][0] = 0;
+        } else if (lane == 0) {
+            ctl->hw[wid][1] += n1;
         }
         if (lane == 0) ctl->cntw[wid] = cnt;
         return cnt;
