@@ -155,6 +155,28 @@ __device__ __forceinline__ void scatter3(double *pa, int idx, double v0, double 
     }
 }
 
+// The same for a warp-PRIVATE set laid out as (x, y) pairs [PCAP] followed by z [PCAP], through plain 32-bit
+// shared addresses: two loads and two stores per turn instead of three and three, no address arithmetic inside
+// the loop.  sa = shared address of the set.
+template <int PCAP>
+__device__ __forceinline__ void scatter3p(unsigned sa, int idx, double v0, double v1, double v2, unsigned amask, unsigned ltmask) {
+    const unsigned peers = __match_any_sync(amask, idx);
+    const int rank = __popc(peers & ltmask);
+    const int maxr = __reduce_max_sync(amask, rank);
+    const unsigned axy = sa + 16u * (unsigned)idx, az = sa + 16u * PCAP + 8u * (unsigned)idx;
+    for (int r = 0; r <= maxr; r++) {
+        if (rank == r) {
+            double x, y, z;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(axy) : "memory");
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(z) : "r"(az) : "memory");
+            x += v0; y += v1; z += v2;
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(axy), "d"(x), "d"(y) : "memory");
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(az), "d"(z) : "memory");
+        }
+        __syncwarp(amask);
+    }
+}
+
 extern __shared__ __align__(16) unsigned char smem[];   // dynamic shared memory: Hot<PCAP> arrays, then SmemLayout
 // work counters (gapcu_ctx_work_counters) of this CTA, flushed once at its exit: 29 global atomics per centre
 // on ten addresses were a serial point of their own.  File scope: a fixed address, no pointer to carry.
@@ -681,6 +703,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
     auto backward_list = [&]() {
         const bool priv = a.npa > 1;
         double *pa = priv ? s_pa + wid * (3 * PCAP) : s_acc;
+        const unsigned pa_sa = (unsigned)__cvta_generic_to_shared(s_pa + wid * (3 * PCAP));   // private set: (x, y)[PCAP] then z[PCAP]
         if (priv) {
             for (int t = lane; t < 3 * PCAP; t += 32) pa[t] = 0.0;
             __syncwarp();
@@ -815,8 +838,8 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             }
             if (priv) {
                 if (act) {
-                    scatter3<PCAP>(pa, ra, v0, v1, v2, am, ltmask);
-                    scatter3<PCAP>(pa, rb, w0, w1, w2, am, ltmask);
+                    scatter3p<PCAP>(pa_sa, ra, v0, v1, v2, am, ltmask);
+                    scatter3p<PCAP>(pa_sa, rb, w0, w1, w2, am, ltmask);
                 }
             } else {
                 for (int w = 0; w < NW; w++) {
@@ -832,11 +855,14 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         __syncthreads();
         phase_end(14);
         if (priv) {
-            for (int t = tid; t < 3 * PCAP; t += CT) {
-                double v = 0.0;
+            for (int t = tid; t < PCAP; t += CT) {   // private sets: (x, y)[PCAP] then z[PCAP]; s_acc: [3][PCAP]
+                double x = 0.0, y = 0.0, z = 0.0;
 #pragma unroll
-                for (int w = 0; w < NW; w++) v += s_pa[w * (3 * PCAP) + t];
-                s_acc[t] += v;
+                for (int w = 0; w < NW; w++) {
+                    const double2 q = ((const double2 *)(s_pa + w * (3 * PCAP)))[t];
+                    x += q.x; y += q.y; z += s_pa[w * (3 * PCAP) + 2 * PCAP + t];
+                }
+                s_acc[t] += x; s_acc[PCAP + t] += y; s_acc[2 * PCAP + t] += z;
             }
             __syncthreads();
         }
