@@ -83,16 +83,15 @@ struct Hot {
 inline int hot_bytes(int pcap_t, int ncls) { return 48 * pcap_t + 24 * pcap_t + 2 * pcap_t + 16 * ncls * pcap_t; }
 
 // control block in shared memory
-struct Ctl {
+struct __align__(16) Ctl {
     int cntw[NW];               // kept items per warp segment
     int hw[NW][MAXC_DEV + 1];   // kept items per (warp, bucket)
     int basew[NW][MAXC_DEV + 1];// running output position per (warp, bucket)
     int tot[MAXC_DEV + 1];      // items per bucket
     int npre[MAXC_DEV + 1];     // items with bucket > c  (prefix length of class c)
-    int obase[MAXC_DEV + 1];    // start of order slot o (bucket ncls-o) in S
-    int ocnt[MAXC_DEV + 1];
-    int obq[MAXC_DEV + 1];      // batches of order slot o
-    int obp[MAXC_DEV + 2];      // first batch of order slot o
+    // order slot o (= bucket ncls-o, heavy buckets first): x = batches of 32, y = items, z = start in S, w = number
+    // of its first batch; one 128-bit load per batch of the backward pass
+    int4 ob[MAXC_DEV + 2];
     int TB, nkept;
     int pc[MAXC_DEV + 1];       // neighbours that belong to class c (sorted staging: the places 0 .. pc[c]-1)
     int estb;                   // MODE_FUSED_SE: first entry of this CTA's (and chunk's) slice of the parked exponentials
@@ -521,11 +520,11 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         // off/bp are inclusive sums over order slots 0..o
         if (o < ncls) {
             ctl->tot[v] = t;
-            ctl->obase[o] = off - t; ctl->ocnt[o] = t; ctl->obq[o] = nb; ctl->obp[o] = bp - nb;
+            ctl->ob[o] = make_int4(nb, t, off - t, bp - nb);
             for (int w = 0; w < NW; w++) ctl->basew[w][v] += off - t;
             ctl->npre[v - 1] = off;   // items with bucket > v-1, i.e. bucket >= v: slots 0..o
         }
-        if (o == ncls - 1 || (ncls == 0 && o == 0)) { ctl->obp[ncls] = bp; ctl->TB = bp; ctl->nkept = off; }
+        if (o == ncls - 1 || (ncls == 0 && o == 0)) { ctl->TB = bp; ctl->nkept = off; }
         __syncwarp();
         if (count_work) {
             const int tcv = (lane < ncls && s_nf[lane]) ? ctl->npre[lane] : 0;
@@ -717,14 +716,17 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         // the groups is straight-line code.
         const bool g2 = a.share_exp == 2;
         const double al0 = s_galpha[GRP_BEGIN(a, a.c_first)], al1 = s_galpha[GRP_BEGIN(a, a.c_first) + (g2 ? 1 : 0)];
+        const unsigned ob_sa = (unsigned)__cvta_generic_to_shared(&ctl->ob[0]);
         for (int o = 0; o < ncls; o++) {
-            if (ctl->ocnt[o] == 0) continue;
-            for (int qr = 0; qr < ctl->obq[o]; qr += NW) {
-            // the bucket's constants are re-read from shared memory per batch: carried in registers across
-            // the batch they were spilled to local memory, whose loads miss the small L1 this kernel leaves
-            asm volatile("" ::: "memory");
-            const int v = ncls - o, Qb = ctl->obq[o], n = ctl->ocnt[o], base = ctl->obase[o];
-            const int q = qr + ((wid - ctl->obp[o]) & (NW - 1));
+            for (int qr = 0;; qr += NW) {
+            // the bucket's constants are re-read from shared memory per batch (one 128-bit load through a plain
+            // shared address): carried in registers across the batch they were spilled to local memory, whose
+            // loads miss the small L1 this kernel leaves
+            int Qb, n, base, p0;
+            asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(Qb), "=r"(n), "=r"(base), "=r"(p0) : "r"(ob_sa + 16u * (unsigned)o) : "memory");
+            if (qr >= Qb) break;
+            const int v = ncls - o;
+            const int q = qr + ((wid - p0) & (NW - 1));
             // shared accumulator set (very long lists, no room for private sets): the warps of a round add
             // their batches one after the other in warp order, so block barriers sit inside this loop and
             // every warp has to reach them -- a warp without a batch only skips the arithmetic
@@ -988,8 +990,10 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 int k = k0;
                 for (; k + 15 < k1; k += 16, col += 16 * (size_t)Mp) {   // sixteen loads in flight: this loop waits on L2, not on arithmetic
                     double m[16];
+                    // (uniform base + 32-bit byte offset: one add per load instead of 64-bit index arithmetic)
+                    const unsigned o0 = (unsigned)((const char *)col - (const char *)a.gpr_MtT), st = 8u * (unsigned)Mp;
 #pragma unroll
-                    for (int u = 0; u < 16; u++) m[u] = __ldcg(col + u * (size_t)Mp);
+                    for (int u = 0; u < 16; u++) m[u] = __ldcg((const double *)((const char *)a.gpr_MtT + (o0 + u * st)));
 #pragma unroll
                     for (int u = 0; u < 16; u += 4) {
                         const double d0 = s_xs[k + u] - m[u], d1 = s_xs[k + u + 1] - m[u + 1], d2 = s_xs[k + u + 2] - m[u + 2], d3 = s_xs[k + u + 3] - m[u + 3];
@@ -1036,8 +1040,9 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 int j = j0;
                 for (; j + 15 < j1; j += 16, rp += 16 * (size_t)Dp) {
                     double m[16];
+                    const unsigned o0 = (unsigned)((const char *)rp - (const char *)a.gpr_Mt), st = 8u * (unsigned)Dp;
 #pragma unroll
-                    for (int u = 0; u < 16; u++) m[u] = __ldcg(rp + u * (size_t)Dp);
+                    for (int u = 0; u < 16; u++) m[u] = __ldcg((const double *)((const char *)a.gpr_Mt + (o0 + u * st)));
 #pragma unroll
                     for (int u = 0; u < 16; u += 4) {
                         a0 = fma(s_W[j + u], xk - m[u], a0); a1 = fma(s_W[j + u + 1], xk - m[u + 1], a1);
