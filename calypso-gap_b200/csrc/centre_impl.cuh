@@ -247,6 +247,11 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
     const StructDev &sd = a.structs[a.sid[i]];
     const int ntot = a.ntot;
     const int *g_iplus = pl.itab + pl.o_grp_iplus, *g_iminus = pl.itab + pl.o_grp_iminus;
+    // descriptor indices of a group's lambda = +1 / -1 function: a shared copy for the forward sums (the global
+    // table put a load from L1/L2 on the critical path of every class reduction)
+    constexpr int GIDX_CAP = 64;
+    __shared__ int2 s_gidx[GIDX_CAP];
+    const bool gidx_ok = pl.n_grp <= GIDX_CAP;
 
     // ---- 0: tables (centre independent: loaded once per persistent CTA) ----------------
     __shared__ int s_nrad[MAXC_DEV], s_nf[MAXC_DEV];   // per class: radial functions, angular functions (work counters)
@@ -261,6 +266,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             s_nrad[tid] = nr; s_nf[tid] = nf;
         }
         if (tid < 32) s_t32[tid] = a.exp2_table[tid];
+        if (tid < GIDX_CAP && tid < pl.n_grp) s_gidx[tid] = make_int2(g_iplus[tid], g_iminus[tid]);
         if (tid < MAXC_DEV) s_t2[tid] = tid < ncls ? a.cls.t2[tid] : -1.0;
         for (int t = tid; t < pl.n_grp; t += CT) s_galpha[t] = pl.dtab[pl.o_grp_alpha + t];
         for (int t = tid; t < pl.n_rad; t += CT) {
@@ -640,7 +646,9 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                             const double tot = warp_sum4(acc[g][0], acc[g][1], acc[g][2], acc[g][3], lane);
                             const double oth = __shfl_xor_sync(0xffffffffu, tot, 8);
                             if ((lane & 7) == 0) {
-                                const int ip = g_iplus[g0 + g], im = g_iminus[g0 + g];
+                                int ip, im;
+                                if (gidx_ok) { const int2 gi = s_gidx[g0 + g]; ip = gi.x; im = gi.y; }
+                                else { ip = g_iplus[g0 + g]; im = g_iminus[g0 + g]; }
                                 double *gw = s_gw + wid * D + ((lane & 16) ? nsf : 0);
                                 if (!(lane & 8)) { if (ip >= 0) gw[ip] += tot + oth; }
                                 else { if (im >= 0) gw[im] += oth - tot; }
