@@ -1197,7 +1197,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
 // ordered by descending neighbour count (longest first), so that 1000 centres on 444
 // resident CTAs do not cost full waves and the heavy centres do not form the tail.
 template <int MODE, int PCAP, int CS>
-__global__ void __launch_bounds__(CT, 3) k_centre(const CentreArgs a) {
+__global__ void __launch_bounds__(CT, PCAP <= 128 ? 3 : PCAP <= 256 ? 2 : 1) k_centre(const CentreArgs a) {   // residency the tier's shared memory allows: the larger tiers need not squeeze into 80 registers
     __shared__ int s_next;
     if (threadIdx.x < 10) s_work[threadIdx.x] = 0;
     bool first = true;
