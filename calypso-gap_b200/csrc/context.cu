@@ -85,6 +85,10 @@ struct DeviceGuard {
 struct gapcu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    // decomposed runs: the gather of the owned atoms runs here, beside the gradient return on `stream`
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_centres = nullptr, ev_owned = nullptr;
+    bool owned_gather_pending = false;
     // ---- potential
     bool have_sf = false, have_gpr = false;
     std::vector<int> z;
@@ -248,7 +252,14 @@ extern "C" gapcu_ctx *gapcu_ctx_create(int device) {
     }
     gapcu_ctx *c = new gapcu_ctx();
     c->device = device;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    // the main stream at the highest priority, the side stream at the lowest: what the side stream runs (the owned
+    // atoms' gather of a decomposed pass) then yields, CTA by CTA, to the gradient return on the main stream
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_least) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_centres, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_owned, cudaEventDisableTiming) != cudaSuccess) {
         fail(GAPCU_ECUDA, "cudaStreamCreate failed");
         delete c;
         return nullptr;
@@ -284,6 +295,9 @@ extern "C" void gapcu_ctx_destroy(gapcu_ctx *c) {
     domain_destroy(c);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->stage_ev_init) for (auto &e : c->stage_ev) cudaEventDestroy(e);
+    if (c->ev_centres) cudaEventDestroy(c->ev_centres);
+    if (c->ev_owned) cudaEventDestroy(c->ev_owned);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->stream);
     delete c;
 }

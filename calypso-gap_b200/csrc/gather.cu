@@ -39,7 +39,7 @@ k_gather(const GatherArgs g, const int nfin, const FinArgs fin) {
         finalize_partial(g.structs, fin, blockIdx.x % fin.nchunk, blockIdx.x / fin.nchunk);
         return;
     }
-    const int i = blockIdx.x - nfin;
+    const int i = g.i_begin + blockIdx.x - nfin;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (g.nloc && i >= *g.nloc) return;
     const int ntot = g.ntot, cap = g.cap;
@@ -180,11 +180,13 @@ void launch_gather(cudaStream_t st, const GatherArgs &g, long *launches) {
     FinArgs fin;
     fin.eatom = g.eatom; fin.vir = g.vir; fin.partial = g.partial; fin.out8 = g.out8; fin.lgrad = g.lgrad; fin.nchunk = nchunk;
     fin.nstruct = g.nstruct; fin.n_own = g.n_own; fin.raw = g.decomposed;
-    const int ngather = g.lgrad ? g.ntot : 0;   // without gradients only the reduction CTAs run
-    if (!g.lgrad) cudaMemsetAsync(g.force_soa, 0, sizeof(double) * 3 * (size_t)g.ntot, st);
-    k_gather<<<nchunk * g.nstruct + ngather, GT, 0, st>>>(g, nchunk * g.nstruct, fin);
-    if (nchunk > 1) k_finalize<<<g.nstruct, 32, 0, st>>>(g.structs, g.partial, nchunk, g.out8, g.n_own, g.decomposed);
-    if (launches) *launches += nchunk > 1 ? 2 : 1;
+    const int natom = g.i_count > 0 ? g.i_count : g.ntot - g.i_begin;
+    const int ngather = g.lgrad ? natom : 0;   // without gradients only the reduction CTAs run
+    const int nfin = g.no_fin ? 0 : nchunk * g.nstruct;
+    if (!g.lgrad && !g.no_fin) cudaMemsetAsync(g.force_soa, 0, sizeof(double) * 3 * (size_t)g.ntot, st);
+    if (nfin + ngather > 0) k_gather<<<nfin + ngather, GT, 0, st>>>(g, nfin, fin);
+    if (nfin && nchunk > 1) k_finalize<<<g.nstruct, 32, 0, st>>>(g.structs, g.partial, nchunk, g.out8, g.n_own, g.decomposed);
+    if (launches) *launches += (nfin && nchunk > 1) ? 2 : 1;
 }
 
 }  // namespace gapcu

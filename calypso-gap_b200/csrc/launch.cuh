@@ -97,6 +97,10 @@ struct GatherArgs {
     double *ghost_grad;       // [padded ghost slots][3]
     const int *gslot;         // ghost (local index - n_own) -> padded slot
     int decomposed;
+    // part of the atoms served by this launch (decomposed runs split the gather so that the ghost part, which
+    // the gradient return waits for, goes first): atoms [i_begin, i_begin + i_count); i_count = 0: all of them.
+    // no_fin: leave the E / strs reduction to the other launch
+    int i_begin, i_count, no_fin;
 };
 void launch_gather(cudaStream_t st, const GatherArgs &g, long *launches);
 int finalize_chunks(int max_natoms);   // partial needs nstruct * finalize_chunks(max_natoms) * 8 doubles
