@@ -68,10 +68,10 @@ def test_gapcu_read_matches_oracle_reader(lib, shipped_pot):
 
 
 def test_gapcu_read_zero_fill_of_invcmm(lib):
-    """FGAP_READ sets INVCMM = 0 (gap_calc.f90:361).  The library clears only pages that may hold
-    data (present or swapped according to /proc/self/pagemap) and leaves never-touched pages of a
-    fresh anonymous allocation alone -- they already read as zero.  Whatever the history of the
-    buffer, the caller must see zeros everywhere, and nothing outside the buffer may change."""
+    """FGAP_READ sets INVCMM = 0 (gap_calc.f90:361).  The library drops the whole pages of a private
+    anonymous allocation with madvise(MADV_DONTNEED) (zero-fill on demand) and memsets everything
+    else.  Whatever the history of the buffer, the caller must see zeros everywhere, and nothing
+    outside the buffer may change."""
     lib.gapcu_read.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     nsp, dl = C.c_int(), C.c_int()
