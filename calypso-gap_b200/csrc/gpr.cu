@@ -132,13 +132,16 @@ k_gpr(GprDev p, const double *__restrict__ G, int ntot, int mslice, double *__re
         // sparse rows rowmap(2t+e), so B(k=t, n=g) = tile[rowmap(2t+e)][8n+g].
         const double *b0 = tile + r0 * LD + g, *b1 = tile + r1 * LD + g;
         const double *b2 = b0 + 8 * LD, *b3 = b1 + 8 * LD;
+        // k-step outer, descriptor tile inner: consecutive DMMAs write different accumulators (the four k-steps
+        // of one accumulator in a row were a dependent chain on the tensor pipe's latency)
 #pragma unroll
-        for (int n = 0; n < NT; n++) {
-            dmma884(acc[n][0], acc[n][1], w00, b0[8 * n]);
-            dmma884(acc[n][0], acc[n][1], w01, b1[8 * n]);
-            dmma884(acc[n][0], acc[n][1], w10, b2[8 * n]);
-            dmma884(acc[n][0], acc[n][1], w11, b3[8 * n]);
-        }
+        for (int n = 0; n < NT; n++) dmma884(acc[n][0], acc[n][1], w00, b0[8 * n]);
+#pragma unroll
+        for (int n = 0; n < NT; n++) dmma884(acc[n][0], acc[n][1], w01, b1[8 * n]);
+#pragma unroll
+        for (int n = 0; n < NT; n++) dmma884(acc[n][0], acc[n][1], w10, b2[8 * n]);
+#pragma unroll
+        for (int n = 0; n < NT; n++) dmma884(acc[n][0], acc[n][1], w11, b3[8 * n]);
         __syncthreads();                                       // every warp is done with this buffer
     }
     esum += __shfl_xor_sync(0xffffffffu, esum, 1);
