@@ -761,7 +761,7 @@ static int make_centre_args(gapcu_ctx *c, int lgrad, int pcap, CentreArgs *out, 
         const int q = pcap * (pcap - 1) / 2;
         const int want = std::min(8192, std::max(2048, round_up(q, 32)));
         const int mode = fused ? 2 : 1;
-        const size_t targets[3] = {(size_t)((a.variant & 8) ? 112 * 1024 : 74752), 112 * 1024, 220 * 1024};   // 3, 2, 1 CTAs per SM (the kernel's static tables take another 1.7 KB, the system 1 KB per CTA: 3 x (73 + 1.7 + 1) KB fits the 228 KB of an SM)
+        const size_t targets[3] = {(size_t)((a.variant & 8) ? 112 * 1024 : 74752), 110 * 1024, 220 * 1024};   // 3, 2, 1 CTAs per SM (the kernel's static tables take another 1.7 KB, the system 1 KB per CTA: 3 x (73 + 1.7 + 1) KB fits the 228 KB of an SM)
         const int lmin[3] = {3584, 3072, 1024};
         bool ok = false;
         for (int t = 0; t < 3 && !ok; t++)
