@@ -146,6 +146,47 @@ def test_fortran_abi_entry_point(shipped_pot, golden_frames, monkeypatch):
     assert v == 0.0
 
 
+def test_inputs_block_cache_tracks_species_cell_and_potential(bc_structure, oracle, shipped_pot, tmp_path, monkeypatch):
+    """The drop-in call keeps structure ids, block owners and species weights on the device while the atom
+    count, the species array and the potential are unchanged (an MD loop sends cell records and positions
+    only).  Everything that invalidates those parts must be noticed: other species on the same atoms, another
+    cell, another number of atoms, other weights in ./gap_parameters -- each answer must be the oracle's for
+    THAT input, not the previous one."""
+    import shutil
+    import gapcu
+    from oracle import Oracle
+    work = tmp_path / "cwd"
+    work.mkdir()
+    shutil.copy(os.path.join(GOLDEN, "gap_parameters"), work / "gap_parameters")
+    monkeypatch.chdir(work)
+    p = shipped_pot
+    cell, pos, z = bc_structure["cell"], bc_structure["positions"], bc_structure["numbers"].astype(np.int32)
+
+    def check(zz, cc, pp, pot):
+        want = pot.calc_sparse(zz, cc, pp, 6.0, True)
+        e, f, s, _ = gapcu.fortran_calc(zz, cc, pp, pot.theta, pot.mm, pot.coeff, 6.0, True)
+        _cmp({"energy": e, "forces": f, "stress": s}, want)
+        return e
+
+    e0 = check(z, cell, pos, p)
+    assert check(z, cell, pos + 0.01, p) != e0                     # the cached path: positions only
+    z2 = z.copy(); z2[:16] = np.where(z2[:16] == 5, 6, 5)          # other species on the same atoms
+    assert check(z2, cell, pos, p) != e0
+    check(z, cell * 1.01, pos * 1.01, p)                            # other cell, same atom count
+    check(z[:-8], cell, pos[:-8], p)                                # other atom count, then back
+    assert check(z, cell, pos, p) == e0                             # every order is fixed: the first answer, bit for bit
+    # other species weights in the file the call reads from its working directory
+    lines = open(work / "gap_parameters").read().split("\n")
+    nsp = int(lines[0].split()[0])
+    wrow = [k for k in range(1, 1 + nsp) if lines[k].split()[0] == "5"][0]
+    lines[wrow] = "    5       -1.50000"
+    (work / "gap_parameters").write_text("\n".join(lines))
+    st = os.stat(work / "gap_parameters")
+    os.utime(work / "gap_parameters", ns=(st.st_atime_ns, st.st_mtime_ns + 1_000_000_000))   # same size: make the identity differ for sure
+    p2 = Oracle("parity").read(str(work / "gap_parameters"))
+    assert check(z, cell, pos, p2) != e0
+
+
 def test_f2py_module_and_python_classes(golden_frames, bc_structure, oracle, monkeypatch):
     """libgap.GAP.Calculator / libgap.BOND.Bond exactly as example/BC/test.py uses them."""
     monkeypatch.chdir(GOLDEN)
