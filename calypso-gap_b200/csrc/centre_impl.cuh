@@ -213,6 +213,8 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
     const int lcap = a.lcap;
     const SmemLayout &L = a.lay;
     double *s_t32 = (double *)(smem + L.t32);
+    // the two tables of fastmath.cuh as plain shared addresses (exp_neg_s, sincos_tab_s)
+    const unsigned t32_sa = (unsigned)__cvta_generic_to_shared(s_t32);
     double *s_t2 = (double *)(smem + L.t2);       // class thresholds padded with -1 (never passes)
     double *s_galpha = (double *)(smem + L.galpha);
     double *s_gd = (double *)(smem + L.gd);      // [n_grp][4]: DU, DW, DUL, DWL (backward)
@@ -255,7 +257,8 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
 
     // ---- 0: tables (centre independent: loaded once per persistent CTA) ----------------
     __shared__ int s_nrad[MAXC_DEV], s_nf[MAXC_DEV];   // per class: radial functions, angular functions (work counters)
-    __shared__ SinCosEntry s_trig[SINCOS_TAB_N];       // (cos, sin)(k/16) for sincos_tab
+    __shared__ __align__(16) SinCosEntry s_trig[SINCOS_TAB_N];       // (cos, sin)(k/16) for sincos_tab
+    const unsigned trig_sa = (unsigned)__cvta_generic_to_shared(s_trig);
     if (first) {
         if (tid < 2 * SINCOS_TAB_N) ((double *)s_trig)[tid] = a.exp2_table[32 + tid];
         if (tid < MAXC_DEV) {
@@ -365,7 +368,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             if (s < P && c < NCB(s)) {
                 const double pirc = a.cls.pirc[c];
                 double sn, cs;
-                sincos_tab(NB2(s, 1).y * pirc, s_trig, &sn, &cs);
+                sincos_tab_s(NB2(s, 1).y * pirc, trig_sa, &sn, &cs);
                 FCD2(c, s) = make_double2(0.5 * (cs + 1.0), -0.5 * pirc * sn);
             }
         }
@@ -386,13 +389,13 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 const double dis = NB2(s, 1).y, wj = NB2(s, 2).y;
                 if (c < nc) {
                     const double d = t1 ? dis : dis - prm;
-                    const double g = exp_neg((t1 ? -prm : -4.0) * d * d, s_t32) * FCV(c, s);
+                    const double g = exp_neg_s((t1 ? -prm : -4.0) * d * d, t32_sa) * FCV(c, s);
                     gu += g;
                     gwt = fma(g, wj, gwt);
                 }
                 if (c2 < nc) {
                     const double d = t2nd ? dis : dis - prm2;
-                    const double g = exp_neg((t2nd ? -prm2 : -4.0) * d * d, s_t32) * FCV(c2, s);
+                    const double g = exp_neg_s((t2nd ? -prm2 : -4.0) * d * d, t32_sa) * FCV(c2, s);
                     hu += g;
                     hwt = fma(g, wj, hwt);
                 }
@@ -596,7 +599,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 x.ww = aiw.y * biw.y;
                 const double rjk = rjk2 * rsqrt_pos(rjk2);   // two neighbours never coincide (the backward pass divides by rjk as the reference does)
                 double sn, cs;
-                sincos_tab(rjk * pirc, s_trig, &sn, &cs);
+                sincos_tab_s(rjk * pirc, trig_sa, &sn, &cs);
                 x.phi = *(const double *)(fcc + ra * 16) * *(const double *)(fcc + rb * 16) * (0.5 * (cs + 1.0));
                 return x;
             };
@@ -622,8 +625,8 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                         const double2 sx = __ldcg(est + t), sy = __ldcg(est + t + CT);
                         ex0 = sx.x; ex1 = sx.y; ey0 = sy.x; ey1 = sy.y;
                     } else {
-                        ex0 = exp_neg(-al0 * x.ssum, s_t32); ey0 = exp_neg(-al0 * y.ssum, s_t32);
-                        ex1 = exp_neg(-al1 * x.ssum, s_t32); ey1 = exp_neg(-al1 * y.ssum, s_t32);
+                        ex0 = exp_neg_s(-al0 * x.ssum, t32_sa); ey0 = exp_neg_s(-al0 * y.ssum, t32_sa);
+                        ex1 = exp_neg_s(-al1 * x.ssum, t32_sa); ey1 = exp_neg_s(-al1 * y.ssum, t32_sa);
                         if (se) { __stcg(est + t, make_double2(ex0, ex1)); __stcg(est + t + CT, make_double2(ey0, ey1)); }
                     }
                     add(x, ex0, ex1);
@@ -634,7 +637,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                     double ex0, ex1;
                     if (reuse) { const double2 sx = __ldcg(est + t); ex0 = sx.x; ex1 = sx.y; }
                     else {
-                        ex0 = exp_neg(-al0 * x.ssum, s_t32); ex1 = exp_neg(-al1 * x.ssum, s_t32);
+                        ex0 = exp_neg_s(-al0 * x.ssum, t32_sa); ex1 = exp_neg_s(-al1 * x.ssum, t32_sa);
                         if (se) __stcg(est + t, make_double2(ex0, ex1));
                     }
                     add(x, ex0, ex1);
@@ -671,13 +674,13 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                     // groups in pairs without a branch between their exponentials, so the two
                     // dependent chains interleave (same trick as in the backward loop)
                     auto one = [&](double (&ac)[4], int g) {
-                        const double pe = phi * exp_neg(-s_galpha[gb + g] * ssum, s_t32);
+                        const double pe = phi * exp_neg_s(-s_galpha[gb + g] * ssum, t32_sa);
                         const double pw = pe * ww;
                         ac[0] += pe; ac[1] = fma(pe, cosv, ac[1]); ac[2] += pw; ac[3] = fma(pw, cosv, ac[3]);
                     };
                     auto two = [&](double (&a0)[4], double (&a1)[4], int g) {
-                        const double e0 = exp_neg(-s_galpha[gb + g] * ssum, s_t32);
-                        const double e1 = exp_neg(-s_galpha[gb + g + 1] * ssum, s_t32);
+                        const double e0 = exp_neg_s(-s_galpha[gb + g] * ssum, t32_sa);
+                        const double e1 = exp_neg_s(-s_galpha[gb + g + 1] * ssum, t32_sa);
                         const double pe0 = phi * e0, pe1 = phi * e1, pw0 = pe0 * ww, pw1 = pe1 * ww;
                         a0[0] += pe0; a0[1] = fma(pe0, cosv, a0[1]); a0[2] += pw0; a0[3] = fma(pw0, cosv, a0[3]);
                         a1[0] += pe1; a1[1] = fma(pe1, cosv, a1[1]); a1[2] += pw1; a1[3] = fma(pw1, cosv, a1[3]);
@@ -767,7 +770,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
             const double u1 = irb - cosv * ira, u2 = ira - cosv * irb, u3 = -rjk * ira * irb;
             double cij = 0.0, cik = 0.0, cjk = 0.0;
             if (g2) {
-                const double e0 = se ? pk.x : exp_neg(-al0 * ssum, s_t32), e1 = se ? pk.y : exp_neg(-al1 * ssum, s_t32);
+                const double e0 = se ? pk.x : exp_neg_s(-al0 * ssum, t32_sa), e1 = se ? pk.y : exp_neg_s(-al1 * ssum, t32_sa);
                 const double e0w = e0 * ww, e1w = e1 * ww;
 #pragma unroll 2
                 for (int c = 0; c < v; c++) {
@@ -775,7 +778,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                     if (g0 == GRP_BEGIN(a, c + 1)) continue;
                     const double pirc = a.cls.pirc[c];
                     double sn, cs;
-                    sincos_tab(rjk * pirc, s_trig, &sn, &cs);
+                    sincos_tab_s(rjk * pirc, trig_sa, &sn, &cs);
                     const double fjk = 0.5 * (cs + 1.0), dfjk = -0.5 * pirc * sn;
                     const double2 fda = FCD2(c, ra), fdb = FCD2(c, rb);
                     const double fa = fda.x, fb = fdb.x, dfa = fda.y, dfb = fdb.y;
@@ -798,7 +801,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 if (g0 == g1) continue;
                 const double pirc = a.cls.pirc[c];
                 double sn, cs;
-                sincos_tab(rjk * pirc, s_trig, &sn, &cs);
+                sincos_tab_s(rjk * pirc, trig_sa, &sn, &cs);
                 const double fjk = 0.5 * (cs + 1.0), dfjk = -0.5 * pirc * sn;
                 const double2 fda = FCD2(c, ra), fdb = FCD2(c, rb);
                 const double fa = fda.x, fb = fdb.x, dfa = fda.y, dfb = fdb.y;
@@ -809,7 +812,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 int gg = g0;
                 for (; gg + 1 < g1; gg += 2) {
                     const double bl0 = s_galpha[gg], bl1 = s_galpha[gg + 1];
-                    const double e0 = se ? pk.x : exp_neg(-bl0 * ssum, s_t32), e1 = se ? pk.y : exp_neg(-bl1 * ssum, s_t32);
+                    const double e0 = se ? pk.x : exp_neg_s(-bl0 * ssum, t32_sa), e1 = se ? pk.y : exp_neg_s(-bl1 * ssum, t32_sa);
                     const double4 gd0 = *(const double4 *)(s_gd + 4 * gg), gd1 = *(const double4 *)(s_gd + 4 * gg + 4);
                     const double t00 = e0 * fma(ww, gd0.y, gd0.x), t01 = e0 * fma(ww, gd0.w, gd0.z);
                     const double t10 = e1 * fma(ww, gd1.y, gd1.x), t11 = e1 * fma(ww, gd1.w, gd1.z);
@@ -819,7 +822,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                 }
                 if (gg < g1) {
                     const double al = s_galpha[gg];
-                    const double e = se ? pk.x : exp_neg(-al * ssum, s_t32);
+                    const double e = se ? pk.x : exp_neg_s(-al * ssum, t32_sa);
                     const double4 gd = *(const double4 *)(s_gd + 4 * gg);   // DU, DW, DUL, DWL
                     const double t0 = e * fma(ww, gd.y, gd.x), t1 = e * fma(ww, gd.w, gd.z);
                     T0 += t0;
@@ -1023,7 +1026,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
         for (int j = tid; j < Mp; j += CT) {
             double sacc = 0.0;
             for (int h = 0; h < nsA; h++) sacc += part[h * Mp + j];
-            const double wv = (j < M) ? exp_neg(-0.5 * sacc, s_t32) * a.gpr_coeff[j] : 0.0;
+            const double wv = (j < M) ? exp_neg_s(-0.5 * sacc, t32_sa) * a.gpr_coeff[j] : 0.0;
             s_W[j] = wv;
             esum += wv;
         }
@@ -1106,7 +1109,7 @@ __device__ __forceinline__ void process_centre(const CentreArgs &a, const int i,
                         if ((ri.y >> 16) == 1) { const double al = s_radp[q]; arg = -al * dis * dis; dgf = -2.0 * al * dis; }
                         else { const double d = dis - s_radp[q]; arg = -4.0 * d * d; dgf = -8.0 * d; }
                         const double2 fd = FCD2(c, s);
-                        const double dg = exp_neg(arg, s_t32) * fma(dgf, fd.x, fd.y);
+                        const double dg = exp_neg_s(arg, t32_sa) * fma(dgf, fd.x, fd.y);
                         cacc = fma(s_du[ri.x] + wj * s_du[ri.x + nsf], dg, cacc);
                     }
                 }

@@ -150,6 +150,56 @@ static inline void fill_sincos_table(SinCosEntry *T) {
     for (int k = 0; k < SINCOS_TAB_N; k++) { T[k].c = cos(k / 16.0); T[k].s = sin(k / 16.0); }
 }
 
+
+#if defined(__CUDACC__)
+// Device variants of exp_neg / sincos_tab whose tables are given as plain 32-bit SHARED addresses
+// (__cvta_generic_to_shared): the generic-pointer forms re-derive the shared window base at every call site.
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));   // volatile: stays behind the barrier that follows the table fill
+    return v;
+}
+__device__ __forceinline__ double exp_neg_s(double x, unsigned t32_sa) {
+    const double MAGIC = 6755399441055744.0;
+    unsigned int xh = (unsigned int)__double2hiint(x);
+    xh = xh < 0xc16312d0u ? xh : 0xc16312d0u;
+    x = __hiloint2double((int)xh, __double2loint(x));
+    const double kd = fma(x, KC(0), MAGIC);
+    const double kf = kd - MAGIC;
+    const int ki = __double2loint(kd);
+    double r = fma(kf, KC(1), x);
+    r = fma(kf, KC(2), r);
+    double p = fma(r, KC(3), KC(4));
+    p = fma(p, r, KC(5));
+    p = fma(p, r, KC(6));
+    p = fma(p, r, 0.5);
+    p = fma(p, r * r, r);
+    const double t = lds_f64(t32_sa + ((unsigned)(ki & 31) << 3));
+    const double y = fma(t, p, t);
+    int m = ki >> 5;
+    m = m > -1021 ? m : -1021;
+    return __hiloint2double(__double2hiint(y) + (m << 20), __double2loint(y));
+}
+__device__ __forceinline__ void sincos_tab_s(double y, unsigned trig_sa, double *sn, double *cs) {
+    const double MAGIC = 6755399441055744.0;
+    const double kd = fma(y, 16.0, MAGIC);
+    const int k = __double2loint(kd);
+    const double d = fma(kd - MAGIC, -0.0625, y);
+    double ec, es;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ec), "=d"(es) : "r"(trig_sa + ((unsigned)k << 4)));
+    const double z = d * d;
+    double cm1 = fma(z, KC(31), KC(30));
+    cm1 = fma(cm1, z, KC(29));
+    cm1 = fma(cm1, z, -0.5);
+    cm1 *= z;
+    double sp = fma(z, KC(34), KC(33));
+    sp = fma(sp, z, KC(32));
+    const double sd = fma(sp, d * z, d);
+    *cs = fma(-es, sd, fma(ec, cm1, ec));
+    *sn = fma(ec, sd, fma(es, cm1, es));
+}
+#endif
+
 #if defined(__CUDACC__)
 // 1/sqrt(x) for normal positive x: hardware seed (rsqrt.approx.ftz.f64, ~2^-22) refined by two
 // Newton steps (y <- y + y*(1 - x y^2)/2): ~1 ulp, 10 instructions instead of the ~35 of the
