@@ -572,6 +572,7 @@ struct KbSmem {
     double lat[9], org[3];
     int own_start[8], own_off[9];
     int flags[6];
+    int ncand_owned;                           // candidates with an owned atom j (a prefix of the sorted keys)
 };
 
 __global__ void __launch_bounds__(KB_THREADS) k_neigh_block(const NeighBlockArgs B) {
@@ -596,14 +597,17 @@ __global__ void __launch_bounds__(KB_THREADS) k_neigh_block(const NeighBlockArgs
     if (tid < 6) S.flags[tid] = 0;
     // ---- centres of the block
     const int o1 = e1 - B1, o2 = e2 - B2, nown = (e0 - B0) * o1 * o2;
+    __syncwarp();
     if (tid < 8) {
-        int cnt = 0;
+        int cnt = 0, own = 0;
         if (tid < nown) {
             const int id = ((B0 + tid / (o1 * o2)) * nb1 + (B1 + (tid / o2) % o1)) * nb2 + (B2 + tid % o2);
             S.own_start[tid] = A.bin_start[s.bin_off + id];
             cnt = A.bin_start[s.bin_off + id + 1] - S.own_start[tid];
+            own = A.bin_nown ? A.bin_nown[s.bin_off + id] : cnt;
         }
         S.own_off[tid] = cnt;
+        if (own) atomicAdd(&S.flags[5], own);      // centres of the block that this rank owns (decomposed runs)
     }
     __syncthreads();
     if (tid == 0) {
@@ -614,6 +618,10 @@ __global__ void __launch_bounds__(KB_THREADS) k_neigh_block(const NeighBlockArgs
     __syncthreads();
     const int ncentres = S.own_off[8];
     if (ncentres == 0) return;
+    // A block of the ghost shell (no owned centre): its centres only list OWNED neighbours (what the ghost part
+    // of the force gather needs), so only the owned records of the candidate bins -- they come first in every
+    // cell -- are collected and sorted: most shell blocks then hold few candidates or none.
+    const bool all_ghost = A.bin_nown != nullptr && S.flags[5] == 0;
     // ---- candidate bins: [B - m, e - 1 + m] per direction, wrapped (periodic) or clipped (open region)
     const int m0 = s.mscan[0], m1 = s.mscan[1], m2 = s.mscan[2];
     const int w0 = e0 - B0 + 2 * m0, w1 = e1 - B1 + 2 * m1, w2 = e2 - B2 + 2 * m2;
@@ -629,7 +637,7 @@ __global__ void __launch_bounds__(KB_THREADS) k_neigh_block(const NeighBlockArgs
             if (inside) {
                 const int id = ((t0 - s0 * nb0) * nb1 + (t1 - s1 * nb1)) * nb2 + (t2 - s2 * nb2);
                 const int start = A.bin_start[s.bin_off + id];
-                cnt = A.bin_start[s.bin_off + id + 1] - start;
+                cnt = all_ghost ? A.bin_nown[s.bin_off + id] : A.bin_start[s.bin_off + id + 1] - start;
                 S.cb_start[t] = start;
                 S.cb_shift[t] = ((s0 + 512) << 20) | ((s1 + 512) << 10) | (s2 + 512);
             }
@@ -695,6 +703,16 @@ __global__ void __launch_bounds__(KB_THREADS) k_neigh_block(const NeighBlockArgs
         }
         S.fx[c] = gx; S.fy[c] = gy; S.fz[c] = gz;
     }
+    if (tid == 0) {
+        // the keys are sorted by atom index first and a rank's owned atoms come first: the candidates a GHOST
+        // centre may list are a prefix of the array
+        int lo = 0, hi = ncand;
+        if (A.bin_nown) {
+            const uint64_t bound = (uint64_t)(uint32_t)A.n_own << 32;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (S.ck[mid] < bound) lo = mid + 1; else hi = mid; }
+        } else lo = ncand;
+        S.ncand_owned = lo;
+    }
     __syncthreads();
     // ---- every warp walks the sorted candidates for its centres: groups of 128 candidates pass a cheap
     // single-precision pre-filter (a strict superset of dis <= rskin), the survivors are compacted in order
@@ -720,13 +738,14 @@ __global__ void __launch_bounds__(KB_THREADS) k_neigh_block(const NeighBlockArgs
         uint64_t *exact = A.nbr_keys ? A.nbr_keys + (size_t)i * cap : nullptr;
         int ns = 0, ne = 0, nclose = 0;
         double d2min = 1e300;
-        for (int g0 = 0; g0 < ncand; g0 += KB_GROUP) {
+        const int ncand_i = ghost ? S.ncand_owned : ncand;
+        for (int g0 = 0; g0 < ncand_i; g0 += KB_GROUP) {
             int nsv = 0;
 #pragma unroll
             for (int u = 0; u < KB_GROUP / 32; u++) {
                 const int c = g0 + u * 32 + lane;
                 bool pass = false;
-                if (c < ncand) {
+                if (c < ncand_i) {
                     const float dx = S.fx[c] - hx, dy = S.fy[c] - hy, dz = S.fz[c] - hz;
                     pass = fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= B.f2pre;
                 }
