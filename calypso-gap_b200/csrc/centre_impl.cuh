@@ -15,26 +15,35 @@
 //
 // Structure per centre (all orders fixed -> results are bit-reproducible):
 //   1. stage neighbours in shared memory as records (x, y, z, r, 1/r, w) -- absolute image
-//      coordinates in the reference's arithmetic (geom.cuh) -- and (fc, fc') for each
-//      cutoff class the neighbour belongs to (classes = distinct cutoffs, descending, so
-//      the classes of a distance are a prefix).  These arrays sit at COMPILE-TIME offsets
-//      (template PCAP), so the hot loops address them as [index register + immediate];
-//   2. radial functions: one thread per neighbour, warp-shuffle sums;
-//   3. triplet list: all pairs q=(a<b) of the flat triangular index are tested ONCE
-//      with the exact reference arithmetic (squared-distance thresholds equivalent
-//      to the reference's sqrt(..) > cutoff); survivors carry their "bucket" = number
-//      of classes they belong to; a deterministic counting sort orders them by bucket
-//      (descending), so the items of class c are the prefix S[0 .. npre[c]);
+//      coordinates in the reference's arithmetic (geom.cuh).  Tiers with one neighbour per thread
+//      (PCAP <= 256) stage them ORDERED by the number of cutoff classes they belong to (classes =
+//      distinct cutoffs, descending, so the classes of a distance are a prefix): the members of
+//      class c are the places 0 .. pc[c]-1, and a byte permutation maps places back to list slots.
+//      These arrays sit at COMPILE-TIME offsets (template PCAP), so the hot loops address them as
+//      [index register + immediate];
+//   2. pair tests: all pairs q = (a < b) of the flat triangular index are tested ONCE with the
+//      exact reference arithmetic (squared-distance thresholds equivalent to the reference's
+//      sqrt(..) > cutoff); a 32-pair trip tests as many thresholds as its rows' class count asks
+//      for (one for most trips); survivors carry their "bucket" = number of classes they belong to;
+//   3. while ONE warp places the (warp, bucket) runs (a short scan), the other warps fill the
+//      (fc, fc') tables of every (class, member); then the survivors move to their bucket's run of
+//      the sorted list S (descending bucket: the items of class c are the prefix S[0 .. npre[c]))
+//      and the radial functions (one warp task per two functions) run in the same slot;
 //   4. forward: class-outer loop over that prefix, per-thread register accumulators
 //      per (class, alpha) group [sum pe, sum pe*cos, and the two weighted sums; the
 //      lambda=+-1 functions are (sum pe +- sum pe*cos)], one warp reduction per class;
-//   5. (fused) GPR for this atom in the CTA: difference form, no cancellation;
+//   5. (fused) GPR for this atom in the CTA: difference form, no cancellation; the sparse set is
+//      read past L1 (ld.global.cg);
 //   6. backward: warps take batches of 32 triplets of the SAME bucket; per class one
-//      sincos and per (class, alpha) one exp: the sum over symmetry functions is
-//      folded into four per-centre constants per group (sum du, sum dw, sum lam*du,
-//      sum lam*dw), so there is no inner loop over functions; the three leg scalars
+//      sincos and per (class, alpha) one exp (ONE per triplet when every class carries the same
+//      two exponents, fetched from the forward pass's parking buffer in MODE_FUSED_SE): the sum over
+//      symmetry functions is folded into four per-centre constants per group (sum du, sum dw,
+//      sum lam*du, sum lam*dw), so there is no inner loop over functions; the three leg scalars
 //      go to per-warp private accumulators (dE/dx_j = A_j d_j - V_j) with in-warp
 //      conflict serialisation: no atomics anywhere.
+//   The kernel runs at the 80-register cap of three CTAs per SM and leaves ~30 KB of L1: values that
+//   would be spilled across the hot loops (coordinates, bucket constants, the parking buffer's
+//   start) are re-read from shared memory instead -- tools/spill_lines.py shows what is left.
 //
 // Thread-block clusters (template CS = 1, 2 or 4 CTAs per centre): when a launch has fewer
 // centres than the device has CTA slots (a 64-atom MD cell uses 64 of 444), CS CTAs of one
